@@ -1,0 +1,198 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet-50 (reference symbol, 25.5 M params) synthetic-data training throughput,
+images/sec over the whole job, bf16, device-timed, max over ranks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode allreduce|ps_sync|ps_dedicated|nccl|nccl_ps]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...   -> the unmodified reference (unavailable offline)
+
+Reference analogue: `train_imagenet.py --benchmark 1 --kv-store device|dist_sync_device`
+(MX/example/image-classification/README.md:253-258) and the Horovod `train_synthetic.sh` (README.md:149-163).
+Published comparator: ResNet-50 training 363.69 img/s on one V100 (MX/docs/faq/perf.md:219).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+BASELINE_IMG_S_PER_GPU = 363.69  # BASELINE.md row 13 (V100, batch 128, fp32) - the reference's best published ResNet-50 training number
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--mode", default=None, help="allreduce (default) | ps_sync | ps_dedicated | nccl | nccl_ps")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--image-size", type=int, default=224)
+    ap.add_argument("--num-layers", type=int, default=50)
+    ap.add_argument("--bucket-mb", type=float, default=16.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def reference_arm(args):
+    # The reference is CloudFormation JSON + a Python-2/boto agent + git submodules of MXNet 1.3 / TF 1.x;
+    # `pip install /root/reference` finds no setup.py/pyproject, and the vendored MXNet python package needs a
+    # libmxnet.so built with CUDA<=10 / cuDNN 7 (no sm_100 support).  Outcome recorded in DESIGN.md.
+    print(json.dumps({"impl": "reference",
+                      "unavailable": "reference is not pip-installable offline (no setup.py; vendored MXNet 1.3 needs "
+                                     "libmxnet.so built with CUDA<=10/cuDNN7, no sm_100) - see DESIGN.md"}))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from deeplearning_cfn_b200.models import resnet, to_b200_layout
+    from deeplearning_cfn_b200.ops import native
+    from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer
+    from deeplearning_cfn_b200.utils.clocks import ClockSampler
+    from deeplearning_cfn_b200.utils.data import DevicePrefetcher, SyntheticImageSource, synthetic_device_batch
+
+    native.lib()  # fail loudly if the sm_100a library is missing
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(1234)
+
+    mode = args.mode or ("nccl" if args.impl == "nccl" else "allreduce")
+    servers = workers = None
+    if mode == "ps_dedicated":  # BASELINE config 3: 1 server + (N-1) workers
+        mode, servers, workers = "ps_sync", [0], list(range(1, world))
+    if world == 1:
+        mode = "local"
+
+    model = to_b200_layout(resnet(args.num_layers, 1000, args.image_size).to(device), torch.bfloat16)
+    model.train()
+    trainer = DataParallelTrainer(model, mode=mode, optimizer="sgd_mom", lr=0.1, momentum=0.9, wd=1e-4,
+                                  bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
+                                  worker_ranks=workers)
+    n_workers = len(trainer.workers)
+    is_worker = trainer.is_worker
+
+    x, y = synthetic_device_batch(args.batch, args.image_size, 1000, device)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---------------------------------------------------------------- device-timed loop
+    for _ in range(args.warmup):
+        trainer.step(x, y) if is_worker else trainer.step()
+    sync_all()
+    launches0 = native.launch_count
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(gpu_index=local_rank) if rank == 0 else None
+    if sampler:
+        sampler.__enter__()
+    t_start.record()
+    for _ in range(args.steps):
+        trainer.step(x, y) if is_worker else trainer.step()
+    t_end.record()
+    sync_all()
+    if sampler:
+        sampler.__exit__(None, None, None)
+    ms = t_start.elapsed_time(t_end)
+    launches = native.launch_count - launches0
+    trainer.check()
+
+    # ---------------------------------------------------------------- end-to-end loop (public API + H2D/D2H)
+    e2e = None
+    if not args.no_e2e:
+        src = SyntheticImageSource(args.batch, args.image_size, 1000) if is_worker else None
+        pre = DevicePrefetcher(src, device) if is_worker else None
+        host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        for _ in range(3):
+            if is_worker:
+                xb, yb = pre.next()
+                trainer.step(xb, yb)
+            else:
+                trainer.step()
+        sync_all()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        last = 0.0
+        e_start.record()
+        for _ in range(args.steps):
+            if is_worker:
+                xb, yb = pre.next()                      # H2D of this step's inputs (pinned -> device) + normalise
+                loss = trainer.step(xb, yb)
+                host_loss.copy_(loss.detach().float().reshape(1), non_blocking=True)   # D2H of the step's loss
+                torch.cuda.current_stream().synchronize()
+                last = float(host_loss[0])
+            else:
+                trainer.step()
+        e_end.record()
+        sync_all()
+        e_ms = e_start.elapsed_time(e_end)
+        e2e = {"ms": e_ms, "loss": last, "h2d": src.bytes_per_batch if is_worker else 0}
+
+    # ---------------------------------------------------------------- reduce over ranks
+    t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(launches)], device=device, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    else:
+        e_ms = float(t[1])
+    if rank == 0:
+        global_batch = args.batch * n_workers
+        value = global_batch * args.steps / (ms / 1e3)
+        clocks = sampler.summary() if sampler else {}
+        par = {"local": "single", "allreduce": f"dp{world}-fused-allreduce", "ps_sync": f"ps-sync-{len(trainer.servers)}s{n_workers}w",
+               "nccl": f"dp{world}-nccl-allreduce", "nccl_ps": f"dp{world}-nccl-reduce-bcast"}[trainer.mode]
+        rec = {"metric": "resnet50_train_images_per_sec", "value": round(value, 2), "unit": "images/sec",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": round(value / (BASELINE_IMG_S_PER_GPU * world), 3), "dtype": "bf16",
+               "data": "synthetic (random images/labels, random-init weights)",
+               "impl": "ours" if args.impl == "ours" else "nccl-baseline",
+               "config": {"model": f"resnet-{args.num_layers}-v2 (reference symbols/resnet.py)",
+                          "global_batch": global_batch, "per_gpu_batch": args.batch, "image": args.image_size,
+                          "seq_len": None, "parallelism": par, "optimizer": "sgd-momentum multi-precision (fp32 master)",
+                          "bucket_mb": args.bucket_mb, "l2": "inputs+activations larger than L2 (no flush needed)",
+                          "baseline": "363.69 img/s per V100 (perf.md:219) x n_gpus"},
+               "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
+                          "reasons": clocks.get("reasons", [])},
+               "gpu_launches": launches}
+        if e2e:
+            rec["e2e"] = {"value": round(global_batch * args.steps / (e_ms / 1e3), 2), "unit": "images/sec",
+                          "h2d_bytes_per_step": e2e["h2d"] * n_workers if is_worker else 0,
+                          "d2h_bytes_per_step": 4 * n_workers, "last_loss": e2e["loss"]}
+            if not is_worker:  # rank 0 is a dedicated server: bytes come from the workers
+                rec["e2e"]["h2d_bytes_per_step"] = (args.batch * args.image_size * args.image_size * 3 + args.batch * 8) * n_workers
+        print(json.dumps(rec), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

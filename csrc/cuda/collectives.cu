@@ -1,0 +1,525 @@
+// Fused compute+collective kernels over the symmetric peer-HBM heap (sm_100a, NVLink 5 / NVSwitch).
+//
+//  kallreduce      bucket scale (1/world, loss-scale, ...) (+) two-shot all-reduce in ONE kernel:
+//                  every rank reduces its 1/W slice by loading the slice from all peers, scales it in
+//                  fp32 and stores the result straight into every peer's bucket.
+//                  <- replaces Horovod's pack -> ncclAllReduce -> unpack (reference C11, run.sh:70-81)
+//  kps_sync        parameter-server step in ONE kernel: push (server loads the gradient shard from
+//                  every worker's HBM) (+) sum over workers (+) rescale/clip (+) SGD/momentum/Adam on the
+//                  fp32 master copy (+) pull (server stores the new bf16 weights into every worker's HBM).
+//                  <- replaces ZPush -> server merged+=recved -> updater -> ZPull -> Broadcast
+//                     (reference C6/C7/C2: kvstore_dist.h:311-434, kvstore_dist_server.h:346-375,707-735)
+//                  The per-key arrival counter `request.size()==NumWorkers` (kvstore_dist_server.h:348)
+//                  becomes the device-side flag barrier at kernel entry.
+//  kps_async_*     dist_async: the server applies each worker's push as it arrives, no cross-worker wait
+//                  (kvstore_dist_server.h:348,715-723).
+//  kbroadcast      root's bucket -> every peer (initial parameter broadcast; reference C2 ncclBcast).
+//  kbarrier        device-side rendezvous (reference C8: Postoffice::Barrier through the scheduler).
+//
+// All of them are latency/NVLink-bound streaming kernels: 16-byte accesses, >= W independent loads in
+// flight per thread, a small grid (default 32 CTAs x 512 threads ~ 4 MB in flight) so that the rest of
+// the 148 SMs keep running backward while a bucket is on the wire.
+#include "symm.cuh"
+
+namespace dlcfn {
+
+struct OptArgs {
+  int kind;
+  float lr, wd, momentum, beta1, beta2, eps, rescale, clip;
+};
+
+__device__ __forceinline__ void opt_apply(const OptArgs& o, float g, float& w, float& s1, float& s2) {
+  g *= o.rescale;
+  if (o.clip > 0.f) g = fminf(fmaxf(g, -o.clip), o.clip);
+  if (o.kind == 0) {
+    w = (1.f - o.lr * o.wd) * w - o.lr * g;
+  } else if (o.kind == 1) {
+    s1 = o.momentum * s1 - o.lr * o.wd * w - o.lr * g;
+    w += s1;
+  } else if (o.kind == 2) {
+    g += o.wd * w;
+    s1 = o.beta1 * s1 + (1.f - o.beta1) * g;
+    s2 = o.beta2 * s2 + (1.f - o.beta2) * g * g;
+    w -= o.lr * s1 / (sqrtf(s2) + o.eps);
+  } else if (o.kind == 3) {
+    w += g;
+  } else {  // kind 4: no optimizer — store the reduced gradient (kvstore without updater)
+    w = g;
+  }
+}
+
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                      pack_bf16(f[6], f[7]));
+  }
+};
+
+// ------------------------------------------------------------- barrier ------
+__global__ void kbarrier(SymmDev s, int channel) {
+  uint32_t e = epoch_load(s, channel);
+  block_barrier(s, channel, e + 1);
+  epoch_store(s, channel, e + 1);
+}
+
+// ----------------------------------------------------------- all-reduce -----
+// In place on heap[off, off + 16*nvec).  Slice r = vectors [r*per, (r+1)*per) is reduced by rank r.
+template <typename T, int W>
+__global__ void __launch_bounds__(512) kallreduce(SymmDev s, size_t off, size_t nvec, float scale,
+                                                  int channel) {
+  constexpr int N = Vec16<T>::N;
+  const uint32_t e = epoch_load(s, channel);
+  block_barrier(s, channel, e + 1);
+
+  const size_t per = (nvec + W - 1) / W;
+  const size_t lo = per * s.rank;
+  const size_t hi = (lo + per < nvec) ? lo + per : nvec;
+  uint4* buf[W];
+#pragma unroll
+  for (int p = 0; p < W; ++p) buf[p] = reinterpret_cast<uint4*>(s.base[p] + off);
+
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < hi; v += stride) {
+    uint4 x[W];
+#pragma unroll
+    for (int p = 0; p < W; ++p) x[p] = ld_relaxed_sys_v4(buf[p] + v);
+    // fixed summation order (rank 0, 1, ..., W-1): run-to-run deterministic, and since exactly one
+    // rank reduces each element every rank ends up with bit-identical results
+    float acc[N], t[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int p = 0; p < W; ++p) {
+      Vec16<T>::unpack(x[p], t);
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[k] += t[k];
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] *= scale;
+    const uint4 o = Vec16<T>::pack(acc);
+#pragma unroll
+    for (int p = 0; p < W; ++p) st_stream_v4(buf[p] + v, o);
+  }
+
+  block_barrier(s, channel, e + 2);
+  epoch_store(s, channel, e + 2);
+}
+
+// ------------------------------------------------------------ broadcast -----
+__global__ void __launch_bounds__(512) kbroadcast(SymmDev s, size_t off, size_t nvec, int root, int channel) {
+  const uint32_t e = epoch_load(s, channel);
+  block_barrier(s, channel, e + 1);
+  if (s.rank == root) {
+    const uint4* src = reinterpret_cast<const uint4*>(s.base[root] + off);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+      const uint4 x = src[v];
+      for (int p = 1; p < s.world; ++p)
+        st_stream_v4(reinterpret_cast<uint4*>(s.base[(root + p) % s.world] + off) + v, x);
+    }
+  }
+  block_barrier(s, channel, e + 2);
+  epoch_store(s, channel, e + 2);
+}
+
+// ----------------------------------------------------- parameter server -----
+struct PSArgs {
+  size_t grad_off;       // heap byte offset of the flat gradient buffer (every worker, same offset)
+  size_t weight_off;     // heap byte offset of the flat model-weight buffer
+  size_t lo, hi;         // this rank's server shard in 16-byte vectors of T; lo == hi: not a server
+  uint32_t worker_mask;  // ranks that push gradients and receive weights
+  float* master;         // fp32 master weights of the shard (index 0 == element lo*N)
+  float* s1;             // optimizer state 1 (momentum / Adam m) or null
+  float* s2;             // optimizer state 2 (Adam v) or null
+  OptArgs opt;
+  int channel;
+};
+
+// Peer pointer tables are indexed by rank with compile-time indices only, so they live in registers.
+struct PSPtrs {
+  const uint4* g[DLCFN_MAX_RANKS];  // gradient buffer of rank r (peer HBM)
+  uint4* w[DLCFN_MAX_RANKS];        // weight buffer of rank r
+  uint32_t load_mask, store_mask;
+};
+
+__device__ __forceinline__ void ps_make_ptrs(const PSArgs& a, const SymmDev& s, uint32_t worker_mask,
+                                             PSPtrs& P) {
+#pragma unroll
+  for (int r = 0; r < DLCFN_MAX_RANKS; ++r) {
+    P.g[r] = reinterpret_cast<const uint4*>(s.base[r] + a.grad_off);
+    P.w[r] = reinterpret_cast<uint4*>(s.base[r] + a.weight_off);
+  }
+  const uint32_t live = (s.world >= 32) ? 0xffffffffu : ((1u << s.world) - 1u);
+  P.load_mask = worker_mask & live;
+  P.store_mask = (worker_mask | (1u << s.rank)) & live;  // the server keeps its own copy as well
+}
+
+template <typename T>
+__device__ __forceinline__ void ps_update_vec(const PSArgs& a, const PSPtrs& P, size_t v) {
+  constexpr int N = Vec16<T>::N;
+  uint4 x[DLCFN_MAX_RANKS];
+#pragma unroll
+  for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
+    if ((P.load_mask >> r) & 1u) x[r] = ld_relaxed_sys_v4(P.g[r] + v);
+  float g[N], t[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) g[k] = 0.f;
+  // fixed rank order: deterministic, independent of which server owns the shard
+#pragma unroll
+  for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
+    if ((P.load_mask >> r) & 1u) {
+      Vec16<T>::unpack(x[r], t);
+#pragma unroll
+      for (int k = 0; k < N; ++k) g[k] += t[k];
+    }
+  const size_t i0 = (v - a.lo) * N;
+  float w[N], m1[N], m2[N];
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    float4 f = reinterpret_cast<const float4*>(a.master + i0)[q];
+    w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+    if (a.opt.kind == 1 || a.opt.kind == 2) {
+      float4 h = reinterpret_cast<const float4*>(a.s1 + i0)[q];
+      m1[4 * q] = h.x; m1[4 * q + 1] = h.y; m1[4 * q + 2] = h.z; m1[4 * q + 3] = h.w;
+    } else {
+      m1[4 * q] = m1[4 * q + 1] = m1[4 * q + 2] = m1[4 * q + 3] = 0.f;
+    }
+    if (a.opt.kind == 2) {
+      float4 h = reinterpret_cast<const float4*>(a.s2 + i0)[q];
+      m2[4 * q] = h.x; m2[4 * q + 1] = h.y; m2[4 * q + 2] = h.z; m2[4 * q + 3] = h.w;
+    } else {
+      m2[4 * q] = m2[4 * q + 1] = m2[4 * q + 2] = m2[4 * q + 3] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) opt_apply(a.opt, g[k], w[k], m1[k], m2[k]);
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    reinterpret_cast<float4*>(a.master + i0)[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    if (a.opt.kind == 1 || a.opt.kind == 2)
+      reinterpret_cast<float4*>(a.s1 + i0)[q] = make_float4(m1[4 * q], m1[4 * q + 1], m1[4 * q + 2], m1[4 * q + 3]);
+    if (a.opt.kind == 2)
+      reinterpret_cast<float4*>(a.s2 + i0)[q] = make_float4(m2[4 * q], m2[4 * q + 1], m2[4 * q + 2], m2[4 * q + 3]);
+  }
+  const uint4 o = Vec16<T>::pack(w);
+  // pull: the server writes the fresh weights into every worker's model buffer (and its own copy)
+#pragma unroll
+  for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
+    if ((P.store_mask >> r) & 1u) st_stream_v4(P.w[r] + v, o);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) kps_sync(SymmDev s, PSArgs a) {
+  const uint32_t e = epoch_load(s, a.channel);
+  block_barrier(s, a.channel, e + 1);  // every worker's gradients are complete ("all W pushes arrived")
+
+  PSPtrs P;
+  ps_make_ptrs(a, s, a.worker_mask, P);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = a.lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < a.hi; v += stride)
+    ps_update_vec<T>(a, P, v);
+
+  block_barrier(s, a.channel, e + 2);  // every server finished writing: the pull is complete
+  epoch_store(s, a.channel, e + 2);
+}
+
+// dist_async.  Roles are disjoint (a rank is a server or a worker).  Worker side: announce push #k to
+// every server, then wait until every server has answered #k (its weights for this worker are written).
+__global__ void kps_async_worker(SymmDev s, uint32_t server_mask, int channel) {
+  const uint32_t k = epoch_load(s, channel) + 1;
+  __syncthreads();
+  if ((int)threadIdx.x < s.world && ((server_mask >> threadIdx.x) & 1u)) {
+    st_release_sys(sig_slot(s, threadIdx.x, channel, blockIdx.x, s.rank), k);
+    if (!spin_wait_ge(sig_slot(s, s.rank, channel + 1, blockIdx.x, threadIdx.x), k, kSpinTimeoutNs))
+      atomicExch(s.err, 1);
+  }
+  __syncthreads();
+  epoch_store(s, channel, k);
+}
+
+// Server side: one launch serves exactly one push from each worker, in arrival order.  Each CTA owns a
+// fixed slice of the shard, polls the workers' flags for that slice and applies w -= f(g_w) immediately.
+template <typename T>
+__global__ void __launch_bounds__(512) kps_async_server(SymmDev s, PSArgs a) {
+  __shared__ int sh_next;
+  __shared__ uint32_t sh_done;  // bitmask of workers served in this launch
+  const uint32_t k = epoch_load(s, a.channel) + 1;
+  if (threadIdx.x == 0) sh_done = 0;
+  __syncthreads();
+  int nworkers = __popc(a.worker_mask);
+  const size_t span = a.hi - a.lo;
+  const size_t per = (span + gridDim.x - 1) / gridDim.x;
+  const size_t blo = a.lo + per * blockIdx.x;
+  const size_t bhi = (blo + per < a.hi) ? blo + per : a.hi;
+  for (int served = 0; served < nworkers; ++served) {
+    if (threadIdx.x == 0) {
+      int found = -1;
+      long long t0 = clock_now();
+      while (found < 0) {
+        for (int r = 0; r < s.world && found < 0; ++r) {
+          if (!((a.worker_mask >> r) & 1u) || ((sh_done >> r) & 1u)) continue;
+          if ((int32_t)(ld_acquire_sys(sig_slot(s, s.rank, a.channel, blockIdx.x, r)) - k) >= 0) found = r;
+        }
+        if (found < 0 && clock_now() - t0 > kSpinTimeoutNs) {
+          atomicExch(s.err, 1);
+          found = -2;
+        }
+      }
+      sh_next = found;
+      if (found >= 0) sh_done |= 1u << found;
+    }
+    __syncthreads();
+    const int w = sh_next;
+    if (w < 0) break;
+    PSPtrs P;
+    ps_make_ptrs(a, s, 1u << w, P);
+    for (size_t v = blo + threadIdx.x; v < bhi; v += blockDim.x) ps_update_vec<T>(a, P, v);
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(sig_slot(s, w, a.channel + 1, blockIdx.x, s.rank), k);
+  }
+  __syncthreads();
+  epoch_store(s, a.channel, k);
+}
+
+}  // namespace dlcfn
+
+using namespace dlcfn;
+
+// ============================================================ host API ======
+DLCFN_API int dlcfn_symm_create(size_t heap_bytes, int rank, int world, void** out_ctx) {
+  if (world < 1 || world > DLCFN_MAX_RANKS || rank < 0 || rank >= world) return (int)cudaErrorInvalidValue;
+  SymmCtx* c = new SymmCtx();
+  c->rank = rank;
+  c->world = world;
+  c->heap_bytes = heap_bytes;
+  DLCFN_CHECK(cudaGetDevice(&c->device));
+  const size_t total = kHeapOff + ((heap_bytes + 255) & ~(size_t)255);
+  void* p = nullptr;
+  DLCFN_CHECK(cudaMalloc(&p, total));
+  DLCFN_CHECK(cudaMemset(p, 0, kHeapOff));
+  c->local = (char*)p;
+  c->peer[rank] = c->local;
+  *out_ctx = c;
+  return 0;
+}
+
+DLCFN_API int dlcfn_symm_get_handle(void* ctx, void* out64) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  cudaIpcMemHandle_t h;
+  DLCFN_CHECK(cudaIpcGetMemHandle(&h, c->local));
+  static_assert(sizeof(h) == 64, "ipc handle size");
+  memcpy(out64, &h, 64);
+  return 0;
+}
+
+DLCFN_API int dlcfn_symm_open_peer(void* ctx, int peer, const void* handle64) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (peer < 0 || peer >= c->world || peer == c->rank) return (int)cudaErrorInvalidValue;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  DLCFN_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peer[peer] = (char*)p;
+  c->opened_ipc[peer] = true;
+  return 0;
+}
+
+// single-process multi-GPU: the peer allocation is already addressable (peer access enabled by caller)
+DLCFN_API int dlcfn_symm_set_peer_ptr(void* ctx, int peer, void* whole_allocation) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (peer < 0 || peer >= c->world) return (int)cudaErrorInvalidValue;
+  c->peer[peer] = (char*)whole_allocation;
+  return 0;
+}
+
+DLCFN_API void* dlcfn_symm_allocation(void* ctx) { return ((SymmCtx*)ctx)->local; }
+
+DLCFN_API int dlcfn_symm_finalize(void* ctx) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  for (int p = 0; p < c->world; ++p)
+    if (!c->peer[p]) return (int)cudaErrorInvalidValue;
+  for (int p = 0; p < DLCFN_MAX_RANKS; ++p) {
+    char* a = c->peer[p < c->world ? p : c->rank];
+    c->dev.base[p] = a + kHeapOff;
+    c->dev.sig[p] = reinterpret_cast<uint32_t*>(a);
+  }
+  c->dev.epoch = reinterpret_cast<uint32_t*>(c->local + kEpochOff);
+  c->dev.err = reinterpret_cast<int*>(c->local + kErrOff);
+  c->dev.rank = c->rank;
+  c->dev.world = c->world;
+  c->finalized = true;
+  return 0;
+}
+
+DLCFN_API void* dlcfn_symm_heap_ptr(void* ctx, int peer) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (peer < 0 || peer >= c->world || !c->peer[peer]) return nullptr;
+  return c->peer[peer] + kHeapOff;
+}
+
+// Reads and clears the device error word (set when a flag wait timed out).  Synchronises the stream.
+DLCFN_API int dlcfn_symm_check_error(void* ctx, cudaStream_t stream, int* out_err) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  int e = 0;
+  DLCFN_CHECK(cudaMemcpyAsync(&e, c->dev.err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  DLCFN_CHECK(cudaStreamSynchronize(stream));
+  if (e) DLCFN_CHECK(cudaMemsetAsync(c->dev.err, 0, sizeof(int), stream));
+  *out_err = e;
+  return 0;
+}
+
+DLCFN_API int dlcfn_symm_destroy(void* ctx) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  for (int p = 0; p < c->world; ++p)
+    if (c->opened_ipc[p] && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+  if (c->local) cudaFree(c->local);
+  delete c;
+  return 0;
+}
+
+static inline int clamp_blocks(int nblocks, size_t work_vecs, int threads) {
+  if (nblocks <= 0) nblocks = 32;
+  if (nblocks > kSigMaxBlocks) nblocks = kSigMaxBlocks;
+  size_t need = (work_vecs + threads - 1) / threads;
+  if (need < 1) need = 1;
+  if ((size_t)nblocks > need) nblocks = (int)need;
+  return nblocks;
+}
+
+DLCFN_API int dlcfn_barrier(void* ctx, int channel, cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (!c->finalized || channel < 0 || channel >= kSigChannels) return (int)cudaErrorInvalidValue;
+  kbarrier<<<1, 32, 0, stream>>>(c->dev, channel);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int launch_allreduce(SymmCtx* c, size_t off, size_t nvec, float scale, int channel, int nblocks,
+                            cudaStream_t st) {
+  // NOTE: every rank must compute the same grid, so the clamp only depends on (nvec, world)
+  const size_t per = (nvec + c->world - 1) / c->world;
+  const int g = clamp_blocks(nblocks, per, 512);
+  switch (c->world) {
+    case 1: kallreduce<T, 1><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 2: kallreduce<T, 2><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 3: kallreduce<T, 3><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 4: kallreduce<T, 4><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 5: kallreduce<T, 5><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 6: kallreduce<T, 6><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 7: kallreduce<T, 7><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 8: kallreduce<T, 8><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  return (int)cudaGetLastError();
+}
+
+// In-place fused scale + all-reduce of heap[off_bytes, off_bytes + count*sizeof(T)) (padded to 16 B).
+DLCFN_API int dlcfn_allreduce(void* ctx, size_t off_bytes, size_t count, int dtype, float scale, int channel,
+                              int nblocks, cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (!c->finalized || (off_bytes & 15) || channel < 0 || channel >= kSigChannels)
+    return (int)cudaErrorInvalidValue;
+  if (count == 0) return 0;
+  if (dtype == 0) return launch_allreduce<float>(c, off_bytes, (count + 3) / 4, scale, channel, nblocks, stream);
+  if (dtype == 1)
+    return launch_allreduce<__nv_bfloat16>(c, off_bytes, (count + 7) / 8, scale, channel, nblocks, stream);
+  return (int)cudaErrorInvalidValue;
+}
+
+DLCFN_API int dlcfn_broadcast(void* ctx, size_t off_bytes, size_t bytes, int root, int channel, int nblocks,
+                              cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (!c->finalized || (off_bytes & 15) || root < 0 || root >= c->world) return (int)cudaErrorInvalidValue;
+  if (bytes == 0) return 0;
+  const size_t nvec = (bytes + 15) / 16;
+  const int g = clamp_blocks(nblocks, nvec, 512);
+  kbroadcast<<<g, 512, 0, stream>>>(c->dev, off_bytes, nvec, root, channel);
+  return (int)cudaGetLastError();
+}
+
+// One synchronous parameter-server step, launched by EVERY rank (servers and workers alike).
+// shard_lo/shard_hi are element indices (multiples of 16B/sizeof(T)) into the flat buffers.
+DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, size_t total_count,
+                                 size_t shard_lo, size_t shard_hi, uint32_t worker_mask, float* master,
+                                 float* s1, float* s2, int dtype, int opt_kind, float lr, float wd,
+                                 float momentum, float beta1, float beta2, float eps, float rescale,
+                                 float clip, int channel, int nblocks, cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  const int N = dtype == 1 ? 8 : 4;
+  if (!c->finalized || (grad_off & 15) || (weight_off & 15) || (shard_lo % N) || dtype < 0 || dtype > 1)
+    return (int)cudaErrorInvalidValue;
+  if (worker_mask == 0 || channel < 0 || channel >= kSigChannels) return (int)cudaErrorInvalidValue;
+  PSArgs a;
+  a.grad_off = grad_off;
+  a.weight_off = weight_off;
+  a.lo = shard_lo / N;
+  a.hi = (shard_hi + N - 1) / N;
+  a.worker_mask = worker_mask;
+  a.master = master;
+  a.s1 = s1;
+  a.s2 = s2;
+  a.opt = OptArgs{opt_kind, lr, wd, momentum, beta1, beta2, eps, rescale, clip};
+  a.channel = channel;
+  // same grid on every rank: derived from the total size and world only
+  const size_t per = ((total_count + N - 1) / N + c->world - 1) / c->world;
+  const int g = clamp_blocks(nblocks, per, 512);
+  if (dtype == 1) kps_sync<__nv_bfloat16><<<g, 512, 0, stream>>>(c->dev, a);
+  else kps_sync<float><<<g, 512, 0, stream>>>(c->dev, a);
+  return (int)cudaGetLastError();
+}
+
+DLCFN_API int dlcfn_ps_async_worker(void* ctx, uint32_t server_mask, int channel, int nblocks,
+                                    cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (!c->finalized || channel < 0 || channel + 1 >= kSigChannels || nblocks < 1 || nblocks > kSigMaxBlocks)
+    return (int)cudaErrorInvalidValue;
+  kps_async_worker<<<nblocks, 32, 0, stream>>>(c->dev, server_mask, channel);
+  return (int)cudaGetLastError();
+}
+
+DLCFN_API int dlcfn_ps_async_server(void* ctx, size_t grad_off, size_t weight_off, size_t shard_lo,
+                                    size_t shard_hi, uint32_t worker_mask, float* master, float* s1,
+                                    float* s2, int dtype, int opt_kind, float lr, float wd, float momentum,
+                                    float beta1, float beta2, float eps, float rescale, float clip,
+                                    int channel, int nblocks, cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  const int N = dtype == 1 ? 8 : 4;
+  if (!c->finalized || (grad_off & 15) || (weight_off & 15) || (shard_lo % N) || dtype < 0 || dtype > 1)
+    return (int)cudaErrorInvalidValue;
+  if (channel < 0 || channel + 1 >= kSigChannels || nblocks < 1 || nblocks > kSigMaxBlocks)
+    return (int)cudaErrorInvalidValue;
+  PSArgs a;
+  a.grad_off = grad_off;
+  a.weight_off = weight_off;
+  a.lo = shard_lo / N;
+  a.hi = (shard_hi + N - 1) / N;
+  a.worker_mask = worker_mask;
+  a.master = master;
+  a.s1 = s1;
+  a.s2 = s2;
+  a.opt = OptArgs{opt_kind, lr, wd, momentum, beta1, beta2, eps, rescale, clip};
+  a.channel = channel;
+  if (dtype == 1) kps_async_server<__nv_bfloat16><<<nblocks, 512, 0, stream>>>(c->dev, a);
+  else kps_async_server<float><<<nblocks, 512, 0, stream>>>(c->dev, a);
+  return (int)cudaGetLastError();
+}

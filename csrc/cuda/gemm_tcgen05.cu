@@ -1,0 +1,450 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a, with the parameter "pull" fused into the operand loads.
+//
+//   D[M,N] (bf16|fp32) = A[M,K] * B[N,K]^T (+ bias[N]) (+ D)        fp32 accumulation in TMEM
+//
+//  * A and B are bf16.  Each may be K-major (row-major [rows,K]) or MN-major (stored [K,rows]); the
+//    MN-major forms give dgrad (dX = dY * W) and wgrad (dW = dY^T * X) without materialising transposes.
+//  * B may be ROW-SHARDED ACROSS RANKS in the symmetric peer-HBM heap: the producer warp then issues
+//    its TMA loads against the owning peer's tensor map, i.e. the weight "pull"/all-gather of the
+//    parameter-server path (reference C2: ncclBcast root->all, kvstore_nccl.h:380-396; KVStoreDist
+//    PullImpl + Broadcast, kvstore_dist.h:217-269) happens inside the first GEMM that consumes the
+//    parameters - tile by tile over NVLink, overlapped with the tcgen05 math - and the gathered weight
+//    is never materialised in local HBM.
+//
+// Kernel shape (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16), commits
+//                              to the smem-empty and tmem-full mbarriers; owns TMEM alloc/dealloc
+//   warps 2..5  epilogue       tcgen05.ld 32x32b -> registers -> bias/convert -> 16B global stores;
+//                              two TMEM accumulator stages so the epilogue of tile i overlaps the
+//                              mainloop of tile i+1
+#include "common.cuh"
+#include <cuda.h>
+
+namespace dlcfn {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle-128B atom row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxShards = DLCFN_MAX_RANKS;
+
+struct __align__(64) GemmParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB[kMaxShards];
+  int M, N, K;
+  int n_shards;         // 1: B is local.  >1: B rows sharded over n_shards peers
+  int rows_per_shard;   // B rows (or, for MN-major B: contraction rows... see host) per shard
+  void* D;
+  long long ldd;        // row stride of D in elements
+  const float* bias;    // nullable, length N
+  int d_is_fp32;
+  int accumulate;       // D += result
+  int relu;
+};
+
+// ------------------------------------------------------------------ PTX -----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, 128B swizzle (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---------------------------------------------------------------- kernel ----
+template <int BLOCK_N, bool A_MN, bool B_MN>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;   // 16 / 32 KiB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BLOCK_N;           // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // swizzle-128B atoms need 1024 B alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    for (int s = 0; s < p.n_shards; ++s) tma_prefetch_desc(&p.tmB[s]);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(Cfg::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = (tile % num_m) * kBlockM;
+        const int n_idx = (tile / num_m) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int k_idx = kb * kBlockK;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &p.tmA, full_bar(stage), k_idx, m_idx);  // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j)  // box {64 m, 64 k} per 128B-wide MN atom
+              tma_load_2d(sa + j * 8192, &p.tmA, full_bar(stage), m_idx + 64 * j, k_idx);
+          }
+          if constexpr (!B_MN) {
+            // rows of B (= output columns n) may live on a peer: pick the owner's tensor map
+            const int shard = (p.n_shards > 1) ? n_idx / p.rows_per_shard : 0;
+            const int n_loc = n_idx - shard * p.rows_per_shard;
+            tma_load_2d(sb, &p.tmB[shard], full_bar(stage), k_idx, n_loc);  // box {64 k, BLOCK_N n}
+          } else {
+            // MN-major B is stored [K, N]: the CONTRACTION rows may live on a peer
+            const int shard = (p.n_shards > 1) ? k_idx / p.rows_per_shard : 0;
+            const int k_loc = k_idx - shard * p.rows_per_shard;
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * 8192, &p.tmB[shard], full_bar(stage), n_idx + 64 * j, k_loc);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                             ((uint32_t)(kBlockM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // K-major: advance 16 elements = 32 B inside the swizzle atom; SBO = 8 rows * 128 B
+            // MN-major: advance 16 k-rows = 2048 B; LBO = stride between 64-wide MN atoms, SBO = 1024
+            const uint64_t da = A_MN ? umma_desc(sa + k * 2048, 8192, 1024) : umma_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc(sb + k * 2048, 8192, 1024) : umma_desc(sb + k * 32, 16, 1024);
+            tc_mma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_idx = (tile % num_m) * kBlockM;
+      const int n_idx = (tile / num_m) * BLOCK_N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_idx + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        tc_wait_ld();
+        const int col0 = n_idx + c * 32;
+        if (row_ok && col0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.d_is_fp32) {
+            float* d = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j + 3 < p.N) {
+                float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                if (p.accumulate) {
+                  float4 old = *reinterpret_cast<const float4*>(d + j);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(d + j) = o;
+              } else {
+                for (int t = 0; t < 4; ++t)
+                  if (col0 + j + t < p.N) {
+                    float o = f[j + t] + (p.accumulate ? d[j + t] : 0.f);
+                    d[j + t] = p.relu ? fmaxf(o, 0.f) : o;
+                  }
+              }
+            }
+          } else {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j + 7 < p.N) {
+                float o[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) o[t] = f[j + t];
+                if (p.accumulate) {
+                  uint4 old = *reinterpret_cast<const uint4*>(d + j);
+                  o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
+                  o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
+                }
+                *reinterpret_cast<uint4*>(d + j) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                              pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+              } else {
+                for (int t = 0; t < 8; ++t)
+                  if (col0 + j + t < p.N) {
+                    float o = f[j + t] + (p.accumulate ? __bfloat162float(d[j + t]) : 0.f);
+                    d[j + t] = __float2bfloat16(p.relu ? fmaxf(o, 0.f) : o);
+                  }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));  // 128 arrivals release the accumulator stage
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols));
+  }
+}
+
+// ------------------------------------------------------------------ host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] (cols contiguous, row stride ld elements), box {box_cols, box_rows}
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                    uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch(const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN>;
+  auto kern = kgemm<BLOCK_N, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    DLCFN_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  int grid = num_m * num_n;
+  if (grid > num_sms) grid = num_sms;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dlcfn
+
+using namespace dlcfn;
+
+// a_mn / b_mn: 0 = K-major ([rows, K] row-major), 1 = MN-major ([K, rows] row-major).
+// b_shards: array of n_shards device pointers (peer-mapped); shard s holds rows
+//   [s*rows_per_shard, (s+1)*rows_per_shard) of B's ROW dimension as stored
+//   (K-major: output columns n; MN-major: contraction index k).  n_shards == 1: plain local GEMM.
+// lda / ldb: row strides in elements of the stored matrices.  d_dtype: 0 fp32, 1 bf16.
+DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void* const* b_shards, int n_shards,
+                              int rows_per_shard, long long ldb, int b_mn, void* D, long long ldd, int d_dtype,
+                              const float* bias, int M, int N, int K, int accumulate, int relu, int block_n,
+                              int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (n_shards < 1 || n_shards > kMaxShards) return (int)cudaErrorInvalidValue;
+  if ((lda & 7) || (ldb & 7) || (((uintptr_t)A) & 15)) return (int)cudaErrorInvalidValue;
+  if (block_n != 128 && block_n != 256) block_n = (N >= 2048 && M >= 1024) ? 256 : 128;
+  if (num_sms <= 0) {
+    int dev = 0;
+    DLCFN_CHECK(cudaGetDevice(&dev));
+    DLCFN_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.n_shards = n_shards;
+  p.rows_per_shard = rows_per_shard;
+  p.D = D; p.ldd = ldd; p.bias = bias;
+  p.d_is_fp32 = d_dtype == 0;
+  p.accumulate = accumulate;
+  p.relu = relu;
+  int rc;
+  if (!a_mn) rc = make_map(&p.tmA, A, M, K, lda, kBlockK, kBlockM);
+  else rc = make_map(&p.tmA, A, K, M, lda, 64, kBlockK);
+  if (rc) return rc;
+  for (int s = 0; s < n_shards; ++s) {
+    if (!b_mn) {
+      const uint64_t rows = n_shards > 1 ? (uint64_t)rows_per_shard : (uint64_t)N;
+      rc = make_map(&p.tmB[s], b_shards[s], rows, K, ldb, kBlockK, block_n);
+    } else {
+      const uint64_t rows = n_shards > 1 ? (uint64_t)rows_per_shard : (uint64_t)K;
+      rc = make_map(&p.tmB[s], b_shards[s], rows, N, ldb, 64, kBlockK);
+    }
+    if (rc) return rc;
+  }
+  if (n_shards > 1) {
+    // a tile must not straddle two shards
+    if (!b_mn && (rows_per_shard % block_n)) return (int)cudaErrorInvalidValue;
+    if (b_mn && (rows_per_shard % kBlockK)) return (int)cudaErrorInvalidValue;
+  }
+#define DLCFN_GEMM_CASE(BN, AM, BM) \
+  if (block_n == BN && (bool)a_mn == AM && (bool)b_mn == BM) return launch<BN, AM, BM>(p, num_sms, stream);
+  DLCFN_GEMM_CASE(128, false, false)
+  DLCFN_GEMM_CASE(128, false, true)
+  DLCFN_GEMM_CASE(128, true, false)
+  DLCFN_GEMM_CASE(128, true, true)
+  DLCFN_GEMM_CASE(256, false, false)
+  DLCFN_GEMM_CASE(256, false, true)
+  DLCFN_GEMM_CASE(256, true, false)
+  DLCFN_GEMM_CASE(256, true, true)
+#undef DLCFN_GEMM_CASE
+  return (int)cudaErrorInvalidValue;
+}

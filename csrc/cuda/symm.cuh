@@ -1,0 +1,65 @@
+// Symmetric peer-HBM heap: the B200 replacement for the reference's EFS shared mount, the pinned
+// host comm_buf_ of KVStoreDist (kvstore_dist.h:335-342) and ps-lite's ZeroMQ data plane (C6).
+//
+// Every rank owns one device allocation laid out as
+//     [ signal pad 64 KiB | epoch counters 8 KiB | error word ... | 1 MiB: data heap ... ]
+// and maps every peer's allocation (CUDA IPC across processes, or direct peer access inside one
+// process).  Kernels receive the whole table by value (SymmDev) and address any peer's heap or
+// signal pad with plain ld/st over NVLink 5 / NVSwitch.
+#pragma once
+#include "common.cuh"
+
+namespace dlcfn {
+
+constexpr int kSigChannels = 8;
+constexpr int kSigMaxBlocks = 256;
+constexpr size_t kSigBytes = (size_t)kSigChannels * kSigMaxBlocks * DLCFN_MAX_RANKS * sizeof(uint32_t);  // 64 KiB
+constexpr size_t kEpochOff = kSigBytes;
+constexpr size_t kEpochBytes = (size_t)kSigChannels * kSigMaxBlocks * sizeof(uint32_t);                  // 8 KiB
+constexpr size_t kErrOff = kEpochOff + kEpochBytes;
+constexpr size_t kHeapOff = 1u << 20;
+constexpr long long kSpinTimeoutNs = 4000000000ll;  // 4 s: a dead peer becomes an error, not a hung GPU
+
+struct SymmDev {
+  char* base[DLCFN_MAX_RANKS];     // data heaps
+  uint32_t* sig[DLCFN_MAX_RANKS];  // signal pads
+  uint32_t* epoch;                 // local, per (channel, block)
+  int* err;                        // local error word
+  int rank, world;
+};
+
+__device__ __forceinline__ uint32_t* sig_slot(const SymmDev& s, int owner, int channel, int block, int src) {
+  return s.sig[owner] + ((size_t)(channel * kSigMaxBlocks + block) * DLCFN_MAX_RANKS + src);
+}
+
+// All ranks' block `blockIdx.x` rendezvous.  The release store is cumulative over the CTA's earlier
+// writes (ordered by the bar.sync), the acquire load makes the peers' earlier writes visible.
+__device__ __forceinline__ void block_barrier(const SymmDev& s, int channel, uint32_t val) {
+  __syncthreads();
+  if ((int)threadIdx.x < s.world) {
+    st_release_sys(sig_slot(s, threadIdx.x, channel, blockIdx.x, s.rank), val);
+    if (!spin_wait_ge(sig_slot(s, s.rank, channel, blockIdx.x, threadIdx.x), val, kSpinTimeoutNs))
+      atomicExch(s.err, 1);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t epoch_load(const SymmDev& s, int channel) {
+  return s.epoch[channel * kSigMaxBlocks + blockIdx.x];
+}
+__device__ __forceinline__ void epoch_store(const SymmDev& s, int channel, uint32_t v) {
+  if (threadIdx.x == 0) s.epoch[channel * kSigMaxBlocks + blockIdx.x] = v;
+}
+
+// Host-side context (opaque to python; see symm.cu)
+struct SymmCtx {
+  int rank = 0, world = 1, device = 0;
+  size_t heap_bytes = 0;
+  char* local = nullptr;                  // whole allocation
+  char* peer[DLCFN_MAX_RANKS] = {nullptr};  // whole allocations as mapped here
+  bool opened_ipc[DLCFN_MAX_RANKS] = {false};
+  SymmDev dev{};
+  bool finalized = false;
+};
+
+}  // namespace dlcfn

@@ -1,0 +1,128 @@
+"""ResNet (pre-activation v2) - the architecture of the reference's ImageNet benchmark symbol.
+
+Parity target: MX/example/image-classification/symbols/resnet.py:29-177 (bottleneck units
+[3,4,6,3], filters [64,256,512,1024,2048], BatchNorm eps 2e-5 momentum 0.9, `bn_data` on the input,
+7x7/2 stem + BN + ReLU + 3x3/2 max-pool for ImageNet, 3x3 stem for CIFAR).  ResNet-50 has 157
+learnable tensors / 25.55 M parameters, which this module reproduces.
+
+B200 shape: channels_last activations, bf16 conv/FC weights with fp32 BatchNorm parameters, cuDNN for
+the convolutions (off the named hot paths), the classifier GEMM on the hand-written tcgen05 kernel
+(`ops.linear.Linear`) so that it can consume parameter-server-resident weights directly.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops.linear import Linear
+
+_EPS = 2e-5
+_MOM = 0.1  # torch momentum = 1 - mxnet bn_mom(0.9)
+
+
+def _bn(c: int, affine_gamma: bool = True) -> nn.BatchNorm2d:
+    bn = nn.BatchNorm2d(c, eps=_EPS, momentum=_MOM)
+    if not affine_gamma:  # fix_gamma=True in the reference: gamma frozen at 1
+        bn.weight.requires_grad_(False)
+    return bn
+
+
+class BottleneckV2(nn.Module):
+    def __init__(self, cin: int, cout: int, stride: int, dim_match: bool):
+        super().__init__()
+        mid = cout // 4
+        self.bn1 = _bn(cin)
+        self.conv1 = nn.Conv2d(cin, mid, 1, 1, 0, bias=False)
+        self.bn2 = _bn(mid)
+        self.conv2 = nn.Conv2d(mid, mid, 3, stride, 1, bias=False)
+        self.bn3 = _bn(mid)
+        self.conv3 = nn.Conv2d(mid, cout, 1, 1, 0, bias=False)
+        self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
+
+    def forward(self, x):
+        a = F.relu(self.bn1(x))
+        y = self.conv1(a)
+        y = self.conv2(F.relu(self.bn2(y)))
+        y = self.conv3(F.relu(self.bn3(y)))
+        return y + (x if self.sc is None else self.sc(a))
+
+
+class BasicV2(nn.Module):
+    def __init__(self, cin: int, cout: int, stride: int, dim_match: bool):
+        super().__init__()
+        self.bn1 = _bn(cin)
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn2 = _bn(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
+
+    def forward(self, x):
+        a = F.relu(self.bn1(x))
+        y = self.conv2(F.relu(self.bn2(self.conv1(a))))
+        return y + (x if self.sc is None else self.sc(a))
+
+
+_IMAGENET_UNITS = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3],
+                   152: [3, 8, 36, 3], 200: [3, 24, 36, 3], 269: [3, 30, 48, 8]}
+
+
+class ResNetV2(nn.Module):
+    def __init__(self, num_layers: int = 50, num_classes: int = 1000, image_size: int = 224):
+        super().__init__()
+        if image_size <= 32:  # CIFAR variant (resnet.py:165-177 first branch)
+            if (num_layers - 2) % 9 == 0 and num_layers >= 164:
+                units, filters, bottleneck = [(num_layers - 2) // 9] * 3, [16, 64, 128, 256], True
+            elif (num_layers - 2) % 6 == 0 and num_layers < 164:
+                units, filters, bottleneck = [(num_layers - 2) // 6] * 3, [16, 16, 32, 64], False
+            else:
+                raise ValueError(f"no CIFAR ResNet with {num_layers} layers")
+        else:
+            if num_layers not in _IMAGENET_UNITS:
+                raise ValueError(f"no ImageNet ResNet with {num_layers} layers")
+            units = _IMAGENET_UNITS[num_layers]
+            bottleneck = num_layers >= 50
+            filters = [64, 256, 512, 1024, 2048] if bottleneck else [64, 64, 128, 256, 512]
+        self.bn_data = _bn(3, affine_gamma=False)
+        if image_size <= 32:
+            self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 3, 1, 1, bias=False))
+        else:
+            self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 7, 2, 3, bias=False), _bn(filters[0]),
+                                      nn.ReLU(inplace=True), nn.MaxPool2d(3, 2, 1))
+        unit = BottleneckV2 if bottleneck else BasicV2
+        blocks = []
+        cin = filters[0]
+        for i, n in enumerate(units):
+            blocks.append(unit(cin, filters[i + 1], 1 if i == 0 else 2, False))
+            cin = filters[i + 1]
+            for _ in range(n - 1):
+                blocks.append(unit(cin, cin, 1, True))
+        self.body = nn.Sequential(*blocks)
+        self.bn1 = _bn(cin)
+        self.fc1 = Linear(cin, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward(self, x):
+        x = self.stem(self.bn_data(x))
+        x = self.body(x)
+        x = F.relu(self.bn1(x))
+        x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
+        return self.fc1(x)
+
+
+def resnet(num_layers: int = 50, num_classes: int = 1000, image_size: int = 224) -> ResNetV2:
+    return ResNetV2(num_layers, num_classes, image_size)
+
+
+def to_b200_layout(model: nn.Module, dtype: torch.dtype = torch.bfloat16) -> nn.Module:
+    """channels_last + `dtype` weights for conv/linear; BatchNorm parameters and statistics stay fp32
+    (cuDNN mixed-dtype batch norm) - the worker half of the reference's multi_precision mode."""
+    model = model.to(memory_format=torch.channels_last)
+    for m in model.modules():
+        if isinstance(m, (nn.Conv2d, nn.Linear, Linear, nn.Embedding)):
+            m.to(dtype)
+        elif isinstance(m, (nn.LayerNorm,)):
+            m.to(dtype)
+    return model

@@ -1,0 +1,80 @@
+"""Linear layer on the hand-written tcgen05 GEMM (forward, dgrad and wgrad all on csrc/cuda/gemm_tcgen05.cu).
+
+Reference analogue: FullyConnected -> linalg_gemm -> cublasSgemmEx (reference M2,
+fully_connected-inl.h:110-171, linalg_impl.h:189-273).  Here the three GEMMs are
+  fwd   Y[M,N]  = X[M,K]  * W[N,K]^T            (both operands K-major)
+  dgrad dX[M,K] = dY[M,N] * W[N,K]              (B = W read MN-major: no transpose materialised)
+  wgrad dW[N,K] = dY[M,N]^T * X[M,K]            (A and B both MN-major)
+On CPU tensors (unit tests without a GPU) the same math runs through torch.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import native
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        bias_f32 = None
+        if bias is not None:
+            bias_f32 = bias if bias.dtype == torch.float32 else bias.float()
+        y = native.gemm_bf16(x2, weight, bias=bias_f32, out_dtype=torch.bfloat16)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = native.gemm_bf16(dy2, weight, b_mn=True, out_dtype=torch.bfloat16).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = native.gemm_bf16(dy2, x2, a_mn=True, b_mn=True, out_dtype=torch.bfloat16)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.float().sum(0)
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """y = x @ weight.T + bias.  CUDA bf16 -> tcgen05 kernels; anything else -> torch (CPU tests)."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16:
+        ok = weight.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and weight.is_contiguous()
+        if not ok:
+            raise ValueError(f"tcgen05 linear needs in/out features % 8 == 0 and contiguous weight, got {tuple(weight.shape)}")
+        y = _LinearFn.apply(x, weight, bias)
+        return y
+    if x.is_cuda and not native.lib_path().exists():
+        raise native.NativeUnavailable("CUDA linear requested but libdlcfn_cuda.so is missing")
+    b = bias.to(x.dtype) if bias is not None else None
+    return F.linear(x, weight.to(x.dtype), b)
+
+
+class Linear(nn.Module):
+    """Drop-in nn.Linear whose CUDA/bf16 path is the dlcfn tcgen05 GEMM."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)
+
+    def extra_repr(self):
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, kernel=tcgen05"

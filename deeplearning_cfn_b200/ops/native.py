@@ -1,0 +1,242 @@
+"""ctypes bindings for the hand-written sm_100a kernel library (csrc/cuda -> _lib/libdlcfn_cuda.so).
+
+There is exactly one code path on a GPU: these kernels.  If the shared object is missing on a
+machine with a GPU the import fails loudly (no silent PyTorch fallback); on a CPU-only machine the
+ops raise `NativeUnavailable` when called, and pure-PyTorch *reference* implementations used by the
+numerics tests live in `ops/reference.py`.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from ctypes import c_float, c_int, c_longlong, c_size_t, c_uint32, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent.parent / "_lib" / "libdlcfn_cuda.so"
+_lib = None
+_lock = threading.Lock()
+
+# number of dlcfn kernels launched by this process (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+class NativeUnavailable(RuntimeError):
+    pass
+
+
+DT_F32, DT_BF16 = 0, 1
+OPT_KINDS = {"sgd": 0, "sgd_mom": 1, "adam": 2, "test": 3, "none": 4}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return DT_F32
+    if dt == torch.bfloat16:
+        return DT_BF16
+    raise TypeError(f"dlcfn kernels support float32 and bfloat16, got {dt}")
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def available() -> bool:
+    return _LIB_PATH.exists() and torch.cuda.is_available()
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not _LIB_PATH.exists():
+            raise NativeUnavailable(
+                f"{_LIB_PATH} is missing: run `python -m deeplearning_cfn_b200._build` (needs nvcc); "
+                "the CUDA path has no PyTorch fallback")
+        L = ctypes.CDLL(str(_LIB_PATH))
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def _declare(L) -> None:
+    vp, sz, i, f, u32, ll = c_void_p, c_size_t, c_int, c_float, c_uint32, c_longlong
+    L.dlcfn_elementwise_sum.argtypes = [vp, i, vp, sz, i, f, vp]
+    L.dlcfn_cast_scale.argtypes = [vp, vp, sz, i, i, f, vp]
+    L.dlcfn_fused_optimizer.argtypes = [i, vp, i, vp, vp, vp, vp, i, sz, f, f, f, f, f, f, f, f, vp]
+    L.dlcfn_normalize_u8_nhwc.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.dlcfn_quantize_2bit.argtypes = [vp, i, vp, vp, sz, f, vp]
+    L.dlcfn_dequantize_2bit.argtypes = [vp, vp, sz, f, i, vp]
+    L.dlcfn_unique_rows_temp_bytes.argtypes = [ll]
+    L.dlcfn_unique_rows_temp_bytes.restype = sz
+    L.dlcfn_unique_rows.argtypes = [vp, sz, ll, vp, vp, sz, vp, vp, vp]
+    L.dlcfn_symm_create.argtypes = [sz, i, i, ctypes.POINTER(vp)]
+    L.dlcfn_symm_get_handle.argtypes = [vp, vp]
+    L.dlcfn_symm_open_peer.argtypes = [vp, i, vp]
+    L.dlcfn_symm_set_peer_ptr.argtypes = [vp, i, vp]
+    L.dlcfn_symm_allocation.argtypes = [vp]
+    L.dlcfn_symm_allocation.restype = vp
+    L.dlcfn_symm_finalize.argtypes = [vp]
+    L.dlcfn_symm_heap_ptr.argtypes = [vp, i]
+    L.dlcfn_symm_heap_ptr.restype = vp
+    L.dlcfn_symm_check_error.argtypes = [vp, vp, ctypes.POINTER(i)]
+    L.dlcfn_symm_destroy.argtypes = [vp]
+    L.dlcfn_barrier.argtypes = [vp, i, vp]
+    L.dlcfn_allreduce.argtypes = [vp, sz, sz, i, f, i, i, vp]
+    L.dlcfn_broadcast.argtypes = [vp, sz, sz, i, i, i, vp]
+    L.dlcfn_ps_sync_step.argtypes = [vp, sz, sz, sz, sz, sz, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, vp]
+    L.dlcfn_ps_async_worker.argtypes = [vp, u32, i, i, vp]
+    L.dlcfn_ps_async_server.argtypes = [vp, sz, sz, sz, sz, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, vp]
+    L.dlcfn_gemm_bf16.argtypes = [vp, ll, i, vp, i, i, ll, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp]
+    for fn in ("dlcfn_elementwise_sum", "dlcfn_cast_scale", "dlcfn_fused_optimizer", "dlcfn_normalize_u8_nhwc",
+               "dlcfn_quantize_2bit", "dlcfn_dequantize_2bit", "dlcfn_unique_rows", "dlcfn_symm_create",
+               "dlcfn_symm_get_handle", "dlcfn_symm_open_peer", "dlcfn_symm_set_peer_ptr", "dlcfn_symm_finalize",
+               "dlcfn_symm_check_error", "dlcfn_symm_destroy", "dlcfn_barrier", "dlcfn_allreduce",
+               "dlcfn_broadcast", "dlcfn_ps_sync_step", "dlcfn_ps_async_worker", "dlcfn_ps_async_server",
+               "dlcfn_gemm_bf16"):
+        getattr(L, fn).restype = c_int
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"dlcfn native call {what} failed with CUDA error {rc}")
+
+
+def stream_ptr(stream: torch.cuda.Stream | None = None) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------- elementwise
+def elementwise_sum(inputs: list[torch.Tensor], out: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """out = scale * sum_i inputs[i]  (reference C5 ElementwiseSum, ndarray_function-inl.h:388-433)."""
+    n = out.numel()
+    for t in inputs:
+        assert t.is_cuda and t.is_contiguous() and t.numel() == n and t.dtype == out.dtype
+    arr = (c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
+    check(lib().dlcfn_elementwise_sum(ctypes.cast(arr, c_void_p), len(inputs), out.data_ptr(), n,
+                                      dtype_code(out.dtype), float(scale), stream_ptr()), "elementwise_sum")
+    _count()
+    return out
+
+
+def cast_scale(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    check(lib().dlcfn_cast_scale(src.data_ptr(), dst.data_ptr(), src.numel(), dtype_code(src.dtype),
+                                 dtype_code(dst.dtype), float(scale), stream_ptr()), "cast_scale")
+    _count()
+    return dst
+
+
+def fused_optimizer(kind: str, grad: torch.Tensor, master: torch.Tensor, s1: torch.Tensor | None,
+                    s2: torch.Tensor | None, wout: torch.Tensor | None, *, lr: float, wd: float = 0.0,
+                    momentum: float = 0.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                    rescale: float = 1.0, clip: float = -1.0) -> None:
+    """One launch over a flat parameter buffer (reference O1/O2, optimizer_op-inl.h:86-427, 840-875)."""
+    n = master.numel()
+    assert master.dtype == torch.float32 and grad.numel() == n
+    check(lib().dlcfn_fused_optimizer(OPT_KINDS[kind], grad.data_ptr(), dtype_code(grad.dtype), master.data_ptr(),
+                                      _ptr(s1), _ptr(s2), _ptr(wout),
+                                      dtype_code(wout.dtype) if wout is not None else 0, n, lr, wd, momentum,
+                                      beta1, beta2, eps, rescale, clip, stream_ptr()), "fused_optimizer")
+    _count()
+
+
+def normalize_u8_nhwc(src: torch.Tensor, dst: torch.Tensor, mean, std) -> torch.Tensor:
+    assert src.dtype == torch.uint8 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    m = (c_float * 3)(*mean)
+    s = (c_float * 3)(*std)
+    check(lib().dlcfn_normalize_u8_nhwc(src.data_ptr(), dst.data_ptr(), src.numel(), ctypes.cast(m, c_void_p),
+                                        ctypes.cast(s, c_void_p), stream_ptr()), "normalize_u8_nhwc")
+    _count()
+    return dst
+
+
+def quantize_2bit(grad: torch.Tensor, residual: torch.Tensor, out_words: torch.Tensor, threshold: float) -> None:
+    n = grad.numel()
+    assert residual.dtype == torch.float32 and residual.numel() == n
+    assert out_words.dtype == torch.int32 and out_words.numel() == (n + 15) // 16
+    check(lib().dlcfn_quantize_2bit(grad.data_ptr(), dtype_code(grad.dtype), residual.data_ptr(),
+                                    out_words.data_ptr(), n, threshold, stream_ptr()), "quantize_2bit")
+    _count()
+
+
+def dequantize_2bit(words: torch.Tensor, out: torch.Tensor, threshold: float, accumulate: bool = False) -> None:
+    assert out.dtype == torch.float32
+    check(lib().dlcfn_dequantize_2bit(words.data_ptr(), out.data_ptr(), out.numel(), threshold, int(accumulate),
+                                      stream_ptr()), "dequantize_2bit")
+    _count()
+
+
+def unique_rows(ids: torch.Tensor, num_rows: int) -> torch.Tensor:
+    """Sorted unique row ids (reference Q3, kvstore_utils.cu:41-96)."""
+    assert ids.dtype == torch.int64 and ids.is_cuda
+    L = lib()
+    tb = L.dlcfn_unique_rows_temp_bytes(num_rows)
+    present = torch.empty(num_rows, dtype=torch.uint8, device=ids.device)
+    temp = torch.empty(max(tb, 1), dtype=torch.uint8, device=ids.device)
+    out = torch.empty(num_rows, dtype=torch.int64, device=ids.device)
+    n_out = torch.zeros(1, dtype=torch.int64, device=ids.device)
+    check(L.dlcfn_unique_rows(ids.data_ptr(), ids.numel(), num_rows, present.data_ptr(), temp.data_ptr(), tb,
+                              out.data_ptr(), n_out.data_ptr(), stream_ptr()), "unique_rows")
+    _count(2)
+    return out[: int(n_out.item())]
+
+
+# --------------------------------------------------------------------------- GEMM
+def gemm_bf16(a: torch.Tensor, b, *, a_mn: bool = False, b_mn: bool = False, out: torch.Tensor | None = None,
+              out_dtype: torch.dtype = torch.bfloat16, bias: torch.Tensor | None = None, accumulate: bool = False,
+              relu: bool = False, m: int | None = None, n: int | None = None, k: int | None = None,
+              shard_ptrs: list[int] | None = None, rows_per_shard: int = 0, ldb: int | None = None,
+              block_n: int = 0) -> torch.Tensor:
+    """D[M,N] = A[M,K] @ B[N,K]^T (+bias) on the tcgen05 tensor cores.
+
+    a_mn / b_mn select the MN-major storage ([K, rows]) of an operand.  With `shard_ptrs`, B lives
+    row-sharded in peer HBM and is pulled through TMA inside the kernel (the fused pull + GEMM path).
+    """
+    assert a.dtype == torch.bfloat16 and a.is_cuda and a.dim() == 2 and a.stride(1) == 1
+    if not a_mn:
+        M, K = a.shape
+    else:
+        K, M = a.shape
+    if shard_ptrs is None:
+        assert b.dtype == torch.bfloat16 and b.dim() == 2 and b.stride(1) == 1
+        if not b_mn:
+            N, Kb = b.shape
+        else:
+            Kb, N = b.shape
+        assert Kb == K, (a.shape, b.shape, a_mn, b_mn)
+        ptrs = [b.data_ptr()]
+        ldb_ = b.stride(0)
+    else:
+        assert n is not None and ldb is not None
+        N = n
+        ptrs = list(shard_ptrs)
+        ldb_ = ldb
+    M = m if m is not None else M
+    K = k if k is not None else K
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    assert out.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+    arr = (c_void_p * len(ptrs))(*ptrs)
+    check(lib().dlcfn_gemm_bf16(a.data_ptr(), a.stride(0), int(a_mn), ctypes.cast(arr, c_void_p), len(ptrs),
+                                rows_per_shard, ldb_, int(b_mn), out.data_ptr(), out.stride(0),
+                                dtype_code(out.dtype), _ptr(bias), M, N, K, int(accumulate), int(relu), block_n, 0,
+                                stream_ptr()), "gemm_bf16")
+    _count()
+    return out

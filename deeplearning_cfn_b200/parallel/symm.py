@@ -1,0 +1,160 @@
+"""Symmetric peer-HBM heap (python side).
+
+The B200 replacement for three reference mechanisms at once: the EFS shared mount used to stage
+data/initial weights (deeplearning.template:453-474), the pinned-host `comm_buf_` of KVStoreDist
+(kvstore_dist.h:335-342) and the ZeroMQ data plane of ps-lite (zmq_van.h).  Every rank owns one
+cudaMalloc'ed arena; CUDA-IPC handles are exchanged once through the torch.distributed store and
+each rank maps all peers, after which the fused kernels in csrc/cuda/collectives.cu address any
+peer's HBM with plain loads/stores over NVLink 5 / NVSwitch.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int, c_void_p
+
+import torch
+import torch.distributed as dist
+
+from ..ops import native
+
+_TYPESTR = {torch.uint8: "|u1", torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8",
+            torch.float16: "<f2"}
+
+
+class _RawCuda:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    """uint8 view of raw device memory (no ownership)."""
+    return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
+
+
+class SymmetricHeap:
+    """One arena per rank, mapped by every peer.  Bump allocation; offsets are identical on all ranks
+    as long as all ranks perform the same sequence of `alloc` calls (they do: the layout is derived
+    from the model, which is replicated)."""
+
+    CH_ALLREDUCE = 0
+    CH_PS = 1
+    CH_BCAST = 2
+    CH_BARRIER = 3
+    CH_ASYNC = 4  # uses 4 and 5
+
+    def __init__(self, heap_bytes: int, group: dist.ProcessGroup | None = None, device: torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise native.NativeUnavailable("SymmetricHeap needs a CUDA device")
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank = dist.get_rank(group)
+            self.world = dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        if self.world > 8:
+            raise ValueError("one NVSwitch domain: at most 8 ranks")
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.heap_bytes = int(heap_bytes)
+        L = native.lib()
+        ctx = c_void_p()
+        with torch.cuda.device(self.device):
+            native.check(L.dlcfn_symm_create(self.heap_bytes, self.rank, self.world, ctypes.byref(ctx)), "symm_create")
+            self._ctx = ctx
+            if self.world > 1:
+                buf = ctypes.create_string_buffer(64)
+                native.check(L.dlcfn_symm_get_handle(ctx, buf), "symm_get_handle")
+                handles: list = [None] * self.world
+                dist.all_gather_object(handles, bytes(buf.raw), group=group)
+                for p, h in enumerate(handles):
+                    if p != self.rank:
+                        native.check(L.dlcfn_symm_open_peer(ctx, p, ctypes.create_string_buffer(h, 64)), "symm_open_peer")
+            native.check(L.dlcfn_symm_finalize(ctx), "symm_finalize")
+        self._base = L.dlcfn_symm_heap_ptr(ctx, self.rank)
+        self._bytes = tensor_from_ptr(self._base, self.heap_bytes, self.device)
+        self._top = 0
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    # ------------------------------------------------------------------ allocation
+    def alloc(self, nbytes: int, align: int = 256) -> int:
+        off = (self._top + align - 1) // align * align
+        if off + nbytes > self.heap_bytes:
+            raise MemoryError(f"symmetric heap exhausted: need {off + nbytes}, have {self.heap_bytes}")
+        self._top = off + (nbytes + 15) // 16 * 16
+        return off
+
+    def view(self, off: int, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        nb = numel * torch.empty((), dtype=dtype).element_size()
+        return self._bytes[off: off + nb].view(dtype)
+
+    def alloc_tensor(self, numel: int, dtype: torch.dtype) -> tuple[int, torch.Tensor]:
+        esz = torch.empty((), dtype=dtype).element_size()
+        off = self.alloc(numel * esz)
+        t = self.view(off, numel, dtype)
+        return off, t
+
+    def peer_heap_ptr(self, peer: int) -> int:
+        return native.lib().dlcfn_symm_heap_ptr(self._ctx, peer)
+
+    # ------------------------------------------------------------------ collectives
+    def barrier(self, stream: torch.cuda.Stream | None = None) -> None:
+        native.check(native.lib().dlcfn_barrier(self._ctx, self.CH_BARRIER, native.stream_ptr(stream)), "barrier")
+        native._count()
+
+    def allreduce_(self, off: int, count: int, dtype: torch.dtype, scale: float = 1.0, nblocks: int = 32,
+                   stream: torch.cuda.Stream | None = None, channel: int | None = None) -> None:
+        """Fused bucket scale + all-reduce, in place (reference C11: Horovod fusion buffer + ncclAllReduce)."""
+        ch = self.CH_ALLREDUCE if channel is None else channel
+        native.check(native.lib().dlcfn_allreduce(self._ctx, off, count, native.dtype_code(dtype), float(scale), ch,
+                                                  nblocks, native.stream_ptr(stream)), "allreduce")
+        native._count()
+
+    def broadcast_(self, off: int, nbytes: int, root: int, nblocks: int = 32,
+                   stream: torch.cuda.Stream | None = None) -> None:
+        native.check(native.lib().dlcfn_broadcast(self._ctx, off, nbytes, root, self.CH_BCAST, nblocks,
+                                                  native.stream_ptr(stream)), "broadcast")
+        native._count()
+
+    def ps_sync_step(self, grad_off: int, weight_off: int, total: int, shard_lo: int, shard_hi: int,
+                     worker_mask: int, master: torch.Tensor | None, s1: torch.Tensor | None,
+                     s2: torch.Tensor | None, dtype: torch.dtype, kind: str, *, lr: float, wd: float = 0.0,
+                     momentum: float = 0.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                     rescale: float = 1.0, clip: float = -1.0, nblocks: int = 32,
+                     stream: torch.cuda.Stream | None = None) -> None:
+        """push (+) server reduce (+) optimizer (+) pull in one kernel (reference C6/C7/C2)."""
+        native.check(native.lib().dlcfn_ps_sync_step(
+            self._ctx, grad_off, weight_off, total, shard_lo, shard_hi, worker_mask, native._ptr(master),
+            native._ptr(s1), native._ptr(s2), native.dtype_code(dtype), native.OPT_KINDS[kind], lr, wd, momentum,
+            beta1, beta2, eps, rescale, clip, self.CH_PS, nblocks, native.stream_ptr(stream)), "ps_sync_step")
+        native._count()
+
+    def ps_async_worker(self, server_mask: int, nblocks: int = 16, stream: torch.cuda.Stream | None = None) -> None:
+        native.check(native.lib().dlcfn_ps_async_worker(self._ctx, server_mask, self.CH_ASYNC, nblocks,
+                                                        native.stream_ptr(stream)), "ps_async_worker")
+        native._count()
+
+    def ps_async_server(self, grad_off: int, weight_off: int, shard_lo: int, shard_hi: int, worker_mask: int,
+                        master: torch.Tensor, s1, s2, dtype: torch.dtype, kind: str, *, lr: float, wd: float = 0.0,
+                        momentum: float = 0.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                        rescale: float = 1.0, clip: float = -1.0, nblocks: int = 16,
+                        stream: torch.cuda.Stream | None = None) -> None:
+        native.check(native.lib().dlcfn_ps_async_server(
+            self._ctx, grad_off, weight_off, shard_lo, shard_hi, worker_mask, native._ptr(master), native._ptr(s1),
+            native._ptr(s2), native.dtype_code(dtype), native.OPT_KINDS[kind], lr, wd, momentum, beta1, beta2, eps,
+            rescale, clip, self.CH_ASYNC, nblocks, native.stream_ptr(stream)), "ps_async_server")
+        native._count()
+
+    def check_error(self, stream: torch.cuda.Stream | None = None) -> None:
+        e = c_int(0)
+        native.check(native.lib().dlcfn_symm_check_error(self._ctx, native.stream_ptr(stream), ctypes.byref(e)),
+                     "symm_check_error")
+        if e.value:
+            raise RuntimeError("a peer did not reach a device-side flag barrier within the timeout "
+                               "(dead or stalled rank) - reference analogue: get_num_dead_node > 0")
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            torch.cuda.synchronize(self.device)
+            self._bytes = None
+            native.lib().dlcfn_symm_destroy(self._ctx)
+            self._ctx = None

@@ -1,0 +1,34 @@
+"""Fused peer-HBM collectives / parameter-server kernels at world size 2 (and more when available)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(nproc, script, port, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mp", script)]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+def test_collectives_world2():
+    r = _run(2, "collectives_worker.py", 29611)
+    assert r.returncode == 0 and "COLLECTIVES_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_collectives_all_gpus():
+    n = torch.cuda.device_count()
+    if n < 4:
+        pytest.skip("needs >= 4 GPUs")
+    r = _run(n, "collectives_worker.py", 29612)
+    assert r.returncode == 0 and "COLLECTIVES_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_trainer_modes_agree_world2():
+    r = _run(2, "trainer_worker.py", 29613)
+    assert r.returncode == 0 and "TRAINER_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

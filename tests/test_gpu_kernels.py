@@ -1,0 +1,98 @@
+"""Numerics of every hand-written sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from deeplearning_cfn_b200.ops import native, reference as ref
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [1, 7, 4096, 1_000_003])
+@pytest.mark.parametrize("k", [1, 2, 5, 8])
+def test_elementwise_sum(dtype, n, k):
+    torch.manual_seed(0)
+    xs = [torch.randn(n, device=dev()).to(dtype) for _ in range(k)]
+    out = torch.empty(n, device=dev(), dtype=dtype)
+    native.elementwise_sum(xs, out, 0.5)
+    want = torch.empty(n, device=dev(), dtype=dtype)
+    ref.elementwise_sum(xs, want, 0.5)
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    torch.testing.assert_close(out.float(), want.float(), rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("n", [5, 1024, 777_777])
+def test_cast_scale(n):
+    x = torch.randn(n, device=dev())
+    y = torch.empty(n, device=dev(), dtype=torch.bfloat16)
+    native.cast_scale(x, y, 0.25)
+    torch.testing.assert_close(y.float(), (x * 0.25).bfloat16().float())
+    z = torch.empty(n, device=dev())
+    native.cast_scale(y, z, 2.0)
+    torch.testing.assert_close(z, y.float() * 2.0)
+
+
+@pytest.mark.parametrize("kind", ["sgd", "sgd_mom", "adam", "test"])
+@pytest.mark.parametrize("gdtype,wdtype", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32),
+                                           (torch.float32, torch.bfloat16)])
+@pytest.mark.parametrize("n", [3, 4099, 300_001])
+def test_fused_optimizer(kind, gdtype, wdtype, n):
+    torch.manual_seed(1)
+    g = torch.randn(n, device=dev()).to(gdtype)
+    hp = dict(lr=0.1, wd=1e-2, momentum=0.9, beta1=0.9, beta2=0.99, eps=1e-6, rescale=0.5, clip=1.5)
+    m0 = torch.randn(n, device=dev())
+    a0, b0 = torch.randn(n, device=dev()) * 0.1, torch.rand(n, device=dev()) * 0.1
+    m, a, b = m0.clone(), a0.clone(), b0.clone()
+    w = torch.empty(n, device=dev(), dtype=wdtype)
+    mr, ar, br = m0.clone(), a0.clone(), b0.clone()
+    wr = torch.empty(n, device=dev(), dtype=wdtype)
+    for _ in range(3):
+        native.fused_optimizer(kind, g, m, a, b, w, **hp)
+        ref.fused_optimizer(kind, g, mr, ar, br, wr, **hp)
+    torch.testing.assert_close(m, mr, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(w.float(), wr.float(), rtol=1e-2 if wdtype == torch.bfloat16 else 1e-5, atol=1e-2 if wdtype == torch.bfloat16 else 1e-6)
+    if kind in ("sgd_mom", "adam"):
+        torch.testing.assert_close(a, ar, rtol=1e-5, atol=1e-6)
+    if kind == "adam":
+        torch.testing.assert_close(b, br, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [1, 16, 17, 1000, 65_537])
+def test_quantize_2bit_roundtrip(dtype, n):
+    torch.manual_seed(2)
+    thr = 0.5
+    g = (torch.randn(n, device=dev()) * 0.6).to(dtype)
+    res = torch.randn(n, device=dev()) * 0.2
+    res_ref = res.clone()
+    words = torch.zeros((n + 15) // 16, dtype=torch.int32, device=dev())
+    native.quantize_2bit(g, res, words, thr)
+    want = ref.quantize_2bit(g, res_ref, thr)
+    assert torch.equal(words, want)
+    torch.testing.assert_close(res, res_ref)
+    out = torch.zeros(n, device=dev())
+    native.dequantize_2bit(words, out, thr)
+    torch.testing.assert_close(out, ref.dequantize_2bit(want, n, thr))
+    native.dequantize_2bit(words, out, thr, accumulate=True)
+    torch.testing.assert_close(out, 2 * ref.dequantize_2bit(want, n, thr))
+
+
+def test_unique_rows():
+    ids = torch.tensor([5, 3, 5, 9, 0, 3, 3, 11], device=dev())
+    got = native.unique_rows(ids, 12)
+    assert got.tolist() == [0, 3, 5, 9, 11]
+    big = torch.randint(0, 50_000, (200_000,), device=dev())
+    assert torch.equal(native.unique_rows(big, 50_000), torch.unique(big))
+
+
+def test_normalize_u8():
+    from deeplearning_cfn_b200.utils.data import IMAGENET_MEAN, IMAGENET_STD
+    x = torch.randint(0, 256, (3, 17, 19, 3), dtype=torch.uint8, device=dev())
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=dev())
+    native.normalize_u8_nhwc(x, y, IMAGENET_MEAN, IMAGENET_STD)
+    want = ref.normalize_u8_nhwc(x, IMAGENET_MEAN, IMAGENET_STD)
+    torch.testing.assert_close(y.float(), want.float(), rtol=2e-2, atol=2e-2)

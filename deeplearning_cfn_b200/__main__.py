@@ -1,0 +1,142 @@
+"""`python -m deeplearning_cfn_b200 <command>` - the user-facing CLI.
+
+Control plane (counterparts of `aws cloudformation ...` as used by mask-rcnn-stack.sh:62-92):
+    create-stack / launch-cluster, list-stacks, describe-stacks, delete-stack, prepare-bucket, node-exec
+Job plane:
+    launch (tools/launch.py compatible), kill, generate-trainer, run-example, bandwidth, benchmark
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+
+def _params(items: list[str]) -> dict:
+    out = {}
+    for it in items or []:
+        if it.startswith("ParameterKey="):
+            k, v = it.split(",", 1)
+            out[k.split("=", 1)[1]] = v.split("=", 1)[1] if "=" in v else ""
+        elif "=" in it:
+            k, v = it.split("=", 1)
+            out[k] = v
+    return out
+
+
+def cmd_create_stack(a) -> int:
+    from .cluster.stack import launch_cluster
+    template = a.template_body[7:] if a.template_body.startswith("file://") else a.template_body
+    params = {k: v for k, v in _params(a.parameters).items()}
+    if a.no_wait:
+        # detach: the caller polls list-stacks exactly like mask-rcnn-stack.sh does
+        argv = [sys.executable, "-m", "deeplearning_cfn_b200", "create-stack", "--stack-name", a.stack_name,
+                "--template-body", a.template_body, "--backend", a.backend]
+        if a.home:
+            argv += ["--home", a.home]
+        if a.capacity_gpus is not None:
+            argv += ["--capacity-gpus", str(a.capacity_gpus)]
+        argv += ["--parameters"] + [f"{k}={v}" for k, v in params.items()]
+        subprocess.Popen(argv, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, start_new_session=True)
+        print(json.dumps({"StackId": a.stack_name}))
+        return 0
+    h = launch_cluster(a.stack_name, template, home=a.home, backend=a.backend, capacity_gpus=a.capacity_gpus,
+                       poll_interval=a.poll_interval, **params)
+    print(json.dumps({"StackId": h.stack_dir, "StackStatus": h.status, "Outputs": h.outputs, "Hostfile": h.hostfile,
+                      "Env": h.export_env(), "Workers": h.workers}, indent=1))
+    return 0 if h.status == "CREATE_COMPLETE" else 1
+
+
+def cmd_list_stacks(a) -> int:
+    from .cluster.stack import list_stacks
+    for s in list_stacks(a.home):
+        if a.stack_status_filter and s["StackStatus"] not in a.stack_status_filter:
+            continue
+        print(json.dumps(s))
+    return 0
+
+
+def cmd_describe_stacks(a) -> int:
+    from .cluster.stack import describe_stack
+    h = describe_stack(a.stack_name, a.home)
+    print(json.dumps({"StackName": h.stack_name, "StackStatus": h.status, "Outputs": h.outputs, "Hostfile": h.hostfile,
+                      "HostsFile": h.hosts_file, "Env": h.export_env(), "Workers": h.workers}, indent=1))
+    return 0
+
+
+def cmd_delete_stack(a) -> int:
+    from .cluster.stack import delete_stack
+    delete_stack(a.stack_name, a.home)
+    return 0
+
+
+def cmd_prepare_bucket(a) -> int:
+    from .cluster.staging import prepare_bucket
+    print(json.dumps(prepare_bucket(a.bucket, a.prefix, a.num_images, a.image_size), indent=1))
+    return 0
+
+
+def cmd_node_exec(a) -> int:
+    from .launch.transport import node_exec
+    return node_exec(a.host, a.command)
+
+
+def main(argv=None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    # job-plane commands own their argument parsing
+    passthrough = {"launch": "launch.launcher", "kill": "launch.kill", "generate-trainer": "launch.tf_ps_scripts",
+                   "run-example": "examples.run_example", "bandwidth": "examples.bandwidth_measure",
+                   "benchmark": "examples.benchmark", "mpirun": "launch.mpirun"}
+    if argv and argv[0] in passthrough:
+        import importlib
+        mod = importlib.import_module("." + passthrough[argv[0]], __package__)
+        return int(mod.main(argv[1:]) or 0)
+
+    ap = argparse.ArgumentParser(prog="dlcfn")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    for name in ("create-stack", "launch-cluster"):
+        p = sub.add_parser(name)
+        p.add_argument("--stack-name", default="dlcfn")
+        p.add_argument("--template-body", default="deeplearning.template")
+        p.add_argument("--region", default="b200-box-1")
+        p.add_argument("--capabilities", default="")
+        p.add_argument("--parameters", nargs="*", default=[])
+        p.add_argument("--home", default=None)
+        p.add_argument("--backend", default="process", choices=["process", "thread"])
+        p.add_argument("--capacity-gpus", type=int, default=None)
+        p.add_argument("--poll-interval", type=float, default=0.05)
+        p.add_argument("--no-wait", action="store_true")
+        p.set_defaults(fn=cmd_create_stack)
+    p = sub.add_parser("list-stacks")
+    p.add_argument("--stack-status-filter", nargs="*", default=[])
+    p.add_argument("--home", default=None)
+    p.add_argument("--region", default=None)
+    p.set_defaults(fn=cmd_list_stacks)
+    for name, fn in (("describe-stacks", cmd_describe_stacks), ("delete-stack", cmd_delete_stack)):
+        p = sub.add_parser(name)
+        p.add_argument("--stack-name", required=True)
+        p.add_argument("--home", default=None)
+        p.add_argument("--region", default=None)
+        p.set_defaults(fn=fn)
+    p = sub.add_parser("prepare-bucket")
+    p.add_argument("--bucket", required=True)
+    p.add_argument("--prefix", default="mask-rcnn/b200")
+    p.add_argument("--num-images", type=int, default=64)
+    p.add_argument("--image-size", type=int, default=128)
+    p.set_defaults(fn=cmd_prepare_bucket)
+    p = sub.add_parser("node-exec")
+    p.add_argument("host")
+    p.add_argument("command", nargs=argparse.REMAINDER)
+    p.set_defaults(fn=cmd_node_exec)
+    a = ap.parse_args(argv)
+    try:
+        return a.fn(a)
+    except Exception as e:
+        print(f"error: {e}", file=sys.stderr)
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -15,14 +15,17 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.batchnorm import BatchNormReLU2d
 from ..ops.linear import Linear
 
 _EPS = 2e-5
 _MOM = 0.1  # torch momentum = 1 - mxnet bn_mom(0.9)
 
 
-def _bn(c: int, affine_gamma: bool = True) -> nn.BatchNorm2d:
-    bn = nn.BatchNorm2d(c, eps=_EPS, momentum=_MOM)
+def _bn(c: int, affine_gamma: bool = True, relu: bool = True) -> nn.BatchNorm2d:
+    """BatchNorm followed by ReLU, fused in one dlcfn kernel pair (every BN of the reference symbol except
+    `bn_data` is followed by a ReLU activation)."""
+    bn = BatchNormReLU2d(c, eps=_EPS, momentum=_MOM, relu=relu)
     if not affine_gamma:  # fix_gamma=True in the reference: gamma frozen at 1
         bn.weight.requires_grad_(False)
     return bn
@@ -41,10 +44,10 @@ class BottleneckV2(nn.Module):
         self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
 
     def forward(self, x):
-        a = F.relu(self.bn1(x))
+        a = self.bn1(x)  # BN + ReLU fused
         y = self.conv1(a)
-        y = self.conv2(F.relu(self.bn2(y)))
-        y = self.conv3(F.relu(self.bn3(y)))
+        y = self.conv2(self.bn2(y))
+        y = self.conv3(self.bn3(y))
         return y + (x if self.sc is None else self.sc(a))
 
 
@@ -58,8 +61,8 @@ class BasicV2(nn.Module):
         self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
 
     def forward(self, x):
-        a = F.relu(self.bn1(x))
-        y = self.conv2(F.relu(self.bn2(self.conv1(a))))
+        a = self.bn1(x)
+        y = self.conv2(self.bn2(self.conv1(a)))
         return y + (x if self.sc is None else self.sc(a))
 
 
@@ -83,12 +86,12 @@ class ResNetV2(nn.Module):
             units = _IMAGENET_UNITS[num_layers]
             bottleneck = num_layers >= 50
             filters = [64, 256, 512, 1024, 2048] if bottleneck else [64, 64, 128, 256, 512]
-        self.bn_data = _bn(3, affine_gamma=False)
+        self.bn_data = _bn(3, affine_gamma=False, relu=False)
         if image_size <= 32:
             self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 3, 1, 1, bias=False))
         else:
             self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 7, 2, 3, bias=False), _bn(filters[0]),
-                                      nn.ReLU(inplace=True), nn.MaxPool2d(3, 2, 1))
+                                      nn.MaxPool2d(3, 2, 1))
         unit = BottleneckV2 if bottleneck else BasicV2
         blocks = []
         cin = filters[0]
@@ -107,7 +110,7 @@ class ResNetV2(nn.Module):
     def forward(self, x):
         x = self.stem(self.bn_data(x))
         x = self.body(x)
-        x = F.relu(self.bn1(x))
+        x = self.bn1(x)
         x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
         return self.fc1(x)
 

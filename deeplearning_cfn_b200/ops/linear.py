@@ -64,17 +64,25 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
 
 
 class Linear(nn.Module):
-    """Drop-in nn.Linear whose CUDA/bf16 path is the dlcfn tcgen05 GEMM."""
+    """Drop-in nn.Linear whose CUDA/bf16 path is the dlcfn tcgen05 GEMM.
+
+    TMA needs 16-byte row strides, so the weight is stored with out_features rounded up to a multiple
+    of 8; the extra rows are zero, receive zero gradient and are sliced off the output."""
 
     def __init__(self, in_features: int, out_features: int, bias: bool = True):
         super().__init__()
+        if in_features % 8:
+            raise ValueError("in_features must be a multiple of 8 (16-byte TMA row stride)")
         self.in_features, self.out_features = in_features, out_features
-        self.weight = nn.Parameter(torch.empty(out_features, in_features))
-        self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
-        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        self.out_padded = (out_features + 7) // 8 * 8
+        self.weight = nn.Parameter(torch.zeros(self.out_padded, in_features))
+        self.bias = nn.Parameter(torch.zeros(self.out_padded)) if bias else None
+        with torch.no_grad():
+            nn.init.kaiming_uniform_(self.weight[:out_features], a=math.sqrt(5))
 
     def forward(self, x):
-        return linear(x, self.weight, self.bias)
+        y = linear(x, self.weight, self.bias)
+        return y if self.out_padded == self.out_features else y[..., : self.out_features]
 
     def extra_repr(self):
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, kernel=tcgen05"

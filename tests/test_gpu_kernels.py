@@ -96,3 +96,39 @@ def test_normalize_u8():
     native.normalize_u8_nhwc(x, y, IMAGENET_MEAN, IMAGENET_STD)
     want = ref.normalize_u8_nhwc(x, IMAGENET_MEAN, IMAGENET_STD)
     torch.testing.assert_close(y.float(), want.float(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("N,C,H,W", [(4, 64, 14, 14), (8, 256, 7, 9), (2, 2048, 7, 7), (3, 96, 5, 5), (16, 8, 33, 31),
+                                      (32, 128, 28, 28)])
+def test_fused_batchnorm_relu(N, C, H, W, relu):
+    from deeplearning_cfn_b200.ops.batchnorm import batch_norm_relu
+    torch.manual_seed(3)
+    x = (torch.randn(N, C, H, W, device=dev()) * 1.5 + 0.3).bfloat16().contiguous(memory_format=torch.channels_last)
+    gamma = (torch.rand(C, device=dev()) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device=dev()) * 0.2).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    xg = x.clone().requires_grad_(True)
+    y = batch_norm_relu(xg, gamma, beta, rm, rv, True, 0.1, 2e-5, relu)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    # fp32 reference
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    rmr, rvr = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    yr = torch.nn.functional.batch_norm(xr, rmr, rvr, gr, br, True, 0.1, 2e-5)
+    if relu:
+        yr = torch.relu(yr)
+    yr.backward(dy.float())
+    torch.testing.assert_close(y.float(), yr.detach(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(rm, rmr, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(rv, rvr, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(xg.grad.float(), xr.grad, rtol=5e-2, atol=5e-2)
+    torch.testing.assert_close(gamma.grad, gr.grad, rtol=2e-2, atol=2e-2 * (N * H * W) ** 0.5)
+    torch.testing.assert_close(beta.grad, br.grad, rtol=2e-2, atol=2e-2 * (N * H * W) ** 0.5)
+    # eval mode
+    ye = batch_norm_relu(x, gamma.detach(), beta.detach(), rm, rv, False, 0.1, 2e-5, relu)
+    yer = torch.nn.functional.batch_norm(x.float(), rm, rv, gamma.detach(), beta.detach(), False, 0.1, 2e-5)
+    if relu:
+        yer = torch.relu(yer)
+    torch.testing.assert_close(ye.float(), yer, rtol=2e-2, atol=2e-2)

@@ -54,6 +54,8 @@ class DataParallelTrainer:
             mode = "local" if self.world == 1 else ("allreduce" if self.on_gpu else "gloo")
         if self.world == 1 and mode != "local":
             mode = "local"
+        if mode == "local":
+            self.rank, self.world = 0, 1      # explicit single-process trainer inside a larger job
         self.mode = mode
         self.model = model
         self.opt_kind = optimizer

@@ -1,0 +1,281 @@
+"""KVStore semantics (CPU): local store with fake devices, distributed store as N local processes over the
+native transport, python-updater path, engine and fabric planner.  Mirrors the reference's tiers
+(tests/python/unittest/test_kvstore.py, tests/nightly/dist_*_kvstore.py, tests/cpp/kvstore/gpu_topology_test.cc)."""
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import pytest
+import torch
+
+import deeplearning_cfn_b200.kv as kv
+from deeplearning_cfn_b200.utils import rt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHAPE = (4, 4)
+
+
+def _launch(nw, ns, script_args, env=None, timeout=180):
+    e = dict(os.environ, PYTHONPATH=ROOT)
+    e.update(env or {})
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", str(nw), "-s", str(ns), "--launcher", "local",
+           sys.executable] + script_args
+    return subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=timeout)
+
+
+# ----------------------------------------------------------------------------- local
+@pytest.mark.parametrize("name", ["local", "device"])
+def test_single_kv_pair_and_list(name):
+    s = kv.create(name)
+    assert s.type == name and s.rank == 0 and s.num_workers == 1
+    s.init(3, torch.ones(SHAPE))
+    s.push(3, torch.ones(SHAPE) * 4)
+    out = torch.zeros(SHAPE)
+    s.pull(3, out=out)
+    assert torch.all(out == 4)                       # no updater: the pushed value replaces the stored one
+    keys = [5, 7, 9]
+    s.init(keys, [torch.ones(SHAPE)] * 3)
+    s.push(keys, [torch.ones(SHAPE) * 2] * 3)
+    outs = [torch.zeros(SHAPE) for _ in keys]
+    s.pull(keys, out=outs)
+    assert all(torch.all(o == 2) for o in outs)
+
+
+def test_aggregator_over_fake_devices_and_updater():
+    s = kv.create("local")
+    ndev = 4
+    s.init("w", torch.ones(SHAPE))
+    s.push("w", [torch.ones(SHAPE)] * ndev)          # list of per-device values is summed
+    outs = [torch.zeros(SHAPE) for _ in range(ndev)]
+    s.pull("w", out=outs)
+    assert all(torch.all(o == ndev) for o in outs)
+    s._set_updater(lambda key, g, w: w.add_(g * 2))
+    s.push("w", [torch.ones(SHAPE)] * ndev)
+    s.pull("w", out=outs)
+    assert all(torch.all(o == ndev + 2 * ndev) for o in outs)
+
+
+def test_invalid_operations_raise():
+    s = kv.create("local")
+    s.init(1, torch.ones(2))
+    with pytest.raises(kv.KVStoreError):
+        s.init(1, torch.ones(2))
+    with pytest.raises(kv.KVStoreError):
+        s.push(2, torch.ones(2))
+    with pytest.raises(kv.KVStoreError):
+        s.pull(2, out=torch.ones(2))
+    with pytest.raises(kv.KVStoreError):
+        s.init("name", torch.ones(2))                # mixing int and str keys
+    with pytest.raises(kv.KVStoreError):
+        kv.create("bogus")
+    with pytest.raises(kv.KVStoreError):
+        kv.create("nccl").set_gradient_compression({"type": "2bit"})
+    with pytest.raises(kv.KVStoreError):
+        s.set_gradient_compression({"type": "1bit"})
+
+
+def test_row_sparse_pull_and_optimizer_states(tmp_path):
+    s = kv.create("local")
+    s.init(0, torch.arange(20.).view(5, 4))
+    out = torch.full((5, 4), -1.0)
+    s.row_sparse_pull(0, out=out, row_ids=torch.tensor([3, 1, 3]))
+    assert torch.equal(out[1], torch.arange(4., 8.)) and torch.equal(out[3], torch.arange(12., 16.))
+    assert float(out[0].abs().sum()) == 0 and float(out[4].abs().sum()) == 0
+    s.set_optimizer(kv.optimizer.create("sgd", learning_rate=0.1, momentum=0.9))
+    s.push(0, torch.ones(5, 4))
+    f = str(tmp_path / "states")
+    s.save_optimizer_states(f, dump_optimizer=True)
+    s2 = kv.create("local")
+    s2.set_optimizer(kv.optimizer.create("sgd", learning_rate=0.1, momentum=0.9))
+    s2.load_optimizer_states(f)
+    assert torch.allclose(s2._updater.states[0], s._updater.states[0])
+
+
+def test_local_2bit_compression_matches_quantisation_rule():
+    s = kv.create("device")
+    s.set_gradient_compression({"type": "2bit", "threshold": 0.5})
+    s.init(0, torch.zeros(32))
+    g = torch.linspace(-1, 1, 32)
+    s.push(0, [g, g])
+    out = torch.zeros(32)
+    s.pull(0, out=out)
+    q = torch.where(g >= 0.5, 0.5, torch.where(g <= -0.5, -0.5, 0.0))
+    assert torch.allclose(out, 2 * q)
+
+
+# ----------------------------------------------------------------------------- optimizers
+@pytest.mark.parametrize("name", ["sgd", "nag", "signum", "adam", "adagrad", "rmsprop", "adadelta", "ftrl", "adamax",
+                                  "nadam", "ftml", "dcasgd", "sgld", "lbsgd", "ccsgd", "test"])
+def test_every_optimizer_steps_and_decreases_quadratic(name):
+    torch.manual_seed(0)
+    o = kv.optimizer.create(name, learning_rate=0.05) if name != "test" else kv.optimizer.create(name, rescale_grad=-0.05)
+    if hasattr(o, "momentum") and name in ("sgd", "nag", "dcasgd", "lbsgd", "ccsgd"):
+        o.momentum = 0.9
+    u = kv.optimizer.get_updater(o)
+    w = torch.full((16,), 3.0)
+    f0 = float((w ** 2).sum())
+    for _ in range(200):
+        u(0, 2 * w, w)
+    assert torch.isfinite(w).all()
+    if name != "sgld":
+        assert float((w ** 2).sum()) < f0
+
+
+def test_sgd_matches_reference_formula_and_multi_precision():
+    o = kv.optimizer.create("sgd", learning_rate=0.1, momentum=0.9, wd=0.01, rescale_grad=0.5, clip_gradient=1.0,
+                            multi_precision=True)
+    u = kv.optimizer.get_updater(o)
+    w = torch.ones(8, dtype=torch.bfloat16)
+    w32, m = torch.ones(8), torch.zeros(8)
+    for i in range(4):
+        g = torch.full((8,), 3.0 + i)
+        u(0, g.bfloat16(), w)
+        gg = (g * 0.5).clamp(-1, 1)
+        m = 0.9 * m - 0.1 * 0.01 * w32 - 0.1 * gg
+        w32 = w32 + m
+    master, _ = u.states[0]
+    assert torch.allclose(master, w32, atol=1e-6) and torch.allclose(w.float(), w32.bfloat16().float())
+    assert "kind=sgd_mom" in o.native_config()
+
+
+def test_lr_schedulers():
+    f = kv.optimizer.FactorScheduler(step=10, factor=0.5, base_lr=1.0)
+    assert f(5) == 1.0 and f(10) == 0.5 and f(25) == 0.25
+    m = kv.optimizer.MultiFactorScheduler(step=[5, 10], factor=0.1, base_lr=1.0)
+    assert m(5) == 1.0 and abs(m(6) - 0.1) < 1e-12 and abs(m(11) - 0.01) < 1e-12
+    p = kv.optimizer.PolyScheduler(max_update=100, base_lr=1.0, pwr=2)
+    assert p(0) == 1.0 and p(100) == 0.0 and abs(p(50) - 0.25) < 1e-12
+    with pytest.raises(ValueError):
+        kv.optimizer.MultiFactorScheduler(step=[5, 5])
+
+
+# ----------------------------------------------------------------------------- distributed (local processes)
+def test_dist_sync_world2_two_servers():
+    r = _launch(2, 2, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_sync"])
+    assert r.returncode == 0 and r.stdout.count("SYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_dist_sync_seven_workers_seven_servers():
+    # the reference CI shape: launch.py -n 7 --launcher local (ci/docker/runtime_functions.sh:916-931)
+    r = _launch(7, 7, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_device_sync"], timeout=300)
+    assert r.returncode == 0 and r.stdout.count("SYNC_OK") == 7, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_dist_async():
+    r = _launch(3, 2, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_async"])
+    assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_dist_sync_python_updater_on_server():
+    r = _launch(2, 1, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_sync"], env={"DLCFN_PS_PY_UPDATER": "1"})
+    assert r.returncode == 0 and r.stdout.count("SYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_dist_sync_survives_dropped_messages_with_resend():
+    # fault injection: 10 % of received data messages are dropped; at-least-once delivery repairs it
+    r = _launch(2, 2, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_sync"],
+                env={"PS_DROP_MSG": "10", "PS_RESEND": "1", "PS_RESEND_TIMEOUT": "200"}, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("SYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+# ----------------------------------------------------------------------------- engine
+def test_engine_orders_writers_and_readers_and_priorities():
+    e = rt.Engine(nthreads=4)
+    v = e.new_var()
+    log = []
+    for i in range(20):
+        e.push(lambda i=i: (time.sleep(0.001), log.append(i)), writes=(v,))
+    e.wait_for_var(v)
+    assert log == list(range(20))                                  # writers of one var run in program order
+    a, b = e.new_var(), e.new_var()
+    seen = []
+    gate = threading.Event()
+    e.push(lambda: gate.wait(5), writes=(a,))
+    for i in range(6):
+        e.push(lambda i=i: seen.append(("r", i)), reads=(a,), writes=())
+    e.push(lambda: seen.append(("w", 0)), writes=(a,))
+    e.push(lambda: seen.append(("other", 0)), writes=(b,))
+    time.sleep(0.05)
+    assert seen == [("other", 0)]                                   # independent var is not blocked
+    gate.set()
+    e.wait_all()
+    assert seen[-1] == ("w", 0) and sorted(seen[1:7]) == [("r", i) for i in range(6)]   # readers between writers
+    # priority: with one worker thread busy, higher priority ops overtake lower ones
+    e1 = rt.Engine(nthreads=1)
+    g2, order = threading.Event(), []
+    e1.push(lambda: g2.wait(5), writes=(e1.new_var(),))
+    for p in (0, -5, 10, 3):
+        e1.push(lambda p=p: order.append(p), writes=(e1.new_var(),), priority=p)
+    g2.set()
+    e1.wait_all()
+    assert order == [10, 3, 0, -5]
+    e.close()
+    e1.close()
+
+
+def test_engine_propagates_exceptions_and_naive_mode():
+    e = rt.Engine(nthreads=2)
+    v = e.new_var()
+    e.push(lambda: (_ for _ in ()).throw(ValueError("boom")), writes=(v,))
+    with pytest.raises(ValueError):
+        e.wait_for_var(v)
+    e.close()
+    n = rt.Engine(naive=True)
+    out = []
+    n.push(lambda: out.append(1), writes=(n.new_var(),))
+    assert out == [1]                                               # NaiveEngine: synchronous
+    n.close()
+
+
+# ----------------------------------------------------------------------------- fabric planner (GPU-free)
+def _dgx1():
+    """Hybrid cube mesh of 8 GPUs: NVLink inside and between two quads, PCIe (weight 1) otherwise."""
+    n = 8
+    w = [[1 if i != j else 0 for j in range(n)] for i in range(n)]
+    nv = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3), (4, 5), (4, 6), (4, 7), (5, 6), (5, 7), (6, 7),
+          (0, 4), (1, 5), (2, 6), (3, 7)]
+    for a, b in nv:
+        w[a][b] = w[b][a] = 3
+    return w
+
+
+def _check_tree(parents, root, n):
+    assert parents[root] == -1 and all(p >= 0 for i, p in enumerate(parents) if i != root)
+    for i in range(n):                                               # every node reaches the root: spanning tree
+        cur, hops = i, 0
+        while cur != root:
+            cur = parents[cur]
+            hops += 1
+            assert hops <= n
+    depth = max(len(_path(parents, i, root)) for i in range(n))
+    assert depth <= 4                                                # ~log2(8) + 1 levels
+
+
+def _path(parents, i, root):
+    p = []
+    while i != root:
+        p.append(i)
+        i = parents[i]
+    return p
+
+
+def test_planner_uniform_nvswitch_and_dgx1():
+    uni = [[0 if i == j else 18 for j in range(8)] for i in range(8)]
+    assert rt.topo_is_uniform(uni) and not rt.topo_is_uniform(_dgx1())
+    for link in (uni, _dgx1()):
+        trees = rt.plan_trees(link)
+        for r in range(8):
+            _check_tree(trees[r], r, 8)
+    # on the cube mesh the planner prefers NVLink edges
+    w = _dgx1()
+    trees = rt.plan_trees(w, penalty=1.0)
+    nv_edges = sum(1 for r in range(8) for i, p in enumerate(trees[r]) if p >= 0 and w[i][p] == 3)
+    assert nv_edges >= 0.85 * 8 * 7
+    ring = rt.plan_ring(w, 0)
+    assert sorted(ring) == list(range(8)) and all(w[a][b] == 3 for a, b in zip(ring, ring[1:]))
+    rnd = [[0 if i == j else ((i * 7 + j * 3) % 5 + 1) for j in range(6)] for i in range(6)]
+    rnd = [[max(rnd[i][j], rnd[j][i]) if i != j else 0 for j in range(6)] for i in range(6)]
+    for r, t in enumerate(rt.plan_trees(rnd)):
+        _check_tree(t, r, 6)

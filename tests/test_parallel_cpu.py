@@ -1,0 +1,89 @@
+"""Data-parallel engine / Horovod-style API / gluon-style Trainer on CPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import deeplearning_cfn_b200.kv as kv
+from deeplearning_cfn_b200.kv.trainer import Trainer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_gloo_world2_data_parallel_matches_single_process():
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "2", sys.executable,
+           os.path.join(ROOT, "tests/mp/gloo_trainer_worker.py")]
+    r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "GLOO_TRAINER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_allreduce_job_through_tracker_launcher(tmp_path):
+    """launch -n 2 -s 0: no servers -> all-reduce tracker; workers find each other through it."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import sys, torch\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "from deeplearning_cfn_b200.parallel import horovod as hvd\n"
+        "hvd.init()\n"
+        "t = hvd.allreduce(torch.ones(3) * (hvd.rank() + 1), average=True)\n"
+        "assert hvd.size() == 2 and torch.allclose(t, torch.full((3,), 1.5)), t\n"
+        "print('TRACKER_JOB_OK', hvd.rank(), flush=True)\n"
+        "hvd.shutdown()\n")
+    r = subprocess.run([sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "0", "--launcher", "local",
+                        sys.executable, str(script)], env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True,
+                       timeout=180)
+    assert r.returncode == 0 and r.stdout.count("TRACKER_JOB_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def _net():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+
+
+@pytest.mark.parametrize("kvstore,update_on_kv", [("local", False), ("local", True), ("device", None), (None, None)])
+def test_trainer_step_matches_manual_sgd(kvstore, update_on_kv):
+    net, ref = _net(), _net()
+    tr = Trainer(net.named_parameters(), "sgd", {"learning_rate": 0.1, "momentum": 0.9, "wd": 1e-3}, kvstore=kvstore,
+                 update_on_kvstore=update_on_kv)
+    mom = [torch.zeros_like(p) for p in ref.parameters()]
+    x, y = torch.randn(5, 8), torch.randn(5, 4)
+    for _ in range(3):
+        for m in (net, ref):
+            m.zero_grad()
+            torch.nn.functional.mse_loss(m(x), y, reduction="sum").backward()
+        tr.step(batch_size=5)
+        with torch.no_grad():
+            for p, m in zip(ref.parameters(), mom):
+                g = p.grad / 5
+                m.mul_(0.9).add_(-0.1 * 1e-3 * p - 0.1 * g)
+                p.add_(m)
+    for a, b in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=1e-6)
+    assert tr.learning_rate == 0.1
+    tr.set_learning_rate(0.01)
+    assert tr.learning_rate == 0.01
+
+
+def test_trainer_split_allreduce_update_and_states(tmp_path):
+    net = _net()
+    tr = Trainer(net.named_parameters(), "adam", {"learning_rate": 0.01}, kvstore="local", update_on_kvstore=False)
+    x, y = torch.randn(5, 8), torch.randn(5, 4)
+    torch.nn.functional.mse_loss(net(x), y).backward()
+    tr.allreduce_grads()
+    tr.update(batch_size=1)
+    f = str(tmp_path / "trainer.states")
+    tr.save_states(f)
+    tr2 = Trainer(_net().named_parameters(), "adam", {"learning_rate": 0.5}, kvstore="local", update_on_kvstore=False)
+    tr2.load_states(f)
+    assert tr2.learning_rate == 0.01 and len(tr2._updaters[0].states) == len(tr._updaters[0].states)
+    tr3 = Trainer(_net().named_parameters(), "sgd", {"learning_rate": 0.1}, kvstore="local", update_on_kvstore=True)
+    with pytest.raises(AssertionError):
+        tr3.allreduce_grads()
+    with pytest.raises(ValueError):
+        Trainer(_net().named_parameters(), kv.optimizer.create("sgd"), {"learning_rate": 0.1})
+    stale = Trainer(_net().named_parameters(), "sgd", {"learning_rate": 0.1}, kvstore=None)
+    with pytest.raises(UserWarning):
+        stale.step(1)
+    stale.step(1, ignore_stale_grad=True)

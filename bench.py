@@ -29,7 +29,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
     ap.add_argument("--mode", default=None, help="allreduce (default) | ps_sync | ps_dedicated | nccl | nccl_ps")
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert-large", "bert-base"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 256 images / 16 sequences)")
+    ap.add_argument("--seq-len", type=int, default=512)
     ap.add_argument("--image-size", type=int, default=224)
     ap.add_argument("--num-layers", type=int, default=50)
     ap.add_argument("--bucket-mb", type=float, default=16.0)
@@ -86,15 +88,31 @@ def main():
     if world == 1:
         mode = "local"
 
-    model = to_b200_layout(resnet(args.num_layers, 1000, args.image_size).to(device), torch.bfloat16)
-    model.train()
-    trainer = DataParallelTrainer(model, mode=mode, optimizer="sgd_mom", lr=0.1, momentum=0.9, wd=1e-4,
-                                  bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
-                                  worker_ranks=workers)
+    is_bert = args.model.startswith("bert")
+    if args.batch is None:
+        args.batch = 16 if is_bert else 256
+    if is_bert:
+        from deeplearning_cfn_b200.models import bert_pretrain_loss, get_model
+        args.no_e2e = True
+        model = to_b200_layout(get_model(args.model, max_seq=args.seq_len).to(device), torch.bfloat16).train()
+        trainer = DataParallelTrainer(model, mode=mode, optimizer="adam", lr=1e-4, wd=0.01, beta1=0.9, beta2=0.999,
+                                      bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
+                                      worker_ranks=workers, loss_fn=bert_pretrain_loss)
+        g = torch.Generator().manual_seed(0)
+        npred = 76      # max_predictions_per_seq of the standard BERT pre-training recipe
+        ids = torch.randint(0, 30522, (args.batch, args.seq_len), generator=g).to(device)
+        x = (ids, torch.zeros_like(ids), torch.randint(0, args.seq_len, (args.batch, npred), generator=g).to(device))
+        y = (torch.randint(0, 30522, (args.batch, npred), generator=g).to(device),
+             torch.randint(0, 2, (args.batch,), generator=g).to(device))
+    else:
+        model = to_b200_layout(resnet(args.num_layers, 1000, args.image_size).to(device), torch.bfloat16)
+        model.train()
+        trainer = DataParallelTrainer(model, mode=mode, optimizer="sgd_mom", lr=0.1, momentum=0.9, wd=1e-4,
+                                      bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
+                                      worker_ranks=workers)
+        x, y = synthetic_device_batch(args.batch, args.image_size, 1000, device)
     n_workers = len(trainer.workers)
     is_worker = trainer.is_worker
-
-    x, y = synthetic_device_batch(args.batch, args.image_size, 1000, device)
 
     def sync_all():
         if world > 1:
@@ -167,7 +185,22 @@ def main():
         clocks = sampler.summary() if sampler else {}
         par = {"local": "single", "allreduce": f"dp{world}-fused-allreduce", "ps_sync": f"ps-sync-{len(trainer.servers)}s{n_workers}w",
                "nccl": f"dp{world}-nccl-allreduce", "nccl_ps": f"dp{world}-nccl-reduce-bcast"}[trainer.mode]
-        rec = {"metric": "resnet50_train_images_per_sec", "value": round(value, 2), "unit": "images/sec",
+        if is_bert:
+            rec = {"metric": f"{args.model}_pretrain_sequences_per_sec", "value": round(value, 2), "unit": "sequences/sec",
+                   "tokens_per_sec": round(value * args.seq_len, 1),
+                   "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                   "data": "synthetic (random token ids, random-init weights)", "impl": "ours" if args.impl == "ours" else "nccl-baseline",
+                   "config": {"model": args.model, "global_batch": global_batch, "per_gpu_batch": args.batch,
+                              "seq_len": args.seq_len, "parallelism": par, "optimizer": "adam multi-precision (fp32 master)",
+                              "bucket_mb": args.bucket_mb, "l2": "activations larger than L2",
+                              "baseline": "none published (the reference has no transformer workload)"},
+                   "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", [])},
+                   "gpu_launches": launches}
+            print(json.dumps(rec), flush=True)
+            rec = None
+        else:
+          rec = {"metric": "resnet50_train_images_per_sec", "value": round(value, 2), "unit": "images/sec",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": round(value / (BASELINE_IMG_S_PER_GPU * world), 3), "dtype": "bf16",
@@ -181,13 +214,14 @@ def main():
                "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                           "reasons": clocks.get("reasons", [])},
                "gpu_launches": launches}
-        if e2e:
+        if e2e and rec is not None:
             rec["e2e"] = {"value": round(global_batch * args.steps / (e_ms / 1e3), 2), "unit": "images/sec",
                           "h2d_bytes_per_step": e2e["h2d"] * n_workers if is_worker else 0,
                           "d2h_bytes_per_step": 4 * n_workers, "last_loss": e2e["loss"]}
             if not is_worker:  # rank 0 is a dedicated server: bytes come from the workers
                 rec["e2e"]["h2d_bytes_per_step"] = (args.batch * args.image_size * args.image_size * 3 + args.batch * 8) * n_workers
-        print(json.dumps(rec), flush=True)
+        if rec is not None:
+            print(json.dumps(rec), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,0 +1,93 @@
+"""Shared pieces of the example scripts: datasets (synthetic when no local copy exists - there is no network),
+batch iteration sharded by rank (reference `SplitSampler`, MX/example/distributed_training/cifar10_dist.py:54-81),
+accuracy metric."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+DATASETS = {"mnist": (1, 28, 10), "cifar10": (3, 32, 10), "caltech101": (3, 224, 101), "imagenet": (3, 224, 1000),
+            "dummy": (3, 224, 1000)}
+
+
+class SyntheticDataset:
+    """Fixed random images with labels that are a (noisy) function of the image so that training can learn."""
+
+    def __init__(self, name: str, size: int, num: int = 2048, image_size: int | None = None, seed: int = 0):
+        ch, side, classes = DATASETS.get(name, DATASETS["dummy"])
+        side = image_size or side
+        g = torch.Generator().manual_seed(seed)
+        self.classes = classes
+        protos = torch.randn(classes, ch, 8, 8, generator=g)
+        self.y = torch.randint(0, classes, (num,), generator=g)
+        base = torch.nn.functional.interpolate(protos[self.y], size=(side, side), mode="nearest")
+        self.x = base + 0.5 * torch.randn(num, ch, side, side, generator=g)
+
+    def __len__(self):
+        return self.x.shape[0]
+
+
+def load_dataset(name: str, data_dir: str | None, train: bool = True, image_size: int | None = None, num: int = 2048):
+    """CIFAR-10 python batches under data_dir are used when present; otherwise synthetic data of the same shape."""
+    if name == "cifar10" and data_dir:
+        d = os.path.join(data_dir, "cifar-10-batches-py")
+        if os.path.isdir(d):
+            import pickle
+            files = [f"data_batch_{i}" for i in range(1, 6)] if train else ["test_batch"]
+            xs, ys = [], []
+            for f in files:
+                with open(os.path.join(d, f), "rb") as fh:
+                    b = pickle.load(fh, encoding="bytes")
+                xs.append(np.asarray(b[b"data"], dtype=np.uint8).reshape(-1, 3, 32, 32))
+                ys.append(np.asarray(b[b"labels"]))
+            ds = SyntheticDataset.__new__(SyntheticDataset)
+            ds.x = (torch.from_numpy(np.concatenate(xs)).float() / 255.0 - 0.5) / 0.25
+            ds.y = torch.from_numpy(np.concatenate(ys)).long()
+            ds.classes = 10
+            return ds
+    return SyntheticDataset(name, 0, num=num, image_size=image_size, seed=0 if train else 1)
+
+
+class SplitSampler:
+    """Each worker sees its own 1/num_parts slice, reshuffled every epoch (cifar10_dist.py:54-81)."""
+
+    def __init__(self, length: int, num_parts: int = 1, part_index: int = 0, seed: int = 0):
+        self.part_len = length // num_parts
+        self.start = self.part_len * part_index
+        self.seed = seed
+        self.epoch = 0
+
+    def indices(self) -> torch.Tensor:
+        g = torch.Generator().manual_seed(self.seed + self.epoch)
+        self.epoch += 1
+        return self.start + torch.randperm(self.part_len, generator=g)
+
+    def __len__(self):
+        return self.part_len
+
+
+def batches(ds, batch_size: int, sampler: SplitSampler, device, dtype=torch.float32, channels_last: bool = True):
+    idx = sampler.indices()
+    for i in range(0, len(idx) - batch_size + 1, batch_size):
+        j = idx[i:i + batch_size]
+        x = ds.x[j].to(device=device, dtype=dtype, non_blocking=True)
+        if channels_last and x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        yield x, ds.y[j].to(device, non_blocking=True)
+
+
+class Accuracy:
+    def __init__(self):
+        self.correct = self.total = 0
+
+    def update(self, out, y):
+        self.correct += int((out.argmax(-1) == y).sum())
+        self.total += int(y.numel())
+
+    def get(self) -> float:
+        return self.correct / max(1, self.total)
+
+    def reset(self):
+        self.correct = self.total = 0

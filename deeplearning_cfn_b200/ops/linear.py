@@ -45,7 +45,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = native.gemm_bf16(dy2, x2, a_mn=True, b_mn=True, out_dtype=torch.bfloat16)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.float().sum(0)
+            db = dy2.sum(0, dtype=torch.float32)
         return dx, dw, db
 
 
@@ -66,21 +66,22 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
 class Linear(nn.Module):
     """Drop-in nn.Linear whose CUDA/bf16 path is the dlcfn tcgen05 GEMM.
 
-    TMA needs 16-byte row strides, so the weight is stored with out_features rounded up to a multiple
-    of 8; the extra rows are zero, receive zero gradient and are sliced off the output."""
+    TMA needs 16-byte row strides, so the weight is stored with in/out features rounded up to multiples of 8;
+    the padding rows/columns are zero, receive zero gradient, and are sliced off the output."""
 
     def __init__(self, in_features: int, out_features: int, bias: bool = True):
         super().__init__()
-        if in_features % 8:
-            raise ValueError("in_features must be a multiple of 8 (16-byte TMA row stride)")
         self.in_features, self.out_features = in_features, out_features
+        self.in_padded = (in_features + 7) // 8 * 8
         self.out_padded = (out_features + 7) // 8 * 8
-        self.weight = nn.Parameter(torch.zeros(self.out_padded, in_features))
+        self.weight = nn.Parameter(torch.zeros(self.out_padded, self.in_padded))
         self.bias = nn.Parameter(torch.zeros(self.out_padded)) if bias else None
         with torch.no_grad():
-            nn.init.kaiming_uniform_(self.weight[:out_features], a=math.sqrt(5))
+            nn.init.kaiming_uniform_(self.weight[:out_features, :in_features], a=math.sqrt(5))
 
     def forward(self, x):
+        if self.in_padded != self.in_features:
+            x = F.pad(x, (0, self.in_padded - self.in_features))
         y = linear(x, self.weight, self.bias)
         return y if self.out_padded == self.out_features else y[..., : self.out_features]
 

@@ -224,7 +224,7 @@ class DataParallelTrainer:
         self._ready = [False] * len(self.flat.buckets)
         self._next = 0
         self.flat.zero_grad()
-        out = self.model(x)
+        out = self.model(*x) if isinstance(x, (tuple, list)) else self.model(x)
         loss = self.loss_fn(out, y)
         loss.backward()
         return loss

@@ -54,6 +54,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path | None:
         return out if out.exists() else None
     srcs = sorted(CUDA_SRC.glob("*.cu"))
     hdrs = sorted(CUDA_SRC.glob("*.cuh"))
+    if not srcs:     # a staged copy of the package without csrc/: nothing to build here
+        return out if out.exists() else None
     LIB_DIR.mkdir(exist_ok=True)
     obj_dir = ROOT / "build" / "cuda"
     obj_dir.mkdir(parents=True, exist_ok=True)

@@ -1,0 +1,126 @@
+"""The bundled example recipes run end to end on CPU (small shapes): run_example equivalents of the reference
+README flows."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENV = dict(os.environ, PYTHONPATH=ROOT, DLCFN_FAKE_GPUS="0", CUDA_VISIBLE_DEVICES="")
+PY = sys.executable
+
+
+def run(cmd, env=None, timeout=600):
+    return subprocess.run(cmd, env=dict(ENV, **(env or {})), capture_output=True, text=True, timeout=timeout)
+
+
+def test_readme_flow_mxnet_style_ps_over_stack(tmp_path):
+    """create-stack -> launch -n $COUNT -H $PATH image_classification --kvstore dist_device_sync (README.md:139)."""
+    from deeplearning_cfn_b200.cluster.stack import launch_cluster
+    os.environ["DLCFN_FAKE_GPUS"] = "0"
+    h = launch_cluster("ex", home=str(tmp_path), backend="thread", WorkerCount=1, InstanceType="cpu.large", ImageType="CPUGloo")
+    env = h.export_env()
+    r = run([PY, "-m", "deeplearning_cfn_b200", "launch", "-n", env["DEEPLEARNING_WORKERS_COUNT"], "-H",
+             env["DEEPLEARNING_WORKERS_PATH"], PY, "-m", "deeplearning_cfn_b200.examples.image_classification",
+             "--dataset", "cifar10", "--model", "resnet20", "--epochs", "1", "--kvstore", "dist_device_sync",
+             "--batch-size", "16", "--num-samples", "64", "--log-interval", "1"], env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    out = r.stdout + r.stderr
+    assert "Node[0] Epoch[0]" in out and "Node[1] Epoch[0]" in out and out.count("validation: accuracy") == 2
+
+
+def test_tf_style_async_ps_from_generated_scripts(tmp_path):
+    """generate-trainer -> one script per host -> ps + workers train asynchronously, chief checkpoints."""
+    from deeplearning_cfn_b200.cluster.stack import launch_cluster
+    h = launch_cluster("tf", home=str(tmp_path), backend="thread", WorkerCount=1, InstanceType="cpu.large", ImageType="CPUGloo")
+    env = h.export_env()
+    sdir, ldir, tdir = str(tmp_path / "scripts"), str(tmp_path / "logs"), str(tmp_path / "train")
+    r = run([PY, "-m", "deeplearning_cfn_b200", "generate-trainer", "--trainer_script_dir", sdir, "--log_dir", ldir,
+             "--workers_file_path", h.hostfile, "--worker_count", "2", "--worker_gpu_count", "1", "--training_script",
+             os.path.join(ROOT, "deeplearning_cfn_b200/examples/cifar10_multi_machine_train.py"), "--max_steps", "6", "--batch_size", "8",
+             "--train_dir", tdir, "--log_frequency", "2"], env=env)
+    assert r.returncode == 0, r.stderr
+    scripts = sorted(os.listdir(sdir))
+    assert scripts == ["deeplearning-worker1.sh", "deeplearning-worker2.sh"]
+    procs = []
+    for s in scripts:   # what the user does by hand in the reference: run each host's script on that host
+        text = open(os.path.join(sdir, s)).read().replace("source /etc/profile\n", "")
+        open(os.path.join(sdir, s), "w").write(text + "\nwait\n")
+        procs.append(subprocess.Popen(["bash", os.path.join(sdir, s)], env=dict(ENV, **env, DLCFN_PY=PY)))
+    deadline = time.time() + 300
+    for p in procs:
+        assert p.wait(max(1, deadline - time.time())) == 0
+    logs = {f: open(os.path.join(ldir, f)).read() for f in os.listdir(ldir)}
+    assert set(logs) == {"ps0", "ps1", "worker0", "worker1"}
+    assert "step 6, loss" in logs["worker0"] and "examples/sec" in logs["worker1"], logs["worker0"][-800:]
+    assert os.path.exists(os.path.join(tdir, "model.ckpt"))
+
+
+def test_horovod_style_runner_over_maskrcnn_stack(tmp_path):
+    """prepare-bucket -> mask-rcnn stack -> run.sh (hostfile with slots -> dlcfn mpirun -> horovod trainer)."""
+    pytest.importorskip("torchvision")
+    from deeplearning_cfn_b200.cluster.staging import prepare_bucket
+    from deeplearning_cfn_b200.cluster.stack import launch_cluster
+    bucket = str(tmp_path / "bucket")
+    prepare_bucket(bucket, num_images=8, image_size=64)
+    h = launch_cluster("mr", "mask-rcnn.template", home=str(tmp_path), backend="thread", WorkerCount=1,
+                       InstanceType="cpu.large", ImageType="CPUGloo", S3Bucket=bucket, EFSServesData="true")
+    env = h.export_env()
+    home = os.path.join(h.master_root, "home")
+    # run from the master's home directory, like the reference
+    job_env = dict(ENV)
+    job_env.update(env)
+    job_env.update(HOME=home, DLCFN_PY=PY, DEEPLEARNING_WORKER_GPU_COUNT="1", STEPS_PER_EPOCH_OVERRIDE="2",
+                   EXTRA_CONFIG="PREPROC.MAX_SIZE=64 DATA.NUM_CLASS=5")
+    r = subprocess.run(["bash", os.path.join(home, "run.sh")], cwd=home, capture_output=True, text=True, timeout=900,
+                       env=job_env)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-2500:]
+    assert "Data directory: " + os.path.join(env["EFS_MOUNT"], "data") in r.stdout
+    assert "Number of parallel ranks: 2" in r.stdout and "Training finished" in r.stdout
+    assert open(os.path.join(home, "hostfile")).read() == "deeplearning-worker1 slots=1\ndeeplearning-worker2 slots=1\n"
+    runs = [d for d in os.listdir(env["EFS_MOUNT"]) if d.startswith("mask-rcnn-coco-2-efs-")]
+    assert runs and os.path.exists(os.path.join(env["EFS_MOUNT"], runs[0], "train_log/maskrcnn/checkpoint.pt"))
+
+
+def test_train_imagenet_checkpoint_and_resume(tmp_path):
+    prefix = str(tmp_path / "ck" / "r20")
+    base = [PY, "-m", "deeplearning_cfn_b200.examples.train_imagenet", "--benchmark", "1", "--network", "resnet",
+            "--num-layers", "20", "--image-shape", "3,32,32", "--num-classes", "10", "--batch-size", "8",
+            "--num-batches", "3", "--disp-batches", "1", "--model-prefix", prefix, "--lr-step-epochs", "1"]
+    r = run(base + ["--num-epochs", "1"])
+    assert r.returncode == 0 and os.path.exists(prefix + "-0001.params") and os.path.exists(prefix + "-symbol.json"), r.stderr[-2000:]
+    assert "Speed:" in r.stderr + r.stdout
+    r = run(base + ["--num-epochs", "2", "--load-epoch", "1"])
+    assert r.returncode == 0 and os.path.exists(prefix + "-0002.params"), r.stderr[-2000:]
+    assert "Epoch[1]" in r.stderr + r.stdout and "Epoch[0] Batch" not in r.stderr + r.stdout
+
+
+def test_run_example_cli_lists_and_builds_commands():
+    r = run([PY, "-m", "deeplearning_cfn_b200", "run-example", "--list"])
+    assert r.returncode == 0 and "mxnet-cifar10-ps" in r.stdout and "maskrcnn-horovod" in r.stdout
+    r = run([PY, "-m", "deeplearning_cfn_b200", "run-example", "resnet50-ps", "--gpus", "8", "--dry-run"])
+    assert "mpirun -np 8" in r.stdout and "--kv-store dist_sync_device" in r.stdout
+    r = run([PY, "-m", "deeplearning_cfn_b200", "benchmark", "--dry-run", "--gpu_count", "8", "--kv-stores", "allreduce"])
+    assert r.stdout.count("train_imagenet") == 4 and "-np 8" in r.stdout
+
+
+def test_profiler_trace_and_aggregate(tmp_path):
+    from deeplearning_cfn_b200.utils import profiler
+    profiler.set_config(filename=str(tmp_path / "trace.json"))
+    profiler.set_state("run")
+    for _ in range(3):
+        with profiler.scope("KVStoreDistDefaultPush", "kvstore"):
+            time.sleep(0.002)
+    profiler.marker("epoch-end")
+    c = profiler.Counter("bytes_pushed")
+    c.increment(10)
+    table = profiler.dumps()
+    assert "KVStoreDistDefaultPush" in table and " 3 " in table
+    fn = profiler.dump()
+    ev = json.load(open(fn))["traceEvents"]
+    assert sum(1 for e in ev if e["name"] == "KVStoreDistDefaultPush" and e["ph"] == "X") == 3
+    assert any(e["ph"] == "i" for e in ev) and any(e["ph"] == "C" for e in ev)
+    assert not profiler.is_running()

@@ -85,7 +85,7 @@ __global__ void kbarrier(SymmDev s, int channel) {
 // ----------------------------------------------------------- all-reduce -----
 // In place on heap[off, off + 16*nvec).  Slice r = vectors [r*per, (r+1)*per) is reduced by rank r.
 template <typename T, int W>
-__global__ void __launch_bounds__(512) kallreduce(SymmDev s, size_t off, size_t nvec, float scale,
+__global__ void __launch_bounds__(512) kallreduce(SymmDev s, size_t off, size_t dst_off, size_t nvec, float scale,
                                                   int channel) {
   constexpr int N = Vec16<T>::N;
   const uint32_t e = epoch_load(s, channel);
@@ -95,8 +95,12 @@ __global__ void __launch_bounds__(512) kallreduce(SymmDev s, size_t off, size_t 
   const size_t lo = per * s.rank;
   const size_t hi = (lo + per < nvec) ? lo + per : nvec;
   uint4* buf[W];
+  uint4* dst[W];
 #pragma unroll
-  for (int p = 0; p < W; ++p) buf[p] = reinterpret_cast<uint4*>(s.base[p] + off);
+  for (int p = 0; p < W; ++p) {
+    buf[p] = reinterpret_cast<uint4*>(s.base[p] + off);
+    dst[p] = reinterpret_cast<uint4*>(s.base[p] + dst_off);
+  }
 
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t v = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < hi; v += stride) {
@@ -118,9 +122,86 @@ __global__ void __launch_bounds__(512) kallreduce(SymmDev s, size_t off, size_t 
     for (int k = 0; k < N; ++k) acc[k] *= scale;
     const uint4 o = Vec16<T>::pack(acc);
 #pragma unroll
-    for (int p = 0; p < W; ++p) st_stream_v4(buf[p] + v, o);
+    for (int p = 0; p < W; ++p) st_stream_v4(dst[p] + v, o);
   }
 
+  block_barrier(s, channel, e + 2);
+  epoch_store(s, channel, e + 2);
+}
+
+// NVLS variant: the reduction happens INSIDE the NVSwitch.  One multimem.ld_reduce returns the sum over all
+// ranks of a 16-byte vector (fp32 accumulation), one multimem.st writes the scaled result to every rank.
+// Per GPU the wire carries 1/W of the bucket in each direction instead of (W-1)/W.
+template <typename T>
+__device__ __forceinline__ uint4 mc_ld_reduce(const void* p);
+template <>
+__device__ __forceinline__ uint4 mc_ld_reduce<__nv_bfloat16>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+template <>
+__device__ __forceinline__ uint4 mc_ld_reduce<float>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(*reinterpret_cast<float*>(&r.x)), "=f"(*reinterpret_cast<float*>(&r.y)),
+                 "=f"(*reinterpret_cast<float*>(&r.z)), "=f"(*reinterpret_cast<float*>(&r.w))
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st(void* p, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+               "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) kallreduce_mc(SymmDev s, size_t off, size_t dst_off, size_t nvec, float scale,
+                                                     int channel) {
+  constexpr int N = Vec16<T>::N;
+  const uint32_t e = epoch_load(s, channel);
+  block_barrier(s, channel, e + 1);
+  const int W = s.world;
+  const size_t per = (nvec + W - 1) / W;
+  const size_t lo = per * s.rank;
+  const size_t hi = (lo + per < nvec) ? lo + per : nvec;
+  const uint4* src = reinterpret_cast<const uint4*>(s.mc + off);
+  uint4* dst = reinterpret_cast<uint4*>(s.mc + dst_off);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t v = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; v + stride < hi; v += 2 * stride) {   // two switch reductions in flight per thread
+    uint4 x0 = mc_ld_reduce<T>(src + v);
+    uint4 x1 = mc_ld_reduce<T>(src + v + stride);
+    if (scale != 1.f) {
+      float f[N];
+      Vec16<T>::unpack(x0, f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) f[k] *= scale;
+      x0 = Vec16<T>::pack(f);
+      Vec16<T>::unpack(x1, f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) f[k] *= scale;
+      x1 = Vec16<T>::pack(f);
+    }
+    mc_st(dst + v, x0);
+    mc_st(dst + v + stride, x1);
+  }
+  for (; v < hi; v += stride) {
+    uint4 x0 = mc_ld_reduce<T>(src + v);
+    if (scale != 1.f) {
+      float f[N];
+      Vec16<T>::unpack(x0, f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) f[k] *= scale;
+      x0 = Vec16<T>::pack(f);
+    }
+    mc_st(dst + v, x0);
+  }
   block_barrier(s, channel, e + 2);
   epoch_store(s, channel, e + 2);
 }
@@ -323,6 +404,31 @@ DLCFN_API int dlcfn_symm_create(size_t heap_bytes, int rank, int world, void** o
   return 0;
 }
 
+// Adopt memory that somebody else allocated and mapped on every rank (torch symmetric memory): `local_alloc` is
+// this rank's whole allocation (kHeapOff header + heap), peers are registered with dlcfn_symm_set_peer_ptr.
+DLCFN_API int dlcfn_symm_create_external(void* local_alloc, size_t total_bytes, int rank, int world, void** out_ctx) {
+  if (world < 1 || world > DLCFN_MAX_RANKS || rank < 0 || rank >= world || total_bytes <= kHeapOff)
+    return (int)cudaErrorInvalidValue;
+  SymmCtx* c = new SymmCtx();
+  c->rank = rank;
+  c->world = world;
+  c->heap_bytes = total_bytes - kHeapOff;
+  c->external = true;
+  DLCFN_CHECK(cudaGetDevice(&c->device));
+  DLCFN_CHECK(cudaMemset(local_alloc, 0, kHeapOff));
+  c->local = (char*)local_alloc;
+  c->peer[rank] = c->local;
+  *out_ctx = c;
+  return 0;
+}
+
+DLCFN_API int dlcfn_symm_set_multicast(void* ctx, void* mc_alloc) {
+  ((SymmCtx*)ctx)->mc_alloc = (char*)mc_alloc;
+  return 0;
+}
+
+DLCFN_API int dlcfn_symm_has_multicast(void* ctx) { return ((SymmCtx*)ctx)->dev.mc != nullptr ? 1 : 0; }
+
 DLCFN_API int dlcfn_symm_get_handle(void* ctx, void* out64) {
   SymmCtx* c = (SymmCtx*)ctx;
   cudaIpcMemHandle_t h;
@@ -365,6 +471,7 @@ DLCFN_API int dlcfn_symm_finalize(void* ctx) {
   }
   c->dev.epoch = reinterpret_cast<uint32_t*>(c->local + kEpochOff);
   c->dev.err = reinterpret_cast<int*>(c->local + kErrOff);
+  c->dev.mc = c->mc_alloc ? c->mc_alloc + kHeapOff : nullptr;
   c->dev.rank = c->rank;
   c->dev.world = c->world;
   c->finalized = true;
@@ -392,7 +499,7 @@ DLCFN_API int dlcfn_symm_destroy(void* ctx) {
   SymmCtx* c = (SymmCtx*)ctx;
   for (int p = 0; p < c->world; ++p)
     if (c->opened_ipc[p] && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
-  if (c->local) cudaFree(c->local);
+  if (c->local && !c->external) cudaFree(c->local);
   delete c;
   return 0;
 }
@@ -414,36 +521,50 @@ DLCFN_API int dlcfn_barrier(void* ctx, int channel, cudaStream_t stream) {
 }
 
 template <typename T>
-static int launch_allreduce(SymmCtx* c, size_t off, size_t nvec, float scale, int channel, int nblocks,
-                            cudaStream_t st) {
+static int launch_allreduce(SymmCtx* c, size_t off, size_t dst_off, size_t nvec, float scale, int channel, int nblocks,
+                            int algo, cudaStream_t st) {
   // NOTE: every rank must compute the same grid, so the clamp only depends on (nvec, world)
   const size_t per = (nvec + c->world - 1) / c->world;
   const int g = clamp_blocks(nblocks, per, 512);
+  if (algo == 1) {
+    if (c->dev.mc == nullptr) return (int)cudaErrorNotSupported;
+    kallreduce_mc<T><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel);
+    return (int)cudaGetLastError();
+  }
   switch (c->world) {
-    case 1: kallreduce<T, 1><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
-    case 2: kallreduce<T, 2><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
-    case 3: kallreduce<T, 3><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
-    case 4: kallreduce<T, 4><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
-    case 5: kallreduce<T, 5><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
-    case 6: kallreduce<T, 6><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
-    case 7: kallreduce<T, 7><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
-    case 8: kallreduce<T, 8><<<g, 512, 0, st>>>(c->dev, off, nvec, scale, channel); break;
+    case 1: kallreduce<T, 1><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+    case 2: kallreduce<T, 2><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+    case 3: kallreduce<T, 3><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+    case 4: kallreduce<T, 4><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+    case 5: kallreduce<T, 5><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+    case 6: kallreduce<T, 6><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+    case 7: kallreduce<T, 7><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+    case 8: kallreduce<T, 8><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
     default: return (int)cudaErrorInvalidValue;
   }
   return (int)cudaGetLastError();
 }
 
-// In-place fused scale + all-reduce of heap[off_bytes, off_bytes + count*sizeof(T)) (padded to 16 B).
+// Fused scale + all-reduce of heap[src_off, +count*sizeof(T)) into heap[dst_off, ...) on every rank
+// (dst_off == src_off: in place).  algo 0: peer ld/st two-shot;  algo 1: NVLS multimem (needs a multicast mapping).
+DLCFN_API int dlcfn_allreduce_ex(void* ctx, size_t src_off, size_t dst_off, size_t count, int dtype, float scale,
+                                 int channel, int nblocks, int algo, cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (!c->finalized || (src_off & 15) || (dst_off & 15) || channel < 0 || channel >= kSigChannels)
+    return (int)cudaErrorInvalidValue;
+  if (count == 0) return 0;
+  if (dtype == 0)
+    return launch_allreduce<float>(c, src_off, dst_off, (count + 3) / 4, scale, channel, nblocks, algo, stream);
+  if (dtype == 1)
+    return launch_allreduce<__nv_bfloat16>(c, src_off, dst_off, (count + 7) / 8, scale, channel, nblocks, algo, stream);
+  return (int)cudaErrorInvalidValue;
+}
+
 DLCFN_API int dlcfn_allreduce(void* ctx, size_t off_bytes, size_t count, int dtype, float scale, int channel,
                               int nblocks, cudaStream_t stream) {
   SymmCtx* c = (SymmCtx*)ctx;
-  if (!c->finalized || (off_bytes & 15) || channel < 0 || channel >= kSigChannels)
-    return (int)cudaErrorInvalidValue;
-  if (count == 0) return 0;
-  if (dtype == 0) return launch_allreduce<float>(c, off_bytes, (count + 3) / 4, scale, channel, nblocks, stream);
-  if (dtype == 1)
-    return launch_allreduce<__nv_bfloat16>(c, off_bytes, (count + 7) / 8, scale, channel, nblocks, stream);
-  return (int)cudaErrorInvalidValue;
+  return dlcfn_allreduce_ex(ctx, off_bytes, off_bytes, count, dtype, scale, channel, nblocks,
+                            c->dev.mc != nullptr && c->world > 1 ? 1 : 0, stream);
 }
 
 DLCFN_API int dlcfn_broadcast(void* ctx, size_t off_bytes, size_t bytes, int root, int channel, int nblocks,

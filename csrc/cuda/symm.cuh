@@ -25,6 +25,7 @@ struct SymmDev {
   uint32_t* sig[DLCFN_MAX_RANKS];  // signal pads
   uint32_t* epoch;                 // local, per (channel, block)
   int* err;                        // local error word
+  char* mc;                        // NVLS multicast mapping of the data heaps (nullptr when unavailable)
   int rank, world;
 };
 
@@ -56,6 +57,8 @@ struct SymmCtx {
   int rank = 0, world = 1, device = 0;
   size_t heap_bytes = 0;
   char* local = nullptr;                  // whole allocation
+  char* mc_alloc = nullptr;               // multicast mapping of the whole allocation (external backend only)
+  bool external = false;                  // memory owned by the caller (torch symmetric memory)
   char* peer[DLCFN_MAX_RANKS] = {nullptr};  // whole allocations as mapped here
   bool opened_ipc[DLCFN_MAX_RANKS] = {false};
   SymmDev dev{};

@@ -52,7 +52,7 @@ def network_shapes(name: str, num_layers: int, num_classes: int, image_shape: st
 
 
 class Runner:
-    def __init__(self, kind: str, dtype: torch.dtype, max_elems: int):
+    def __init__(self, kind: str, dtype: torch.dtype, max_elems: int, total_elems: int | None = None):
         from ..parallel.symm import SymmetricHeap
         self.kind, self.dtype = kind, dtype
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
@@ -60,71 +60,78 @@ class Runner:
         esz = 2 if dtype == torch.bfloat16 else 4
         self.esz = esz
         self.heap = None
+        cap = (total_elems or max_elems) + 64
         if kind in ("allreduce", "ps"):
-            self.heap = SymmetricHeap(2 * (max_elems * esz + 4096) + (1 << 20))
-            self.goff, self.g = self.heap.alloc_tensor(max_elems + 16, dtype)
-            self.woff, self.w = self.heap.alloc_tensor(max_elems + 16, dtype)
+            self.heap = SymmetricHeap(2 * (cap * esz + 4096) + (1 << 20))
+            self.goff, self.g = self.heap.alloc_tensor(cap, dtype)
+            self.woff, self.w = self.heap.alloc_tensor(cap, dtype)
             self.master = torch.zeros(max_elems // self.world + 64, device=self.dev)
         else:
-            self.g = torch.empty(max_elems, dtype=dtype, device=self.dev)
-            self.w = torch.empty(max_elems, dtype=dtype, device=self.dev)
+            self.g = torch.empty(cap, dtype=dtype, device=self.dev)
+            self.w = torch.empty(cap, dtype=dtype, device=self.dev)
 
-    def fill(self, n: int, it: int) -> None:
-        self.g[:n] = float(self.rank + 1 + it % 3)
+    def fill(self, n: int, it: int, at: int = 0) -> None:
+        self.g[at:at + n] = float(self.rank + 1 + it % 3)
 
     def expected(self, n: int, it: int) -> float:
         return float(sum(r + 1 + it % 3 for r in range(self.world)))
 
-    def run(self, n: int) -> torch.Tensor:
-        """One push+pull (or all-reduce) of n elements; returns the tensor holding the reduced values."""
+    def run(self, n: int, at: int = 0) -> torch.Tensor:
+        """One push+pull (or all-reduce) of n elements at element offset `at` (a multiple of 64); returns a view of
+        the reduced values."""
         k = self.kind
+        b = at * self.esz
         if k == "allreduce":
-            self.heap.allreduce_(self.goff, n, self.dtype, 1.0)
-            return self.g
+            self.heap.allreduce_(self.goff + b, n, self.dtype, 1.0)
+            return self.g[at:at + n]
         if k == "ps":
             vec = 16 // self.esz
             nvec = (n + vec - 1) // vec
             per = (nvec + self.world - 1) // self.world
             lo, hi = min(self.rank * per, nvec) * vec, min((self.rank + 1) * per, nvec) * vec
-            self.heap.ps_sync_step(self.goff, self.woff, n, lo, hi, (1 << self.world) - 1, self.master, None, None,
-                                   self.dtype, "none", lr=0.0)
-            return self.w
+            self.heap.ps_sync_step(self.goff + b, self.woff + b, n, lo, hi, (1 << self.world) - 1, self.master, None,
+                                   None, self.dtype, "none", lr=0.0)
+            return self.w[at:at + n]
         if k == "nccl":
-            dist.all_reduce(self.g[:n])
-            return self.g
+            dist.all_reduce(self.g[at:at + n])
+            return self.g[at:at + n]
         if k == "nccl_ps":
-            dist.reduce(self.g[:n], dst=0)
+            dist.reduce(self.g[at:at + n], dst=0)
             if self.rank == 0:
-                self.w[:n].copy_(self.g[:n])
-            dist.broadcast(self.w[:n], src=0)
-            return self.w
+                self.w[at:at + n].copy_(self.g[at:at + n])
+            dist.broadcast(self.w[at:at + n], src=0)
+            return self.w[at:at + n]
         raise ValueError(k)
 
 
 def measure(r: Runner, sizes: list[int], num_batches: int, check: bool) -> tuple[float, float]:
     """Returns (seconds per batch [max over ranks], max abs error)."""
     err = 0.0
+    offs, cur = [], 0
+    for n in sizes:                          # every array gets its own 128-byte aligned region
+        offs.append(cur)
+        cur += (n + 63) // 64 * 64
     for it in range(2):                      # warm-up
-        for n in sizes:
-            r.fill(n, it)
-            r.run(n)
+        for n, at in zip(sizes, offs):
+            r.fill(n, it, at)
+            r.run(n, at)
     torch.cuda.synchronize()
     dist.barrier()
     total_ms = 0.0
     for it in range(num_batches):
-        for n in sizes:
-            r.fill(n, it)
+        for n, at in zip(sizes, offs):
+            r.fill(n, it, at)
         torch.cuda.synchronize()
         dist.barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        outs = [(n, r.run(n)) for n in sizes]
+        outs = [(n, r.run(n, at)) for n, at in zip(sizes, offs)]
         e.record()
         torch.cuda.synchronize()
         total_ms += s.elapsed_time(e)
         if check:
-            n, out = outs[-1]
-            err = max(err, float((out[:n].float() - r.expected(n, it)).abs().max()))
+            for n, out in outs[-3:] + outs[:1]:
+                err = max(err, float((out.float() - r.expected(n, it)).abs().max()))
     t = torch.tensor([total_ms / num_batches / 1e3, err], device=r.dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0]), float(t[1])
@@ -158,7 +165,7 @@ def main(argv=None) -> int:
                 print(f"{a.kv_store:9s} {nb:>11d} B  {sec * 1e6:10.1f} us  {bw:8.2f} GB/s per GPU  error {err:g}", flush=True)
     else:
         shapes = network_shapes(a.network, a.num_layers, a.num_classes, a.image_shape)
-        r = Runner(a.kv_store, dtype, max(shapes))
+        r = Runner(a.kv_store, dtype, max(shapes), sum((n + 63) // 64 * 64 for n in shapes))
         nbytes = sum(shapes) * esz
         if rank == 0:
             print(f"num of arrays = {len(shapes)}, total size = {nbytes / 1e6:f} MB", flush=True)
@@ -172,6 +179,7 @@ def main(argv=None) -> int:
         with open(a.out, "w") as f:
             json.dump({"kv_store": a.kv_store, "world": world, "dtype": a.dtype, "results": results}, f, indent=1)
     dist.barrier()
+    dist.destroy_process_group()
     return 0
 
 

@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from ..ops.batchnorm import BatchNormReLU2d
 from ..ops.linear import Linear
+from ..ops.pool import MaxPool2d
 
 _EPS = 2e-5
 _MOM = 0.1  # torch momentum = 1 - mxnet bn_mom(0.9)
@@ -91,7 +92,7 @@ class ResNetV2(nn.Module):
             self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 3, 1, 1, bias=False))
         else:
             self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 7, 2, 3, bias=False), _bn(filters[0]),
-                                      nn.MaxPool2d(3, 2, 1))
+                                      MaxPool2d(3, 2, 1))
         unit = BottleneckV2 if bottleneck else BasicV2
         blocks = []
         cin = filters[0]

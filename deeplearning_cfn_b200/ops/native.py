@@ -76,6 +76,10 @@ def _declare(L) -> None:
     L.dlcfn_unique_rows.argtypes = [vp, sz, ll, vp, vp, sz, vp, vp, vp]
     L.dlcfn_symm_create.argtypes = [sz, i, i, ctypes.POINTER(vp)]
     L.dlcfn_symm_get_handle.argtypes = [vp, vp]
+    L.dlcfn_symm_create_external.argtypes = [vp, sz, i, i, ctypes.POINTER(vp)]
+    L.dlcfn_symm_set_multicast.argtypes = [vp, vp]
+    L.dlcfn_symm_has_multicast.argtypes = [vp]
+    L.dlcfn_allreduce_ex.argtypes = [vp, sz, sz, sz, i, f, i, i, i, vp]
     L.dlcfn_symm_open_peer.argtypes = [vp, i, vp]
     L.dlcfn_symm_set_peer_ptr.argtypes = [vp, i, vp]
     L.dlcfn_symm_allocation.argtypes = [vp]
@@ -97,7 +101,8 @@ def _declare(L) -> None:
                "dlcfn_symm_get_handle", "dlcfn_symm_open_peer", "dlcfn_symm_set_peer_ptr", "dlcfn_symm_finalize",
                "dlcfn_symm_check_error", "dlcfn_symm_destroy", "dlcfn_barrier", "dlcfn_allreduce",
                "dlcfn_broadcast", "dlcfn_ps_sync_step", "dlcfn_ps_async_worker", "dlcfn_ps_async_server",
-               "dlcfn_gemm_bf16"):
+               "dlcfn_gemm_bf16", "dlcfn_symm_create_external", "dlcfn_symm_set_multicast", "dlcfn_symm_has_multicast",
+               "dlcfn_allreduce_ex"):
         getattr(L, fn).restype = c_int
 
 

@@ -10,6 +10,7 @@ peer's HBM with plain loads/stores over NVLink 5 / NVSwitch.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_int, c_void_p
 
 import torch
@@ -57,23 +58,65 @@ class SymmetricHeap:
         self.heap_bytes = int(heap_bytes)
         L = native.lib()
         ctx = c_void_p()
+        self.backend = "ipc"
+        self._symm_tensor = None
+        want = os.environ.get("DLCFN_SYMM_BACKEND", "auto")
         with torch.cuda.device(self.device):
-            native.check(L.dlcfn_symm_create(self.heap_bytes, self.rank, self.world, ctypes.byref(ctx)), "symm_create")
+            if self.world > 1 and want in ("auto", "torch"):
+                try:
+                    ctx = self._create_torch_backend(L)
+                    self.backend = "torch-symm"
+                except Exception as e:          # no symmetric-memory support here: CUDA-IPC arena instead
+                    if want == "torch":
+                        raise
+                    self._why_not_torch = repr(e)
+                    ctx = c_void_p()
+            if self.backend == "ipc":
+                native.check(L.dlcfn_symm_create(self.heap_bytes, self.rank, self.world, ctypes.byref(ctx)), "symm_create")
+                if self.world > 1:
+                    buf = ctypes.create_string_buffer(64)
+                    native.check(L.dlcfn_symm_get_handle(ctx, buf), "symm_get_handle")
+                    handles: list = [None] * self.world
+                    dist.all_gather_object(handles, bytes(buf.raw), group=group)
+                    for p, h in enumerate(handles):
+                        if p != self.rank:
+                            native.check(L.dlcfn_symm_open_peer(ctx, p, ctypes.create_string_buffer(h, 64)), "symm_open_peer")
             self._ctx = ctx
-            if self.world > 1:
-                buf = ctypes.create_string_buffer(64)
-                native.check(L.dlcfn_symm_get_handle(ctx, buf), "symm_get_handle")
-                handles: list = [None] * self.world
-                dist.all_gather_object(handles, bytes(buf.raw), group=group)
-                for p, h in enumerate(handles):
-                    if p != self.rank:
-                        native.check(L.dlcfn_symm_open_peer(ctx, p, ctypes.create_string_buffer(h, 64)), "symm_open_peer")
             native.check(L.dlcfn_symm_finalize(ctx), "symm_finalize")
+        self.has_multicast = bool(L.dlcfn_symm_has_multicast(ctx))
+        algo = os.environ.get("DLCFN_ALLREDUCE_ALGO", "auto")
+        self.allreduce_algo = 1 if (self.has_multicast and algo in ("auto", "nvls")) else 0
         self._base = L.dlcfn_symm_heap_ptr(ctx, self.rank)
         self._bytes = tensor_from_ptr(self._base, self.heap_bytes, self.device)
         self._top = 0
         if self.world > 1:
             dist.barrier(group=group)
+
+    def _create_torch_backend(self, L):
+        """Arena from torch symmetric memory: same layout, every peer already mapped, plus (when the fabric
+        supports it) an NVLS multicast mapping that the multimem all-reduce kernel uses."""
+        import torch.distributed._symmetric_memory as symm_mem
+        total = (1 << 20) + (self.heap_bytes + 255) // 256 * 256
+        group = self.group if self.group is not None else dist.group.WORLD
+        t = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        try:
+            hdl = symm_mem.rendezvous(t, group=group)
+        except TypeError:
+            hdl = symm_mem.rendezvous(t, group.group_name)
+        ptrs = list(hdl.buffer_ptrs)
+        ctx = c_void_p()
+        native.check(L.dlcfn_symm_create_external(ptrs[self.rank], total, self.rank, self.world, ctypes.byref(ctx)),
+                     "symm_create_external")
+        for p, ptr in enumerate(ptrs):
+            if p != self.rank:
+                native.check(L.dlcfn_symm_set_peer_ptr(ctx, p, ptr), "symm_set_peer_ptr")
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc:
+            native.check(L.dlcfn_symm_set_multicast(ctx, mc), "symm_set_multicast")
+        self._symm_tensor, self._symm_handle = t, hdl
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        return ctx
 
     # ------------------------------------------------------------------ allocation
     def alloc(self, nbytes: int, align: int = 256) -> int:
@@ -102,11 +145,15 @@ class SymmetricHeap:
         native._count()
 
     def allreduce_(self, off: int, count: int, dtype: torch.dtype, scale: float = 1.0, nblocks: int = 32,
-                   stream: torch.cuda.Stream | None = None, channel: int | None = None) -> None:
-        """Fused bucket scale + all-reduce, in place (reference C11: Horovod fusion buffer + ncclAllReduce)."""
+                   stream: torch.cuda.Stream | None = None, channel: int | None = None, dst_off: int | None = None,
+                   algo: int | None = None) -> None:
+        """Fused bucket scale + all-reduce (reference C11: Horovod fusion buffer + ncclAllReduce).  In place unless
+        dst_off is given.  algo 0 = peer ld/st two-shot, 1 = NVLS multimem (default when a multicast mapping exists)."""
         ch = self.CH_ALLREDUCE if channel is None else channel
-        native.check(native.lib().dlcfn_allreduce(self._ctx, off, count, native.dtype_code(dtype), float(scale), ch,
-                                                  nblocks, native.stream_ptr(stream)), "allreduce")
+        a = self.allreduce_algo if algo is None else algo
+        native.check(native.lib().dlcfn_allreduce_ex(self._ctx, off, off if dst_off is None else dst_off, count,
+                                                     native.dtype_code(dtype), float(scale), ch, nblocks, a,
+                                                     native.stream_ptr(stream)), "allreduce")
         native._count()
 
     def broadcast_(self, off: int, nbytes: int, root: int, nblocks: int = 32,
@@ -158,3 +205,4 @@ class SymmetricHeap:
             self._bytes = None
             native.lib().dlcfn_symm_destroy(self._ctx)
             self._ctx = None
+            self._symm_tensor = None

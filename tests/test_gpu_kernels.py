@@ -132,3 +132,25 @@ def test_fused_batchnorm_relu(N, C, H, W, relu):
     if relu:
         yer = torch.relu(yer)
     torch.testing.assert_close(ye.float(), yer, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("N,C,H,W,k,s,p", [(2, 64, 12, 12, 3, 2, 1), (4, 8, 7, 9, 3, 2, 1), (2, 16, 8, 8, 2, 2, 0),
+                                            (1, 128, 15, 13, 3, 1, 1), (8, 64, 56, 56, 3, 2, 1)])
+def test_maxpool_nhwc(N, C, H, W, k, s, p):
+    from deeplearning_cfn_b200.ops.pool import max_pool2d
+    torch.manual_seed(4)
+    # distinct values so arg-max ties cannot make the two implementations disagree
+    x = torch.randperm(N * C * H * W, device=dev()).float().view(N, C, H, W).mul_(1e-3).bfloat16().float()
+    x = x + torch.randn_like(x) * 4
+    x = x.bfloat16().contiguous(memory_format=torch.channels_last)
+    xa = x.clone().requires_grad_(True)
+    y = max_pool2d(xa, k, s, p)
+    xr = x.float().requires_grad_(True)
+    yr = torch.nn.functional.max_pool2d(xr, k, s, p)
+    assert y.shape == yr.shape and torch.equal(y.float(), yr)
+    dy = torch.randn_like(yr)
+    y.backward(dy.bfloat16())
+    yr.backward(dy.bfloat16().float())
+    torch.testing.assert_close(xa.grad.float().sum(), xr.grad.sum(), rtol=1e-2, atol=1e-1)
+    close = torch.isclose(xa.grad.float(), xr.grad, rtol=2e-2, atol=2e-2).float().mean().item()
+    assert close > 0.995, close

@@ -174,22 +174,22 @@ __global__ void __launch_bounds__(512) kallreduce_mc(SymmDev s, size_t off, size
   uint4* dst = reinterpret_cast<uint4*>(s.mc + dst_off);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t v = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  for (; v + stride < hi; v += 2 * stride) {   // two switch reductions in flight per thread
-    uint4 x0 = mc_ld_reduce<T>(src + v);
-    uint4 x1 = mc_ld_reduce<T>(src + v + stride);
+  for (; v + 3 * stride < hi; v += 4 * stride) {   // four switch reductions in flight per thread
+    uint4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = mc_ld_reduce<T>(src + v + u * stride);
     if (scale != 1.f) {
-      float f[N];
-      Vec16<T>::unpack(x0, f);
 #pragma unroll
-      for (int k = 0; k < N; ++k) f[k] *= scale;
-      x0 = Vec16<T>::pack(f);
-      Vec16<T>::unpack(x1, f);
+      for (int u = 0; u < 4; ++u) {
+        float f[N];
+        Vec16<T>::unpack(x[u], f);
 #pragma unroll
-      for (int k = 0; k < N; ++k) f[k] *= scale;
-      x1 = Vec16<T>::pack(f);
+        for (int k = 0; k < N; ++k) f[k] *= scale;
+        x[u] = Vec16<T>::pack(f);
+      }
     }
-    mc_st(dst + v, x0);
-    mc_st(dst + v + stride, x1);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) mc_st(dst + v + u * stride, x[u]);
   }
   for (; v < hi; v += stride) {
     uint4 x0 = mc_ld_reduce<T>(src + v);
@@ -234,6 +234,8 @@ struct PSArgs {
   float* s2;             // optimizer state 2 (Adam v) or null
   OptArgs opt;
   int channel;
+  int use_mc;            // 1: push = multimem.ld_reduce, pull = multimem.st (ranks that are not workers must hold
+                         //    zero gradients: the switch sums over every rank)
 };
 
 // Peer pointer tables are indexed by rank with compile-time indices only, so they live in registers.
@@ -256,23 +258,33 @@ __device__ __forceinline__ void ps_make_ptrs(const PSArgs& a, const SymmDev& s, 
 }
 
 template <typename T>
-__device__ __forceinline__ void ps_update_vec(const PSArgs& a, const PSPtrs& P, size_t v) {
+__device__ __forceinline__ uint4 mc_ld_reduce(const void* p);
+__device__ __forceinline__ void mc_st(void* p, const uint4& v);
+
+template <typename T>
+__device__ __forceinline__ void ps_update_vec(const PSArgs& a, const PSPtrs& P, size_t v, const char* mc = nullptr) {
   constexpr int N = Vec16<T>::N;
-  uint4 x[DLCFN_MAX_RANKS];
-#pragma unroll
-  for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
-    if ((P.load_mask >> r) & 1u) x[r] = ld_relaxed_sys_v4(P.g[r] + v);
   float g[N], t[N];
+  if (mc != nullptr) {
+    // push through the switch: one load returns the sum over all ranks
+    const uint4 xs = mc_ld_reduce<T>(mc + a.grad_off + v * 16);
+    Vec16<T>::unpack(xs, g);
+  } else {
+    uint4 x[DLCFN_MAX_RANKS];
 #pragma unroll
-  for (int k = 0; k < N; ++k) g[k] = 0.f;
-  // fixed rank order: deterministic, independent of which server owns the shard
+    for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
+      if ((P.load_mask >> r) & 1u) x[r] = ld_relaxed_sys_v4(P.g[r] + v);
 #pragma unroll
-  for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
-    if ((P.load_mask >> r) & 1u) {
-      Vec16<T>::unpack(x[r], t);
+    for (int k = 0; k < N; ++k) g[k] = 0.f;
+    // fixed rank order: deterministic, independent of which server owns the shard
 #pragma unroll
-      for (int k = 0; k < N; ++k) g[k] += t[k];
-    }
+    for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
+      if ((P.load_mask >> r) & 1u) {
+        Vec16<T>::unpack(x[r], t);
+#pragma unroll
+        for (int k = 0; k < N; ++k) g[k] += t[k];
+      }
+  }
   const size_t i0 = (v - a.lo) * N;
   float w[N], m1[N], m2[N];
 #pragma unroll
@@ -304,6 +316,10 @@ __device__ __forceinline__ void ps_update_vec(const PSArgs& a, const PSPtrs& P, 
   }
   const uint4 o = Vec16<T>::pack(w);
   // pull: the server writes the fresh weights into every worker's model buffer (and its own copy)
+  if (mc != nullptr) {
+    mc_st(const_cast<char*>(mc) + a.weight_off + v * 16, o);   // one store, the switch replicates it
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < DLCFN_MAX_RANKS; ++r)
     if ((P.store_mask >> r) & 1u) st_stream_v4(P.w[r] + v, o);
@@ -317,8 +333,9 @@ __global__ void __launch_bounds__(512) kps_sync(SymmDev s, PSArgs a) {
   PSPtrs P;
   ps_make_ptrs(a, s, a.worker_mask, P);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const char* mc = a.use_mc ? s.mc : nullptr;
   for (size_t v = a.lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < a.hi; v += stride)
-    ps_update_vec<T>(a, P, v);
+    ps_update_vec<T>(a, P, v, mc);
 
   block_barrier(s, a.channel, e + 2);  // every server finished writing: the pull is complete
   epoch_store(s, a.channel, e + 2);
@@ -504,6 +521,16 @@ DLCFN_API int dlcfn_symm_destroy(void* ctx) {
   return 0;
 }
 
+// nblocks <= 0: pick the grid from the message size - the peer ld/st kernels need ~128 CTAs x 512 threads of
+// 16-byte requests in flight to fill an NVLink-5 port (measured: 32 CTAs 246 GB/s, 128 CTAs 656 GB/s at 256 MiB,
+// N = 2), small messages only pay for the barrier, so they get few CTAs.  `total_vecs` must be rank-independent.
+static inline int auto_blocks(size_t total_vecs) {
+  size_t b = total_vecs * 16 / (128 * 1024);
+  if (b < 8) b = 8;
+  if (b > 128) b = 128;
+  return (int)b;
+}
+
 static inline int clamp_blocks(int nblocks, size_t work_vecs, int threads) {
   if (nblocks <= 0) nblocks = 32;
   if (nblocks > kSigMaxBlocks) nblocks = kSigMaxBlocks;
@@ -525,6 +552,7 @@ static int launch_allreduce(SymmCtx* c, size_t off, size_t dst_off, size_t nvec,
                             int algo, cudaStream_t st) {
   // NOTE: every rank must compute the same grid, so the clamp only depends on (nvec, world)
   const size_t per = (nvec + c->world - 1) / c->world;
+  if (nblocks <= 0) nblocks = auto_blocks(nvec);
   const int g = clamp_blocks(nblocks, per, 512);
   if (algo == 1) {
     if (c->dev.mc == nullptr) return (int)cudaErrorNotSupported;
@@ -590,6 +618,8 @@ DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, 
   if (!c->finalized || (grad_off & 15) || (weight_off & 15) || (shard_lo % N) || dtype < 0 || dtype > 1)
     return (int)cudaErrorInvalidValue;
   if (worker_mask == 0 || channel < 0 || channel >= kSigChannels) return (int)cudaErrorInvalidValue;
+  int use_mc = 0;
+  if (nblocks >= 10000) { use_mc = c->dev.mc != nullptr; nblocks -= 10000; }   // python encodes algo in nblocks
   PSArgs a;
   a.grad_off = grad_off;
   a.weight_off = weight_off;
@@ -601,8 +631,10 @@ DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, 
   a.s2 = s2;
   a.opt = OptArgs{opt_kind, lr, wd, momentum, beta1, beta2, eps, rescale, clip};
   a.channel = channel;
+  a.use_mc = use_mc;
   // same grid on every rank: derived from the total size and world only
   const size_t per = ((total_count + N - 1) / N + c->world - 1) / c->world;
+  if (nblocks <= 0) nblocks = auto_blocks((total_count + N - 1) / N);
   const int g = clamp_blocks(nblocks, per, 512);
   if (dtype == 1) kps_sync<__nv_bfloat16><<<g, 512, 0, stream>>>(c->dev, a);
   else kps_sync<float><<<g, 512, 0, stream>>>(c->dev, a);
@@ -640,6 +672,7 @@ DLCFN_API int dlcfn_ps_async_server(void* ctx, size_t grad_off, size_t weight_of
   a.s2 = s2;
   a.opt = OptArgs{opt_kind, lr, wd, momentum, beta1, beta2, eps, rescale, clip};
   a.channel = channel;
+  a.use_mc = 0;
   if (dtype == 1) kps_async_server<__nv_bfloat16><<<nblocks, 512, 0, stream>>>(c->dev, a);
   else kps_async_server<float><<<nblocks, 512, 0, stream>>>(c->dev, a);
   return (int)cudaGetLastError();

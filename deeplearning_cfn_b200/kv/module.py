@@ -1,0 +1,151 @@
+"""`Module` - the symbolic-API training wrapper (reference Y6: MX/python/mxnet/module/module.py,
+base_module.py): `bind` -> `init_params` -> `init_optimizer(kvstore, optimizer, optimizer_params)` (rescale_grad =
+1/(batch_size * num_workers) when the kvstore is `dist_sync`, module.py:474-556) -> `fit(train_data, num_epoch,
+batch_end_callback, epoch_end_callback, ...)` whose inner loop is `forward_backward` + `update`
+(base_module.py:516-529; `update` = `_update_params_on_kvstore` push/pull with priority -index, or pull grads +
+local updater, model.py:145-176), plus `save_checkpoint` / `load` / `score`."""
+from __future__ import annotations
+
+import logging
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import optimizer as opt
+from .kvstore import KVStore, create
+
+
+class Module:
+    def __init__(self, symbol: torch.nn.Module, data_names=("data",), label_names=("softmax_label",), context=None,
+                 loss=None):
+        self.symbol = symbol
+        self.device = torch.device(context) if context is not None else next(symbol.parameters()).device
+        self.loss = loss or (lambda out, y: F.cross_entropy(out.float(), y, reduction="sum"))
+        self.binded = self.params_initialized = self.optimizer_initialized = False
+        self._kv: KVStore | None = None
+        self._update_on_kvstore = False
+        self._params = [p for p in symbol.parameters() if p.requires_grad]
+        self._batch_size = None
+        self._outputs = None
+
+    def bind(self, data_shapes, label_shapes=None, for_training: bool = True, **_):
+        self._batch_size = data_shapes[0][1][0] if isinstance(data_shapes[0], tuple) else data_shapes[0]
+        self.binded = True
+
+    def init_params(self, initializer=None, arg_params=None, aux_params=None, allow_missing=False, force_init=False):
+        if arg_params or aux_params:
+            self.symbol.load_state_dict({**(arg_params or {}), **(aux_params or {})}, strict=not allow_missing)
+        elif initializer is not None:
+            for p in self._params:
+                initializer(p)
+        self.params_initialized = True
+
+    def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),),
+                       force_init: bool = False):
+        assert self.binded and self.params_initialized
+        kv = create(kvstore) if isinstance(kvstore, str) else kvstore
+        params = dict(optimizer_params)
+        batch = self._batch_size or 1
+        if kv is not None and "dist" in kv.type and "_sync" in kv.type:
+            batch *= kv.num_workers
+        params.setdefault("rescale_grad", 1.0 / batch)
+        self._optimizer = opt.create(optimizer, **params) if isinstance(optimizer, str) else optimizer
+        self._kv = kv
+        # update_on_kvstore: true for distributed stores, false when there is nothing to aggregate (model.py:77-114)
+        self._update_on_kvstore = kv is not None and "dist" in kv.type
+        self._updater = opt.get_updater(self._optimizer)
+        if kv is not None:
+            for i, p in enumerate(self._params):
+                kv.init(i, p.data)
+            if self._update_on_kvstore:
+                kv.set_optimizer(self._optimizer)
+            for i, p in enumerate(self._params):
+                kv.pull(i, out=p.data, priority=-i)
+        self.optimizer_initialized = True
+
+    def forward_backward(self, data_batch):
+        x, y = data_batch
+        self.symbol.zero_grad(set_to_none=True)
+        self._outputs = self.symbol(x)
+        self._loss = self.loss(self._outputs, y)
+        self._loss.backward()
+
+    @torch.no_grad()
+    def update(self):
+        kv = self._kv
+        for i, p in enumerate(self._params):
+            if p.grad is None:
+                continue
+            if kv is not None:
+                kv.push(i, p.grad, priority=-i)
+                if self._update_on_kvstore:
+                    kv.pull(i, out=p.data, priority=-i)
+                else:
+                    kv.pull(i, out=p.grad, priority=-i)
+                    self._updater(i, p.grad, p.data)
+            else:
+                self._updater(i, p.grad, p.data)
+
+    def get_outputs(self):
+        return [self._outputs]
+
+    def fit(self, train_data, eval_data=None, eval_metric="acc", epoch_end_callback=None, batch_end_callback=None,
+            kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), initializer=None,
+            arg_params=None, aux_params=None, begin_epoch: int = 0, num_epoch: int | None = None, batch_size=None):
+        assert num_epoch is not None, "please specify number of epochs"
+        if not self.binded:
+            self.bind([("data", (batch_size or 1,))])
+        if not self.params_initialized:
+            self.init_params(initializer, arg_params, aux_params)
+        if not self.optimizer_initialized:
+            self.init_optimizer(kvstore, optimizer, optimizer_params)
+        for epoch in range(begin_epoch, num_epoch):
+            tic = time.time()
+            correct = total = 0
+            self.symbol.train()
+            it = train_data() if callable(train_data) else train_data
+            for nbatch, batch in enumerate(it):
+                self.forward_backward(batch)
+                self.update()
+                correct += int((self._outputs.argmax(-1) == batch[1]).sum())
+                total += int(batch[1].numel())
+                for cb in _as_list(batch_end_callback):
+                    cb(epoch, nbatch, {"accuracy": correct / max(1, total)})
+            logging.info("Epoch[%d] Train-accuracy=%f", epoch, correct / max(1, total))
+            logging.info("Epoch[%d] Time cost=%.3f", epoch, time.time() - tic)
+            for cb in _as_list(epoch_end_callback):
+                cb(epoch, self.symbol, None, None)
+            if eval_data is not None:
+                logging.info("Epoch[%d] Validation-accuracy=%f", epoch, self.score(eval_data))
+
+    @torch.no_grad()
+    def score(self, eval_data) -> float:
+        self.symbol.eval()
+        correct = total = 0
+        it = eval_data() if callable(eval_data) else eval_data
+        for x, y in it:
+            correct += int((self.symbol(x).argmax(-1) == y).sum())
+            total += int(y.numel())
+        return correct / max(1, total)
+
+    def save_checkpoint(self, prefix: str, epoch: int, save_optimizer_states: bool = False):
+        from ..utils.callback import save_checkpoint
+        save_checkpoint(prefix, epoch, self.symbol)
+        if save_optimizer_states:
+            with open(f"{prefix}-{epoch:04d}.states", "wb") as f:
+                f.write(self._updater.get_states(dump_optimizer=True))
+
+    @staticmethod
+    def load(prefix: str, epoch: int, symbol: torch.nn.Module, **kw) -> "Module":
+        from ..utils.callback import load_checkpoint
+        load_checkpoint(prefix, epoch, symbol)
+        m = Module(symbol, **kw)
+        m.params_initialized = True
+        return m
+
+
+def _as_list(x):
+    if x is None:
+        return []
+    return list(x) if isinstance(x, (list, tuple)) else [x]

@@ -71,6 +71,20 @@ _IMAGENET_UNITS = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3
                    152: [3, 8, 36, 3], 200: [3, 24, 36, 3], 269: [3, 30, 48, 8]}
 
 
+class StemConv(nn.Conv2d):
+    """The first convolution (Cin = 3).  Tensor-core implicit-GEMM kernels want 16-byte (8 x bf16) channel
+    vectors; with 3 input channels cuDNN pads and re-lays-out the activation on every call (separate kernels that
+    cost more than the convolution).  The parameter keeps the reference shape [Cout, 3, k, k]; on CUDA/bf16 the
+    input and a zero-extended view of the weight are padded to 8 channels, which is mathematically identical."""
+
+    def forward(self, x):
+        if x.is_cuda and x.dtype == torch.bfloat16 and self.in_channels == 3:
+            x8 = F.pad(x, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
+            w8 = F.pad(self.weight, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
+            return F.conv2d(x8, w8, self.bias, self.stride, self.padding)
+        return super().forward(x)
+
+
 class ResNetV2(nn.Module):
     def __init__(self, num_layers: int = 50, num_classes: int = 1000, image_size: int = 224):
         super().__init__()
@@ -89,9 +103,9 @@ class ResNetV2(nn.Module):
             filters = [64, 256, 512, 1024, 2048] if bottleneck else [64, 64, 128, 256, 512]
         self.bn_data = _bn(3, affine_gamma=False, relu=False)
         if image_size <= 32:
-            self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 3, 1, 1, bias=False))
+            self.stem = nn.Sequential(StemConv(3, filters[0], 3, 1, 1, bias=False))
         else:
-            self.stem = nn.Sequential(nn.Conv2d(3, filters[0], 7, 2, 3, bias=False), _bn(filters[0]),
+            self.stem = nn.Sequential(StemConv(3, filters[0], 7, 2, 3, bias=False), _bn(filters[0]),
                                       MaxPool2d(3, 2, 1))
         unit = BottleneckV2 if bottleneck else BasicV2
         blocks = []

@@ -144,7 +144,7 @@ class SymmetricHeap:
         native.check(native.lib().dlcfn_barrier(self._ctx, self.CH_BARRIER, native.stream_ptr(stream)), "barrier")
         native._count()
 
-    def allreduce_(self, off: int, count: int, dtype: torch.dtype, scale: float = 1.0, nblocks: int = 32,
+    def allreduce_(self, off: int, count: int, dtype: torch.dtype, scale: float = 1.0, nblocks: int = 0,
                    stream: torch.cuda.Stream | None = None, channel: int | None = None, dst_off: int | None = None,
                    algo: int | None = None) -> None:
         """Fused bucket scale + all-reduce (reference C11: Horovod fusion buffer + ncclAllReduce).  In place unless
@@ -166,9 +166,13 @@ class SymmetricHeap:
                      worker_mask: int, master: torch.Tensor | None, s1: torch.Tensor | None,
                      s2: torch.Tensor | None, dtype: torch.dtype, kind: str, *, lr: float, wd: float = 0.0,
                      momentum: float = 0.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
-                     rescale: float = 1.0, clip: float = -1.0, nblocks: int = 32,
-                     stream: torch.cuda.Stream | None = None) -> None:
-        """push (+) server reduce (+) optimizer (+) pull in one kernel (reference C6/C7/C2)."""
+                     rescale: float = 1.0, clip: float = -1.0, nblocks: int = 0,
+                     stream: torch.cuda.Stream | None = None, algo: int | None = None) -> None:
+        """push (+) server reduce (+) optimizer (+) pull in one kernel (reference C6/C7/C2).  algo 1 routes the push
+        through multimem.ld_reduce and the pull through multimem.st (ranks that are not workers must keep a zero
+        gradient buffer); nblocks 0 = size-based grid."""
+        a = self.allreduce_algo if algo is None else algo
+        nblocks = int(nblocks) + (10000 if a == 1 and self.has_multicast else 0)
         native.check(native.lib().dlcfn_ps_sync_step(
             self._ctx, grad_off, weight_off, total, shard_lo, shard_hi, worker_mask, native._ptr(master),
             native._ptr(s1), native._ptr(s2), native.dtype_code(dtype), native.OPT_KINDS[kind], lr, wd, momentum,

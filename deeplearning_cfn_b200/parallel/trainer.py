@@ -45,7 +45,7 @@ class DataParallelTrainer:
                  momentum: float = 0.9, wd: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999,
                  eps: float = 1e-8, clip: float = -1.0, bucket_bytes: int | None = None,
                  server_ranks: list[int] | None = None, worker_ranks: list[int] | None = None,
-                 comm_blocks: int = 32, loss_fn=None, heap: SymmetricHeap | None = None,
+                 comm_blocks: int = 0, loss_fn=None, heap: SymmetricHeap | None = None,
                  broadcast_from: int | None = 0):
         self.rank, self.world = _dist_info()
         self.device = next(model.parameters()).device
@@ -102,7 +102,7 @@ class DataParallelTrainer:
     def _broadcast_initial(self, root: int) -> None:
         if self.mode in ("allreduce", "ps_sync"):
             for g in self.flat.groups:
-                self.heap.broadcast_(g.weight_off, g.numel * g.esize, root, nblocks=self.comm_blocks)
+                self.heap.broadcast_(g.weight_off, g.numel * g.esize, root, nblocks=self.comm_blocks or 32)
             torch.cuda.synchronize(self.device)
         else:
             for g in self.flat.groups:

@@ -32,3 +32,8 @@ def test_collectives_all_gpus():
 def test_trainer_modes_agree_world2():
     r = _run(2, "trainer_worker.py", 29613)
     assert r.returncode == 0 and "TRAINER_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_kvstore_dist_device_world2():
+    r = _run(2, "kv_device_worker.py", 29614)
+    assert r.returncode == 0 and "KV_DEVICE_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -87,3 +87,38 @@ def test_trainer_split_allreduce_update_and_states(tmp_path):
     with pytest.raises(UserWarning):
         stale.step(1)
     stale.step(1, ignore_stale_grad=True)
+
+
+def test_module_fit_and_recordio(tmp_path):
+    import numpy as np
+    from deeplearning_cfn_b200.kv.module import Module
+    from deeplearning_cfn_b200.utils import recordio
+    from deeplearning_cfn_b200.utils.callback import Speedometer
+    # write a small .rec/.idx, read it back through the prefetching iterator
+    rec = recordio.MXIndexedRecordIO(str(tmp_path / "d.idx"), str(tmp_path / "d.rec"), "w")
+    rng = np.random.default_rng(0)
+    for i in range(40):
+        img = np.full((8, 8, 3), (i % 4) * 60, dtype=np.uint8) + rng.integers(0, 10, (8, 8, 3), dtype=np.uint8)
+        rec.write_idx(i, recordio.pack_img(recordio.IRHeader(0, i % 4, i, 0), img))
+    rec.close()
+    r = recordio.MXRecordIO(str(tmp_path / "d.rec"), "r")
+    h, img = recordio.unpack_img(r.read())
+    assert h.label == 0.0 and img.shape == (8, 8, 3)
+    it = recordio.ImageRecordIter(str(tmp_path / "d.rec"), batch_size=8, data_shape=(3, 8, 8), shuffle=True, num_parts=2,
+                                  part_index=1, preprocess_threads=2)
+    batches = list(it)
+    assert len(batches) == 2 and batches[0][0].shape == (8, 8, 8, 3) and batches[0][0].dtype == torch.uint8
+
+    def data():
+        it.reset()
+        for x, y in it:
+            yield x.permute(0, 3, 1, 2).float() / 64.0 - 1.5, y
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4))
+    mod = Module(net)
+    mod.fit(data, num_epoch=120, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.2),),
+            batch_size=8, batch_end_callback=Speedometer(8, 1000))
+    assert mod.score(data) > 0.9
+    mod.save_checkpoint(str(tmp_path / "m"), 120, save_optimizer_states=True)
+    m2 = Module.load(str(tmp_path / "m"), 120, torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)))
+    assert abs(m2.score(data) - mod.score(data)) < 1e-6

@@ -229,6 +229,7 @@ struct PSArgs {
   size_t weight_off;     // heap byte offset of the flat model-weight buffer
   size_t lo, hi;         // this rank's server shard in 16-byte vectors of T; lo == hi: not a server
   uint32_t worker_mask;  // ranks that push gradients and receive weights
+  uint32_t pull_mask;    // ranks that receive the new weights (0: same as worker_mask)
   float* master;         // fp32 master weights of the shard (index 0 == element lo*N)
   float* s1;             // optimizer state 1 (momentum / Adam m) or null
   float* s2;             // optimizer state 2 (Adam v) or null
@@ -254,7 +255,7 @@ __device__ __forceinline__ void ps_make_ptrs(const PSArgs& a, const SymmDev& s, 
   }
   const uint32_t live = (s.world >= 32) ? 0xffffffffu : ((1u << s.world) - 1u);
   P.load_mask = worker_mask & live;
-  P.store_mask = (worker_mask | (1u << s.rank)) & live;  // the server keeps its own copy as well
+  P.store_mask = ((a.pull_mask ? a.pull_mask : worker_mask) | (1u << s.rank)) & live;  // + the server's own copy
 }
 
 template <typename T>
@@ -608,6 +609,10 @@ DLCFN_API int dlcfn_broadcast(void* ctx, size_t off_bytes, size_t bytes, int roo
 
 // One synchronous parameter-server step, launched by EVERY rank (servers and workers alike).
 // shard_lo/shard_hi are element indices (multiples of 16B/sizeof(T)) into the flat buffers.
+static uint32_t g_next_pull_mask = 0;
+// one-shot modifier for the next dlcfn_ps_sync_step: restrict the ranks that receive the updated weights
+DLCFN_API void dlcfn_ps_set_next_pull_mask(uint32_t mask) { g_next_pull_mask = mask; }
+
 DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, size_t total_count,
                                  size_t shard_lo, size_t shard_hi, uint32_t worker_mask, float* master,
                                  float* s1, float* s2, int dtype, int opt_kind, float lr, float wd,
@@ -626,6 +631,8 @@ DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, 
   a.lo = shard_lo / N;
   a.hi = (shard_hi + N - 1) / N;
   a.worker_mask = worker_mask;
+  a.pull_mask = g_next_pull_mask;
+  g_next_pull_mask = 0;
   a.master = master;
   a.s1 = s1;
   a.s2 = s2;
@@ -673,6 +680,7 @@ DLCFN_API int dlcfn_ps_async_server(void* ctx, size_t grad_off, size_t weight_of
   a.opt = OptArgs{opt_kind, lr, wd, momentum, beta1, beta2, eps, rescale, clip};
   a.channel = channel;
   a.use_mc = 0;
+  a.pull_mask = 0;
   if (dtype == 1) kps_async_server<__nv_bfloat16><<<nblocks, 512, 0, stream>>>(c->dev, a);
   else kps_async_server<float><<<nblocks, 512, 0, stream>>>(c->dev, a);
   return (int)cudaGetLastError();

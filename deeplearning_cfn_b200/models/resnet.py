@@ -73,16 +73,33 @@ _IMAGENET_UNITS = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3
 
 class StemConv(nn.Conv2d):
     """The first convolution (Cin = 3).  Tensor-core implicit-GEMM kernels want 16-byte (8 x bf16) channel
-    vectors; with 3 input channels cuDNN pads and re-lays-out the activation on every call (separate kernels that
-    cost more than the convolution).  The parameter keeps the reference shape [Cout, 3, k, k]; on CUDA/bf16 the
-    input and a zero-extended view of the weight are padded to 8 channels, which is mathematically identical."""
+    vectors and a deep reduction; with 3 input channels cuDNN pads and re-lays-out the activation on every call and
+    then runs a K = 147 GEMM on a legacy kernel.  The parameter keeps the reference shape [Cout, 3, k, k]; on
+    CUDA/bf16 the same convolution is evaluated in a tensor-core friendly form:
+      * 7x7 / stride 2 / pad 3 (ImageNet stem): space-to-depth by 2.  With the kernel zero-extended to 8x8 taps,
+        out[o] = sum_k w[k] xp[2o+k] = sum_{a<4, b<2} w[2a+b] s2d[o+a][b], i.e. a 4x4 stride-1 convolution over the
+        (115 x 115 x 12 -> 16 channel) space-to-depth image - identical math, K = 256;
+      * anything else: input and weight zero-padded to 8 channels."""
 
     def forward(self, x):
-        if x.is_cuda and x.dtype == torch.bfloat16 and self.in_channels == 3:
-            x8 = F.pad(x, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
-            w8 = F.pad(self.weight, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
-            return F.conv2d(x8, w8, self.bias, self.stride, self.padding)
-        return super().forward(x)
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and self.in_channels == 3):
+            return super().forward(x)
+        w = self.weight
+        if self.kernel_size == (7, 7) and self.stride == (2, 2) and self.padding == (3, 3) and x.shape[-1] % 2 == 0 \
+                and x.shape[-2] % 2 == 0:
+            N, C, H, W = x.shape
+            xp = F.pad(x, (3, 3, 3, 3))                                            # [N,3,H+6,W+6]
+            Hs, Ws = (H + 6) // 2, (W + 6) // 2
+            s2d = xp.reshape(N, C, Hs, 2, Ws, 2).permute(0, 1, 3, 5, 2, 4).reshape(N, C * 4, Hs, Ws)
+            s2d = F.pad(s2d, (0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last)   # 12 -> 16 channels
+            w8 = F.pad(w, (0, 1, 0, 1))                                            # [O,3,8,8], last tap row/col zero
+            O = w.shape[0]
+            w4 = w8.reshape(O, C, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(O, C * 4, 4, 4)
+            w4 = F.pad(w4, (0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last)
+            return F.conv2d(s2d, w4, self.bias, 1, 0)
+        x8 = F.pad(x, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
+        w8 = F.pad(w, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
+        return F.conv2d(x8, w8, self.bias, self.stride, self.padding)
 
 
 class ResNetV2(nn.Module):

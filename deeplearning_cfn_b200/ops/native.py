@@ -94,6 +94,8 @@ def _declare(L) -> None:
     L.dlcfn_broadcast.argtypes = [vp, sz, sz, i, i, i, vp]
     L.dlcfn_ps_sync_step.argtypes = [vp, sz, sz, sz, sz, sz, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, vp]
     L.dlcfn_ps_async_worker.argtypes = [vp, u32, i, i, vp]
+    L.dlcfn_ps_set_next_pull_mask.argtypes = [u32]
+    L.dlcfn_ps_set_next_pull_mask.restype = None
     L.dlcfn_ps_async_server.argtypes = [vp, sz, sz, sz, sz, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, vp]
     L.dlcfn_gemm_bf16.argtypes = [vp, ll, i, vp, i, i, ll, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp]
     for fn in ("dlcfn_elementwise_sum", "dlcfn_cast_scale", "dlcfn_fused_optimizer", "dlcfn_normalize_u8_nhwc",

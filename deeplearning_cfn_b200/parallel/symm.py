@@ -167,12 +167,15 @@ class SymmetricHeap:
                      s2: torch.Tensor | None, dtype: torch.dtype, kind: str, *, lr: float, wd: float = 0.0,
                      momentum: float = 0.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
                      rescale: float = 1.0, clip: float = -1.0, nblocks: int = 0,
-                     stream: torch.cuda.Stream | None = None, algo: int | None = None) -> None:
+                     stream: torch.cuda.Stream | None = None, algo: int | None = None,
+                     pull_mask: int | None = None) -> None:
         """push (+) server reduce (+) optimizer (+) pull in one kernel (reference C6/C7/C2).  algo 1 routes the push
         through multimem.ld_reduce and the pull through multimem.st (ranks that are not workers must keep a zero
         gradient buffer); nblocks 0 = size-based grid."""
         a = self.allreduce_algo if algo is None else algo
         nblocks = int(nblocks) + (10000 if a == 1 and self.has_multicast else 0)
+        if pull_mask is not None:      # only these ranks (plus the server itself) receive the new weights
+            native.lib().dlcfn_ps_set_next_pull_mask(int(pull_mask))
         native.check(native.lib().dlcfn_ps_sync_step(
             self._ctx, grad_off, weight_off, total, shard_lo, shard_hi, worker_mask, native._ptr(master),
             native._ptr(s1), native._ptr(s2), native.dtype_code(dtype), native.OPT_KINDS[kind], lr, wd, momentum,

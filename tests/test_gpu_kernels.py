@@ -154,3 +154,22 @@ def test_maxpool_nhwc(N, C, H, W, k, s, p):
     torch.testing.assert_close(xa.grad.float().sum(), xr.grad.sum(), rtol=1e-2, atol=1e-1)
     close = torch.isclose(xa.grad.float(), xr.grad, rtol=2e-2, atol=2e-2).float().mean().item()
     assert close > 0.995, close
+
+
+@pytest.mark.parametrize("k,s,p,size", [(7, 2, 3, 64), (3, 1, 1, 32)])
+def test_stem_conv_tensor_core_form_matches_plain_conv(k, s, p, size):
+    from deeplearning_cfn_b200.models.resnet import StemConv
+    torch.manual_seed(5)
+    conv = StemConv(3, 64, k, s, p, bias=False).to(dev()).bfloat16().to(memory_format=torch.channels_last)
+    x = torch.randn(4, 3, size, size, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = conv.weight.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, None, s, p)
+    yr.backward(gy.float())
+    assert y.shape == yr.shape
+    torch.testing.assert_close(y.float(), yr, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(conv.weight.grad.float(), wr.grad, rtol=5e-2, atol=5e-1)
+    torch.testing.assert_close(x.grad.float(), xr.grad, rtol=5e-2, atol=5e-2)

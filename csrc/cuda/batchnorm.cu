@@ -75,7 +75,10 @@ __device__ __forceinline__ void block_reduce_store(float* a, float* b, int CV, i
 }
 
 // ------------------------------------------------------------ forward -------
-__global__ void __launch_bounds__(256) kbn_stats(const uint4* __restrict__ x, long long M, int CV, int RL,
+// x2 != nullptr: fused residual add - the tensor that gets normalised is z = x + x2, it is written to `z` (bf16) and
+// the statistics are taken over the ROUNDED values so that the apply pass, which re-reads z, is consistent.
+__global__ void __launch_bounds__(256) kbn_stats(const uint4* __restrict__ x, const uint4* __restrict__ x2,
+                                                   uint4* __restrict__ z, long long M, int CV, int RL,
                                                    float* __restrict__ part) {
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   float s[8], q[8];
@@ -83,24 +86,60 @@ __global__ void __launch_bounds__(256) kbn_stats(const uint4* __restrict__ x, lo
   for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
   const long long step = (long long)gridDim.x * RL;
   long long r = (long long)blockIdx.x * RL + ty;
-  // 4 independent 16-byte loads in flight per thread
-  for (; r + 3 * step < M; r += 4 * step) {
-    uint4 v[4];
+  if (x2 == nullptr) {
+    // 4 independent 16-byte loads in flight per thread
+    for (; r + 3 * step < M; r += 4 * step) {
+      uint4 v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld_stream_v4(x + (r + u * step) * CV + tx);
+      for (int u = 0; u < 4; ++u) v[u] = ld_stream_v4(x + (r + u * step) * CV + tx);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+      }
+    }
+    for (; r < M; r += step) {
       float f[8];
-      unpack8(v[u], f);
+      unpack8(ld_stream_v4(x + r * CV + tx), f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
     }
-  }
-  for (; r < M; r += step) {
-    float f[8];
-    unpack8(ld_stream_v4(x + r * CV + tx), f);
+  } else {
+    for (; r + step < M; r += 2 * step) {
+      uint4 va[2], vb[2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+      for (int u = 0; u < 2; ++u) {
+        va[u] = ld_stream_v4(x + (r + u * step) * CV + tx);
+        vb[u] = ld_stream_v4(x2 + (r + u * step) * CV + tx);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float fa[8], fb[8];
+        unpack8(va[u], fa);
+        unpack8(vb[u], fb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+        const uint4 o = pack8(fa);
+        z[(r + u * step) * CV + tx] = o;
+        unpack8(o, fa);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += fa[k]; q[k] = fmaf(fa[k], fa[k], q[k]); }
+      }
+    }
+    for (; r < M; r += step) {
+      float fa[8], fb[8];
+      unpack8(ld_stream_v4(x + r * CV + tx), fa);
+      unpack8(ld_stream_v4(x2 + r * CV + tx), fb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+      const uint4 o = pack8(fa);
+      z[r * CV + tx] = o;
+      unpack8(o, fa);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s[k] += fa[k]; q[k] = fmaf(fa[k], fa[k], q[k]); }
+    }
   }
   block_reduce_store(s, q, CV, RL, CV * 8, part);
 }
@@ -279,7 +318,9 @@ __global__ void __launch_bounds__(256) kbn_bwd_apply(const uint4* __restrict__ x
                                                        const float* __restrict__ invstd,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int relu,
-                                                       const float* __restrict__ coef) {
+                                                       const float* __restrict__ coef,
+                                                       const uint4* __restrict__ extra) {
+  // extra != nullptr: dx += extra (the gradient arriving at the same tensor through the residual connection)
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   const int C = CV * 8;
   float mu[8], is[8], g[8], b[8], c0[8], c1[8], c2[8];
@@ -310,6 +351,12 @@ __global__ void __launch_bounds__(256) kbn_bwd_apply(const uint4* __restrict__ x
         const float d = (relu && fmaf(xh, g[k], b[k]) <= 0.f) ? 0.f : fd[k];
         o[k] = c0[k] * (d - c1[k] - xh * c2[k]);
       }
+      if (extra != nullptr) {
+        float ex[8];
+        unpack8(ld_stream_v4(extra + (r + u * step) * CV + tx), ex);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += ex[k];
+      }
       dx[(r + u * step) * CV + tx] = pack8(o);
     }
   }
@@ -322,6 +369,12 @@ __global__ void __launch_bounds__(256) kbn_bwd_apply(const uint4* __restrict__ x
       const float xh = (fx[k] - mu[k]) * is[k];
       const float d = (relu && fmaf(xh, g[k], b[k]) <= 0.f) ? 0.f : fd[k];
       o[k] = c0[k] * (d - c1[k] - xh * c2[k]);
+    }
+    if (extra != nullptr) {
+      float ex[8];
+      unpack8(ld_stream_v4(extra + r * CV + tx), ex);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += ex[k];
     }
     dx[r * CV + tx] = pack8(o);
   }
@@ -341,18 +394,33 @@ static inline bool bn_supported(long long M, int C) { return C % 8 == 0 && C >= 
 
 // y = relu?(gamma * (x - mean) * invstd + beta); writes mean/invstd (saved for backward) and updates the
 // running statistics.  x, y: bf16 [M, C].  gamma/beta/mean/invstd/running_*: fp32 [C].  3 launches.
+DLCFN_API int dlcfn_bn_forward_ex(const void* x, const void* x2, void* z, void* y, long long M, int C,
+                                  const float* gamma, const float* beta, float* mean, float* invstd,
+                                  float* running_mean, float* running_var, float momentum, float eps, int relu,
+                                  float* workspace, cudaStream_t stream);
+
 DLCFN_API int dlcfn_bn_forward(const void* x, void* y, long long M, int C, const float* gamma, const float* beta,
                                float* mean, float* invstd, float* running_mean, float* running_var,
                                float momentum, float eps, int relu, float* workspace, cudaStream_t stream) {
+  return dlcfn_bn_forward_ex(x, nullptr, nullptr, y, M, C, gamma, beta, mean, invstd, running_mean, running_var, momentum,
+                             eps, relu, workspace, stream);
+}
+
+// x2 != nullptr: z = x + x2 is materialised (bf16) and normalised: y = relu?(bn(z)).  4 launches worth of work in 3.
+DLCFN_API int dlcfn_bn_forward_ex(const void* x, const void* x2, void* z, void* y, long long M, int C,
+                                  const float* gamma, const float* beta, float* mean, float* invstd,
+                                  float* running_mean, float* running_var, float momentum, float eps, int relu,
+                                  float* workspace, cudaStream_t stream) {
   if (!bn_supported(M, C)) return (int)cudaErrorInvalidValue;
   BnGeom g = bn_geom(M, C);
   float* part = workspace;
   float* scale_shift = workspace + (size_t)g.grid * 2 * C;
   const size_t sh = (size_t)g.threads * 16 * sizeof(float);
-  kbn_stats<<<g.grid, g.threads, sh, stream>>>((const uint4*)x, M, g.CV, g.RL, part);
+  kbn_stats<<<g.grid, g.threads, sh, stream>>>((const uint4*)x, (const uint4*)x2, (uint4*)z, M, g.CV, g.RL, part);
+  const void* xin = x2 ? z : x;
   kbn_fwd_finalize<<<(C + 31) / 32, dim3(32, 8), 0, stream>>>(part, g.grid, C, M, eps, momentum, gamma, beta, mean,
                                                         invstd, running_mean, running_var, scale_shift);
-  kbn_apply<<<g.grid, g.threads, 0, stream>>>((const uint4*)x, (uint4*)y, M, g.CV, g.RL, scale_shift, relu);
+  kbn_apply<<<g.grid, g.threads, 0, stream>>>((const uint4*)xin, (uint4*)y, M, g.CV, g.RL, scale_shift, relu);
   return (int)cudaGetLastError();
 }
 
@@ -361,10 +429,24 @@ DLCFN_API int dlcfn_bn_inference(const void* x, void* y, long long M, int C, con
                                  const float* beta, const float* running_mean, const float* running_var,
                                  float eps, int relu, float* workspace, cudaStream_t stream);
 
+DLCFN_API int dlcfn_bn_backward_ex(const void* x, const void* dy, const void* extra, void* dx, long long M, int C,
+                                   const float* gamma, const float* beta, const float* mean, const float* invstd,
+                                   float* dgamma, float* dbeta, int accumulate_grads, int relu, float* workspace,
+                                   cudaStream_t stream);
+
 DLCFN_API int dlcfn_bn_backward(const void* x, const void* dy, void* dx, long long M, int C, const float* gamma,
                                 const float* beta, const float* mean, const float* invstd, float* dgamma,
                                 float* dbeta, int accumulate_grads, int relu, float* workspace,
                                 cudaStream_t stream) {
+  return dlcfn_bn_backward_ex(x, dy, nullptr, dx, M, C, gamma, beta, mean, invstd, dgamma, dbeta, accumulate_grads, relu,
+                              workspace, stream);
+}
+
+// extra != nullptr: dx = bn_backward(dy) + extra  (gradient of the fused residual add)
+DLCFN_API int dlcfn_bn_backward_ex(const void* x, const void* dy, const void* extra, void* dx, long long M, int C,
+                                   const float* gamma, const float* beta, const float* mean, const float* invstd,
+                                   float* dgamma, float* dbeta, int accumulate_grads, int relu, float* workspace,
+                                   cudaStream_t stream) {
   if (!bn_supported(M, C)) return (int)cudaErrorInvalidValue;
   BnGeom g = bn_geom(M, C);
   float* part = workspace;
@@ -375,7 +457,7 @@ DLCFN_API int dlcfn_bn_backward(const void* x, const void* dy, void* dx, long lo
   kbn_bwd_finalize<<<(C + 31) / 32, dim3(32, 8), 0, stream>>>(part, g.grid, C, M, gamma, invstd, dgamma, dbeta,
                                                         accumulate_grads, coef);
   kbn_bwd_apply<<<g.grid, g.threads, 0, stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, M, g.CV, g.RL,
-                                                  mean, invstd, gamma, beta, relu, coef);
+                                                  mean, invstd, gamma, beta, relu, coef, (const uint4*)extra);
   return (int)cudaGetLastError();
 }
 

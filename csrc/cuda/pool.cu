@@ -120,3 +120,96 @@ DLCFN_API int dlcfn_maxpool_nhwc_bwd(const void* dy, const void* idx, void* dx, 
   kmaxpool_bwd<<<pool_grid(total), 256, 0, stream>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, g);
   return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Stem input transform: NHWC 8-channel image (3 real channels, output of the padded bn_data) -> space-to-depth-by-2
+// NHWC 16-channel image with the 7x7/pad-3 convolution's zero border folded in:
+//     s2d[n, i, j, c*4 + bh*2 + bw] = x[n, 2i+bh-3, 2j+bw-3, c]   (0 outside the image),  c < 3, channels 12..15 = 0
+// so that the stem convolution becomes a 4x4 stride-1 convolution with K = 256 (models/resnet.py:StemConv).  One
+// pass each way; the framework's pad/reshape/permute/contiguous chain cost 2.7 ms per step on B200.
+namespace dlcfn {
+
+__global__ void __launch_bounds__(256) kstem_s2d_fwd(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H,
+                                                      int W, int Hs, int Ws) {
+  const long long total = (long long)N * Hs * Ws;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % Ws);
+    const int i = (int)((t / Ws) % Hs);
+    const int n = (int)(t / ((long long)Ws * Hs));
+    uint16_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0;
+#pragma unroll
+    for (int bh = 0; bh < 2; ++bh)
+#pragma unroll
+      for (int bw = 0; bw < 2; ++bw) {
+        const int r = 2 * i + bh - 3, c = 2 * j + bw - 3;
+        if (r >= 0 && r < H && c >= 0 && c < W) {
+          const uint4 p = x[((long long)n * H + r) * W + c];
+          v[0 * 4 + bh * 2 + bw] = (uint16_t)(p.x & 0xffff);
+          v[1 * 4 + bh * 2 + bw] = (uint16_t)(p.x >> 16);
+          v[2 * 4 + bh * 2 + bw] = (uint16_t)(p.y & 0xffff);
+        }
+      }
+    uint4 o0, o1;
+    o0.x = v[0] | ((uint32_t)v[1] << 16); o0.y = v[2] | ((uint32_t)v[3] << 16);
+    o0.z = v[4] | ((uint32_t)v[5] << 16); o0.w = v[6] | ((uint32_t)v[7] << 16);
+    o1.x = v[8] | ((uint32_t)v[9] << 16); o1.y = v[10] | ((uint32_t)v[11] << 16);
+    o1.z = 0; o1.w = 0;
+    y[2 * t] = o0;
+    y[2 * t + 1] = o1;
+  }
+}
+
+__global__ void __launch_bounds__(256) kstem_s2d_bwd(const uint16_t* __restrict__ dy, uint4* __restrict__ dx, int N, int H,
+                                                      int W, int Hs, int Ws) {
+  const long long total = (long long)N * H * W;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % W);
+    const int r = (int)((t / W) % H);
+    const int n = (int)(t / ((long long)W * H));
+    const int i = (r + 3) >> 1, bh = (r + 3) & 1, j = (c + 3) >> 1, bw = (c + 3) & 1;
+    const uint16_t* src = dy + (((long long)n * Hs + i) * Ws + j) * 16 + bh * 2 + bw;
+    const uint32_t a = src[0], b = src[4], d = src[8];
+    dx[t] = make_uint4(a | (b << 16), d, 0u, 0u);
+  }
+}
+
+}  // namespace dlcfn
+
+DLCFN_API int dlcfn_stem_s2d_fwd(const void* x8, void* y16, int N, int H, int W, cudaStream_t stream) {
+  if ((H & 1) || (W & 1)) return (int)cudaErrorInvalidValue;
+  const int Hs = (H + 6) / 2, Ws = (W + 6) / 2;
+  const long long total = (long long)N * Hs * Ws;
+  if (total == 0) return 0;
+  dlcfn::kstem_s2d_fwd<<<pool_grid(total), 256, 0, stream>>>((const uint4*)x8, (uint4*)y16, N, H, W, Hs, Ws);
+  return (int)cudaGetLastError();
+}
+
+DLCFN_API int dlcfn_stem_s2d_bwd(const void* dy16, void* dx8, int N, int H, int W, cudaStream_t stream) {
+  if ((H & 1) || (W & 1)) return (int)cudaErrorInvalidValue;
+  const int Hs = (H + 6) / 2, Ws = (W + 6) / 2;
+  const long long total = (long long)N * H * W;
+  if (total == 0) return 0;
+  dlcfn::kstem_s2d_bwd<<<pool_grid(total), 256, 0, stream>>>((const uint16_t*)dy16, (uint4*)dx8, N, H, W, Hs, Ws);
+  return (int)cudaGetLastError();
+}
+
+// 3-channel NHWC bf16 image -> 8-channel NHWC (channels 3..7 zero): 6 bytes in, one 16-byte vector out per pixel.
+namespace dlcfn {
+__global__ void __launch_bounds__(256) kpad3to8(const uint16_t* __restrict__ x, uint4* __restrict__ y, long long npix) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < npix; t += (long long)gridDim.x * blockDim.x) {
+    const uint16_t* p = x + 3 * t;
+    const uint32_t a = p[0], b = p[1], c = p[2];
+    y[t] = make_uint4(a | (b << 16), c, 0u, 0u);
+  }
+}
+}  // namespace dlcfn
+
+DLCFN_API int dlcfn_pad3to8_nhwc(const void* x3, void* y8, long long npix, cudaStream_t stream) {
+  if (npix == 0) return 0;
+  dlcfn::kpad3to8<<<pool_grid(npix), 256, 0, stream>>>((const uint16_t*)x3, (uint4*)y8, npix);
+  return (int)cudaGetLastError();
+}

@@ -45,11 +45,16 @@ class BottleneckV2(nn.Module):
         self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
 
     def forward(self, x):
-        a = self.bn1(x)  # BN + ReLU fused
+        """`x` is either a tensor or the un-summed pair (branch, shortcut) of the previous unit; the pair's add is fused
+        into this unit's first BatchNorm.  Returns this unit's own un-summed pair."""
+        if isinstance(x, tuple):
+            x, a = self.bn1.forward_add(x[0], x[1])
+        else:
+            a = self.bn1(x)  # BN + ReLU fused
         y = self.conv1(a)
         y = self.conv2(self.bn2(y))
         y = self.conv3(self.bn3(y))
-        return y + (x if self.sc is None else self.sc(a))
+        return y, (x if self.sc is None else self.sc(a))
 
 
 class BasicV2(nn.Module):
@@ -62,13 +67,39 @@ class BasicV2(nn.Module):
         self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
 
     def forward(self, x):
-        a = self.bn1(x)
+        if isinstance(x, tuple):
+            x, a = self.bn1.forward_add(x[0], x[1])
+        else:
+            a = self.bn1(x)
         y = self.conv2(self.bn2(self.conv1(a)))
-        return y + (x if self.sc is None else self.sc(a))
+        return y, (x if self.sc is None else self.sc(a))
 
 
 _IMAGENET_UNITS = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3],
                    152: [3, 8, 36, 3], 200: [3, 24, 36, 3], 269: [3, 30, 48, 8]}
+
+
+class DataBatchNorm(BatchNormReLU2d):
+    """`bn_data`: BatchNorm over the 3 input channels (gamma fixed, reference `fix_gamma=True`).  On CUDA/bf16 the
+    image is zero-padded to 8 channels first so that the dlcfn NHWC kernels (16-byte channel vectors) apply; the
+    parameters and running statistics keep their reference shape [3].  Returns the 8-channel tensor (channels 3..7
+    are exactly zero) - `StemConv` knows how to consume it."""
+
+    def forward(self, x):
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and self.num_features == 3 and x.shape[1] == 3):
+            return super().forward(x)
+        from ..ops.batchnorm import batch_norm_relu
+        from ..ops.pool import pad3to8
+        x8 = pad3to8(x)
+        g8 = F.pad(self.weight, (0, 5), value=1.0)
+        b8 = F.pad(self.bias, (0, 5))
+        rm8, rv8 = F.pad(self.running_mean, (0, 5)), F.pad(self.running_var, (0, 5), value=1.0)
+        y8 = batch_norm_relu(x8, g8, b8, rm8, rv8, self.training, self.momentum, self.eps, relu=False)
+        if self.training:
+            with torch.no_grad():
+                self.running_mean.copy_(rm8[:3])
+                self.running_var.copy_(rv8[:3])
+        return y8
 
 
 class StemConv(nn.Conv2d):
@@ -83,20 +114,24 @@ class StemConv(nn.Conv2d):
 
     def forward(self, x):
         if not (x.is_cuda and x.dtype == torch.bfloat16 and self.in_channels == 3):
-            return super().forward(x)
+            return super().forward(x[:, :3] if x.shape[1] != 3 else x)
         w = self.weight
+        if x.shape[1] == 8 and not (self.kernel_size == (7, 7) and self.stride == (2, 2)):
+            w8 = F.pad(w, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)   # input already 8-channel
+            return F.conv2d(x, w8, self.bias, self.stride, self.padding)
         if self.kernel_size == (7, 7) and self.stride == (2, 2) and self.padding == (3, 3) and x.shape[-1] % 2 == 0 \
                 and x.shape[-2] % 2 == 0:
-            N, C, H, W = x.shape
-            xp = F.pad(x, (3, 3, 3, 3))                                            # [N,3,H+6,W+6]
-            Hs, Ws = (H + 6) // 2, (W + 6) // 2
-            s2d = xp.reshape(N, C, Hs, 2, Ws, 2).permute(0, 1, 3, 5, 2, 4).reshape(N, C * 4, Hs, Ws)
-            s2d = F.pad(s2d, (0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last)   # 12 -> 16 channels
+            from ..ops.pool import stem_space_to_depth
+            if x.shape[1] == 3:
+                x = F.pad(x, (0, 0, 0, 0, 0, 5))
+            s2d = stem_space_to_depth(x)                                            # one fused kernel each way
+            O, C = w.shape[0], 3
             w8 = F.pad(w, (0, 1, 0, 1))                                            # [O,3,8,8], last tap row/col zero
-            O = w.shape[0]
             w4 = w8.reshape(O, C, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(O, C * 4, 4, 4)
             w4 = F.pad(w4, (0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last)
             return F.conv2d(s2d, w4, self.bias, 1, 0)
+        if x.shape[1] != 3:
+            x = x[:, :3]
         x8 = F.pad(x, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
         w8 = F.pad(w, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
         return F.conv2d(x8, w8, self.bias, self.stride, self.padding)
@@ -118,7 +153,8 @@ class ResNetV2(nn.Module):
             units = _IMAGENET_UNITS[num_layers]
             bottleneck = num_layers >= 50
             filters = [64, 256, 512, 1024, 2048] if bottleneck else [64, 64, 128, 256, 512]
-        self.bn_data = _bn(3, affine_gamma=False, relu=False)
+        self.bn_data = DataBatchNorm(3, eps=_EPS, momentum=_MOM, relu=False)
+        self.bn_data.weight.requires_grad_(False)      # fix_gamma=True
         if image_size <= 32:
             self.stem = nn.Sequential(StemConv(3, filters[0], 3, 1, 1, bias=False))
         else:
@@ -141,8 +177,8 @@ class ResNetV2(nn.Module):
 
     def forward(self, x):
         x = self.stem(self.bn_data(x))
-        x = self.body(x)
-        x = self.bn1(x)
+        x = self.body(x)                       # (branch, shortcut) of the last unit, still un-summed
+        _, x = self.bn1.forward_add(x[0], x[1])
         x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
         return self.fc1(x)
 

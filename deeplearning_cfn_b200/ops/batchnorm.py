@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from . import native
 
 _MAX_C = 2048
+_DEBUG_LAYOUT = __import__("os").environ.get("DLCFN_DEBUG_LAYOUT", "0") == "1"
 
 
 def _declare():
@@ -33,6 +34,12 @@ def _declare():
     L.dlcfn_bn_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.dlcfn_bn_backward.restype = c_int
+    L.dlcfn_bn_forward_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p]
+    L.dlcfn_bn_forward_ex.restype = c_int
+    L.dlcfn_bn_backward_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    L.dlcfn_bn_backward_ex.restype = c_int
     L._bn_declared = True
     return L
 
@@ -41,8 +48,15 @@ def fused_supported(x: torch.Tensor, C: int) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and C % 8 == 0 and 8 <= C <= _MAX_C
 
 
+layout_copies: list = []      # (shape, strides) of tensors that had to be re-laid-out (DLCFN_DEBUG_LAYOUT=1)
+
+
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
-    return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+    if x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    if _DEBUG_LAYOUT:
+        layout_copies.append((tuple(x.shape), tuple(x.stride())))
+    return x.contiguous(memory_format=torch.channels_last)
 
 
 class _BNReLUFn(torch.autograd.Function):
@@ -84,6 +98,62 @@ class _BNReLUFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, None, None
 
 
+class _AddBNReLUFn(torch.autograd.Function):
+    """(z, y) = (a + b, relu?(bn(a + b))) with the add fused into the statistics pass; backward fuses the gradient
+    that reaches z through the residual connection into the BN backward apply pass."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, running_mean, running_var, momentum, eps, relu):
+        L = _declare()
+        a, b = _nhwc(a), _nhwc(b)
+        N, C, H, W = a.shape
+        M = N * H * W
+        z = torch.empty_like(a, memory_format=torch.channels_last)
+        y = torch.empty_like(a, memory_format=torch.channels_last)
+        mean = torch.empty(C, dtype=torch.float32, device=a.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=a.device)
+        ws = torch.empty(L.dlcfn_bn_workspace_floats(M, C), dtype=torch.float32, device=a.device)
+        native.check(L.dlcfn_bn_forward_ex(a.data_ptr(), b.data_ptr(), z.data_ptr(), y.data_ptr(), M, C,
+                                           native._ptr(gamma), native._ptr(beta), mean.data_ptr(), invstd.data_ptr(),
+                                           native._ptr(running_mean), native._ptr(running_var), momentum, eps, int(relu),
+                                           ws.data_ptr(), native.stream_ptr()), "bn_forward_ex")
+        native._count(3)
+        ctx.save_for_backward(z, gamma, beta, mean, invstd)
+        ctx.relu = relu
+        ctx.mark_non_differentiable()
+        return z, y
+
+    @staticmethod
+    def backward(ctx, dz, dy):
+        L = _declare()
+        z, gamma, beta, mean, invstd = ctx.saved_tensors
+        N, C, H, W = z.shape
+        M = N * H * W
+        dy = _nhwc(dy)
+        extra = _nhwc(dz) if dz is not None else None
+        dx = torch.empty_like(z, memory_format=torch.channels_last)
+        dgamma = torch.empty(C, dtype=torch.float32, device=z.device) if gamma is not None else None
+        dbeta = torch.empty(C, dtype=torch.float32, device=z.device) if beta is not None else None
+        ws = torch.empty(L.dlcfn_bn_workspace_floats(M, C), dtype=torch.float32, device=z.device)
+        native.check(L.dlcfn_bn_backward_ex(z.data_ptr(), dy.data_ptr(), native._ptr(extra), dx.data_ptr(), M, C,
+                                            native._ptr(gamma), native._ptr(beta), mean.data_ptr(), invstd.data_ptr(),
+                                            native._ptr(dgamma), native._ptr(dbeta), 0, int(ctx.relu), ws.data_ptr(),
+                                            native.stream_ptr()), "bn_backward_ex")
+        native._count(3)
+        return dx, dx, dgamma, dbeta, None, None, None, None, None
+
+
+def add_batch_norm_relu(a, b, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float,
+                        relu: bool = True):
+    """Returns (z, y) with z = a + b and y = relu?(batch_norm(z))."""
+    C = a.shape[1]
+    if training and fused_supported(a, C) and b.dtype == a.dtype and b.shape == a.shape and \
+            (gamma is None or gamma.dtype == torch.float32):
+        return _AddBNReLUFn.apply(a, b, gamma, beta, running_mean, running_var, momentum, eps, relu)
+    z = a + b
+    return z, batch_norm_relu(z, gamma, beta, running_mean, running_var, training, momentum, eps, relu)
+
+
 def batch_norm_relu(x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float,
                     relu: bool = True):
     C = x.shape[1]
@@ -116,6 +186,11 @@ class BatchNormReLU2d(nn.BatchNorm2d):
     def forward(self, x):
         return batch_norm_relu(x, self.weight, self.bias, self.running_mean, self.running_var, self.training,
                                self.momentum, self.eps, self.relu)
+
+    def forward_add(self, a, b):
+        """(a + b, bn_relu(a + b)) - the residual add fused into this layer's statistics pass."""
+        return add_batch_norm_relu(a, b, self.weight, self.bias, self.running_mean, self.running_var, self.training,
+                                   self.momentum, self.eps, self.relu)
 
     def extra_repr(self):
         return super().extra_repr() + f", relu={self.relu}, kernel=dlcfn-nhwc"

@@ -17,6 +17,13 @@ def _declare():
     L.dlcfn_maxpool_nhwc_fwd.restype = c_int
     L.dlcfn_maxpool_nhwc_bwd.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]
     L.dlcfn_maxpool_nhwc_bwd.restype = c_int
+    L.dlcfn_stem_s2d_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    L.dlcfn_stem_s2d_fwd.restype = c_int
+    L.dlcfn_stem_s2d_bwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    L.dlcfn_stem_s2d_bwd.restype = c_int
+    from ctypes import c_longlong
+    L.dlcfn_pad3to8_nhwc.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p]
+    L.dlcfn_pad3to8_nhwc.restype = c_int
     L._pool_declared = True
     return L
 
@@ -69,3 +76,48 @@ class MaxPool2d(nn.Module):
 
     def extra_repr(self):
         return f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}, kernel=dlcfn-nhwc"
+
+
+class _StemS2DFn(torch.autograd.Function):
+    """[N,8,H,W] channels_last (3 real channels) -> space-to-depth [N,16,(H+6)/2,(W+6)/2] channels_last with the 7x7/pad-3
+    border folded in (csrc/cuda/pool.cu:kstem_s2d_*)."""
+
+    @staticmethod
+    def forward(ctx, x8):
+        L = _declare()
+        if not x8.is_contiguous(memory_format=torch.channels_last):
+            x8 = x8.contiguous(memory_format=torch.channels_last)
+        N, C, H, W = x8.shape
+        y = torch.empty((N, 16, (H + 6) // 2, (W + 6) // 2), dtype=x8.dtype, device=x8.device, memory_format=torch.channels_last)
+        native.check(L.dlcfn_stem_s2d_fwd(x8.data_ptr(), y.data_ptr(), N, H, W, native.stream_ptr()), "stem_s2d_fwd")
+        native._count()
+        ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _declare()
+        N, C, H, W = ctx.shape
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, 8, H, W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        native.check(L.dlcfn_stem_s2d_bwd(dy.data_ptr(), dx.data_ptr(), N, H, W, native.stream_ptr()), "stem_s2d_bwd")
+        native._count()
+        return dx
+
+
+def stem_space_to_depth(x8: torch.Tensor) -> torch.Tensor:
+    return _StemS2DFn.apply(x8)
+
+
+def pad3to8(x: torch.Tensor) -> torch.Tensor:
+    """[N,3,H,W] channels_last bf16 (no grad) -> [N,8,H,W] channels_last with zero channels 3..7, one kernel."""
+    if x.requires_grad or not (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] == 3 and
+                                x.is_contiguous(memory_format=torch.channels_last)):
+        return F.pad(x, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)
+    L = _declare()
+    N, _, H, W = x.shape
+    y = torch.empty((N, 8, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    native.check(L.dlcfn_pad3to8_nhwc(x.data_ptr(), y.data_ptr(), N * H * W, native.stream_ptr()), "pad3to8")
+    native._count()
+    return y

@@ -173,3 +173,57 @@ def test_stem_conv_tensor_core_form_matches_plain_conv(k, s, p, size):
     torch.testing.assert_close(y.float(), yr, rtol=3e-2, atol=3e-2)
     torch.testing.assert_close(conv.weight.grad.float(), wr.grad, rtol=5e-2, atol=5e-1)
     torch.testing.assert_close(x.grad.float(), xr.grad, rtol=5e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("relu", [True, False])
+def test_fused_add_batchnorm_relu(relu):
+    from deeplearning_cfn_b200.ops.batchnorm import add_batch_norm_relu
+    torch.manual_seed(6)
+    N, C, H, W = 8, 128, 14, 14
+    mk = lambda: (torch.randn(N, C, H, W, device=dev()) * 1.2).bfloat16().contiguous(memory_format=torch.channels_last)  # noqa: E731
+    a0, b0 = mk(), mk()
+    gamma = (torch.rand(C, device=dev()) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device=dev()) * 0.2).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    z, y = add_batch_norm_relu(a, b, gamma, beta, rm, rv, True, 0.1, 2e-5, relu)
+    gz, gy = torch.randn_like(z), torch.randn_like(y)
+    (z * gz).sum().add((y * gy).sum()).backward()
+    ar, br = a0.float().requires_grad_(True), b0.float().requires_grad_(True)
+    gr, ber = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    zr = (ar + br)
+    zq = zr + (zr.detach().bfloat16().float() - zr.detach())   # the kernel normalises the bf16-rounded sum (straight-through)
+    yr = torch.nn.functional.batch_norm(zq, torch.zeros(C, device=dev()), torch.ones(C, device=dev()), gr, ber, True, 0.1, 2e-5)
+    if relu:
+        yr = torch.relu(yr)
+    ((zr * gz.float()).sum() + (yr * gy.float()).sum()).backward()
+    torch.testing.assert_close(z.float(), zr.detach().bfloat16().float())
+    torch.testing.assert_close(y.float(), yr.detach(), rtol=2e-2, atol=2e-2)
+    # a ReLU mask may flip for values that round to ~0: require almost-everywhere agreement
+    for got, want in ((a.grad.float(), ar.grad), (b.grad.float(), br.grad)):
+        frac = torch.isclose(got, want, rtol=5e-2, atol=5e-2).float().mean().item()
+        assert frac > 0.995, frac
+    torch.testing.assert_close(gamma.grad, gr.grad, rtol=5e-2, atol=2.0)
+    torch.testing.assert_close(beta.grad, ber.grad, rtol=5e-2, atol=2.0)
+
+
+def test_stem_space_to_depth_and_pad_kernels():
+    from deeplearning_cfn_b200.ops.pool import pad3to8, stem_space_to_depth
+    import torch.nn.functional as F
+    torch.manual_seed(7)
+    x3 = torch.randn(3, 3, 20, 16, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last)
+    x8 = pad3to8(x3)
+    assert x8.shape == (3, 8, 20, 16) and torch.equal(x8[:, :3], x3) and float(x8[:, 3:].abs().sum()) == 0
+    xg = x8.clone().requires_grad_(True)
+    s = stem_space_to_depth(xg)
+    N, C, H, W = 3, 3, 20, 16
+    xp = F.pad(x3, (3, 3, 3, 3))
+    ref = xp.reshape(N, C, (H + 6) // 2, 2, (W + 6) // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(N, 12, (H + 6) // 2, (W + 6) // 2)
+    assert s.shape == (3, 16, 13, 11) and torch.equal(s[:, :12], ref) and float(s[:, 12:].abs().sum()) == 0
+    g = torch.randn_like(s)
+    s.backward(g)
+    xr = x3.clone().float().requires_grad_(True)
+    xpr = F.pad(xr, (3, 3, 3, 3))
+    refr = xpr.reshape(N, C, (H + 6) // 2, 2, (W + 6) // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(N, 12, (H + 6) // 2, (W + 6) // 2)
+    refr.backward(g[:, :12].float())
+    assert torch.equal(xg.grad[:, :3].float(), xr.grad) and float(xg.grad[:, 3:].abs().sum()) == 0

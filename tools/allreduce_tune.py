@@ -16,7 +16,7 @@ def main():
     torch.cuda.set_device(lrank)
     dev = torch.device("cuda", lrank)
     dist.init_process_group("nccl", device_id=dev)
-    sizes = [1 << 20, 16 << 20, 64 << 20, 256 << 20]
+    sizes = [int(x) << 20 for x in os.environ.get("TUNE_MIB", "1,16,64,256").split(",")]
     blocks = [int(b) for b in os.environ.get("TUNE_BLOCKS", "32,64,128").split(",")]
     heap = SymmetricHeap(2 * max(sizes) + (8 << 20))
     if rank == 0:

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== tests"; timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_trainer.py -q -m gpu --timeout 300 -x -k "stem or maxpool or batchnorm or trainer or smoke or pad" 2>&1 | tail -4
+echo "=== bench"; timeout 600 python bench.py --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench1_resnet_v6.log | cut -c1-330
+echo "=== profile"; timeout 600 python tools/profile_step.py 256 2>&1 | grep -v "aten::\|_BNReLU\|_MaxPool\|_LinearFn\|_AddBN" | head -24
+cp gpurun_out/profile_resnet50.txt gpurun_out/profile_resnet50_v6.txt

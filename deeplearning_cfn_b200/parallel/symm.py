@@ -153,6 +153,8 @@ class SymmetricHeap:
         dst_off is given.  algo 0 = peer ld/st two-shot, 1 = NVLS multimem (default when a multicast mapping exists)."""
         ch = self.CH_ALLREDUCE if channel is None else channel
         a = self.allreduce_algo if algo is None else algo
+        if algo is None and a == 1 and count * (2 if dtype == torch.bfloat16 else 4) < (2 << 20):
+            a = 0      # below ~2 MiB the switch round trip costs more than it saves (profiles/scale8/README.md)
         native.check(native.lib().dlcfn_allreduce_ex(self._ctx, off, off if dst_off is None else dst_off, count,
                                                      native.dtype_code(dtype), float(scale), ch, nblocks, a,
                                                      native.stream_ptr(stream)), "allreduce")

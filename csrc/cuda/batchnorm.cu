@@ -402,6 +402,7 @@ DLCFN_API int dlcfn_bn_forward_ex(const void* x, const void* x2, void* z, void* 
 DLCFN_API int dlcfn_bn_forward(const void* x, void* y, long long M, int C, const float* gamma, const float* beta,
                                float* mean, float* invstd, float* running_mean, float* running_var,
                                float momentum, float eps, int relu, float* workspace, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   return dlcfn_bn_forward_ex(x, nullptr, nullptr, y, M, C, gamma, beta, mean, invstd, running_mean, running_var, momentum,
                              eps, relu, workspace, stream);
 }
@@ -411,6 +412,7 @@ DLCFN_API int dlcfn_bn_forward_ex(const void* x, const void* x2, void* z, void* 
                                   const float* gamma, const float* beta, float* mean, float* invstd,
                                   float* running_mean, float* running_var, float momentum, float eps, int relu,
                                   float* workspace, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (!bn_supported(M, C)) return (int)cudaErrorInvalidValue;
   BnGeom g = bn_geom(M, C);
   float* part = workspace;
@@ -438,6 +440,7 @@ DLCFN_API int dlcfn_bn_backward(const void* x, const void* dy, void* dx, long lo
                                 const float* beta, const float* mean, const float* invstd, float* dgamma,
                                 float* dbeta, int accumulate_grads, int relu, float* workspace,
                                 cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   return dlcfn_bn_backward_ex(x, dy, nullptr, dx, M, C, gamma, beta, mean, invstd, dgamma, dbeta, accumulate_grads, relu,
                               workspace, stream);
 }
@@ -447,6 +450,7 @@ DLCFN_API int dlcfn_bn_backward_ex(const void* x, const void* dy, const void* ex
                                    const float* gamma, const float* beta, const float* mean, const float* invstd,
                                    float* dgamma, float* dbeta, int accumulate_grads, int relu, float* workspace,
                                    cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (!bn_supported(M, C)) return (int)cudaErrorInvalidValue;
   BnGeom g = bn_geom(M, C);
   float* part = workspace;
@@ -477,6 +481,7 @@ __global__ void kbn_inf_coef(int C, const float* __restrict__ gamma, const float
 DLCFN_API int dlcfn_bn_inference(const void* x, void* y, long long M, int C, const float* gamma,
                                  const float* beta, const float* running_mean, const float* running_var,
                                  float eps, int relu, float* workspace, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (!bn_supported(M, C)) return (int)cudaErrorInvalidValue;
   BnGeom g = bn_geom(M, C);
   float* scale_shift = workspace + (size_t)g.grid * 2 * C;

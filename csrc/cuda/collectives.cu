@@ -406,6 +406,7 @@ using namespace dlcfn;
 
 // ============================================================ host API ======
 DLCFN_API int dlcfn_symm_create(size_t heap_bytes, int rank, int world, void** out_ctx) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (world < 1 || world > DLCFN_MAX_RANKS || rank < 0 || rank >= world) return (int)cudaErrorInvalidValue;
   SymmCtx* c = new SymmCtx();
   c->rank = rank;
@@ -425,6 +426,7 @@ DLCFN_API int dlcfn_symm_create(size_t heap_bytes, int rank, int world, void** o
 // Adopt memory that somebody else allocated and mapped on every rank (torch symmetric memory): `local_alloc` is
 // this rank's whole allocation (kHeapOff header + heap), peers are registered with dlcfn_symm_set_peer_ptr.
 DLCFN_API int dlcfn_symm_create_external(void* local_alloc, size_t total_bytes, int rank, int world, void** out_ctx) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (world < 1 || world > DLCFN_MAX_RANKS || rank < 0 || rank >= world || total_bytes <= kHeapOff)
     return (int)cudaErrorInvalidValue;
   SymmCtx* c = new SymmCtx();
@@ -441,6 +443,7 @@ DLCFN_API int dlcfn_symm_create_external(void* local_alloc, size_t total_bytes, 
 }
 
 DLCFN_API int dlcfn_symm_set_multicast(void* ctx, void* mc_alloc) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   ((SymmCtx*)ctx)->mc_alloc = (char*)mc_alloc;
   return 0;
 }
@@ -448,6 +451,7 @@ DLCFN_API int dlcfn_symm_set_multicast(void* ctx, void* mc_alloc) {
 DLCFN_API int dlcfn_symm_has_multicast(void* ctx) { return ((SymmCtx*)ctx)->dev.mc != nullptr ? 1 : 0; }
 
 DLCFN_API int dlcfn_symm_get_handle(void* ctx, void* out64) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   cudaIpcMemHandle_t h;
   DLCFN_CHECK(cudaIpcGetMemHandle(&h, c->local));
@@ -457,6 +461,7 @@ DLCFN_API int dlcfn_symm_get_handle(void* ctx, void* out64) {
 }
 
 DLCFN_API int dlcfn_symm_open_peer(void* ctx, int peer, const void* handle64) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   if (peer < 0 || peer >= c->world || peer == c->rank) return (int)cudaErrorInvalidValue;
   cudaIpcMemHandle_t h;
@@ -470,6 +475,7 @@ DLCFN_API int dlcfn_symm_open_peer(void* ctx, int peer, const void* handle64) {
 
 // single-process multi-GPU: the peer allocation is already addressable (peer access enabled by caller)
 DLCFN_API int dlcfn_symm_set_peer_ptr(void* ctx, int peer, void* whole_allocation) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   if (peer < 0 || peer >= c->world) return (int)cudaErrorInvalidValue;
   c->peer[peer] = (char*)whole_allocation;
@@ -479,6 +485,7 @@ DLCFN_API int dlcfn_symm_set_peer_ptr(void* ctx, int peer, void* whole_allocatio
 DLCFN_API void* dlcfn_symm_allocation(void* ctx) { return ((SymmCtx*)ctx)->local; }
 
 DLCFN_API int dlcfn_symm_finalize(void* ctx) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   for (int p = 0; p < c->world; ++p)
     if (!c->peer[p]) return (int)cudaErrorInvalidValue;
@@ -504,6 +511,7 @@ DLCFN_API void* dlcfn_symm_heap_ptr(void* ctx, int peer) {
 
 // Reads and clears the device error word (set when a flag wait timed out).  Synchronises the stream.
 DLCFN_API int dlcfn_symm_check_error(void* ctx, cudaStream_t stream, int* out_err) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   int e = 0;
   DLCFN_CHECK(cudaMemcpyAsync(&e, c->dev.err, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -514,6 +522,7 @@ DLCFN_API int dlcfn_symm_check_error(void* ctx, cudaStream_t stream, int* out_er
 }
 
 DLCFN_API int dlcfn_symm_destroy(void* ctx) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   for (int p = 0; p < c->world; ++p)
     if (c->opened_ipc[p] && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
@@ -542,6 +551,7 @@ static inline int clamp_blocks(int nblocks, size_t work_vecs, int threads) {
 }
 
 DLCFN_API int dlcfn_barrier(void* ctx, int channel, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   if (!c->finalized || channel < 0 || channel >= kSigChannels) return (int)cudaErrorInvalidValue;
   kbarrier<<<1, 32, 0, stream>>>(c->dev, channel);
@@ -578,6 +588,7 @@ static int launch_allreduce(SymmCtx* c, size_t off, size_t dst_off, size_t nvec,
 // (dst_off == src_off: in place).  algo 0: peer ld/st two-shot;  algo 1: NVLS multimem (needs a multicast mapping).
 DLCFN_API int dlcfn_allreduce_ex(void* ctx, size_t src_off, size_t dst_off, size_t count, int dtype, float scale,
                                  int channel, int nblocks, int algo, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   if (!c->finalized || (src_off & 15) || (dst_off & 15) || channel < 0 || channel >= kSigChannels)
     return (int)cudaErrorInvalidValue;
@@ -591,6 +602,7 @@ DLCFN_API int dlcfn_allreduce_ex(void* ctx, size_t src_off, size_t dst_off, size
 
 DLCFN_API int dlcfn_allreduce(void* ctx, size_t off_bytes, size_t count, int dtype, float scale, int channel,
                               int nblocks, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   return dlcfn_allreduce_ex(ctx, off_bytes, off_bytes, count, dtype, scale, channel, nblocks,
                             c->dev.mc != nullptr && c->world > 1 ? 1 : 0, stream);
@@ -598,6 +610,7 @@ DLCFN_API int dlcfn_allreduce(void* ctx, size_t off_bytes, size_t count, int dty
 
 DLCFN_API int dlcfn_broadcast(void* ctx, size_t off_bytes, size_t bytes, int root, int channel, int nblocks,
                               cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   if (!c->finalized || (off_bytes & 15) || root < 0 || root >= c->world) return (int)cudaErrorInvalidValue;
   if (bytes == 0) return 0;
@@ -618,6 +631,7 @@ DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, 
                                  float* s1, float* s2, int dtype, int opt_kind, float lr, float wd,
                                  float momentum, float beta1, float beta2, float eps, float rescale,
                                  float clip, int channel, int nblocks, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   const int N = dtype == 1 ? 8 : 4;
   if (!c->finalized || (grad_off & 15) || (weight_off & 15) || (shard_lo % N) || dtype < 0 || dtype > 1)
@@ -650,6 +664,7 @@ DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, 
 
 DLCFN_API int dlcfn_ps_async_worker(void* ctx, uint32_t server_mask, int channel, int nblocks,
                                     cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   if (!c->finalized || channel < 0 || channel + 1 >= kSigChannels || nblocks < 1 || nblocks > kSigMaxBlocks)
     return (int)cudaErrorInvalidValue;
@@ -662,6 +677,7 @@ DLCFN_API int dlcfn_ps_async_server(void* ctx, size_t grad_off, size_t weight_of
                                     float* s2, int dtype, int opt_kind, float lr, float wd, float momentum,
                                     float beta1, float beta2, float eps, float rescale, float clip,
                                     int channel, int nblocks, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   const int N = dtype == 1 ? 8 : 4;
   if (!c->finalized || (grad_off & 15) || (weight_off & 15) || (shard_lo % N) || dtype < 0 || dtype > 1)

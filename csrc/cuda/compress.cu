@@ -127,6 +127,7 @@ static inline int grid1d(size_t n, int threads) {
 
 DLCFN_API int dlcfn_quantize_2bit(const void* grad, int grad_dtype, float* residual, uint32_t* out, size_t n,
                                   float threshold, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (n == 0) return 0;
   size_t nwords = (n + 15) / 16;
   if (grad_dtype == 0)
@@ -141,6 +142,7 @@ DLCFN_API int dlcfn_quantize_2bit(const void* grad, int grad_dtype, float* resid
 
 DLCFN_API int dlcfn_dequantize_2bit(const uint32_t* in, float* out, size_t n, float threshold, int accumulate,
                                     cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (n == 0) return 0;
   kdequant2<<<grid1d((n + 15) / 16, 256), 256, 0, stream>>>(in, out, n, threshold, accumulate);
   return (int)cudaGetLastError();
@@ -158,6 +160,7 @@ DLCFN_API size_t dlcfn_unique_rows_temp_bytes(int64_t num_rows) {
 
 DLCFN_API int dlcfn_unique_rows(const int64_t* ids, size_t n, int64_t num_rows, uint8_t* present, void* temp,
                                 size_t temp_bytes, int64_t* out, int64_t* n_out, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   DLCFN_CHECK(cudaMemsetAsync(present, 0, (size_t)num_rows, stream));
   if (n) kmark_rows<<<grid1d(n, 256), 256, 0, stream>>>(ids, n, num_rows, present);
   cub::CountingInputIterator<int64_t> it(0);

@@ -259,6 +259,7 @@ using namespace dlcfn;
 // dtype codes shared with python: 0 = fp32, 1 = bf16
 DLCFN_API int dlcfn_elementwise_sum(const void* const* inputs, int n_in, void* out, size_t n, int dtype,
                                     float scale, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (n_in < 1 || n_in > DLCFN_MAX_RANKS * 2) return (int)cudaErrorInvalidValue;
   if (n == 0) return 0;
   SumArgs a;
@@ -276,6 +277,7 @@ DLCFN_API int dlcfn_elementwise_sum(const void* const* inputs, int n_in, void* o
 
 DLCFN_API int dlcfn_cast_scale(const void* in, void* out, size_t n, int in_dtype, int out_dtype, float scale,
                                cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (n == 0) return 0;
   int g = grid_for(n / 8 + 1, 256);
   if (in_dtype == 0 && out_dtype == 1)
@@ -291,6 +293,7 @@ DLCFN_API int dlcfn_fused_optimizer(int kind, const void* grad, int grad_dtype, 
                                     float* s2, void* wout, int w_dtype, size_t n, float lr, float wd,
                                     float momentum, float beta1, float beta2, float eps, float rescale,
                                     float clip, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (n == 0) return 0;
   OptArgs o{kind, lr, wd, momentum, beta1, beta2, eps, rescale, clip};
   int g = grid_for(n / 4 + 1, 256);
@@ -312,6 +315,7 @@ DLCFN_API int dlcfn_fused_optimizer(int kind, const void* grad, int grad_dtype, 
 
 DLCFN_API int dlcfn_normalize_u8_nhwc(const uint8_t* in, void* out_bf16, size_t n, const float* mean3,
                                       const float* std3, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (n == 0) return 0;
   knorm_u8_bf16<<<grid_for(n / 48 + 1, 256), 256, 0, stream>>>(in, (__nv_bfloat16*)out_bf16, n, mean3[0],
                                                                mean3[1], mean3[2], std3[0], std3[1],

@@ -398,6 +398,7 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
                               int rows_per_shard, long long ldb, int b_mn, void* D, long long ldd, int d_dtype,
                               const float* bias, int M, int N, int K, int accumulate, int relu, int block_n,
                               int num_sms, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (n_shards < 1 || n_shards > kMaxShards) return (int)cudaErrorInvalidValue;
   if ((lda & 7) || (ldb & 7) || (((uintptr_t)A) & 15)) return (int)cudaErrorInvalidValue;

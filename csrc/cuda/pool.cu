@@ -103,6 +103,7 @@ static inline int pool_grid(long long total) {
 // x: bf16 [N,H,W,C] (C % 8 == 0) -> y [N,OH,OW,C], idx: one byte per output element (arg-max tap)
 DLCFN_API int dlcfn_maxpool_nhwc_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int K, int S,
                                      int P, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (C % 8 || K < 1 || K > 15 || S < 1) return (int)cudaErrorInvalidValue;
   PoolGeom g{N, H, W, C / 8, (H + 2 * P - K) / S + 1, (W + 2 * P - K) / S + 1, K, S, P};
   const long long total = (long long)N * g.OH * g.OW * g.CV;
@@ -113,6 +114,7 @@ DLCFN_API int dlcfn_maxpool_nhwc_fwd(const void* x, void* y, void* idx, int N, i
 
 DLCFN_API int dlcfn_maxpool_nhwc_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, int K,
                                      int S, int P, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (C % 8 || K < 1 || K > 15 || S < 1) return (int)cudaErrorInvalidValue;
   PoolGeom g{N, H, W, C / 8, (H + 2 * P - K) / S + 1, (W + 2 * P - K) / S + 1, K, S, P};
   const long long total = (long long)N * H * W * g.CV;
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(256) kstem_s2d_bwd(const uint16_t* __restrict_
 }  // namespace dlcfn
 
 DLCFN_API int dlcfn_stem_s2d_fwd(const void* x8, void* y16, int N, int H, int W, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if ((H & 1) || (W & 1)) return (int)cudaErrorInvalidValue;
   const int Hs = (H + 6) / 2, Ws = (W + 6) / 2;
   const long long total = (long long)N * Hs * Ws;
@@ -189,6 +192,7 @@ DLCFN_API int dlcfn_stem_s2d_fwd(const void* x8, void* y16, int N, int H, int W,
 }
 
 DLCFN_API int dlcfn_stem_s2d_bwd(const void* dy16, void* dx8, int N, int H, int W, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if ((H & 1) || (W & 1)) return (int)cudaErrorInvalidValue;
   const int Hs = (H + 6) / 2, Ws = (W + 6) / 2;
   const long long total = (long long)N * H * W;
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(256) kpad3to8(const uint16_t* __restrict__ x, 
 }  // namespace dlcfn
 
 DLCFN_API int dlcfn_pad3to8_nhwc(const void* x3, void* y8, long long npix, cudaStream_t stream) {
+  (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (npix == 0) return 0;
   dlcfn::kpad3to8<<<pool_grid(npix), 256, 0, stream>>>((const uint16_t*)x3, (uint4*)y8, npix);
   return (int)cudaGetLastError();

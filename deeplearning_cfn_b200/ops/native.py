@@ -241,9 +241,13 @@ def gemm_bf16(a: torch.Tensor, b, *, a_mn: bool = False, b_mn: bool = False, out
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= N
     arr = (c_void_p * len(ptrs))(*ptrs)
-    check(lib().dlcfn_gemm_bf16(a.data_ptr(), a.stride(0), int(a_mn), ctypes.cast(arr, c_void_p), len(ptrs),
-                                rows_per_shard, ldb_, int(b_mn), out.data_ptr(), out.stride(0),
-                                dtype_code(out.dtype), _ptr(bias), M, N, K, int(accumulate), int(relu), block_n, 0,
-                                stream_ptr()), "gemm_bf16")
+    rc = lib().dlcfn_gemm_bf16(a.data_ptr(), a.stride(0), int(a_mn), ctypes.cast(arr, c_void_p), len(ptrs),
+                               rows_per_shard, ldb_, int(b_mn), out.data_ptr(), out.stride(0),
+                               dtype_code(out.dtype), _ptr(bias), M, N, K, int(accumulate), int(relu), block_n, 0,
+                               stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"dlcfn gemm_bf16 failed with CUDA error {rc}: M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn} "
+                           f"lda={a.stride(0)} ldb={ldb_} ldd={out.stride(0)} a%16={a.data_ptr() % 16} "
+                           f"b%16={ptrs[0] % 16} d%16={out.data_ptr() % 16} shards={len(ptrs)} block_n={block_n}")
     _count()
     return out

@@ -20,6 +20,7 @@
 //                              mainloop of tile i+1
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdio>
 
 namespace dlcfn {
 
@@ -365,7 +366,10 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+  if (r != CUDA_SUCCESS)
+    fprintf(stderr, "[dlcfn] cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%llu cols=%llu ld=%llu box=%ux%u\n", (int)r, ptr,
+            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+  return r == CUDA_SUCCESS ? 0 : 10000 + (int)r;
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -374,7 +378,11 @@ static int launch(const GemmParams& p, int num_sms, cudaStream_t stream) {
   auto kern = kgemm<BLOCK_N, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
-    DLCFN_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (ae != cudaSuccess) {
+      fprintf(stderr, "[dlcfn] cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(ae));
+      return (int)ae;
+    }
     configured = true;
   }
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
@@ -382,7 +390,10 @@ static int launch(const GemmParams& p, int num_sms, cudaStream_t stream) {
   int grid = num_m * num_n;
   if (grid > num_sms) grid = num_sms;
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
-  return (int)cudaGetLastError();
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess)
+    fprintf(stderr, "[dlcfn] kgemm launch failed: %s (grid %d, smem %d)\n", cudaGetErrorString(le), grid, Cfg::kSmemBytes);
+  return (int)le;
 }
 
 }  // namespace dlcfn
@@ -398,6 +409,14 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
                               int rows_per_shard, long long ldb, int b_mn, void* D, long long ldd, int d_dtype,
                               const float* bias, int M, int N, int K, int accumulate, int relu, int block_n,
                               int num_sms, cudaStream_t stream) {
+  // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread.  Autograd
+  // worker threads for device 0 have none until the first runtime call (torch skips cudaSetDevice
+  // when the ordinal already matches), so bind the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    DLCFN_CHECK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (n_shards < 1 || n_shards > kMaxShards) return (int)cudaErrorInvalidValue;

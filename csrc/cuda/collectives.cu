@@ -20,33 +20,9 @@
 // flight per thread, a small grid (default 32 CTAs x 512 threads ~ 4 MB in flight) so that the rest of
 // the 148 SMs keep running backward while a bucket is on the wire.
 #include "symm.cuh"
+#include "optimizer.cuh"
 
 namespace dlcfn {
-
-struct OptArgs {
-  int kind;
-  float lr, wd, momentum, beta1, beta2, eps, rescale, clip;
-};
-
-__device__ __forceinline__ void opt_apply(const OptArgs& o, float g, float& w, float& s1, float& s2) {
-  g *= o.rescale;
-  if (o.clip > 0.f) g = fminf(fmaxf(g, -o.clip), o.clip);
-  if (o.kind == 0) {
-    w = (1.f - o.lr * o.wd) * w - o.lr * g;
-  } else if (o.kind == 1) {
-    s1 = o.momentum * s1 - o.lr * o.wd * w - o.lr * g;
-    w += s1;
-  } else if (o.kind == 2) {
-    g += o.wd * w;
-    s1 = o.beta1 * s1 + (1.f - o.beta1) * g;
-    s2 = o.beta2 * s2 + (1.f - o.beta2) * g * g;
-    w -= o.lr * s1 / (sqrtf(s2) + o.eps);
-  } else if (o.kind == 3) {
-    w += g;
-  } else {  // kind 4: no optimizer — store the reduced gradient (kvstore without updater)
-    w = g;
-  }
-}
 
 template <typename T>
 struct Vec16;
@@ -292,13 +268,13 @@ __device__ __forceinline__ void ps_update_vec(const PSArgs& a, const PSPtrs& P, 
   for (int q = 0; q < N / 4; ++q) {
     float4 f = reinterpret_cast<const float4*>(a.master + i0)[q];
     w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
-    if (a.opt.kind == 1 || a.opt.kind == 2) {
+    if (opt_uses_s1(a.opt.kind)) {
       float4 h = reinterpret_cast<const float4*>(a.s1 + i0)[q];
       m1[4 * q] = h.x; m1[4 * q + 1] = h.y; m1[4 * q + 2] = h.z; m1[4 * q + 3] = h.w;
     } else {
       m1[4 * q] = m1[4 * q + 1] = m1[4 * q + 2] = m1[4 * q + 3] = 0.f;
     }
-    if (a.opt.kind == 2) {
+    if (opt_uses_s2(a.opt.kind)) {
       float4 h = reinterpret_cast<const float4*>(a.s2 + i0)[q];
       m2[4 * q] = h.x; m2[4 * q + 1] = h.y; m2[4 * q + 2] = h.z; m2[4 * q + 3] = h.w;
     } else {
@@ -310,9 +286,9 @@ __device__ __forceinline__ void ps_update_vec(const PSArgs& a, const PSPtrs& P, 
 #pragma unroll
   for (int q = 0; q < N / 4; ++q) {
     reinterpret_cast<float4*>(a.master + i0)[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-    if (a.opt.kind == 1 || a.opt.kind == 2)
+    if (opt_uses_s1(a.opt.kind))
       reinterpret_cast<float4*>(a.s1 + i0)[q] = make_float4(m1[4 * q], m1[4 * q + 1], m1[4 * q + 2], m1[4 * q + 3]);
-    if (a.opt.kind == 2)
+    if (opt_uses_s2(a.opt.kind))
       reinterpret_cast<float4*>(a.s2 + i0)[q] = make_float4(m2[4 * q], m2[4 * q + 1], m2[4 * q + 2], m2[4 * q + 3]);
   }
   const uint4 o = Vec16<T>::pack(w);

@@ -10,6 +10,7 @@
 // 148 SMs x resident CTAs; fp32 math, bf16 (or fp32) storage.  HBM3e is the
 // bound, so each kernel touches every byte exactly once.
 #include "common.cuh"
+#include "optimizer.cuh"
 
 namespace dlcfn {
 
@@ -127,34 +128,7 @@ __global__ void __launch_bounds__(256) kcast_scale_bf16_f32(const __nv_bfloat16*
 // One launch updates a whole flat parameter buffer.  Multi-precision layout
 // (reference MP_SGDMomKernel, optimizer_op-inl.h:403-427): fp32 master weight +
 // fp32 state in HBM, bf16 gradient in, bf16 model weight out.
-//   kind 0: SGD            w32 = (1-lr*wd) w32 - lr * clip(rescale*g)
-//   kind 1: SGD momentum   m = mu*m - lr*wd*w32 - lr*clip(rescale*g); w32 += m
-//   kind 2: Adam           g' = rescale*g + wd*w32 ; m,v update ; w32 -= lr*m/(sqrt(v)+eps)
-//                          (bias correction folded into lr by the caller, optimizer.py:1080-1082)
-//   kind 3: "Test"         w32 += rescale * g   (reference Test optimizer, optimizer.py:1486-1499)
-struct OptArgs {
-  int kind;
-  float lr, wd, momentum, beta1, beta2, eps, rescale, clip;  // clip<=0: off
-};
-
-__device__ __forceinline__ void opt_apply(const OptArgs& o, float g, float& w, float& s1, float& s2) {
-  g *= o.rescale;
-  if (o.clip > 0.f) g = fminf(fmaxf(g, -o.clip), o.clip);
-  if (o.kind == 0) {
-    w = (1.f - o.lr * o.wd) * w - o.lr * g;
-  } else if (o.kind == 1) {
-    s1 = o.momentum * s1 - o.lr * o.wd * w - o.lr * g;
-    w += s1;
-  } else if (o.kind == 2) {
-    g += o.wd * w;
-    s1 = o.beta1 * s1 + (1.f - o.beta1) * g;
-    s2 = o.beta2 * s2 + (1.f - o.beta2) * g * g;
-    w -= o.lr * s1 / (sqrtf(s2) + o.eps);
-  } else {
-    w += g;
-  }
-}
-
+// The per-element math for all 13 optimizer kinds is in optimizer.cuh (shared with the fused PS kernels).
 // G = gradient storage type, W = model-weight storage type (master is always fp32)
 template <typename G, typename W>
 __global__ void __launch_bounds__(256) kopt(OptArgs o, const G* __restrict__ grad,
@@ -175,20 +149,20 @@ __global__ void __launch_bounds__(256) kopt(OptArgs o, const G* __restrict__ gra
     float4 w4 = reinterpret_cast<float4*>(master)[v];
     float w[4] = {w4.x, w4.y, w4.z, w4.w};
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-    if (o.kind == 1 || o.kind == 2) {
+    if (opt_uses_s1(o.kind)) {
       float4 t = reinterpret_cast<float4*>(s1)[v];
       a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
     }
-    if (o.kind == 2) {
+    if (opt_uses_s2(o.kind)) {
       float4 t = reinterpret_cast<float4*>(s2)[v];
       b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) opt_apply(o, g[k], w[k], a[k], b[k]);
     reinterpret_cast<float4*>(master)[v] = make_float4(w[0], w[1], w[2], w[3]);
-    if (o.kind == 1 || o.kind == 2)
+    if (opt_uses_s1(o.kind))
       reinterpret_cast<float4*>(s1)[v] = make_float4(a[0], a[1], a[2], a[3]);
-    if (o.kind == 2) reinterpret_cast<float4*>(s2)[v] = make_float4(b[0], b[1], b[2], b[3]);
+    if (opt_uses_s2(o.kind)) reinterpret_cast<float4*>(s2)[v] = make_float4(b[0], b[1], b[2], b[3]);
     if (wout != nullptr) {
       if constexpr (sizeof(W) == 2) {
         uint2 ov;
@@ -205,12 +179,12 @@ __global__ void __launch_bounds__(256) kopt(OptArgs o, const G* __restrict__ gra
     if constexpr (sizeof(G) == 2) g = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad)[i]);
     else g = grad[i];
     float w = master[i];
-    float a = (o.kind == 1 || o.kind == 2) ? s1[i] : 0.f;
-    float b = (o.kind == 2) ? s2[i] : 0.f;
+    float a = opt_uses_s1(o.kind) ? s1[i] : 0.f;
+    float b = opt_uses_s2(o.kind) ? s2[i] : 0.f;
     opt_apply(o, g, w, a, b);
     master[i] = w;
-    if (o.kind == 1 || o.kind == 2) s1[i] = a;
-    if (o.kind == 2) s2[i] = b;
+    if (opt_uses_s1(o.kind)) s1[i] = a;
+    if (opt_uses_s2(o.kind)) s2[i] = b;
     if (wout != nullptr) {
       if constexpr (sizeof(W) == 2) reinterpret_cast<__nv_bfloat16*>(wout)[i] = __float2bfloat16(w);
       else wout[i] = w;

@@ -266,7 +266,14 @@ static bool ParseOpt(const std::string& body, OptimizerConfig* o) {
     size_t eq = kv.find('=');
     if (eq == std::string::npos) continue;
     std::string k = kv.substr(0, eq), v = kv.substr(eq + 1);
-    if (k == "kind") o->kind = v == "sgd" ? 0 : v == "sgd_mom" ? 1 : v == "adam" ? 2 : v == "test" ? 3 : -1;
+    if (k == "kind") {
+      // numbering shared with csrc/cuda/optimizer.cuh
+      static const char* const names[] = {"sgd", "sgd_mom", "adam", "test", "none", "nag", "signum", "signsgd",
+                                          "adagrad", "rmsprop", "adadelta", "ftrl", "adamax"};
+      o->kind = -1;
+      for (int i = 0; i < 13; ++i) if (v == names[i]) o->kind = i;
+      if (o->kind == 4) o->kind = -1;
+    }
     else if (k == "lr") o->lr = (float)atof(v.c_str());
     else if (k == "wd") o->wd = (float)atof(v.c_str());
     else if (k == "momentum") o->momentum = (float)atof(v.c_str());
@@ -310,29 +317,76 @@ void KVServer::ApplyUpdate(uint64_t key, Entry& e, size_t begin, size_t n) {
   if (py_updater_) { py_updater_((int)(key - node_->ServerKeyRange(node_->my_rank()).first), g, w, n, py_user_); return; }
   OptimizerConfig& o = opt_;
   if (o.kind < 0) { memcpy(w, g, n * 4); return; }   // no updater: store the aggregate (kvstore_dist_server.h:358-361)
-  if ((o.kind == 1 || o.kind == 2) && e.s1.size() != e.store.size()) e.s1.assign(e.store.size(), 0.f);
-  if (o.kind == 2 && e.s2.size() != e.store.size()) e.s2.assign(e.store.size(), 0.f);
+  const bool use1 = o.kind == 1 || o.kind == 2 || o.kind == 5 || o.kind == 6 || (o.kind >= 8 && o.kind <= 12);
+  const bool use2 = o.kind == 2 || (o.kind >= 10 && o.kind <= 12);
+  if (use1 && e.s1.size() != e.store.size()) e.s1.assign(e.store.size(), 0.f);
+  if (use2 && e.s2.size() != e.store.size()) e.s2.assign(e.store.size(), 0.f);
   float lr = o.lr;
-  if (o.kind == 2) {
-    const double t = (double)(o.t + 1);
+  const double t = (double)(e.t + 1);
+  if (o.kind == 2)
     lr = (float)(o.lr * std::sqrt(1.0 - std::pow((double)o.beta2, t)) / (1.0 - std::pow((double)o.beta1, t)));
-  }
+  else if (o.kind == 12)
+    lr = (float)(o.lr / (1.0 - std::pow((double)o.beta1, t)));
   float* s1 = e.s1.empty() ? nullptr : e.s1.data() + begin;
   float* s2 = e.s2.empty() ? nullptr : e.s2.data() + begin;
+  auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
+  // same per-element math as csrc/cuda/optimizer.cuh:opt_apply
   for (size_t i = 0; i < n; ++i) {
     float gi = g[i] * o.rescale;
     if (o.clip > 0.f) gi = std::min(std::max(gi, -o.clip), o.clip);
+    float& wi = w[i];
     switch (o.kind) {
-      case 0: w[i] = (1.f - lr * o.wd) * w[i] - lr * gi; break;
-      case 1: s1[i] = o.momentum * s1[i] - lr * o.wd * w[i] - lr * gi; w[i] += s1[i]; break;
-      case 2: {
-        gi += o.wd * w[i];
+      case 0: wi = (1.f - lr * o.wd) * wi - lr * gi; break;
+      case 1: s1[i] = o.momentum * s1[i] - lr * o.wd * wi - lr * gi; wi += s1[i]; break;
+      case 2:
+        gi += o.wd * wi;
         s1[i] = o.beta1 * s1[i] + (1.f - o.beta1) * gi;
         s2[i] = o.beta2 * s2[i] + (1.f - o.beta2) * gi * gi;
-        w[i] -= lr * s1[i] / (std::sqrt(s2[i]) + o.eps);
+        wi -= lr * s1[i] / (std::sqrt(s2[i]) + o.eps);
+        break;
+      case 5:
+        gi += o.wd * wi;
+        s1[i] = o.momentum * s1[i] + gi;
+        wi -= lr * (gi + o.momentum * s1[i]);
+        break;
+      case 6:
+        gi += o.wd * wi;
+        s1[i] = o.momentum * s1[i] - (1.f - o.momentum) * gi;
+        wi = (1.f - lr * o.beta1) * wi + lr * sgn(s1[i]);
+        break;
+      case 7:
+        gi += o.wd * wi;
+        wi = (1.f - lr * o.beta1) * wi - lr * sgn(gi);
+        break;
+      case 8:
+        s1[i] += gi * gi;
+        wi -= lr * (gi / std::sqrt(s1[i] + o.eps) + o.wd * wi);
+        break;
+      case 9:
+        gi += o.wd * wi;
+        s1[i] = o.beta1 * s1[i] + (1.f - o.beta1) * gi * gi;
+        wi -= lr * gi / std::sqrt(s1[i] + o.eps);
+        if (o.beta2 > 0.f) wi = std::min(std::max(wi, -o.beta2), o.beta2);
+        break;
+      case 10: {
+        s1[i] = o.beta1 * s1[i] + (1.f - o.beta1) * gi * gi;
+        const float d = std::sqrt(s2[i] + o.eps) / std::sqrt(s1[i] + o.eps) * gi;
+        s2[i] = o.beta1 * s2[i] + (1.f - o.beta1) * d * d;
+        wi = wi - d - o.wd * wi;
         break;
       }
-      default: w[i] += gi; break;  // Test optimizer: w += rescale * g
+      case 11:
+        s1[i] += gi - (std::sqrt(s2[i] + gi * gi) - std::sqrt(s2[i])) * wi / lr;
+        s2[i] += gi * gi;
+        wi = std::fabs(s1[i]) > o.beta1 ? (sgn(s1[i]) * o.beta1 - s1[i]) / ((o.beta2 + std::sqrt(s2[i])) / lr + o.wd) : 0.f;
+        break;
+      case 12:
+        gi += o.wd * wi;
+        s1[i] = o.beta1 * s1[i] + (1.f - o.beta1) * gi;
+        s2[i] = std::max(o.beta2 * s2[i], std::fabs(gi));
+        wi -= lr * s1[i] / (s2[i] + 1e-38f);
+        break;
+      default: wi += gi; break;  // Test optimizer: w += rescale * g
     }
   }
 }
@@ -426,6 +480,7 @@ void KVServer::HandleData(Message&& m) {
     } else {
       ApplyUpdate(key, e, 0, e.store.size());
     }
+    ++e.t;
   };
 
   if (!sync_mode_) {
@@ -438,7 +493,6 @@ void KVServer::HandleData(Message&& m) {
   e.waiting.push_back(std::move(m));
   if ((int)e.waiting.size() == node_->num_workers()) {
     apply();
-    ++opt_.t;  // counts aggregated rounds of the most recently updated key; Adam uses per-key t via python when needed
     std::vector<Message> done;
     done.swap(e.waiting);
     lk.unlock();

@@ -149,9 +149,8 @@ inline int PairCmd(int a, int b) { return (a + b) * (a + b + 1) / 2 + b; }
 void UnpairCmd(int z, int* a, int* b);
 
 struct OptimizerConfig {
-  int kind = -1;  // -1 none, 0 sgd, 1 sgd_mom, 2 adam, 3 test
+  int kind = -1;  // -1 none, else the numbering of csrc/cuda/optimizer.cuh (0 sgd ... 12 adamax)
   float lr = 0.01f, wd = 0.f, momentum = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, rescale = 1.f, clip = -1.f;
-  long long t = 0;
 };
 
 class KVWorker {
@@ -196,6 +195,7 @@ class KVServer {
     std::vector<uint8_t> touched;  // row-sparse: rows seen this round
     std::vector<Message> waiting;  // queued push requests of this round
     bool initialized = false;
+    long long t = 0;               // updates applied to this key (Adam / Adamax bias correction)
   };
   void HandleData(Message&& m);
   void HandleCommand(Message&& m);

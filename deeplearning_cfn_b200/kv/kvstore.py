@@ -536,7 +536,7 @@ class KVStoreDistDevice(KVStore):
         o = opt.create(optimizer) if not isinstance(optimizer, opt.Optimizer) else optimizer
         cfg = o.native_config()
         if cfg is None:
-            raise KVStoreError(f"{type(o).__name__} has no fused server kernel; use sgd / adam / test on dist_device_sync")
+            raise KVStoreError(f"{type(o).__name__} has no fused server kernel (csrc/cuda/optimizer.cuh lists the 13 that do)")
         self._optimizer = o
         d = dict(kv.split("=") for kv in cfg.split(";"))
         self._opt_kind = d.pop("kind")
@@ -559,8 +559,8 @@ class KVStoreDistDevice(KVStore):
     def _alloc_state(self, st: dict) -> None:
         n = st["hi"] - st["lo"]
         dev = self.heap.device
-        need1 = self._opt_kind in ("sgd_mom", "adam")
-        need2 = self._opt_kind == "adam"
+        need1 = self._opt_kind in native.OPT_USES_S1
+        need2 = self._opt_kind in native.OPT_USES_S2
         if n and st.get("master") is None:
             st["master"] = st["w"][st["lo"]:st["hi"]].float().clone()
         st["s1"] = torch.zeros(n, device=dev) if (need1 and n) else None
@@ -610,6 +610,8 @@ class KVStoreDistDevice(KVStore):
                 o = self._optimizer
                 t = o._update_count(ik)
                 hp["lr"] = hp["lr"] * (1 - hp["beta2"] ** t) ** 0.5 / (1 - hp["beta1"] ** t)
+            elif kind == "adamax":
+                hp["lr"] = hp["lr"] / (1 - hp["beta1"] ** self._optimizer._update_count(ik))
             self.heap.ps_sync_step(st["goff"], st["woff"], st["npad"], st["lo"], st["hi"], (1 << self._world) - 1,
                                    st["master"], st["s1"], st["s2"], st["dtype"], kind, **hp)
 

@@ -12,6 +12,7 @@ import time
 import torch
 import torch.nn.functional as F
 
+from ..ops.nn import softmax_cross_entropy
 from . import optimizer as opt
 from .kvstore import KVStore, create
 
@@ -21,7 +22,7 @@ class Module:
                  loss=None):
         self.symbol = symbol
         self.device = torch.device(context) if context is not None else next(symbol.parameters()).device
-        self.loss = loss or (lambda out, y: F.cross_entropy(out.float(), y, reduction="sum"))
+        self.loss = loss or (lambda out, y: softmax_cross_entropy(out, y, reduction="sum"))
         self.binded = self.params_initialized = self.optimizer_initialized = False
         self._kv: KVStore | None = None
         self._update_on_kvstore = False

@@ -151,10 +151,54 @@ class Optimizer:
         else:
             self.update(index, weight, grad, state)
 
+    def update_row_sparse(self, index, weight, row_ids, grad_rows, state):
+        """Lazy update with a row-sparse gradient: only the rows in `row_ids` (duplicates are summed) and their state
+        rows change (reference SGDMomStdDnsRspDns / AdamStdDnsRspDns / _sparse_adagrad_update, optimizer_op.cu:33-262).
+        CUDA fp32 tables with a natively known optimizer run on one dlcfn kernel; everything else gathers the rows,
+        runs the dense rule on them and scatters them back."""
+        from ..ops import sparse as sparse_ops
+        rows, g = sparse_ops.coalesce(row_ids.to(weight.device), grad_rows.to(weight.device))
+        cfg = self.native_config()
+        if weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous() and cfg is not None:
+            d = dict(kv.split("=") for kv in cfg.split(";"))
+            kind = d.pop("kind")
+            hp = {k: float(v) for k, v in d.items()}
+            t = self._update_count(index)
+            if kind == "adam":
+                hp["lr"] *= (1.0 - hp["beta2"] ** t) ** 0.5 / (1.0 - hp["beta1"] ** t)
+            elif kind == "adamax":
+                hp["lr"] /= (1.0 - hp["beta1"] ** t)
+            st = state if isinstance(state, (tuple, list)) else (state,)
+            s1 = st[0] if len(st) > 0 else None
+            s2 = st[1] if len(st) > 1 else None
+            sparse_ops.sparse_row_update(kind, rows, g, weight, s1, s2, None, **hp)
+            return
+        gather = lambda s: None if s is None else s[rows].clone()        # noqa: E731
+        w_sub = weight[rows].clone()
+        if isinstance(state, (tuple, list)):
+            st_sub = type(state)(gather(s) for s in state)
+        else:
+            st_sub = gather(state)
+        self.update(index, w_sub, g.view(w_sub.shape), st_sub)
+        weight[rows] = w_sub
+        if isinstance(state, (tuple, list)):
+            for s, ss in zip(state, st_sub):
+                if s is not None:
+                    s[rows] = ss
+        elif state is not None:
+            state[rows] = st_sub
+
     def native_config(self) -> str | None:
         """`kind=...;lr=...` string understood by the C++ server / CUDA kernels, or None if this optimizer
         has no native implementation (then it is pickled to the servers, kvstore.py:480-497)."""
         return None
+
+    def _cfg(self, kind, **extra):
+        if self.lr_scheduler is not None or self.lr_mult or self.wd_mult:
+            return None
+        clip = self.clip_gradient if self.clip_gradient is not None else -1.0
+        items = dict(kind=kind, lr=self.lr, wd=self.wd, rescale=self.rescale_grad, clip=clip, **extra)
+        return ";".join(f"{k}={v}" for k, v in items.items())
 
 
 @register
@@ -205,6 +249,9 @@ class NAG(SGD):
         else:
             weight.add_((-lr * g).to(weight.dtype))
 
+    def native_config(self):
+        return self._cfg("nag", momentum=self.momentum) if self.momentum != 0.0 else SGD.native_config(self)
+
 
 @register
 class Signum(Optimizer):
@@ -225,6 +272,11 @@ class Signum(Optimizer):
         else:
             step = -torch.sign(g)
         weight.copy_(((1 - lr * self.wd_lh) * weight.float() + lr * step).to(weight.dtype))
+
+    def native_config(self):
+        if self.momentum != 0.0:
+            return self._cfg("signum", momentum=self.momentum, beta1=self.wd_lh)
+        return self._cfg("signsgd", beta1=self.wd_lh)
 
 
 @register
@@ -305,6 +357,52 @@ class AdaGrad(Optimizer):
         w = weight.float()
         weight.copy_((w - lr * (g / (state + self.float_stable_eps).sqrt() + wd * w)).to(weight.dtype))
 
+    def native_config(self):
+        return self._cfg("adagrad", eps=self.float_stable_eps)
+
+
+@register
+class GroupAdaGrad(Optimizer):
+    """contrib.optimizer.GroupAdaGrad: one accumulator per row (embedding-style tables),
+    hist += mean(g^2, axis=1); w -= lr * g / sqrt(hist + eps)  (contrib/optimizer_op.cu group_adagrad_update)."""
+
+    def __init__(self, eps=1e-5, **kw):
+        super().__init__(**kw)
+        self.float_stable_eps = eps
+
+    def create_state(self, index, weight):
+        assert weight.dim() == 2, "GroupAdaGrad needs 2-D weights"
+        return torch.zeros((weight.shape[0], 1), dtype=torch.float32, device=weight.device)
+
+    def update(self, index, weight, grad, state):
+        self._update_count(index)
+        lr = self._get_lr(index)
+        assert self._get_wd(index) == 0, "weight decay is not supported by GroupAdaGrad"
+        if weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous():
+            from ..ops import sparse as sparse_ops
+            clip = self.clip_gradient if self.clip_gradient is not None else -1.0
+            sparse_ops.group_adagrad_update(None, grad, weight, state.view(-1), lr=lr, eps=self.float_stable_eps,
+                                            rescale=self.rescale_grad, clip=clip)
+            return
+        g = self._grad(grad)
+        state.add_((g * g).mean(dim=1, keepdim=True))
+        weight.copy_((weight.float() - lr * g / (state + self.float_stable_eps).sqrt()).to(weight.dtype))
+
+    def update_row_sparse(self, index, weight, row_ids, grad_rows, state):
+        from ..ops import sparse as sparse_ops
+        rows, g = sparse_ops.coalesce(row_ids.to(weight.device), grad_rows.to(weight.device))
+        self._update_count(index)
+        lr = self._get_lr(index)
+        if weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous():
+            clip = self.clip_gradient if self.clip_gradient is not None else -1.0
+            sparse_ops.group_adagrad_update(rows, g, weight, state.view(-1), lr=lr, eps=self.float_stable_eps,
+                                            rescale=self.rescale_grad, clip=clip)
+            return
+        g = self._grad(g)
+        h = state[rows] + (g * g).mean(dim=1, keepdim=True)
+        state[rows] = h
+        weight[rows] = (weight[rows].float() - lr * g / (h + self.float_stable_eps).sqrt()).to(weight.dtype)
+
 
 @register
 class RMSProp(Optimizer):
@@ -337,6 +435,11 @@ class RMSProp(Optimizer):
             w = w.clamp(-self.clip_weights, self.clip_weights)
         weight.copy_(w.to(weight.dtype))
 
+    def native_config(self):
+        if self.centered:
+            return None          # three states: python updater
+        return self._cfg("rmsprop", beta1=self.gamma1, beta2=self.clip_weights or -1.0, eps=self.epsilon)
+
 
 @register
 class AdaDelta(Optimizer):
@@ -357,6 +460,9 @@ class AdaDelta(Optimizer):
         acc_d.mul_(self.rho).addcmul_(d, d, value=1 - self.rho)
         w = weight.float()
         weight.copy_((w - d - wd * w).to(weight.dtype))
+
+    def native_config(self):
+        return self._cfg("adadelta", beta1=self.rho, eps=self.epsilon)
 
 
 @register
@@ -379,6 +485,9 @@ class Ftrl(Optimizer):
         neww = (torch.sign(z) * self.lamda1 - z) / ((self.beta + n.sqrt()) / lr + wd) * (z.abs() > self.lamda1)
         weight.copy_(neww.to(weight.dtype))
 
+    def native_config(self):
+        return self._cfg("ftrl", beta1=self.lamda1, beta2=self.beta)
+
 
 @register
 class Adamax(Optimizer):
@@ -398,6 +507,9 @@ class Adamax(Optimizer):
         m.mul_(self.beta1).add_(g, alpha=1 - self.beta1)
         torch.maximum(u * self.beta2, g.abs(), out=u)
         weight.copy_((weight.float() - lr * m / (u + 1e-38)).to(weight.dtype))
+
+    def native_config(self):
+        return self._cfg("adamax", beta1=self.beta1, beta2=self.beta2)
 
 
 @register
@@ -507,6 +619,12 @@ class Updater:
         if index not in self.states:
             self.states[index] = self.optimizer.create_state_multi_precision(index, weight)
         self.optimizer.update_multi_precision(index, weight, grad, self.states[index])
+
+    def update_row_sparse(self, index, row_ids, grad_rows, weight):
+        """Row-sparse flavour of __call__ (the reference passes a RowSparseNDArray gradient to the same updater)."""
+        if index not in self.states:
+            self.states[index] = self.optimizer.create_state(index, weight)
+        self.optimizer.update_row_sparse(index, weight, row_ids, grad_rows, self.states[index])
 
     def get_states(self, dump_optimizer: bool = False) -> bytes:
         cpu = {k: _to_cpu(v) for k, v in self.states.items()}

@@ -73,15 +73,21 @@ class Bert(nn.Module):
         pooled = torch.tanh(self.pooler(x[:, 0]))
         h = x if mlm_positions is None else torch.gather(x, 1, mlm_positions[..., None].expand(-1, -1, x.shape[-1]))
         h = self.mlm_ln(F.gelu(self.mlm_dense(h)))
-        logits = linear(h, self.tok.weight, self.mlm_bias)[..., : self.vocab]     # decoder tied to the embedding
-        return logits, self.nsp(pooled)
+        logits = linear(h, self.tok.weight, self.mlm_bias)                        # decoder tied to the embedding
+        if getattr(self, "padded_logits", False):
+            # keep the TMA padding columns: bert_pretrain_loss masks them inside the fused loss kernel instead of
+            # paying a slice copy forward and a zero-pad copy backward on the [tokens, vocab] tensor
+            return logits, self.nsp(pooled), self.vocab
+        return logits[..., : self.vocab], self.nsp(pooled)
 
 
 def bert_pretrain_loss(out, target):
-    logits, nsp = out
+    from ..ops.nn import softmax_cross_entropy
+    logits, nsp = out[0], out[1]
+    vocab = out[2] if len(out) > 2 else None
     mlm_labels, nsp_labels = target
-    l1 = F.cross_entropy(logits.float().reshape(-1, logits.shape[-1]), mlm_labels.reshape(-1), ignore_index=-100)
-    return l1 + F.cross_entropy(nsp.float(), nsp_labels)
+    l1 = softmax_cross_entropy(logits, mlm_labels, ignore_index=-100, num_classes=vocab)
+    return l1 + softmax_cross_entropy(nsp, nsp_labels)
 
 
 def bert_large(**kw) -> Bert:

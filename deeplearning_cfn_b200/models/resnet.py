@@ -5,9 +5,11 @@ Parity target: MX/example/image-classification/symbols/resnet.py:29-177 (bottlen
 7x7/2 stem + BN + ReLU + 3x3/2 max-pool for ImageNet, 3x3 stem for CIFAR).  ResNet-50 has 157
 learnable tensors / 25.55 M parameters, which this module reproduces.
 
-B200 shape: channels_last activations, bf16 conv/FC weights with fp32 BatchNorm parameters, cuDNN for
-the convolutions (off the named hot paths), the classifier GEMM on the hand-written tcgen05 kernel
-(`ops.linear.Linear`) so that it can consume parameter-server-resident weights directly.
+B200 shape: channels_last activations, bf16 conv/FC weights with fp32 BatchNorm parameters.  The 1x1 convolutions
+(2/3 of the conv layers) are `ops.conv.Conv1x1`: in NHWC they are plain GEMMs and can run on the hand-written
+tcgen05 kernel (backend switch in ops/conv.py, cuDNN is the yardstick); the 3x3 / stem convolutions go through cuDNN;
+the classifier GEMM is always on the tcgen05 kernel (`ops.linear.Linear`) so that it can consume
+parameter-server-resident weights directly.
 """
 from __future__ import annotations
 
@@ -16,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops.batchnorm import BatchNormReLU2d
+from ..ops.conv import Conv1x1
 from ..ops.linear import Linear
 from ..ops.pool import MaxPool2d
 
@@ -37,12 +40,12 @@ class BottleneckV2(nn.Module):
         super().__init__()
         mid = cout // 4
         self.bn1 = _bn(cin)
-        self.conv1 = nn.Conv2d(cin, mid, 1, 1, 0, bias=False)
+        self.conv1 = Conv1x1(cin, mid)
         self.bn2 = _bn(mid)
         self.conv2 = nn.Conv2d(mid, mid, 3, stride, 1, bias=False)
         self.bn3 = _bn(mid)
-        self.conv3 = nn.Conv2d(mid, cout, 1, 1, 0, bias=False)
-        self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
+        self.conv3 = Conv1x1(mid, cout)
+        self.sc = None if dim_match else Conv1x1(cin, cout, stride)
 
     def forward(self, x):
         """`x` is either a tensor or the un-summed pair (branch, shortcut) of the previous unit; the pair's add is fused
@@ -64,7 +67,7 @@ class BasicV2(nn.Module):
         self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
         self.bn2 = _bn(cout)
         self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
-        self.sc = None if dim_match else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
+        self.sc = None if dim_match else Conv1x1(cin, cout, stride)
 
     def forward(self, x):
         if isinstance(x, tuple):

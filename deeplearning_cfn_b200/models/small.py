@@ -6,6 +6,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops.linear import Linear
+from ..ops.nn import LocalResponseNorm, local_response_norm
 
 
 class Cifar10CNN(nn.Module):
@@ -27,9 +28,9 @@ class Cifar10CNN(nn.Module):
     def forward(self, x):
         x = F.relu(self.conv1(x))
         x = F.max_pool2d(x, 3, 2, padding=1)
-        x = F.local_response_norm(x, 9, alpha=0.001 / 9.0 * 9, beta=0.75, k=1.0)   # depth_radius 4 -> size 9
+        x = local_response_norm(x, 9, alpha=0.001 / 9.0, beta=0.75, k=1.0, tf_style=True)   # depth_radius 4 -> size 9
         x = F.relu(self.conv2(x))
-        x = F.local_response_norm(x, 9, alpha=0.001 / 9.0 * 9, beta=0.75, k=1.0)
+        x = local_response_norm(x, 9, alpha=0.001 / 9.0, beta=0.75, k=1.0, tf_style=True)
         x = F.max_pool2d(x, 3, 2, padding=1)
         x = torch.flatten(x, 1)
         x = F.relu(self.local3(x))
@@ -71,8 +72,8 @@ class AlexNet(nn.Module):
     def __init__(self, num_classes: int = 1000, image_size: int = 224):
         super().__init__()
         self.features = nn.Sequential(
-            nn.Conv2d(3, 96, 11, 4), nn.ReLU(inplace=True), nn.LocalResponseNorm(5, alpha=1e-4, beta=0.75, k=2), nn.MaxPool2d(3, 2),
-            nn.Conv2d(96, 256, 5, padding=2), nn.ReLU(inplace=True), nn.LocalResponseNorm(5, alpha=1e-4, beta=0.75, k=2), nn.MaxPool2d(3, 2),
+            nn.Conv2d(3, 96, 11, 4), nn.ReLU(inplace=True), LocalResponseNorm(5, alpha=1e-4, beta=0.75, k=2), nn.MaxPool2d(3, 2),
+            nn.Conv2d(96, 256, 5, padding=2), nn.ReLU(inplace=True), LocalResponseNorm(5, alpha=1e-4, beta=0.75, k=2), nn.MaxPool2d(3, 2),
             nn.Conv2d(256, 384, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(384, 384, 3, padding=1), nn.ReLU(inplace=True),
             nn.Conv2d(384, 256, 3, padding=1), nn.ReLU(inplace=True), nn.MaxPool2d(3, 2))
         with torch.no_grad():

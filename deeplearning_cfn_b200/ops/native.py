@@ -27,7 +27,10 @@ class NativeUnavailable(RuntimeError):
 
 
 DT_F32, DT_BF16 = 0, 1
-OPT_KINDS = {"sgd": 0, "sgd_mom": 1, "adam": 2, "test": 3, "none": 4}
+OPT_KINDS = {"sgd": 0, "sgd_mom": 1, "adam": 2, "test": 3, "none": 4, "nag": 5, "signum": 6, "signsgd": 7,
+             "adagrad": 8, "rmsprop": 9, "adadelta": 10, "ftrl": 11, "adamax": 12}
+OPT_USES_S1 = {"sgd_mom", "adam", "nag", "signum", "adagrad", "rmsprop", "adadelta", "ftrl", "adamax"}
+OPT_USES_S2 = {"adam", "adadelta", "ftrl", "adamax"}
 
 
 def dtype_code(dt: torch.dtype) -> int:

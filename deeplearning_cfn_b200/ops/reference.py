@@ -38,6 +38,40 @@ def fused_optimizer(kind, grad, master, s1, s2, wout, *, lr, wd=0.0, momentum=0.
         w.add_(g)
     elif kind == "none":
         w.copy_(g)
+    elif kind == "nag":
+        g = g + wd * w
+        s1.mul_(momentum).add_(g)
+        w.add_(g + momentum * s1, alpha=-lr)
+    elif kind == "signum":      # beta1 carries wd_lh
+        g = g + wd * w
+        s1.mul_(momentum).add_(g, alpha=-(1.0 - momentum))
+        w.mul_(1.0 - lr * beta1).add_(torch.sign(s1), alpha=lr)
+    elif kind == "signsgd":
+        g = g + wd * w
+        w.mul_(1.0 - lr * beta1).add_(torch.sign(g), alpha=-lr)
+    elif kind == "adagrad":
+        s1.addcmul_(g, g)
+        w.sub_(lr * (g / (s1 + eps).sqrt() + wd * w))
+    elif kind == "rmsprop":     # beta1 = gamma1, beta2 = clip_weights (<= 0: off)
+        g = g + wd * w
+        s1.mul_(beta1).addcmul_(g, g, value=1.0 - beta1)
+        w.sub_(lr * g / (s1 + eps).sqrt())
+        if beta2 > 0:
+            w.clamp_(-beta2, beta2)
+    elif kind == "adadelta":    # beta1 = rho
+        s1.mul_(beta1).addcmul_(g, g, value=1.0 - beta1)
+        d = (s2 + eps).sqrt() / (s1 + eps).sqrt() * g
+        s2.mul_(beta1).addcmul_(d, d, value=1.0 - beta1)
+        w.sub_(d + wd * w)
+    elif kind == "ftrl":        # s1 = z, s2 = n, beta1 = lamda1, beta2 = beta
+        s1.add_(g - ((s2 + g * g).sqrt() - s2.sqrt()) * w / lr)
+        s2.addcmul_(g, g)
+        w.copy_((torch.sign(s1) * beta1 - s1) / ((beta2 + s2.sqrt()) / lr + wd) * (s1.abs() > beta1))
+    elif kind == "adamax":      # lr pre-divided by (1 - beta1^t)
+        g = g + wd * w
+        s1.mul_(beta1).add_(g, alpha=1.0 - beta1)
+        torch.maximum(s2 * beta2, g.abs(), out=s2)
+        w.sub_(lr * s1 / (s2 + 1e-38))
     else:
         raise ValueError(kind)
     if wout is not None:

@@ -27,6 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops import native
+from ..ops.nn import softmax_cross_entropy
 from ..ops import reference as ref_ops
 from .flat import Bucket, FlatModel
 from .symm import SymmetricHeap
@@ -61,7 +62,7 @@ class DataParallelTrainer:
         self.opt_kind = optimizer
         self.hp = dict(lr=lr, wd=wd, momentum=momentum, beta1=beta1, beta2=beta2, eps=eps, clip=clip)
         self.comm_blocks = comm_blocks
-        self.loss_fn = loss_fn or (lambda out, y: F.cross_entropy(out.float(), y))
+        self.loss_fn = loss_fn or softmax_cross_entropy     # fused loss kernels on CUDA, torch on CPU
         self.step_count = 0
 
         fused = mode in ("allreduce", "ps_sync")
@@ -124,8 +125,8 @@ class DataParallelTrainer:
         return lo, hi
 
     def _init_state(self) -> None:
-        need1 = self.opt_kind in ("sgd_mom", "adam")
-        need2 = self.opt_kind == "adam"
+        need1 = self.opt_kind in native.OPT_USES_S1
+        need2 = self.opt_kind in native.OPT_USES_S2
         self.state: dict = {}
         if self.mode in ("ps_sync", "nccl_ps"):
             for b in self.flat.buckets:
@@ -168,6 +169,8 @@ class DataParallelTrainer:
         if self.opt_kind == "adam":  # bias correction folded into lr (optimizer.py:1080-1082)
             t = self.step_count + 1
             lr = lr * (1.0 - self.hp["beta2"] ** t) ** 0.5 / (1.0 - self.hp["beta1"] ** t)
+        elif self.opt_kind == "adamax":
+            lr = lr / (1.0 - self.hp["beta1"] ** (self.step_count + 1))
         return lr
 
     def _launch_bucket(self, b: Bucket) -> None:

@@ -19,7 +19,42 @@ def check(t, want, what):
         raise AssertionError(f"{what}: got {t.reshape(-1)[:4].tolist()} want {want}")
 
 
+def optimizer_parity():
+    """Every optimizer that has a native server implementation (csrc/rt/kv.cpp:ApplyUpdate, same numbering as
+    csrc/cuda/optimizer.cuh) against the python definition in kv/optimizer.py, 2 workers x 1+ servers."""
+    store = kv.create("dist_sync")
+    r, n = store.rank, store.num_workers
+    cases = [("sgd", dict(momentum=0.9, wd=0.01)), ("nag", dict(momentum=0.9, wd=0.01)),
+             ("signum", dict(momentum=0.9, wd_lh=0.01)), ("signum", dict(momentum=0.0)),
+             ("adam", dict(wd=0.01)), ("adagrad", dict(wd=0.01)), ("rmsprop", dict(wd=0.01, clip_weights=2.0)),
+             ("adadelta", dict(wd=0.001)), ("ftrl", dict(lamda1=0.01, wd=0.01)), ("adamax", dict(wd=0.01))]
+    torch.manual_seed(0)
+    for ci, (name, kw) in enumerate(cases):
+        key = 100 + ci
+        w0 = torch.randn(37)
+        store.init(key, w0)
+        o = kv.optimizer.create(name, learning_rate=0.05, rescale_grad=0.5, clip_gradient=1.5, **kw)
+        assert o.native_config() is not None, name
+        store.set_optimizer(o)
+        local = kv.optimizer.get_updater(kv.optimizer.create(name, learning_rate=0.05, rescale_grad=0.5,
+                                                             clip_gradient=1.5, **kw))
+        wl = w0.clone()
+        for i in range(4):
+            gs = [torch.randn(37) * (w + 1) for w in range(n)]      # same stream on every worker
+            store.push(key, gs[r])
+            out = torch.zeros(37)
+            store.pull(key, out=out)
+            local(key, sum(gs), wl)
+            if not torch.allclose(out, wl, rtol=2e-4, atol=2e-5):
+                raise AssertionError(f"{name} round {i}: server {out[:4].tolist()} python {wl[:4].tolist()}")
+    store._barrier()
+    print(f"worker {r} OPT_OK", flush=True)
+    store.close()
+
+
 def main():
+    if mode == "opt_parity":
+        return optimizer_parity()
     store = kv.create(mode)
     r, n = store.rank, store.num_workers
     assert store.type == mode and 0 <= r < n

@@ -168,6 +168,40 @@ def test_dist_async():
     assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_native_server_optimizers_match_python_definitions():
+    r = _launch(2, 2, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "opt_parity"])
+    assert r.returncode == 0 and r.stdout.count("OPT_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name,kw", [("nag", dict(momentum=0.9, wd=0.01)), ("signum", dict(momentum=0.9, wd_lh=0.01)),
+                                     ("signum", dict(momentum=0.0)), ("adagrad", dict(wd=0.01)),
+                                     ("rmsprop", dict(wd=0.01, clip_weights=2.0)), ("adadelta", dict(wd=0.001)),
+                                     ("ftrl", dict(lamda1=0.01, wd=0.01)), ("adamax", dict(wd=0.01)),
+                                     ("sgd", dict(momentum=0.9, wd=0.01)), ("adam", dict(wd=0.01))])
+def test_flat_reference_optimizer_matches_python_definitions(name, kw):
+    """ops.reference.fused_optimizer is what the CUDA kernels are tested against; pin it to kv/optimizer.py."""
+    from deeplearning_cfn_b200.ops import reference as ref_ops
+    torch.manual_seed(3)
+    o = kv.optimizer.create(name, learning_rate=0.05, rescale_grad=0.5, clip_gradient=1.5, **kw)
+    cfg = dict(x.split("=") for x in o.native_config().split(";"))
+    kind = cfg.pop("kind")
+    hp = {k: float(v) for k, v in cfg.items()}
+    u = kv.optimizer.get_updater(o)
+    w_py = torch.randn(50)
+    master = w_py.clone()
+    s1, s2 = torch.zeros(50), torch.zeros(50)
+    for t in range(1, 5):
+        g = torch.randn(50) * 2
+        u(0, g, w_py)
+        lr = hp["lr"]
+        if kind == "adam":
+            lr = lr * (1 - hp["beta2"] ** t) ** 0.5 / (1 - hp["beta1"] ** t)
+        elif kind == "adamax":
+            lr = lr / (1 - hp["beta1"] ** t)
+        ref_ops.fused_optimizer(kind, g, master, s1, s2, None, **{**hp, "lr": lr})
+        assert torch.allclose(master, w_py, rtol=1e-5, atol=1e-6), (name, t)
+
+
 def test_dist_sync_python_updater_on_server():
     r = _launch(2, 1, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_sync"], env={"DLCFN_PS_PY_UPDATER": "1"})
     assert r.returncode == 0 and r.stdout.count("SYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
@@ -279,3 +313,27 @@ def test_planner_uniform_nvswitch_and_dgx1():
     rnd = [[max(rnd[i][j], rnd[j][i]) if i != j else 0 for j in range(6)] for i in range(6)]
     for r, t in enumerate(rt.plan_trees(rnd)):
         _check_tree(t, r, 6)
+
+
+# ----------------------------------------------------------------------------- row-sparse (lazy) updates
+@pytest.mark.parametrize("name,kw", [("sgd", dict(momentum=0.9)), ("adam", {}), ("adagrad", {}), ("ftrl", {}),
+                                     ("groupadagrad", {})])
+def test_row_sparse_update_touches_only_listed_rows_and_matches_dense_rule(name, kw):
+    torch.manual_seed(5)
+    o = kv.optimizer.create(name, learning_rate=0.1, **kw)
+    u = kv.optimizer.get_updater(o)
+    w = torch.randn(12, 6)
+    w0 = w.clone()
+    ids = torch.tensor([3, 7, 3, 11])                       # row 3 twice: gradients are summed first
+    g = torch.randn(4, 6)
+    u.update_row_sparse(0, ids, g, w)
+    untouched = [r for r in range(12) if r not in (3, 7, 11)]
+    assert torch.equal(w[untouched], w0[untouched])
+    # dense rule on the touched rows only
+    o2 = kv.optimizer.create(name, learning_rate=0.1, **kw)
+    sub = w0[[3, 7, 11]].clone()
+    gd = torch.stack([g[0] + g[2], g[1], g[3]])
+    st = o2.create_state(0, sub)
+    o2.update(0, sub, gd, st)
+    assert torch.allclose(w[[3, 7, 11]], sub, atol=1e-6)
+    assert not torch.equal(w[[3, 7, 11]], w0[[3, 7, 11]])

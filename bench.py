@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--num-layers", type=int, default=50)
     ap.add_argument("--bucket-mb", type=float, default=16.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn"],
+                    help="backend of the 1x1 convolutions (default: ops.conv default / DLCFN_CONV1X1)")
     return ap.parse_args()
 
 
@@ -88,6 +90,9 @@ def main():
     if world == 1:
         mode = "local"
 
+    from deeplearning_cfn_b200.ops import conv as conv_ops
+    if args.conv1x1:
+        conv_ops.set_conv1x1_backend(args.conv1x1)
     is_bert = args.model.startswith("bert")
     if args.batch is None:
         args.batch = 16 if is_bert else 256
@@ -95,6 +100,7 @@ def main():
         from deeplearning_cfn_b200.models import bert_pretrain_loss, get_model
         args.no_e2e = True
         model = to_b200_layout(get_model(args.model, max_seq=args.seq_len).to(device), torch.bfloat16).train()
+        model.padded_logits = True     # the fused loss kernel masks the TMA padding columns of the vocabulary
         trainer = DataParallelTrainer(model, mode=mode, optimizer="adam", lr=1e-4, wd=0.01, beta1=0.9, beta2=0.999,
                                       bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
                                       worker_ranks=workers, loss_fn=bert_pretrain_loss)
@@ -210,6 +216,7 @@ def main():
                           "global_batch": global_batch, "per_gpu_batch": args.batch, "image": args.image_size,
                           "seq_len": None, "parallelism": par, "optimizer": "sgd-momentum multi-precision (fp32 master)",
                           "bucket_mb": args.bucket_mb, "l2": "inputs+activations larger than L2 (no flush needed)",
+                          "conv1x1": conv_ops.conv1x1_backend(),
                           "baseline": "363.69 img/s per V100 (perf.md:219) x n_gpus"},
                "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                           "reasons": clocks.get("reasons", [])},

@@ -15,19 +15,29 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16), commits
 //                              to the smem-empty and tmem-full mbarriers; owns TMEM alloc/dealloc
-//   warps 2..5  epilogue       tcgen05.ld 32x32b -> registers -> bias/convert -> 16B global stores;
-//                              two TMEM accumulator stages so the epilogue of tile i overlaps the
-//                              mainloop of tile i+1
+//   warps 2..9  epilogue       tcgen05.ld 32x32b -> registers -> bias/convert -> 16B global stores;
+//                              two warps per TMEM lane quarter (each takes half of the tile's columns and
+//                              issues all of its tcgen05.ld before one wait), two TMEM accumulator stages so
+//                              the epilogue of tile i overlaps the mainloop of tile i+1
+//
+// Split-K: when the output has fewer tiles than SMs but a long reduction (wgrad of a convolution:
+// dW[Cout,Cin] = dY[M,Cout]^T X[M,Cin] with M ~ 10^5..10^6) the K loop is cut into `splits` slices, every
+// (tile, slice) pair is one work item of the persistent grid and writes an fp32 partial tile to a
+// stream-ordered workspace; ksplitk_reduce sums the slices in a fixed order (deterministic) and applies
+// bias / accumulate / relu / the output conversion.
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace dlcfn {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle-128B atom row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kMaxShards = DLCFN_MAX_RANKS;
 
 struct __align__(64) GemmParams {
@@ -42,6 +52,10 @@ struct __align__(64) GemmParams {
   int d_is_fp32;
   int accumulate;       // D += result
   int relu;
+  int splits;           // >1: split-K, partial tiles go to ws[split][M][N] (fp32)
+  int kb_per_split;     // k-blocks (of kBlockK) per split
+  float* ws;
+  int split_k_ok;       // host-side switch (DLCFN_GEMM_SPLITK=0 disables)
 };
 
 // ------------------------------------------------------------------ PTX -----
@@ -149,6 +163,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int num_items = num_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -159,7 +174,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,10 +193,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile = item % num_tiles, split = item / num_tiles;
         const int m_idx = (tile % num_m) * kBlockM;
         const int n_idx = (tile / num_m) * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int k_idx = kb * kBlockK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -222,11 +239,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item / num_tiles;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -237,7 +256,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
             // MN-major: advance 16 k-rows = 2048 B; LBO = stride between 64-wide MN atoms, SBO = 1024
             const uint64_t da = A_MN ? umma_desc(sa + k * 2048, 8192, 1024) : umma_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc(sb + k * 2048, 8192, 1024) : umma_desc(sb + k * 32, 16, 1024);
-            tc_mma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -247,66 +266,83 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp owns
+    constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp
+    const bool splitk = p.splits > 1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item % num_tiles, split = item / num_tiles;
       const int m_idx = (tile % num_m) * kBlockM;
       const int n_idx = (tile / num_m) * BLOCK_N;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m_idx + q * 32 + lane;
       const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        tc_wait_ld();
-        const int col0 = n_idx + c * 32;
+      // all of this warp's accumulator columns in flight at once, one wait
+      uint32_t r[kChunks][32];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c)
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + (half * kChunks + c) * 32, r[c]);
+      tc_wait_ld();
+      // the accumulator stage is free as soon as it sits in registers: let the next tile's MMAs start
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      const bool d_fp32 = splitk || p.d_is_fp32;
+      const bool accum = !splitk && p.accumulate;
+      const bool relu = !splitk && p.relu;
+      const float* bias = splitk ? nullptr : p.bias;
+      const long long ldd = splitk ? (long long)p.N : p.ldd;
+      void* dbase = splitk ? (void*)(p.ws + (size_t)split * p.M * p.N) : p.D;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col0 = n_idx + (half * kChunks + c) * 32;
         if (row_ok && col0 < p.N) {
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[c][j]);
+          if (bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+              if (col0 + j < p.N) f[j] += __ldg(bias + col0 + j);
           }
-          if (p.d_is_fp32) {
-            float* d = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+          if (d_fp32) {
+            float* d = reinterpret_cast<float*>(dbase) + (size_t)row * ldd + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (col0 + j + 3 < p.N) {
                 float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (p.accumulate) {
+                if (accum) {
                   float4 old = *reinterpret_cast<const float4*>(d + j);
                   o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                 }
-                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 *reinterpret_cast<float4*>(d + j) = o;
               } else {
                 for (int t = 0; t < 4; ++t)
                   if (col0 + j + t < p.N) {
-                    float o = f[j + t] + (p.accumulate ? d[j + t] : 0.f);
-                    d[j + t] = p.relu ? fmaxf(o, 0.f) : o;
+                    float o = f[j + t] + (accum ? d[j + t] : 0.f);
+                    d[j + t] = relu ? fmaxf(o, 0.f) : o;
                   }
               }
             }
           } else {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dbase) + (size_t)row * ldd + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (col0 + j + 7 < p.N) {
                 float o[8];
 #pragma unroll
                 for (int t = 0; t < 8; ++t) o[t] = f[j + t];
-                if (p.accumulate) {
+                if (accum) {
                   uint4 old = *reinterpret_cast<const uint4*>(d + j);
                   o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
                   o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
                 }
-                if (p.relu) {
+                if (relu) {
 #pragma unroll
                   for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
                 }
@@ -315,17 +351,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
               } else {
                 for (int t = 0; t < 8; ++t)
                   if (col0 + j + t < p.N) {
-                    float o = f[j + t] + (p.accumulate ? __bfloat162float(d[j + t]) : 0.f);
-                    d[j + t] = __float2bfloat16(p.relu ? fmaxf(o, 0.f) : o);
+                    float o = f[j + t] + (accum ? __bfloat162float(d[j + t]) : 0.f);
+                    d[j + t] = __float2bfloat16(relu ? fmaxf(o, 0.f) : o);
                   }
               }
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));  // 128 arrivals release the accumulator stage
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -334,6 +367,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols));
+  }
+}
+
+// sum the split-K partials in slice order, then bias / accumulate / relu / convert
+__global__ void __launch_bounds__(256) ksplitk_reduce(const float* __restrict__ ws, int splits, int M, int N, void* D,
+                                                       long long ldd, int d_is_fp32, const float* __restrict__ bias,
+                                                       int accumulate, int relu) {
+  const long long MN = (long long)M * N;
+  const long long nvec = MN / 4;   // N % 4 == 0 is guaranteed by the host
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(ws)[v];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = reinterpret_cast<const float4*>(ws + (size_t)s * MN)[v];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const long long e = v * 4;
+    const int row = (int)(e / N), col = (int)(e - (long long)row * N);
+    if (bias != nullptr) { a.x += bias[col]; a.y += bias[col + 1]; a.z += bias[col + 2]; a.w += bias[col + 3]; }
+    if (d_is_fp32) {
+      float* d = reinterpret_cast<float*>(D) + (size_t)row * ldd + col;
+      if (accumulate) { a.x += d[0]; a.y += d[1]; a.z += d[2]; a.w += d[3]; }
+      if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+      *reinterpret_cast<float4*>(d) = a;
+    } else {
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(D) + (size_t)row * ldd + col;
+      if (accumulate) {
+        const uint2 old = *reinterpret_cast<const uint2*>(d);
+        a.x += bf16_lo(old.x); a.y += bf16_hi(old.x); a.z += bf16_lo(old.y); a.w += bf16_hi(old.y);
+      }
+      if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+      *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+    }
   }
 }
 
@@ -373,7 +438,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-static int launch(const GemmParams& p, int num_sms, cudaStream_t stream) {
+static int launch(GemmParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN>;
   auto kern = kgemm<BLOCK_N, A_MN, B_MN>;
   static bool configured = false;
@@ -387,12 +452,42 @@ static int launch(const GemmParams& p, int num_sms, cudaStream_t stream) {
   }
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  int grid = num_m * num_n;
+  const int tiles = num_m * num_n;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  // split-K when the tiles alone cannot fill the machine and the reduction is long enough to cut
+  p.splits = 1;
+  p.kb_per_split = num_kb;
+  p.ws = nullptr;
+  if (p.split_k_ok && tiles * 2 <= num_sms && num_kb >= 8 && (p.N % 4) == 0) {
+    int splits = num_sms / tiles;
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits >= 2) {
+      p.kb_per_split = (num_kb + splits - 1) / splits;
+      p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // every slice owns >= 1 k-block
+    }
+  }
+  if (p.splits > 1) {
+    void* ws = nullptr;
+    DLCFN_CHECK(cudaMallocAsync(&ws, (size_t)p.splits * p.M * p.N * sizeof(float), stream));
+    p.ws = (float*)ws;
+  }
+  int grid = tiles * p.splits;
   if (grid > num_sms) grid = num_sms;
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess)
     fprintf(stderr, "[dlcfn] kgemm launch failed: %s (grid %d, smem %d)\n", cudaGetErrorString(le), grid, Cfg::kSmemBytes);
+  if (p.splits > 1) {
+    if (le == cudaSuccess) {
+      const long long nvec = (long long)p.M * p.N / 4;
+      long long rb = (nvec + 255) / 256;
+      if (rb > 148 * 8) rb = 148 * 8;
+      ksplitk_reduce<<<(int)rb, 256, 0, stream>>>(p.ws, p.splits, p.M, p.N, p.D, p.ldd, p.d_is_fp32, p.bias, p.accumulate,
+                                                  p.relu);
+      le = cudaGetLastError();
+    }
+    cudaFreeAsync(p.ws, stream);
+  }
   return (int)le;
 }
 
@@ -436,6 +531,8 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   p.d_is_fp32 = d_dtype == 0;
   p.accumulate = accumulate;
   p.relu = relu;
+  static const bool splitk_env = [] { const char* e = getenv("DLCFN_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
+  p.split_k_ok = splitk_env ? 1 : 0;
   int rc;
   if (!a_mn) rc = make_map(&p.tmA, A, M, K, lda, kBlockK, kBlockM);
   else rc = make_map(&p.tmA, A, K, M, lda, 64, kBlockK);

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "ps.h"
+#include <memory>
 
 namespace dlcfn {
 
@@ -237,8 +238,42 @@ void KVWorker::SendCommand(int head, const std::string& body) {
 KVServer::KVServer(Node* node) : node_(node) {}
 
 void KVServer::Run() {
-  std::unique_lock<std::mutex> lk(mu_);
-  cv_.wait(lk, [&] { return stop_; });
+  main_thread_ = std::this_thread::get_id();
+  running_ = true;
+  std::unique_lock<std::mutex> lk(exec_mu_);
+  for (;;) {
+    exec_cv_.wait(lk, [&] { return !exec_q_.empty() || exec_stop_.load(); });   // never takes mu_ (lock order)
+    while (!exec_q_.empty()) {
+      ExecTask* t = exec_q_.front();
+      exec_q_.pop_front();
+      lk.unlock();
+      t->fn();
+      lk.lock();
+      if (t->detached) delete t;
+      else { t->done = true; exec_done_cv_.notify_all(); }
+    }
+    if (exec_stop_.load() && exec_q_.empty()) break;
+  }
+  running_ = false;
+}
+
+void KVServer::ExecOnMain(const std::function<void()>& fn) {
+  if (!running_ || std::this_thread::get_id() == main_thread_) { fn(); return; }
+  ExecTask t;
+  t.fn = fn;
+  std::unique_lock<std::mutex> lk(exec_mu_);
+  exec_q_.push_back(&t);
+  exec_cv_.notify_all();
+  exec_done_cv_.wait(lk, [&] { return t.done; });
+}
+
+void KVServer::PostToMain(std::function<void()> fn) {
+  ExecTask* t = new ExecTask;
+  t->fn = std::move(fn);
+  t->detached = true;
+  std::lock_guard<std::mutex> lk(exec_mu_);
+  exec_q_.push_back(t);
+  exec_cv_.notify_all();
 }
 
 void KVServer::Respond(const Message& req, const std::string* payload) {
@@ -290,7 +325,7 @@ void KVServer::HandleCommand(Message&& m) {
   {
     std::lock_guard<std::mutex> lk(mu_);
     switch (m.head) {
-      case kStopServer: stop_ = true; break;
+      case kStopServer: stop_ = true; exec_stop_ = true; break;
       case kSyncMode: sync_mode_ = true; break;
       case kSetMultiPrecision: multi_precision_ = true; break;
       case kSetGradientCompression: {
@@ -306,15 +341,30 @@ void KVServer::HandleCommand(Message&& m) {
       default: break;
     }
   }
-  if (py_controller_) py_controller_(m.head, m.body.data(), m.body.size(), py_ctl_user_);
+  if (py_controller_) {
+    // python part + the response that releases the worker run on the Run() thread, in arrival order
+    auto msg = std::make_shared<Message>(std::move(m));
+    PostToMain([this, msg] {
+      py_controller_(msg->head, msg->body.data(), msg->body.size(), py_ctl_user_);
+      Respond(*msg);
+    });
+    return;
+  }
   Respond(m);
-  if (m.head == kStopServer) cv_.notify_all();
+  if (m.head == kStopServer) {
+    std::lock_guard<std::mutex> lk(exec_mu_);
+    exec_cv_.notify_all();
+  }
 }
 
 void KVServer::ApplyUpdate(uint64_t key, Entry& e, size_t begin, size_t n) {
   float* w = e.store.data() + begin;
   const float* g = e.merged.data() + begin;
-  if (py_updater_) { py_updater_((int)(key - node_->ServerKeyRange(node_->my_rank()).first), g, w, n, py_user_); return; }
+  if (py_updater_) {
+    const int rel = (int)(key - node_->ServerKeyRange(node_->my_rank()).first);
+    ExecOnMain([&] { py_updater_(rel, g, w, n, py_user_); });
+    return;
+  }
   OptimizerConfig& o = opt_;
   if (o.kind < 0) { memcpy(w, g, n * 4); return; }   // no updater: store the aggregate (kvstore_dist_server.h:358-361)
   const bool use1 = o.kind == 1 || o.kind == 2 || o.kind == 5 || o.kind == 6 || (o.kind >= 8 && o.kind <= 12);

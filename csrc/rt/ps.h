@@ -22,6 +22,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -200,6 +201,18 @@ class KVServer {
   void HandleData(Message&& m);
   void HandleCommand(Message&& m);
   void ApplyUpdate(uint64_t key, Entry& e, size_t begin, size_t n);
+  // Executor: python callbacks (pickled-optimizer controller, python updater) run on the thread that called
+  // Run() - the interpreter's main thread - never on the transport's receiver thread (the reference's
+  // single-threaded Executor, kvstore_dist_server.h:95-153).  Besides keeping python single-threaded this is what
+  // lets a callback import modules while the server loop itself sits inside `import <package>.kv`.
+  struct ExecTask { std::function<void()> fn; bool done = false; bool detached = false; };
+  void ExecOnMain(const std::function<void()>& fn);      // blocks until run (inline when no loop is active)
+  void PostToMain(std::function<void()> fn);             // fire-and-forget, order preserved
+  std::mutex exec_mu_;
+  std::condition_variable exec_cv_, exec_done_cv_;
+  std::deque<ExecTask*> exec_q_;
+  std::atomic<bool> running_{false}, exec_stop_{false};
+  std::thread::id main_thread_;
   void Respond(const Message& req, const std::string* payload = nullptr);
   Node* node_;
   std::mutex mu_;

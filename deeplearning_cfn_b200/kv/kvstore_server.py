@@ -33,7 +33,8 @@ class KVStoreServer:
             raw = ctypes.string_at(body, length)
             try:
                 optimizer = pickle.loads(raw)
-            except Exception:
+            except Exception as e:      # a server that cannot build its updater must say so: workers would hang
+                print(f"[dlcfn server] cannot unpickle the optimizer sent by the workers: {e!r}", file=sys.stderr, flush=True)
                 return
             if isinstance(optimizer, opt.Optimizer):
                 self.updater = opt.get_updater(optimizer)

@@ -51,6 +51,28 @@ def test_gemm_bias_fp32_accumulate_relu():
     _check(r, (a.float() @ b.float().t()).clamp_min(0), K)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True), (False, True)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 8192), (128, 256, 4096), (72, 520, 16384 + 40), (1024, 1024, 8192)])
+def test_gemm_split_k(M, N, K, a_mn, b_mn):
+    """Few output tiles + long reduction -> the split-K path (fp32 partial tiles + ordered reduce), incl. the
+    conv-wgrad shape dW[64,64] = dY^T X with a very long K."""
+    a = _mk(M, K, 11) * 0.2
+    b = _mk(N, K, 12) * 0.2
+    bias = torch.randn(N, device="cuda")
+    want = a.float() @ b.float().t()
+    A = a.t().contiguous() if a_mn else a
+    B = b.t().contiguous() if b_mn else b
+    out = native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn)
+    _check(out, want, K)
+    out32 = native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=True, out_dtype=torch.float32)
+    _check(out32, (want + bias).clamp_min(0), K)
+    acc = torch.full((M, N), 2.0, device="cuda")
+    native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn, out=acc, accumulate=True)
+    _check(acc, want + 2.0, K)
+    again = native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn)
+    assert torch.equal(out, again), "split-K reduce must be deterministic"
+
+
 def test_linear_autograd_matches_torch():
     torch.manual_seed(0)
     lin = Linear(2048, 1000).cuda().bfloat16()

@@ -122,3 +122,32 @@ def test_module_fit_and_recordio(tmp_path):
     mod.save_checkpoint(str(tmp_path / "m"), 120, save_optimizer_states=True)
     m2 = Module.load(str(tmp_path / "m"), 120, torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)))
     assert abs(m2.score(data) - mod.score(data)) < 1e-6
+
+
+def test_sync_replicas_with_backup_worker():
+    """TF SyncReplicasOptimizer semantics on the native PS: aggregate 2 of 3 replicas, drop stale gradients."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root, MXNET_KVSTORE_BIGARRAY_BOUND="40")
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "3", "-s", "2", "--launcher", "local",
+           sys.executable, os.path.join(root, "tests/mp/sync_replicas_worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and r.stdout.count("SYNCREP_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_sync_replicas_accumulator_drops_stale_and_averages():
+    from deeplearning_cfn_b200.kv import optimizer as opt
+    from deeplearning_cfn_b200.parallel.sync_replicas import SyncReplicasOptimizer
+    o = SyncReplicasOptimizer(inner=opt.create("sgd", learning_rate=0.5), replicas_to_aggregate=2, total_num_replicas=3)
+    u = opt.get_updater(o)
+    w = torch.tensor([1.0, 1.0, 0.0])                       # [weights..., global_step]
+    u(0, torch.tensor([2.0, 4.0, 0.0]), w)                  # fresh, 1 of 2
+    assert w.tolist() == [1.0, 1.0, 0.0]
+    u(0, torch.tensor([4.0, 0.0, 0.0]), w)                  # fresh, 2 of 2 -> mean (3, 2) applied, step 1
+    assert torch.allclose(w, torch.tensor([1.0 - 0.5 * 3.0, 1.0 - 0.5 * 2.0, 1.0]))
+    u(0, torch.tensor([100.0, 100.0, 0.0]), w)              # stale (local step 0 < global 1): dropped
+    assert torch.allclose(w, torch.tensor([-0.5, 0.0, 1.0])) and o.dropped == 1
+    u(0, torch.tensor([1.0, 1.0, 1.0]), w)
+    u(0, torch.tensor([1.0, 1.0, 1.0]), w)
+    assert torch.allclose(w, torch.tensor([-1.0, -0.5, 2.0])) and o.applied == 2

@@ -15,7 +15,9 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16), commits
 //                              to the smem-empty and tmem-full mbarriers; owns TMEM alloc/dealloc
-//   warps 2..9  epilogue       tcgen05.ld 32x32b -> registers -> bias/convert -> 16B global stores;
+//   warps 2..9  epilogue       tcgen05.ld 32x32b -> registers -> bias/relu/convert -> 128B-swizzled smem
+//                              staging tile -> TMA store (cp.async.bulk.tensor, full 128-byte lines, M/N tails
+//                              clipped by the tensor map); fp32 / accumulate / split-K outputs use direct 16B stores;
 //                              two warps per TMEM lane quarter (each takes half of the tile's columns and
 //                              issues all of its tcgen05.ld before one wait), two TMEM accumulator stages so
 //                              the epilogue of tile i overlaps the mainloop of tile i+1
@@ -43,6 +45,8 @@ constexpr int kMaxShards = DLCFN_MAX_RANKS;
 struct __align__(64) GemmParams {
   CUtensorMap tmA;
   CUtensorMap tmB[kMaxShards];
+  CUtensorMap tmD;      // bf16 output, box {64 cols, 32 rows}, 128B swizzle (valid when tma_store != 0)
+  int tma_store;
   int M, N, K;
   int n_shards;         // 1: B is local.  >1: B rows sharded over n_shards peers
   int rows_per_shard;   // B rows (or, for MN-major B: contraction rows... see host) per shard
@@ -90,6 +94,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -138,7 +150,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BLOCK_N;           // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 4096;          // one 32-row x 128-byte store tile per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -149,12 +162,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   // swizzle-128B atoms need 1024 B alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t stg_base = smem_base + kStages * Cfg::kStageBytes;   // 1024-aligned (stage sizes are multiples of 16 KiB)
+  const uint32_t bar_base = stg_base + Cfg::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 4));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + Cfg::kStagingBytes +
+                                                    8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -168,6 +183,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     for (int s = 0; s < p.n_shards; ++s) tma_prefetch_desc(&p.tmB[s]);
+    if (p.tma_store) tma_prefetch_desc(&p.tmD);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -297,6 +313,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       const float* bias = splitk ? nullptr : p.bias;
       const long long ldd = splitk ? (long long)p.N : p.ldd;
       void* dbase = splitk ? (void*)(p.ws + (size_t)split * p.M * p.N) : p.D;
+      if (p.tma_store && !splitk) {
+        // bf16 output through shared memory: lane = row writes its 64 columns (128 B) as 8 16-byte chunks at the
+        // 128B-swizzled position (chunk ^ (row & 7)) - conflict-free - and one lane hands the tile to TMA.
+        const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
+        uint8_t* stg_gen = smem_gen + (stg - smem_base);
+#pragma unroll
+        for (int bx = 0; bx < kChunks / 2; ++bx) {
+          const int colb = n_idx + (half * kChunks + 2 * bx) * 32;   // first column of this 64-wide box
+          if (colb < p.N) {
+            if (lane == 0) tma_store_wait_read();                    // previous store out of this buffer has been read
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float o[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(r[2 * bx + (j >> 2)][(j & 3) * 8 + t]);
+              if (bias != nullptr) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                  if (colb + j * 8 + t < p.N) o[t] += __ldg(bias + colb + j * 8 + t);
+              }
+              if (relu) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
+              }
+              *reinterpret_cast<uint4*>(stg_gen + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmD, stg, colb, m_idx + q * 32);       // rows >= M / cols >= N are clipped by the map
+              tma_store_commit();
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int col0 = n_idx + (half * kChunks + c) * 32;
@@ -360,6 +414,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
         }
       }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read();   // staging smem must outlive the last bulk store's reads
   }
 
   tc_fence_before();
@@ -516,11 +571,16 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (n_shards < 1 || n_shards > kMaxShards) return (int)cudaErrorInvalidValue;
   if ((lda & 7) || (ldb & 7) || (((uintptr_t)A) & 15)) return (int)cudaErrorInvalidValue;
-  if (block_n != 128 && block_n != 256) block_n = (N >= 2048 && M >= 1024) ? 256 : 128;
   if (num_sms <= 0) {
     int dev = 0;
     DLCFN_CHECK(cudaGetDevice(&dev));
     DLCFN_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (block_n != 128 && block_n != 256) {
+    // 128x256 tiles feed the tensor pipe better (1.35 vs 1.0 PFLOP/s at 8192^3) but halve the tile count: take them
+    // when the wide tiling still gives every SM at least two tiles and N is a whole number of wide tiles
+    const long long wide_tiles = (long long)((M + kBlockM - 1) / kBlockM) * ((N + 255) / 256);
+    block_n = (N >= 256 && N % 256 == 0 && wide_tiles >= 2LL * num_sms) ? 256 : 128;
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -546,6 +606,13 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
       rc = make_map(&p.tmB[s], b_shards[s], rows, N, ldb, 64, kBlockK);
     }
     if (rc) return rc;
+  }
+  // bf16, non-accumulating output with a 16-byte aligned base / row stride goes out through TMA
+  static const bool tma_store_env = [] { const char* e = getenv("DLCFN_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  if (tma_store_env && d_dtype == 1 && !accumulate && N >= 64 && (ldd & 7) == 0 && (((uintptr_t)D) & 15) == 0) {
+    rc = make_map(&p.tmD, D, M, N, ldd, 64, 32);
+    if (rc) return rc;
+    p.tma_store = 1;
   }
   if (n_shards > 1) {
     // a tile must not straddle two shards

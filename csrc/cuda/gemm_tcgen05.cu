@@ -474,9 +474,40 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, cols] (cols contiguous, row stride ld elements), box {box_cols, box_rows}
+// 2-D bf16 tensor [rows, cols] (cols contiguous, row stride ld elements), box {box_cols, box_rows}.
+// A descriptor depends only on (pointer, shape, stride, box), and a training step presents the same few hundred
+// combinations every iteration (the caching allocator hands back the same blocks), so encoded maps are kept in a
+// small per-thread direct-mapped cache instead of calling into the driver three times per GEMM.
+struct MapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_cols, box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows;
+  }
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int kMapCacheSlots = 1024;
+
 static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                     uint32_t box_rows) {
+  static thread_local MapSlot* cache = nullptr;
+  if (!cache) {
+    cache = static_cast<MapSlot*>(aligned_alloc(alignof(MapSlot) < 64 ? 64 : alignof(MapSlot), kMapCacheSlots * sizeof(MapSlot)));
+    if (cache) memset(cache, 0, kMapCacheSlots * sizeof(MapSlot));
+  }
+  const MapKey key{ptr, rows, cols, ld, box_cols, box_rows};
+  uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
+  h ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols * 0x165667B19E3779F9ull) ^ (ld << 17) ^ ((uint64_t)box_cols << 40) ^ box_rows;
+  MapSlot* slot = cache ? &cache[(h >> 20) % kMapCacheSlots] : nullptr;
+  if (slot && slot->valid && slot->key == key) {
+    memcpy(m, &slot->map, sizeof(CUtensorMap));
+    return 0;
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) return (int)cudaErrorNotSupported;
   cuuint64_t gdim[2] = {cols, rows};
@@ -486,10 +517,17 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
+  if (r != CUDA_SUCCESS) {
     fprintf(stderr, "[dlcfn] cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%llu cols=%llu ld=%llu box=%ux%u\n", (int)r, ptr,
             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
-  return r == CUDA_SUCCESS ? 0 : 10000 + (int)r;
+    return 10000 + (int)r;
+  }
+  if (slot) {
+    slot->key = key;
+    memcpy(&slot->map, m, sizeof(CUtensorMap));
+    slot->valid = true;
+  }
+  return 0;
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>

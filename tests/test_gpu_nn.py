@@ -213,3 +213,37 @@ def test_optimizer_update_row_sparse_cuda_matches_cpu():
             u.update_row_sparse(0, ids, g, w)
             uc.update_row_sparse(0, ids.cpu(), g.cpu(), wc)
         torch.testing.assert_close(w.cpu(), wc, rtol=1e-4, atol=1e-5)
+
+
+def test_device_pool_and_pinned_host_pool():
+    from deeplearning_cfn_b200.utils import storage
+    pool = storage.DevicePool()
+    pool.set_strategy("Naive")
+    pool.release_all()
+    s0 = pool.stats()
+    p = pool.alloc(10_000)
+    t = torch.empty(0, device=dev())        # make sure a context exists
+    assert p % 256 == 0
+    pool.free(p)
+    q = pool.alloc(12_000)                   # same 12 KiB page class
+    assert q == p
+    s1 = pool.stats()
+    assert s1["reuses"] == s0["reuses"] + 1 and s1["fresh_allocations"] == s0["fresh_allocations"] + 1
+    pool.free(q)
+    with pytest.raises(RuntimeError):
+        pool.free(q)
+    pool.release_all()
+    assert pool.stats()["bytes_pooled"] == 0
+    # pinned host block: async H2D out of the pool, block recycled with its registration
+    h = storage.pinned_empty((1 << 20,), torch.float32)
+    h.copy_(torch.arange(1 << 20, dtype=torch.float32))
+    d = torch.empty(1 << 20, device=dev())
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    assert float(d[-1]) == float((1 << 20) - 1)
+    addr = h.data_ptr()
+    storage.release(h)
+    h2 = storage.pinned_empty((1 << 20,), torch.float32)
+    assert h2.data_ptr() == addr
+    storage.release(h2)
+    assert storage.release_all() >= 1

@@ -151,3 +151,50 @@ def test_sync_replicas_accumulator_drops_stale_and_averages():
     u(0, torch.tensor([1.0, 1.0, 1.0]), w)
     u(0, torch.tensor([1.0, 1.0, 1.0]), w)
     assert torch.allclose(w, torch.tensor([-1.0, -0.5, 2.0])) and o.applied == 2
+
+
+def test_host_storage_pool_recycles_blocks_by_size_class():
+    from deeplearning_cfn_b200.utils import storage
+    storage.set_strategy("Naive")
+    storage.release_all()
+    s0 = storage.stats()
+    a = storage.host_empty((1000,), torch.float32)            # 4000 B -> one 4 KiB page
+    a.fill_(3.0)
+    addr = a.data_ptr()
+    assert addr % 4096 == 0 and storage.size_class(4000) == 4096
+    storage.release(a)
+    b = storage.host_empty((1024,), torch.float32)            # same size class: the block comes back
+    assert b.data_ptr() == addr
+    s1 = storage.stats()
+    assert s1["reuses"] == s0["reuses"] + 1 and s1["fresh_allocations"] == s0["fresh_allocations"] + 1
+    storage.release(b)
+    with pytest.raises(ValueError):
+        storage.release(b)
+    storage.set_strategy("Round", cutoff_log2=12)
+    assert storage.size_class(5000) == 8192 and storage.size_class(70000) == 131072
+    storage.set_strategy("Naive")
+    assert storage.size_class(5000) == 8192 and storage.size_class(70000) == 73728
+    assert storage.release_all() >= 1
+
+
+def test_shared_memory_tensor_between_processes():
+    import subprocess
+    import sys
+    from deeplearning_cfn_b200.utils import storage
+    name = f"dlcfn_test_{os.getpid()}"
+    seg = storage.SharedTensor.create(name, (4, 5), torch.float32)
+    try:
+        seg.tensor.copy_(torch.arange(20, dtype=torch.float32).view(4, 5))
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        code = ("import torch,sys; sys.path.insert(0, %r); from deeplearning_cfn_b200.utils import storage; "
+                "s = storage.SharedTensor.attach(%r, (4, 5), torch.float32); assert float(s.tensor.sum()) == 190.0; "
+                "s.tensor.mul_(2); s.close(); print('CHILD_OK')") % (root, name)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+        assert "CHILD_OK" in r.stdout, r.stdout + r.stderr
+        assert float(seg.tensor.sum()) == 380.0              # the child's write is visible: same pages
+        with pytest.raises(OSError):
+            storage.SharedTensor.create(name, (4, 5), torch.float32)     # name is taken while the owner lives
+    finally:
+        seg.close()
+    with pytest.raises(OSError):
+        storage.SharedTensor.attach(name, (4, 5), torch.float32)         # owner closed -> unlinked

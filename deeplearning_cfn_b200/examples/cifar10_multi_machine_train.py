@@ -7,6 +7,13 @@ variables placed on the PS tasks, the chief (task 0) checkpoints every 60 s and 
 (:97-107); `_LoggerHook` prints loss and examples/sec every 10 steps (:38-60).  Started on every node by
 the scripts that `generate-trainer` writes.
 
+Training recipe of the tutorial model (TFM/tutorials/image/cifar10/cifar10.py:325-378): SGD with an exponentially
+decayed learning rate (0.1, x0.1 every 350 epochs, staircase) evaluated ON the parameter servers, and an
+exponential moving average (0.9999) of the trained variables kept by the chief and written into the checkpoint.
+`--sync_replicas` switches to the synchronous PS recipe of the reference's other TF trainers
+(inception_distributed_train.py:197, slim train_image_classifier.py:526 - `SyncReplicasOptimizer` with
+`--replicas_to_aggregate`, backup workers allowed): see parallel/sync_replicas.py.
+
 Mapping: ps tasks become dlcfn parameter-server nodes (csrc/rt), ps task 0 also hosts the scheduler at
 port+1 of its address, workers use `kv.create('dist_async')` - every push is applied on arrival, no barrier.
 """
@@ -36,6 +43,11 @@ def parse(argv=None):
     p.add_argument("--log_frequency", type=int, default=10)
     p.add_argument("--save_checkpoint_secs", type=float, default=60.0)
     p.add_argument("--learning_rate", type=float, default=0.1)
+    p.add_argument("--learning_rate_decay_factor", type=float, default=0.1)
+    p.add_argument("--num_epochs_per_decay", type=float, default=350.0)
+    p.add_argument("--moving_average_decay", type=float, default=0.9999)
+    p.add_argument("--sync_replicas", action="store_true", help="synchronous PS with token queue (SyncReplicasOptimizer)")
+    p.add_argument("--replicas_to_aggregate", type=int, default=None, help="default: number of workers")
     return p.parse_args(argv)
 
 
@@ -92,12 +104,23 @@ def main(argv=None) -> int:
         step0 = sd["global_step"]
         print(f"restored {ckpt} at step {step0}", flush=True)
     params = [p for p in net.parameters()]
-    for i, p in enumerate(params):
-        store.init(i, p.data)
-    store.set_optimizer(kv.optimizer.create("sgd", learning_rate=a.learning_rate, rescale_grad=1.0 / a.batch_size))
-    for i, p in enumerate(params):
-        store.pull(i, out=p.data)
     train = load_dataset("cifar10", a.data_dir, True, 24, 4096)
+    # lr = 0.1 * 0.1^floor(step / decay_steps), decay_steps = batches_per_epoch * 350 (cifar10.py:338-346); the schedule
+    # counts updates on the servers, where the optimizer runs
+    decay_steps = max(1, int(len(train) / a.batch_size * a.num_epochs_per_decay))
+    sched_lr = kv.optimizer.FactorScheduler(step=decay_steps, factor=a.learning_rate_decay_factor)
+    sgd = kv.optimizer.create("sgd", learning_rate=a.learning_rate, rescale_grad=1.0 / a.batch_size, lr_scheduler=sched_lr)
+    sync = None
+    if a.sync_replicas:
+        from deeplearning_cfn_b200.parallel.sync_replicas import SyncReplicasTrainer
+        sync = SyncReplicasTrainer(store, params, sgd, None, replicas_to_aggregate=a.replicas_to_aggregate or len(workers))
+    else:
+        for i, p in enumerate(params):
+            store.init(i, p.data)
+        store.set_optimizer(sgd)
+        for i, p in enumerate(params):
+            store.pull(i, out=p.data)
+    ema = [p.detach().clone() for p in params] if is_chief else None      # shadow variables (cifar10.py:368-372)
     if train.x.shape[-1] != 24:
         train.x = train.x[..., 4:28, 4:28].contiguous()       # the tutorial trains on 24x24 crops
     sampler = SplitSampler(len(train), len(workers), a.task_index)
@@ -107,11 +130,19 @@ def main(argv=None) -> int:
             net.zero_grad(set_to_none=True)
             loss = F.cross_entropy(net(x), y, reduction="sum")
             loss.backward()
-            for i, p in enumerate(params):
-                store.push(i, p.grad, priority=-i)              # applied on the servers as they arrive (async)
-            for i, p in enumerate(params):
-                store.pull(i, out=p.data, priority=-i)
+            if sync is not None:
+                sync.step()                                     # push + wait for the token of the next global step
+            else:
+                for i, p in enumerate(params):
+                    store.push(i, p.grad, priority=-i)          # applied on the servers as they arrive (async)
+                for i, p in enumerate(params):
+                    store.pull(i, out=p.data, priority=-i)
             step += 1
+            if ema is not None:
+                d = min(a.moving_average_decay, (1.0 + step) / (10.0 + step))   # tf.train.ExponentialMovingAverage(num_updates)
+                with torch.no_grad():
+                    for e, p in zip(ema, params):
+                        e.mul_(d).add_(p.detach(), alpha=1.0 - d)
             if step % a.log_frequency == 0:
                 dt = time.time() - t0
                 t0 = time.time()
@@ -119,12 +150,12 @@ def main(argv=None) -> int:
                 print(f"{datetime.now()}: step {step}, loss = {float(loss) / a.batch_size:.2f} ({eps:.1f} examples/sec; "
                       f"{dt / a.log_frequency:.3f} sec/batch)", flush=True)
             if is_chief and time.time() - last_save >= a.save_checkpoint_secs:
-                torch.save({"model": net.state_dict(), "global_step": step}, ckpt)
+                torch.save({"model": net.state_dict(), "global_step": step, "moving_average": [e.cpu() for e in ema]}, ckpt)
                 last_save = time.time()
             if step >= a.max_steps:
                 break
     if is_chief:
-        torch.save({"model": net.state_dict(), "global_step": step}, ckpt)
+        torch.save({"model": net.state_dict(), "global_step": step, "moving_average": [e.cpu() for e in ema]}, ckpt)
     store.close()
     if sched is not None:
         sched.wait(30)

@@ -32,8 +32,10 @@ def test_readme_flow_mxnet_style_ps_over_stack(tmp_path):
     assert "Node[0] Epoch[0]" in out and "Node[1] Epoch[0]" in out and out.count("validation: accuracy") == 2
 
 
-def test_tf_style_async_ps_from_generated_scripts(tmp_path):
-    """generate-trainer -> one script per host -> ps + workers train asynchronously, chief checkpoints."""
+@pytest.mark.parametrize("extra", [[], ["--sync_replicas"]], ids=["async", "sync_replicas"])
+def test_tf_style_async_ps_from_generated_scripts(tmp_path, extra):
+    """generate-trainer -> one script per host -> ps + workers train (asynchronously, or with the SyncReplicas token
+    protocol), chief checkpoints weights + moving averages."""
     from deeplearning_cfn_b200.cluster.stack import launch_cluster
     h = launch_cluster("tf", home=str(tmp_path), backend="thread", WorkerCount=1, InstanceType="cpu.large", ImageType="CPUGloo")
     env = h.export_env()
@@ -41,7 +43,7 @@ def test_tf_style_async_ps_from_generated_scripts(tmp_path):
     r = run([PY, "-m", "deeplearning_cfn_b200", "generate-trainer", "--trainer_script_dir", sdir, "--log_dir", ldir,
              "--workers_file_path", h.hostfile, "--worker_count", "2", "--worker_gpu_count", "1", "--training_script",
              os.path.join(ROOT, "deeplearning_cfn_b200/examples/cifar10_multi_machine_train.py"), "--max_steps", "6", "--batch_size", "8",
-             "--train_dir", tdir, "--log_frequency", "2"], env=env)
+             "--train_dir", tdir, "--log_frequency", "2"] + extra, env=env)
     assert r.returncode == 0, r.stderr
     scripts = sorted(os.listdir(sdir))
     assert scripts == ["deeplearning-worker1.sh", "deeplearning-worker2.sh"]
@@ -57,6 +59,9 @@ def test_tf_style_async_ps_from_generated_scripts(tmp_path):
     assert set(logs) == {"ps0", "ps1", "worker0", "worker1"}
     assert "step 6, loss" in logs["worker0"] and "examples/sec" in logs["worker1"], logs["worker0"][-800:]
     assert os.path.exists(os.path.join(tdir, "model.ckpt"))
+    import torch
+    sd = torch.load(os.path.join(tdir, "model.ckpt"), map_location="cpu")
+    assert sd["global_step"] == 6 and len(sd["moving_average"]) == len(sd["model"])
 
 
 def test_horovod_style_runner_over_maskrcnn_stack(tmp_path):

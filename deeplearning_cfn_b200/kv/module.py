@@ -75,6 +75,8 @@ class Module:
     @torch.no_grad()
     def update(self):
         kv = self._kv
+        if kv is not None and "nccl" in kv.type:
+            return self._update_params_on_kvstore_nccl()
         for i, p in enumerate(self._params):
             if p.grad is None:
                 continue
@@ -87,6 +89,23 @@ class Module:
                     self._updater(i, p.grad, p.data)
             else:
                 self._updater(i, p.grad, p.data)
+
+    def _update_params_on_kvstore_nccl(self):
+        """nccl kvstore: keys go to the store in groups of MXNET_UPDATE_AGGREGATION_SIZE (default 16) so that one grouped
+        launch carries many small tensors (reference model.py:125-143, kvstore_nccl.h:221-307)."""
+        import os
+        kv = self._kv
+        size = int(os.environ.get("MXNET_UPDATE_AGGREGATION_SIZE", "16"))
+        idx = [i for i, p in enumerate(self._params) if p.grad is not None]
+        for s0 in range(0, len(idx), size):
+            batch = idx[s0:s0 + size]
+            kv.push(batch, [self._params[i].grad for i in batch], priority=-s0)
+            if self._update_on_kvstore:
+                kv.pull(batch, out=[self._params[i].data for i in batch], priority=-s0)
+            else:
+                kv.pull(batch, out=[self._params[i].grad for i in batch], priority=-s0)
+                for i in batch:
+                    self._updater(i, self._params[i].grad, self._params[i].data)
 
     def get_outputs(self):
         return [self._outputs]

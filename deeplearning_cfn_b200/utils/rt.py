@@ -109,7 +109,14 @@ def plan_trees(link, penalty: float | None = None) -> list[list[int]]:
     out = (c_int * (n * n))()
     if lib().dlcfn_topo_plan_trees(arr, n, penalty, out) != 0:
         raise ValueError("bad link matrix")
-    return [[out[r * n + i] for i in range(n)] for r in range(n)]
+    trees = [[out[r * n + i] for i in range(n)] for r in range(n)]
+    if os.environ.get("MXNET_KVSTORE_LOGTREE", "0") == "1":      # gpu_topology.h:46
+        print("link matrix:")
+        for r in range(n):
+            print("  " + " ".join(f"{arr[r * n + c]:g}" for c in range(n)))
+        for r, t in enumerate(trees):
+            print(f"tree rooted at {r}: parent = {t}")
+    return trees
 
 
 def plan_ring(link, start: int = 0) -> list[int]:

@@ -172,21 +172,98 @@ class KVStore:
 
 # =============================================================================== local / device
 class KVStoreLocal(KVStore):
+    """`local` (host reduce, CommCPU) / `device` (GPU reduce, CommDevice; with MXNET_KVSTORE_USETREE=1 the
+    topology-aware tree reduce of CommDeviceTree).  Runtime knobs honoured, names as in the reference (env_var.md):
+    MXNET_KVSTORE_USETREE, MXNET_KVSTORE_TREE_ARRAY_BOUND (1e7), MXNET_KVSTORE_TREE_LINK_USAGE_PENALTY (0.7),
+    MXNET_KVSTORE_LOGTREE, MXNET_ENABLE_GPU_P2P (1; 0 stages device-to-device copies through the host),
+    MXNET_GPU_COPY_NTHREADS (2; number of copy streams used to stage peer gradients), MXNET_KVSTORE_SERIAL_PUSH
+    (0; 1 synchronises after every push - the reference's benchmarking switch, comm.h:109)."""
+
     def __init__(self, name: str = "local"):
         super().__init__(name)
         self._store: dict = {}
         self._on_device = "device" in name
+        self._use_tree = self._on_device and os.environ.get("MXNET_KVSTORE_USETREE", "0") == "1"
+        self._tree_bound = int(float(os.environ.get("MXNET_KVSTORE_TREE_ARRAY_BOUND", "10000000")))
+        self._p2p = os.environ.get("MXNET_ENABLE_GPU_P2P", "1") != "0"
+        self._serial_push = os.environ.get("MXNET_KVSTORE_SERIAL_PUSH", "0") == "1"
+        self._n_copy_streams = max(1, int(os.environ.get("MXNET_GPU_COPY_NTHREADS", "2")))
+        self._copy_streams: dict = {}
+        self._trees: dict = {}
+        self.link_matrix = None        # optional [n][n] link-strength matrix; default: probe (CUDA) / uniform
+
+    # -- device-to-device staging (reference C4: cudaMemcpyPeerAsync on the copy workers' streams)
+    def _stage(self, v: torch.Tensor, dev, slot: int) -> torch.Tensor:
+        v = v.detach()
+        if v.device == dev:
+            return v.contiguous()
+        if not self._p2p and v.is_cuda:
+            return v.to("cpu").to(dev).contiguous()
+        if v.is_cuda and getattr(dev, "type", None) == "cuda":
+            key = (dev.index, slot % self._n_copy_streams)
+            st = self._copy_streams.get(key)
+            if st is None:
+                st = self._copy_streams[key] = torch.cuda.Stream(device=dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                out = v.to(dev, non_blocking=True).contiguous()
+            torch.cuda.current_stream(dev).wait_stream(st)
+            return out
+        return v.to(dev).contiguous()
+
+    # -- CommDeviceTree (comm_tree.h:181-259, gpu_topology.h): one reduction tree per root from the link matrix
+    def _plan(self, n: int) -> list:
+        if n not in self._trees:
+            link = self.link_matrix
+            if link is None:
+                link = [[0.0 if i == j else 1.0 for j in range(n)] for i in range(n)]    # NVSwitch: uniform
+            self._trees[n] = rt.plan_trees(link)
+        return self._trees[n]
+
+    @staticmethod
+    def _reduce_on_tree(parts: list, parent: list, root: int) -> torch.Tensor:
+        n = len(parts)
+
+        def depth(i):
+            d = 0
+            while parent[i] >= 0:
+                i = parent[i]
+                d += 1
+            return d
+
+        acc = [p.detach() for p in parts]
+        for node in sorted(range(n), key=depth, reverse=True):      # leaves first
+            p = parent[node]
+            if p < 0:
+                continue
+            acc[p] = acc[p] + acc[node].to(acc[p].device)           # one hop along a tree edge
+        return acc[root]
+
+    def _reduce_tree(self, ikey: int, vals: list) -> torch.Tensor:
+        n = len(vals)
+        trees = self._plan(n)
+        v0 = vals[0]
+        if v0.numel() > self._tree_bound and v0.dim() >= 1 and v0.shape[0] >= n:
+            # big array: row-slice into n pieces, reduce-scatter piece j on the tree rooted at j, then gather
+            pieces = [torch.chunk(v.detach(), n, dim=0) for v in vals]
+            merged = [self._reduce_on_tree([pieces[d][j] for d in range(n)], trees[j], j) for j in range(len(pieces[0]))]
+            dev = v0.device
+            return torch.cat([m.to(dev) for m in merged], dim=0)
+        root = ikey % n
+        return self._reduce_on_tree(list(vals), trees[root], root)
 
     def _reduce(self, ikey: int, vals: list) -> torch.Tensor:
         if self._compression is not None:
             vals = [self._compress_roundtrip(ikey, i, v) for i, v in enumerate(vals)]
         if len(vals) == 1:
             return vals[0].detach().clone()
+        if self._use_tree:
+            return self._reduce_tree(ikey, vals)
         if self._on_device and vals[0].is_cuda:
             # merge on the device that holds the stored value (reference: least-loaded GPU, comm.h:678-712)
             dev = self._store[ikey].device if ikey in self._store and self._store[ikey].is_cuda else vals[0].device
             with torch.cuda.device(dev):
-                staged = [v.detach().to(dev, non_blocking=True).contiguous() for v in vals]
+                staged = [self._stage(v, dev, i) for i, v in enumerate(vals)]
                 out = torch.empty_like(staged[0])
                 if out.dtype in (torch.float32, torch.bfloat16):
                     native.elementwise_sum([s.reshape(-1) for s in staged], out.reshape(-1))
@@ -221,6 +298,8 @@ class KVStoreLocal(KVStore):
                 self._updater(ik if not isinstance(k, str) else k, merged, stored)
             else:
                 stored.copy_(merged.to(stored.dtype))
+            if self._serial_push and stored.is_cuda:
+                torch.cuda.synchronize(stored.device)
 
     def pull(self, key, out=None, priority: int = 0, ignore_sparse: bool = True) -> None:
         if out is None:

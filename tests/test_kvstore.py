@@ -337,3 +337,29 @@ def test_row_sparse_update_touches_only_listed_rows_and_matches_dense_rule(name,
     o2.update(0, sub, gd, st)
     assert torch.allclose(w[[3, 7, 11]], sub, atol=1e-6)
     assert not torch.equal(w[[3, 7, 11]], w0[[3, 7, 11]])
+
+
+def test_device_kvstore_tree_reduce_matches_flat_sum(monkeypatch):
+    """CommDeviceTree: topology trees from a (DGX-1 style) link matrix; small keys reduce on one tree, big keys are
+    row-sliced over all trees (reduce-scatter + gather).  Fake devices = CPU tensors, as in the reference unit tests."""
+    monkeypatch.setenv("MXNET_KVSTORE_USETREE", "1")
+    monkeypatch.setenv("MXNET_KVSTORE_TREE_ARRAY_BOUND", "64")
+    s = kv.create("device")
+    n = 8
+    dgx1 = [[0.0] * n for _ in range(n)]
+    for a, b, w in [(0, 1, 1), (0, 2, 1), (0, 3, 2), (1, 2, 2), (1, 3, 1), (2, 3, 1), (4, 5, 1), (4, 6, 1), (4, 7, 2), (5, 6, 2),
+                    (5, 7, 1), (6, 7, 1), (0, 4, 2), (1, 5, 2), (2, 6, 1), (3, 7, 1)]:
+        dgx1[a][b] = dgx1[b][a] = float(w)
+    s.link_matrix = dgx1
+    torch.manual_seed(0)
+    for key, shape in [(3, (4, 4)), (5, (40, 8))]:          # 16 elements: one tree; 320 elements: sliced over 8 trees
+        s.init(key, torch.zeros(shape))
+        grads = [torch.randn(shape) for _ in range(n)]
+        s.push(key, grads)
+        out = torch.zeros(shape)
+        s.pull(key, out=out)
+        assert torch.allclose(out, torch.stack(grads).sum(0), atol=1e-5)
+    trees = s._plan(n)
+    for r, parent in enumerate(trees):                      # every tree spans all devices and only uses real links
+        assert parent[r] == -1 and sorted(i for i, p in enumerate(parent) if p >= 0) == [i for i in range(n) if i != r]
+        assert all(dgx1[i][p] > 0 for i, p in enumerate(parent) if p >= 0)

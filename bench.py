@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--num-layers", type=int, default=50)
     ap.add_argument("--bucket-mb", type=float, default=16.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn"],
+    ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn", "auto"],
                     help="backend of the 1x1 convolutions (default: ops.conv default / DLCFN_CONV1X1)")
     return ap.parse_args()
 

@@ -107,15 +107,15 @@ __global__ void __launch_bounds__(256) kbn_stats(const uint4* __restrict__ x, co
       for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
     }
   } else {
-    for (; r + step < M; r += 2 * step) {
-      uint4 va[2], vb[2];
+    for (; r + 3 * step < M; r += 4 * step) {
+      uint4 va[4], vb[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         va[u] = ld_stream_v4(x + (r + u * step) * CV + tx);
         vb[u] = ld_stream_v4(x2 + (r + u * step) * CV + tx);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         float fa[8], fb[8];
         unpack8(va[u], fa);
         unpack8(vb[u], fb);

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from ..ops.batchnorm import BatchNormReLU2d
 from ..ops.conv import Conv1x1
 from ..ops.linear import Linear
-from ..ops.pool import MaxPool2d
+from ..ops.pool import MaxPool2d, global_avg_pool
 
 _EPS = 2e-5
 _MOM = 0.1  # torch momentum = 1 - mxnet bn_mom(0.9)
@@ -182,8 +182,7 @@ class ResNetV2(nn.Module):
         x = self.stem(self.bn_data(x))
         x = self.body(x)                       # (branch, shortcut) of the last unit, still un-summed
         _, x = self.bn1.forward_add(x[0], x[1])
-        x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
-        return self.fc1(x)
+        return self.fc1(global_avg_pool(x))
 
 
 def resnet(num_layers: int = 50, num_classes: int = 1000, image_size: int = 224) -> ResNetV2:

@@ -121,3 +121,25 @@ def pad3to8(x: torch.Tensor) -> torch.Tensor:
     native.check(L.dlcfn_pad3to8_nhwc(x.data_ptr(), y.data_ptr(), N * H * W, native.stream_ptr()), "pad3to8")
     native._count()
     return y
+
+
+class _GlobalAvgPoolFn(torch.autograd.Function):
+    """[N,C,H,W] -> [N,C] mean over H,W.  The point is the backward: torch's adaptive_avg_pool2d hands back an NCHW
+    gradient, which the NHWC BatchNorm backward then has to transpose; here the broadcast gradient is written directly
+    in channels_last."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        return x.mean(dim=(2, 3))
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.shape
+        g = (dy.float() / float(H * W)).to(dy.dtype)
+        return g.view(N, 1, 1, C).expand(N, H, W, C).contiguous().permute(0, 3, 1, 2)
+
+
+def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
+    """Global average pooling to [N, C] with a channels_last gradient."""
+    return _GlobalAvgPoolFn.apply(x)

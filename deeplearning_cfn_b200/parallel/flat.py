@@ -27,6 +27,7 @@ class Bucket:
     end: int
     params: list = field(default_factory=list)
     pending: int = 0
+    gathered: bool = False   # this step's gradients have been moved into the flat buffer
 
     @property
     def numel(self) -> int:
@@ -71,6 +72,7 @@ class FlatModel:
             by_dtype.setdefault(p.dtype, []).append(p)
         self.groups: list[Group] = []
         self.buckets: list[Bucket] = []
+        self._grad_view: dict = {}
         # largest group first so bucket 0.. belong to the bulk (bf16) weights
         for dtype, plist in sorted(by_dtype.items(), key=lambda kv: -sum(p.numel() for p in kv[1])):
             esz = 2 if dtype in (torch.bfloat16, torch.float16) else 4
@@ -92,7 +94,9 @@ class FlatModel:
                 wv = g.weight[o:o + p.numel()].as_strided(p.shape, p.stride())
                 wv.copy_(p.data)
                 p.data = wv
-                p.grad = g.grad[o:o + p.numel()].as_strided(p.shape, p.stride())
+                gv = g.grad[o:o + p.numel()].as_strided(p.shape, p.stride())
+                p.grad = gv
+                self._grad_view[id(p)] = gv
             # buckets: contiguous runs of parameters
             bstart, bparams = 0, []
             for i, (p, o) in enumerate(zip(plist, offs)):
@@ -116,6 +120,29 @@ class FlatModel:
     def reset_pending(self) -> None:
         for b in self.buckets:
             b.pending = len(b.params)
+            b.gathered = False
+
+    def release_grads(self) -> None:
+        """Start of a step: give the `.grad` slots back to autograd.  With `p.grad is None` the engine hands each
+        parameter its freshly computed gradient tensor as is (no `grad += g` read-modify-write kernel per parameter, no
+        memset of the flat buffer); `gather_bucket` then moves a whole bucket into the flat buffer with one fused
+        multi-tensor copy when its last gradient has arrived."""
+        for g in self.groups:
+            for p in g.params:
+                p.grad = None
+
+    def gather_bucket(self, b: Bucket) -> None:
+        dst, src = [], []
+        for p in b.params:
+            v = self._grad_view[id(p)]
+            if p.grad is None:
+                v.zero_()                       # parameter took no part in this step
+            elif p.grad.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        b.gathered = True
 
     def total_bytes(self) -> int:
         return sum(g.numel * g.esize for g in self.groups)

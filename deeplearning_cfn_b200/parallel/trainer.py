@@ -94,7 +94,7 @@ class DataParallelTrainer:
         self._ready: list[bool] = [False] * len(self.flat.buckets)
         self._next = 0
         self._works: list = []
-        if self.is_worker and self.world > 1:
+        if self.is_worker:
             for b in self.flat.buckets:
                 for p in b.params:
                     p.register_post_accumulate_grad_hook(self._make_hook(b))
@@ -155,8 +155,10 @@ class DataParallelTrainer:
         def hook(_p):
             b.pending -= 1
             if b.pending == 0:
-                self._ready[b.index] = True
-                self._drain()
+                self.flat.gather_bucket(b)          # one fused copy: autograd-owned gradients -> flat bucket
+                if self.world > 1:
+                    self._ready[b.index] = True
+                    self._drain()
         return hook
 
     def _drain(self) -> None:
@@ -175,6 +177,8 @@ class DataParallelTrainer:
 
     def _launch_bucket(self, b: Bucket) -> None:
         g = b.group
+        if self.is_worker and not b.gathered:
+            self.flat.gather_bucket(b)              # flushed before its last hook fired (an unused parameter)
         if self.comm_stream is not None and self.is_worker:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
         if self.mode == "allreduce":
@@ -226,7 +230,7 @@ class DataParallelTrainer:
         self.flat.reset_pending()
         self._ready = [False] * len(self.flat.buckets)
         self._next = 0
-        self.flat.zero_grad()
+        self.flat.release_grads()
         out = self.model(*x) if isinstance(x, (tuple, list)) else self.model(x)
         loss = self.loss_fn(out, y)
         loss.backward()
@@ -234,6 +238,10 @@ class DataParallelTrainer:
 
     def synchronize_and_update(self) -> None:
         """Flush buckets whose hooks never fired, wait for the wire, apply the optimizer."""
+        if self.is_worker:
+            for b in self.flat.buckets:
+                if not b.gathered and self.world == 1:
+                    self.flat.gather_bucket(b)
         if self.world > 1:
             for b in self.flat.buckets[self._next:]:
                 self._launch_bucket(b)

@@ -150,7 +150,11 @@ def main():
     if not args.no_e2e:
         src = SyntheticImageSource(args.batch, args.image_size, 1000) if is_worker else None
         pre = DevicePrefetcher(src, device) if is_worker else None
-        host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # the loss of every step is copied device->host (pinned, async) and READ one step later, when its copy event has
+        # completed: the host never runs more than one step ahead, and it never drains the GPU queue either (a hard
+        # synchronize per step leaves the GPU idle while the host enqueues the next step's first kernels)
+        host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         for _ in range(3):
             if is_worker:
                 xb, yb = pre.next()
@@ -159,17 +163,27 @@ def main():
                 trainer.step()
         sync_all()
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        last = 0.0
+        last, losses_read = 0.0, 0
         e_start.record()
-        for _ in range(args.steps):
+        for i in range(args.steps):
             if is_worker:
                 xb, yb = pre.next()                      # H2D of this step's inputs (pinned -> device) + normalise
                 loss = trainer.step(xb, yb)
-                host_loss.copy_(loss.detach().float().reshape(1), non_blocking=True)   # D2H of the step's loss
-                torch.cuda.current_stream().synchronize()
-                last = float(host_loss[0])
+                k = i & 1
+                host_loss[k].copy_(loss.detach().float().reshape(1), non_blocking=True)   # D2H of this step's loss
+                loss_ev[k].record()
+                if i > 0:                                # read the previous step's loss (its copy has finished)
+                    loss_ev[k ^ 1].synchronize()
+                    last = float(host_loss[k ^ 1][0])
+                    losses_read += 1
             else:
                 trainer.step()
+        if is_worker:                                    # ... and the last step's, still inside the timed region
+            k = (args.steps - 1) & 1
+            loss_ev[k].synchronize()
+            last = float(host_loss[k][0])
+            losses_read += 1
+            assert losses_read == args.steps
         e_end.record()
         sync_all()
         e_ms = e_start.elapsed_time(e_end)
@@ -224,7 +238,8 @@ def main():
         if e2e and rec is not None:
             rec["e2e"] = {"value": round(global_batch * args.steps / (e_ms / 1e3), 2), "unit": "images/sec",
                           "h2d_bytes_per_step": e2e["h2d"] * n_workers if is_worker else 0,
-                          "d2h_bytes_per_step": 4 * n_workers, "last_loss": e2e["loss"]}
+                          "d2h_bytes_per_step": 4 * n_workers, "last_loss": e2e["loss"],
+                          "readback": "loss copied D2H (pinned, async) every step and read on the host one step later"}
             if not is_worker:  # rank 0 is a dedicated server: bytes come from the workers
                 rec["e2e"]["h2d_bytes_per_step"] = (args.batch * args.image_size * args.image_size * 3 + args.batch * 8) * n_workers
         if rec is not None:

@@ -187,6 +187,15 @@ def main():
         e_end.record()
         sync_all()
         e_ms = e_start.elapsed_time(e_end)
+        if os.environ.get("DLCFN_BENCH_DIAG") == "1" and is_worker:    # diagnostics only: is the e2e gap time-dependent?
+            for tag, (xa, ya) in (("device input after e2e", (x, y)), ("last prefetched batch, no copies in flight", (xb, yb))):
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record()
+                for _ in range(args.steps):
+                    trainer.step(xa, ya)
+                d1.record()
+                torch.cuda.synchronize()
+                print(f"[diag] {tag}: {d0.elapsed_time(d1) / args.steps:.3f} ms/step", file=sys.stderr, flush=True)
         e2e = {"ms": e_ms, "loss": last, "h2d": src.bytes_per_batch if is_worker else 0}
 
     # ---------------------------------------------------------------- reduce over ranks

@@ -126,6 +126,10 @@ def main(argv=None) -> int:
     p.add_argument("--num-images", type=int, default=64)
     p.add_argument("--image-size", type=int, default=128)
     p.set_defaults(fn=cmd_prepare_bucket)
+    p = sub.add_parser("package-event-function")
+    p.add_argument("--output", default="dl_cfn_setup_lambda.zip")
+    p.set_defaults(fn=lambda a: (print(__import__("deeplearning_cfn_b200.cluster.staging", fromlist=["x"])
+                                       .package_event_function(a.output)), 0)[1])
     p = sub.add_parser("node-exec")
     p.add_argument("host")
     p.add_argument("command", nargs=argparse.REMAINDER)

@@ -108,3 +108,24 @@ def prepare_bucket(bucket: str, prefix: str = "mask-rcnn/b200", num_images: int 
         out[name] = os.path.join(root, name)
     shutil.rmtree(stage, ignore_errors=True)
     return out
+
+
+def package_event_function(out_path: str) -> str:
+    """Build the deployable archive of the scaling-event function (reference `dl_cfn_setup_lambda.zip`: the packaged
+    copy of cfn-lambda_function/lambda_function.py next to its SAM stub).  The archive holds the handler under the
+    reference's module name plus the control-plane modules it imports and the function template; `Handler:
+    lambda_function.lambda_handler` of templates/event-function.template resolves inside it."""
+    import os
+    import zipfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)) or ".", exist_ok=True)
+    with zipfile.ZipFile(out_path, "w", zipfile.ZIP_DEFLATED) as z:
+        z.writestr("lambda_function.py",
+                   "from deeplearning_cfn_b200.cluster.events import *  # noqa: F401,F403\n"
+                   "from deeplearning_cfn_b200.cluster.events import lambda_handler  # noqa: F401\n")
+        z.writestr("deeplearning_cfn_b200/__init__.py", "")
+        z.writestr("deeplearning_cfn_b200/cluster/__init__.py", "")
+        for mod in ("events.py", "controlplane.py", "queue.py", "spec.py"):
+            z.write(os.path.join(here, mod), f"deeplearning_cfn_b200/cluster/{mod}")
+        z.write(os.path.join(here, "templates", "event-function.template"), "template.json")
+    return out_path

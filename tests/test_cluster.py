@@ -298,3 +298,25 @@ def test_cli_create_list_describe_delete(tmp_path):
     r = subprocess.run(base + ["create-stack", "--stack-name", "c2", "--home", str(tmp_path), "--parameters", "WorkerCount=0"],
                        env=env, capture_output=True, text=True)
     assert r.returncode == 1 and "MinValue" in r.stderr
+
+
+def test_packaged_event_function_is_self_contained(tmp_path):
+    """The scaling-event function ships as an archive (reference dl_cfn_setup_lambda.zip + template.yaml): importable
+    on its own under the reference's handler name, without the rest of the framework."""
+    import json
+    import subprocess
+    import sys
+    import zipfile
+    from deeplearning_cfn_b200.cluster.staging import package_event_function
+    out = package_event_function(str(tmp_path / "dl_cfn_setup_lambda.zip"))
+    names = set(zipfile.ZipFile(out).namelist())
+    assert {"lambda_function.py", "template.json", "deeplearning_cfn_b200/cluster/events.py"} <= names
+    tpl = json.loads(zipfile.ZipFile(out).read("template.json"))
+    assert tpl["Resources"]["EventFunction"]["Properties"]["Handler"] == "lambda_function.lambda_handler"
+    code = ("import sys, json; sys.path.insert(0, %r); import lambda_function as lf; "
+            "ev = {'Records': [{'Sns': {'Message': json.dumps({'Event': 'autoscaling:TEST_NOTIFICATION'})}}]}; "
+            "m = lf.lambda_handler(ev, None); assert m['Event'].endswith('TEST_NOTIFICATION'); "
+            "assert 'torch' not in sys.modules; print('ZIP_OK', lf.__file__)") % out
+    r = subprocess.run([sys.executable, "-S", "-c", code], capture_output=True, text=True, cwd=str(tmp_path),
+                       env={"PATH": os.environ.get("PATH", ""), "AWS_DL_STACK_ID": str(tmp_path)}, timeout=60)
+    assert "ZIP_OK" in r.stdout, r.stdout + r.stderr

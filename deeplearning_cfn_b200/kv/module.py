@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from ..ops.nn import softmax_cross_entropy
+from . import metric as metric_mod
 from . import optimizer as opt
 from .kvstore import KVStore, create
 
@@ -112,42 +113,85 @@ class Module:
 
     def fit(self, train_data, eval_data=None, eval_metric="acc", epoch_end_callback=None, batch_end_callback=None,
             kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), initializer=None,
-            arg_params=None, aux_params=None, begin_epoch: int = 0, num_epoch: int | None = None, batch_size=None):
+            arg_params=None, aux_params=None, begin_epoch: int = 0, num_epoch: int | None = None, batch_size=None,
+            validation_metric=None, monitor=None, eval_end_callback=None, eval_batch_end_callback=None):
         assert num_epoch is not None, "please specify number of epochs"
+        if monitor is not None:
+            monitor.install(self.symbol)
         if not self.binded:
             self.bind([("data", (batch_size or 1,))])
         if not self.params_initialized:
             self.init_params(initializer, arg_params, aux_params)
         if not self.optimizer_initialized:
             self.init_optimizer(kvstore, optimizer, optimizer_params)
+        train_metric = metric_mod.create(eval_metric)
         for epoch in range(begin_epoch, num_epoch):
             tic = time.time()
-            correct = total = 0
+            train_metric.reset()
             self.symbol.train()
+            if hasattr(train_data, "reset"):
+                train_data.reset()
             it = train_data() if callable(train_data) else train_data
             for nbatch, batch in enumerate(it):
-                self.forward_backward(batch)
+                x, y = _unpack(batch)
+                if monitor is not None:
+                    monitor.tic()
+                self.forward_backward((x, y))
                 self.update()
-                correct += int((self._outputs.argmax(-1) == batch[1]).sum())
-                total += int(batch[1].numel())
+                train_metric.update([y], [self._outputs])
+                if monitor is not None:
+                    monitor.toc_print()
                 for cb in _as_list(batch_end_callback):
-                    cb(epoch, nbatch, {"accuracy": correct / max(1, total)})
-            logging.info("Epoch[%d] Train-accuracy=%f", epoch, correct / max(1, total))
+                    cb(epoch, nbatch, train_metric)
+            for name, val in train_metric.get_name_value():
+                logging.info("Epoch[%d] Train-%s=%f", epoch, name, val)
             logging.info("Epoch[%d] Time cost=%.3f", epoch, time.time() - tic)
             for cb in _as_list(epoch_end_callback):
                 cb(epoch, self.symbol, None, None)
             if eval_data is not None:
-                logging.info("Epoch[%d] Validation-accuracy=%f", epoch, self.score(eval_data))
+                res = self.score(eval_data, validation_metric or eval_metric, epoch=epoch,
+                                 batch_end_callback=eval_batch_end_callback, score_end_callback=eval_end_callback)
+                for name, val in res:
+                    logging.info("Epoch[%d] Validation-%s=%f", epoch, name, val)
 
     @torch.no_grad()
-    def score(self, eval_data) -> float:
+    def score(self, eval_data, eval_metric="acc", num_batch: int | None = None, batch_end_callback=None,
+              score_end_callback=None, reset: bool = True, epoch: int = 0):
+        """Run `eval_data` through the network and return `eval_metric.get_name_value()` (base_module.py:171-240).
+        For the default accuracy metric the plain float is also available as `score(...)[0][1]`."""
         self.symbol.eval()
-        correct = total = 0
+        m = metric_mod.create(eval_metric)
+        m.reset()
+        if reset and hasattr(eval_data, "reset"):
+            eval_data.reset()
         it = eval_data() if callable(eval_data) else eval_data
-        for x, y in it:
-            correct += int((self.symbol(x).argmax(-1) == y).sum())
-            total += int(y.numel())
-        return correct / max(1, total)
+        for nbatch, batch in enumerate(it):
+            if num_batch is not None and nbatch == num_batch:
+                break
+            x, y = _unpack(batch)
+            m.update([y], [self.symbol(x)])
+            for cb in _as_list(batch_end_callback):
+                cb(epoch, nbatch, m)
+        for cb in _as_list(score_end_callback):
+            cb(epoch, m)
+        return m.get_name_value()
+
+    def predict(self, eval_data, num_batch: int | None = None, merge_batches: bool = True, reset: bool = True):
+        """Forward only; outputs concatenated over batches with the padding of the last batch removed."""
+        self.symbol.eval()
+        outs = []
+        if reset and hasattr(eval_data, "reset"):
+            eval_data.reset()
+        it = eval_data() if callable(eval_data) else eval_data
+        with torch.no_grad():
+            for nbatch, batch in enumerate(it):
+                if num_batch is not None and nbatch == num_batch:
+                    break
+                x, _ = _unpack(batch)
+                o = self.symbol(x)
+                pad = getattr(batch, "pad", 0)
+                outs.append(o[:o.shape[0] - pad] if pad else o)
+        return torch.cat(outs) if merge_batches else outs
 
     def save_checkpoint(self, prefix: str, epoch: int, save_optimizer_states: bool = False):
         from ..utils.callback import save_checkpoint
@@ -169,3 +213,10 @@ def _as_list(x):
     if x is None:
         return []
     return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+def _unpack(batch):
+    """(x, y) tuple or an io.DataBatch."""
+    if hasattr(batch, "data") and hasattr(batch, "label"):
+        return batch.data[0], (batch.label[0] if batch.label else None)
+    return batch[0], batch[1]

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import json
 import logging
+import math
 import os
 import time
 
@@ -32,9 +33,11 @@ class Speedometer:
                 speed = self.frequent * self.batch_size / (time.time() - self.tic)
                 self.last_speed = speed
                 msg = f"{self.prefix}Epoch[{epoch}] Batch [{nbatch}]\tSpeed: {speed:.2f} samples/sec"
-                for k, v in (metrics or {}).items():
+                for k, v in _metric_pairs(metrics):
                     msg += f"\t{k}={v:f}"
                 logging.info(msg)
+                if self.auto_reset and hasattr(metrics, "reset"):
+                    metrics.reset()
                 self.tic = time.time()
         else:
             self.init = True
@@ -89,3 +92,56 @@ def do_checkpoint(prefix: str, period: int = 1, model=None, trainer=None, rank: 
         if (epoch + 1) % period == 0:
             save_checkpoint(prefix, epoch + 1, model, trainer, rank)
     return _cb
+
+
+# --------------------------------------------------------------------------- remaining reference callbacks
+def _metric_pairs(metrics) -> list:
+    """dict | EvalMetric | None -> [(name, value)]"""
+    if metrics is None:
+        return []
+    if isinstance(metrics, dict):
+        return list(metrics.items())
+    if hasattr(metrics, "get_name_value"):
+        return metrics.get_name_value()
+    return []
+
+
+def module_checkpoint(mod, prefix: str, period: int = 1, save_optimizer_states: bool = False):
+    """Epoch-end callback that checkpoints a `Module` (callback.py:27-53)."""
+    period = int(max(1, period))
+
+    def _cb(epoch: int, *_):
+        if (epoch + 1) % period == 0:
+            mod.save_checkpoint(prefix, epoch + 1, save_optimizer_states)
+    return _cb
+
+
+def log_train_metric(period: int, auto_reset: bool = False):
+    """Batch-end callback: log the training metric every `period` batches (callback.py:93-117)."""
+    def _cb(epoch: int, nbatch: int, metrics=None):
+        if nbatch % period == 0 and metrics is not None:
+            for name, value in _metric_pairs(metrics):
+                logging.info("Iter[%d] Batch[%d] Train-%s=%f", epoch, nbatch, name, value)
+            if auto_reset and hasattr(metrics, "reset"):
+                metrics.reset()
+    return _cb
+
+
+class ProgressBar:
+    """Batch-end callback drawing a text progress bar (callback.py:185-210)."""
+
+    def __init__(self, total: int, length: int = 80):
+        self.bar_len, self.total = length, total
+
+    def __call__(self, epoch: int, nbatch: int, metrics=None) -> None:
+        filled = int(round(self.bar_len * nbatch / float(self.total)))
+        pct = math.ceil(100.0 * nbatch / float(self.total))
+        logging.info("[%s] %s%s\r", "=" * filled + "-" * (self.bar_len - filled), pct, "%")
+
+
+class LogValidationMetricsCallback:
+    """Epoch-end evaluation callback: log every validation metric (callback.py:213-222)."""
+
+    def __call__(self, epoch: int, metrics=None, *_) -> None:
+        for name, value in _metric_pairs(metrics):
+            logging.info("Epoch[%d] Validation-%s=%f", epoch, name, value)

@@ -118,10 +118,10 @@ def test_module_fit_and_recordio(tmp_path):
     mod = Module(net)
     mod.fit(data, num_epoch=120, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.2),),
             batch_size=8, batch_end_callback=Speedometer(8, 1000))
-    assert mod.score(data) > 0.9
+    assert dict(mod.score(data))["accuracy"] > 0.9
     mod.save_checkpoint(str(tmp_path / "m"), 120, save_optimizer_states=True)
     m2 = Module.load(str(tmp_path / "m"), 120, torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)))
-    assert abs(m2.score(data) - mod.score(data)) < 1e-6
+    assert abs(dict(m2.score(data))["accuracy"] - dict(mod.score(data))["accuracy"]) < 1e-6
 
 
 def test_sync_replicas_with_backup_worker():
@@ -198,3 +198,118 @@ def test_shared_memory_tensor_between_processes():
         seg.close()
     with pytest.raises(OSError):
         storage.SharedTensor.attach(name, (4, 5), torch.float32)         # owner closed -> unlinked
+
+
+def test_metrics_match_closed_form():
+    from deeplearning_cfn_b200.kv import metric
+    p = torch.tensor([[0.1, 0.7, 0.2], [0.8, 0.1, 0.1], [0.2, 0.3, 0.5], [0.3, 0.4, 0.3]])
+    y = torch.tensor([1, 2, 2, 0])
+    acc = metric.create("acc")
+    acc.update([y], [p])
+    assert acc.get() == ("accuracy", 0.5)
+    top2 = metric.TopKAccuracy(2)
+    top2.update([y], [p])
+    assert top2.get()[0] == "top_k_accuracy_2" and abs(top2.get()[1] - 0.75) < 1e-9     # rows 0, 2 and 3 (0.3 ties broken by topk)
+    ce = metric.create("ce")
+    ce.update([y], [p])
+    want = -(torch.log(torch.tensor([0.7, 0.1, 0.5, 0.3]))).mean().item()
+    assert abs(ce.get()[1] - want) < 1e-5
+    ppl = metric.Perplexity(ignore_label=0)
+    ppl.update([y], [p])
+    want_ppl = float(torch.exp(-(torch.log(torch.tensor([0.7, 0.1, 0.5]))).mean()))
+    assert abs(ppl.get()[1] - want_ppl) < 1e-4
+    mse, mae, rmse = metric.create("mse"), metric.create("mae"), metric.create("rmse")
+    a, b = torch.tensor([1.0, 2.0, 4.0]), torch.tensor([1.0, 1.0, 2.0])
+    for m in (mse, mae, rmse):
+        m.update([a], [b])
+    assert abs(mse.get()[1] - 5.0 / 3) < 1e-6 and abs(mae.get()[1] - 1.0) < 1e-6 and abs(rmse.get()[1] - (5.0 / 3) ** 0.5) < 1e-6
+    f1 = metric.create("f1")
+    f1.update([torch.tensor([1, 0, 1, 1])], [torch.tensor([[0.2, 0.8], [0.3, 0.7], [0.9, 0.1], [0.4, 0.6]])])
+    assert abs(f1.get()[1] - 2 * (2 / 3) * (2 / 3) / (4 / 3)) < 1e-9
+    comp = metric.create(["acc", "ce"])
+    comp.update([y], [p])
+    assert comp.get_name_value()[0] == ("accuracy", 0.5) and comp.get_name_value()[1][0] == "cross-entropy"
+    comp.reset()
+    assert comp.get()[1][0] != comp.get()[1][0]                      # nan after reset
+    custom = metric.np(lambda label, pred: float((pred.argmax(-1) == label).float().mean()), name="myacc")
+    custom.update([y], [p])
+    assert custom.get() == ("myacc", 0.5)
+    with pytest.raises(ValueError):
+        metric.create("no-such-metric")
+
+
+def test_ndarray_iter_last_batch_handling_and_prefetch():
+    from deeplearning_cfn_b200.utils.io import NDArrayIter, PrefetchingIter, ResizeIter
+    x = torch.arange(10, dtype=torch.float32).view(10, 1)
+    y = torch.arange(10)
+    it = NDArrayIter(x, y, batch_size=4, last_batch_handle="pad")
+    batches = list(it)
+    assert [b.pad for b in batches] == [0, 0, 2] and batches[2].data[0].view(-1).tolist() == [8.0, 9.0, 0.0, 1.0]
+    assert it.provide_data[0].name == "data" and it.provide_data[0].shape == (4, 1) and it.provide_label[0].name == "softmax_label"
+    it = NDArrayIter(x, y, batch_size=4, last_batch_handle="discard")
+    assert len(list(it)) == 2
+    it = NDArrayIter(x, y, batch_size=4, last_batch_handle="roll_over")
+    assert len(list(it)) == 2
+    it.reset()
+    second = list(it)                                  # 2 carried over + 10 fresh = 3 full batches
+    assert len(second) == 3 and second[0].data[0].view(-1).tolist() == [8.0, 9.0, 0.0, 1.0]
+    sh = NDArrayIter(x, y, batch_size=5, shuffle=True, seed=3)
+    seen = torch.cat([b.label[0] for b in sh])
+    assert sorted(seen.tolist()) == list(range(10)) and seen.tolist() != list(range(10))
+    rs = ResizeIter(NDArrayIter(x, y, batch_size=4, last_batch_handle="discard"), size=5)
+    assert len(list(rs)) == 5
+    pf = PrefetchingIter(NDArrayIter(x, y, batch_size=4, last_batch_handle="pad"), depth=2, pin=True)
+    got = [b.data[0].clone() for b in pf]
+    assert len(got) == 3 and got[0].view(-1).tolist() == [0.0, 1.0, 2.0, 3.0]
+    pf.reset()
+    xb, yb = next(iter(pf))                            # DataBatch unpacks like a tuple
+    assert xb.shape == (4, 1) and yb.tolist() == [0, 1, 2, 3]
+    pf.close()
+
+
+def test_module_fit_with_dataiter_metric_monitor_and_model_helpers(tmp_path, caplog):
+    import logging
+    from deeplearning_cfn_b200.kv import metric, model
+    from deeplearning_cfn_b200.kv.module import Module
+    from deeplearning_cfn_b200.utils.callback import LogValidationMetricsCallback, log_train_metric
+    from deeplearning_cfn_b200.utils.io import NDArrayIter
+    from deeplearning_cfn_b200.utils.monitor import Monitor
+    torch.manual_seed(0)
+    x = torch.randn(64, 8)
+    y = (x[:, 0] > 0).long()
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 2))
+    train = NDArrayIter(x, y, batch_size=16, shuffle=True)
+    mon = Monitor(interval=2, pattern=".*")
+    mod = Module(net)
+    with caplog.at_level(logging.INFO):
+        mod.fit(train, eval_data=NDArrayIter(x, y, batch_size=16), eval_metric=["acc", metric.CrossEntropy(from_logits=True)],
+                num_epoch=8, optimizer="sgd", optimizer_params=(("learning_rate", 0.5),), batch_size=16, monitor=mon,
+                batch_end_callback=log_train_metric(2), eval_end_callback=LogValidationMetricsCallback())
+    text = caplog.text
+    assert "Train-accuracy" in text and "Validation-cross-entropy" in text and "_output" in text
+    res = dict(mod.score(NDArrayIter(x, y, batch_size=16), ["acc", metric.TopKAccuracy(2)]))
+    assert res["accuracy"] > 0.85 and res["top_k_accuracy_2"] == 1.0
+    assert mod.predict(NDArrayIter(x, y, batch_size=24, last_batch_handle="pad")).shape == (64, 2)   # padding removed
+    # model.py helpers: store selection, init + update on a 2-"device" local store, checkpoint round trip
+    arg = {"w": torch.ones(4), "b": torch.zeros(2)}
+    kv0, upd0 = model._create_kvstore("local", 1, arg)
+    assert kv0 is None and upd0 is False
+    store, upd = model._create_kvstore("local", 2, arg)
+    assert store is not None and upd is True
+    names = ["w", "b"]
+    params = [[arg["w"].clone(), arg["w"].clone()], [arg["b"].clone(), arg["b"].clone()]]
+    model._initialize_kvstore(store, params, arg, names, upd)
+    store.set_optimizer(kv.optimizer.create("test", rescale_grad=1.0))
+    grads = [[torch.ones(4), torch.ones(4) * 2], [None, None]]
+    model._update_params_on_kvstore(params, grads, store, names)
+    assert torch.equal(params[0][0], torch.full((4,), 4.0)) and torch.equal(params[0][1], params[0][0])
+    assert torch.equal(params[1][0], torch.zeros(2))                    # parameter without gradient untouched
+    store2, _ = model._create_kvstore("device", 2, arg)
+    p2 = [[arg["w"].clone(), arg["w"].clone()]]
+    model._initialize_kvstore(store2, p2, arg, ["w"], False)
+    upd_fn = kv.optimizer.get_updater(kv.optimizer.create("sgd", learning_rate=0.5))
+    model._update_params(p2, [[torch.ones(4), torch.ones(4)]], upd_fn, 2, store2, ["w"])
+    assert torch.allclose(p2[0][0], torch.full((4,), 0.0)) and torch.allclose(p2[0][1], p2[0][0])   # 1 - 0.5 * (1 + 1)
+    model.save_checkpoint(str(tmp_path / "ck"), 3, net, dict(net.named_parameters()), {})
+    sym, a2, aux = model.load_checkpoint(str(tmp_path / "ck"), 3)
+    assert sym["class"] == "Sequential" and set(a2) == {n for n, _ in net.named_parameters()} and aux == {}

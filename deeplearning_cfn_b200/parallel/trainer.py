@@ -90,7 +90,12 @@ class DataParallelTrainer:
         # ---- optimizer state ----
         self._init_state()
 
-        self.comm_stream = torch.cuda.Stream(priority=-1) if (self.on_gpu and self.world > 1) else None
+        # Debugging mode (the reference's MXNET_ENGINE_TYPE=NaiveEngine): no side stream, no overlap - every
+        # bucket's collective is launched after backward, in order, on the main stream, followed by a device
+        # synchronise and a check of the flag-protocol error word, so a failure is attributed to the bucket that caused it.
+        self.naive = (os.environ.get("MXNET_ENGINE_TYPE", "") == "NaiveEngine" or
+                      os.environ.get("DLCFN_NAIVE_COLLECTIVES", "0") == "1")
+        self.comm_stream = torch.cuda.Stream(priority=-1) if (self.on_gpu and self.world > 1 and not self.naive) else None
         self._ready: list[bool] = [False] * len(self.flat.buckets)
         self._next = 0
         self._works: list = []
@@ -156,7 +161,7 @@ class DataParallelTrainer:
             b.pending -= 1
             if b.pending == 0:
                 self.flat.gather_bucket(b)          # one fused copy: autograd-owned gradients -> flat bucket
-                if self.world > 1:
+                if self.world > 1 and not self.naive:
                     self._ready[b.index] = True
                     self._drain()
         return hook
@@ -213,6 +218,9 @@ class DataParallelTrainer:
                     if g.dtype == torch.float32:
                         wview.copy_(self.state[b.index]["master"])
                 dist.broadcast(wview, src=root)
+        if self.naive and self.on_gpu:
+            torch.cuda.synchronize(self.device)
+            self.check()
 
     def _apply_opt(self, grad, st, wout, rescale: float = 1.0) -> None:
         hp = self.hp

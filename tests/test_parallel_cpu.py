@@ -12,10 +12,12 @@ from deeplearning_cfn_b200.kv.trainer import Trainer
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_gloo_world2_data_parallel_matches_single_process():
+@pytest.mark.parametrize("naive", ["0", "1"], ids=["overlapped", "naive-serialised"])
+def test_gloo_world2_data_parallel_matches_single_process(naive):
     cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "2", sys.executable,
            os.path.join(ROOT, "tests/mp/gloo_trainer_worker.py")]
-    r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=300)
+    r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT, DLCFN_NAIVE_COLLECTIVES=naive), capture_output=True,
+                       text=True, timeout=300)
     assert r.returncode == 0 and "GLOO_TRAINER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 

@@ -270,10 +270,13 @@ class KVStoreLocal(KVStore):
                 else:
                     out = torch.stack(staged).sum(0)
             return out
-        # host reduce (CommCPU): copy every device gradient to the host, sum there
-        acc = vals[0].detach().to("cpu", torch.float32).clone()
-        for v in vals[1:]:
-            acc += v.detach().to("cpu", torch.float32)
+        # host reduce (CommCPU): copy every device gradient to the host, sum there with the native threaded reducer
+        host = [v.detach().to("cpu").contiguous() for v in vals]
+        if host[0].dtype in (torch.float32, torch.bfloat16) and all(h.dtype == host[0].dtype for h in host):
+            return rt.reduce_sum_cpu([h.reshape(-1) for h in host]).view(vals[0].shape)
+        acc = host[0].to(torch.float32).clone()
+        for v in host[1:]:
+            acc += v.to(torch.float32)
         return acc.to(vals[0].dtype)
 
     def init(self, key, value) -> None:

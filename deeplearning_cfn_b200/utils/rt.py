@@ -95,6 +95,32 @@ def _mat(link):
     return n, arr
 
 
+def reduce_sum_cpu(srcs: list, out=None, nthreads: int | None = None, bigarray_bound: int | None = None):
+    """out = sum(srcs) on the host with the native reducer (csrc/rt/reduce.cpp; reference CommCPU::ReduceSumCPU):
+    4 inputs per pass, arrays >= MXNET_KVSTORE_BIGARRAY_BOUND elements split into 4096-element chunks over
+    MXNET_KVSTORE_REDUCTION_NTHREADS threads.  fp32 / bf16 contiguous CPU tensors of equal size."""
+    import os
+    import torch
+    L = lib()
+    if not getattr(L, "_reduce_declared", False):
+        L.dlcfn_reduce_sum_cpu.argtypes = [c_void_p, c_int, c_void_p, c_size_t, c_int, c_int, c_size_t]
+        L.dlcfn_reduce_sum_cpu.restype = c_int
+        L._reduce_declared = True
+    t0 = srcs[0]
+    code = {torch.float32: 0, torch.bfloat16: 1}[t0.dtype]
+    srcs = [s.detach().contiguous() for s in srcs]
+    assert all((not s.is_cuda) and s.dtype == t0.dtype and s.numel() == t0.numel() for s in srcs)
+    if out is None:
+        out = torch.empty_like(srcs[0])
+    assert out.is_contiguous() and out.numel() == t0.numel() and out.dtype == t0.dtype
+    nthreads = nthreads if nthreads is not None else int(os.environ.get("MXNET_KVSTORE_REDUCTION_NTHREADS", "4"))
+    bound = bigarray_bound if bigarray_bound is not None else int(os.environ.get("MXNET_KVSTORE_BIGARRAY_BOUND", "1000000"))
+    arr = (c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
+    if L.dlcfn_reduce_sum_cpu(ctypes.cast(arr, c_void_p), len(srcs), out.data_ptr(), t0.numel(), code, nthreads, bound) != 0:
+        raise ValueError("reduce_sum_cpu: bad arguments")
+    return out
+
+
 def topo_is_uniform(link) -> bool:
     n, arr = _mat(link)
     return bool(lib().dlcfn_topo_is_uniform(arr, n))

@@ -363,3 +363,22 @@ def test_device_kvstore_tree_reduce_matches_flat_sum(monkeypatch):
     for r, parent in enumerate(trees):                      # every tree spans all devices and only uses real links
         assert parent[r] == -1 and sorted(i for i, p in enumerate(parent) if p >= 0) == [i for i in range(n) if i != r]
         assert all(dgx1[i][p] > 0 for i, p in enumerate(parent) if p >= 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,k", [(7, 1), (4096 * 3 + 17, 5), (100_000, 9)])
+def test_native_host_reducer_matches_sum(dtype, n, k):
+    """CommCPU::ReduceSumCPU equivalent: 4 inputs per pass, chunked over a thread team above the big-array bound."""
+    torch.manual_seed(n + k)
+    xs = [torch.randn(n).to(dtype) for _ in range(k)]
+    for nthreads, bound in ((1, 10 ** 9), (4, 1000)):
+        out = rt.reduce_sum_cpu(xs, nthreads=nthreads, bigarray_bound=bound)
+        if dtype == torch.float32:
+            want = torch.stack(xs).sum(0)
+            assert torch.allclose(out, want, rtol=1e-5, atol=1e-5)
+        else:
+            want = torch.stack([x.float() for x in xs]).sum(0)
+            assert torch.allclose(out.float(), want, rtol=2e-2, atol=2e-2)
+    inplace = xs[0].clone()
+    rt.reduce_sum_cpu([inplace] + xs[1:], out=inplace, nthreads=4, bigarray_bound=1000)      # dst aliases srcs[0]
+    assert torch.allclose(inplace.float(), torch.stack([x.float() for x in xs]).sum(0), rtol=2e-2, atol=2e-2)

@@ -63,13 +63,19 @@ def parse(argv=None):
     d.add_argument("--num-classes", type=int, default=1000)
     d.add_argument("--num-examples", type=int, default=1281167)
     d.add_argument("--image-shape", type=str, default="3,224,224")
-    d.add_argument("--data-train", type=str, default="")
+    d.add_argument("--data-train", type=str, default="", help="RecordIO file (.rec with its .idx) of training images")
+    d.add_argument("--data-nthreads", type=int, default=4, help="decoder threads of the native record pipeline")
+    d.add_argument("--rand-crop", type=int, default=0)
+    d.add_argument("--rand-mirror", type=int, default=0)
+    d.add_argument("--rgb-mean", type=str, default="123.68,116.779,103.939")
+    d.add_argument("--rgb-std", type=str, default="58.393,57.12,57.375")
     d.add_argument("--num-batches", type=int, default=0, help="stop an epoch after this many batches (benchmark runs)")
     return p.parse_args(argv)
 
 
 def main(argv=None) -> int:
     a = parse(argv)
+    epoch_seed = 0
     from deeplearning_cfn_b200.models import get_model, to_b200_layout
     from deeplearning_cfn_b200.parallel import horovod as hvd
     from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer
@@ -117,6 +123,18 @@ def main(argv=None) -> int:
         profiler.set_state("run")
     x, y = synthetic_device_batch(a.batch_size, size, a.num_classes, dev, dtype=dtype if use_gpu else torch.float32)
     epoch_batches = a.num_batches or max(1, a.num_examples // (a.batch_size * world))
+    loader = None
+    if a.data_train and not a.benchmark:
+        from deeplearning_cfn_b200.utils.data import RecordBatchLoader
+        from deeplearning_cfn_b200.utils.recordio import NativeImageRecordIter
+        c, hh, ww = (int(v) for v in a.image_shape.split(","))
+        rec_it = NativeImageRecordIter(a.data_train, a.batch_size, (c, hh, ww), shuffle=True, num_parts=hvd.size(),
+                                       part_index=rank, preprocess_threads=a.data_nthreads, rand_crop=bool(a.rand_crop),
+                                       rand_mirror=bool(a.rand_mirror), round_batch=False, seed=epoch_seed)
+        mean = tuple(float(v) / 255.0 for v in a.rgb_mean.split(","))
+        std = tuple(float(v) / 255.0 for v in a.rgb_std.split(","))
+        loader = RecordBatchLoader(rec_it, dev, mean, std, dtype if use_gpu else torch.float32)
+        logging.info("training data: %s, %d samples in this shard, %d batches/epoch", a.data_train, rec_it.num_samples, len(rec_it))
     speed = Speedometer(a.batch_size, a.disp_batches)
     for epoch in range(begin, a.num_epochs):
         if epoch in steps:
@@ -124,10 +142,18 @@ def main(argv=None) -> int:
             tr.set_learning_rate(lr)
             logging.info("Update[%d]: Change learning rate to %0.5e", epoch, lr)
         tic = time.time()
-        for i in range(epoch_batches):
-            with profiler.scope("batch", "train", device=use_gpu):
-                loss = tr.step(x, y)
-            speed(epoch, i, None)
+        if loader is not None:       # real data: native record pipeline, sharded by rank
+            for i, (xb, yb) in enumerate(loader):
+                if a.num_batches and i >= a.num_batches:
+                    break
+                with profiler.scope("batch", "train", device=use_gpu):
+                    loss = tr.step(xb, yb)
+                speed(epoch, i, None)
+        else:
+            for i in range(epoch_batches):
+                with profiler.scope("batch", "train", device=use_gpu):
+                    loss = tr.step(x, y)
+                speed(epoch, i, None)
         if use_gpu:
             torch.cuda.synchronize()
         logging.info("Epoch[%d] Train-loss=%f", epoch, float(loss.detach()))

@@ -77,3 +77,43 @@ def synthetic_device_batch(batch: int, size: int, classes: int, device, dtype=to
     x = x.contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, classes, (batch,), generator=g).to(device)
     return x, y
+
+
+class RecordBatchLoader:
+    """Feeds a trainer from a RecordIO file: native decoder ring (utils/recordio.py:NativeImageRecordIter) -> asynchronous
+    H2D out of the page-locked ring slot on a copy stream -> fused uint8->bf16 normalise kernel.  On CPU the batch is
+    normalised with the reference expression.  Yields (x [B,C,H,W] channels_last, y int64)."""
+
+    def __init__(self, it, device: torch.device, mean=IMAGENET_MEAN, std=IMAGENET_STD, dtype=torch.bfloat16):
+        self.it, self.device, self.mean, self.std, self.dtype = it, device, mean, std, dtype
+        self.cuda = device.type == "cuda"
+        self.copy_stream = torch.cuda.Stream() if self.cuda else None
+        self._bufs: list = []          # two device staging sets, alternated
+        self._k = 0
+
+    def __len__(self):
+        return len(self.it)
+
+    def __iter__(self):
+        for x_u8, y in self.it:
+            if not self.cuda:
+                x = ref_ops.normalize_u8_nhwc(x_u8, self.mean, self.std).to(
+                    self.dtype if self.dtype != torch.bfloat16 else torch.float32)
+                yield x.permute(0, 3, 1, 2), y.clone()
+                continue
+            if len(self._bufs) < 2:
+                self._bufs.append({"u8": torch.empty(x_u8.shape, dtype=torch.uint8, device=self.device),
+                                   "y": torch.empty(y.shape, dtype=torch.int64, device=self.device),
+                                   "x": torch.empty(x_u8.shape, dtype=torch.bfloat16, device=self.device),
+                                   "ev": torch.cuda.Event()})
+            s = self._bufs[self._k % 2]
+            self._k += 1
+            self.copy_stream.wait_stream(torch.cuda.current_stream())     # the slot's previous consumer has been enqueued
+            with torch.cuda.stream(self.copy_stream):
+                s["u8"].copy_(x_u8, non_blocking=True)                     # ring slot is page-locked: true async DMA
+                s["y"].copy_(y.pin_memory() if not y.is_pinned() else y, non_blocking=True)
+                s["ev"].record(self.copy_stream)
+            s["ev"].synchronize()      # the ring slot may be recycled `keep` batches later; the copy is short
+            torch.cuda.current_stream().wait_event(s["ev"])
+            native.normalize_u8_nhwc(s["u8"], s["x"], self.mean, self.std)
+            yield s["x"].permute(0, 3, 1, 2), s["y"]

@@ -37,16 +37,25 @@ class MXRecordIO:
         self.f.write(b"\0" * ((4 - n % 4) % 4))
 
     def read(self) -> bytes | None:
-        head = self.f.read(8)
-        if len(head) < 8:
-            return None
-        magic, lrec = struct.unpack("<II", head)
-        if magic != MAGIC:
-            raise IOError(f"bad record magic in {self.uri}")
-        n = lrec & ((1 << 29) - 1)
-        buf = self.f.read(n)
-        self.f.read((4 - n % 4) % 4)
-        return buf
+        """Next record; records that a dmlc writer split at embedded magic words (cflag 1 / 2 / 3) are re-joined."""
+        out, parts = b"", 0
+        while True:
+            head = self.f.read(8)
+            if len(head) < 8:
+                return None if parts == 0 else out
+            magic, lrec = struct.unpack("<II", head)
+            if magic != MAGIC:
+                raise IOError(f"bad record magic in {self.uri}")
+            cflag, n = lrec >> 29, lrec & ((1 << 29) - 1)
+            buf = self.f.read(n)
+            self.f.read((4 - n % 4) % 4)
+            if cflag == 0:
+                return buf
+            out += buf
+            parts += 1
+            if cflag == 3:
+                return out
+            out += struct.pack("<I", MAGIC)
 
     def tell(self) -> int:
         return self.f.tell()
@@ -176,3 +185,168 @@ class ImageRecordIter:
 
     def __len__(self):
         return self._n
+
+
+# ----------------------------------------------------------------------------------------- native pipeline (csrc/rt/recordio.cpp)
+def _rtlib():
+    import ctypes
+    from ctypes import POINTER, c_char_p, c_int, c_long, c_longlong, c_size_t, c_ulonglong, c_void_p
+    from . import rt
+    L = rt.lib()
+    if not getattr(L, "_recio_declared", False):
+        L.dlcfn_rec_open.argtypes = [c_char_p, c_char_p]
+        L.dlcfn_rec_open.restype = c_void_p
+        L.dlcfn_rec_num.argtypes = [c_void_p]
+        L.dlcfn_rec_num.restype = c_long
+        L.dlcfn_rec_key.argtypes = [c_void_p, c_long]
+        L.dlcfn_rec_key.restype = c_longlong
+        L.dlcfn_rec_read.argtypes = [c_void_p, c_long, c_void_p, c_size_t]
+        L.dlcfn_rec_read.restype = c_long
+        L.dlcfn_rec_close.argtypes = [c_void_p]
+        L.dlcfn_rec_writer_open.argtypes = [c_char_p, c_char_p]
+        L.dlcfn_rec_writer_open.restype = c_void_p
+        L.dlcfn_rec_write.argtypes = [c_void_p, c_longlong, c_char_p, c_size_t]
+        L.dlcfn_rec_write.restype = c_int
+        L.dlcfn_rec_writer_close.argtypes = [c_void_p]
+        L.dlcfn_rec_writer_close.restype = c_int
+        L.dlcfn_imgiter_create.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_ulonglong, c_int, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, c_int]
+        L.dlcfn_imgiter_create.restype = c_void_p
+        for f in ("dlcfn_imgiter_num_batches", "dlcfn_imgiter_num_samples", "dlcfn_imgiter_errors"):
+            getattr(L, f).argtypes = [c_void_p]
+            getattr(L, f).restype = c_long
+        L.dlcfn_imgiter_num_slots.argtypes = [c_void_p]
+        L.dlcfn_imgiter_num_slots.restype = c_int
+        L.dlcfn_imgiter_slot_data.argtypes = [c_void_p, c_int]
+        L.dlcfn_imgiter_slot_data.restype = c_void_p
+        L.dlcfn_imgiter_next.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int)]
+        L.dlcfn_imgiter_next.restype = c_int
+        L.dlcfn_imgiter_reset.argtypes = [c_void_p]
+        L.dlcfn_imgiter_destroy.argtypes = [c_void_p]
+        L._recio_declared = True
+    return L, ctypes
+
+
+class NativeRecordIO:
+    """The same .rec / .idx files through the C++ reader / writer (mmap reads, dmlc continuation framing)."""
+
+    def __init__(self, idx_path: str | None, uri: str, flag: str):
+        assert flag in ("r", "w")
+        self.L, self._ct = _rtlib()
+        self.flag = flag
+        enc = lambda p: p.encode() if p else None      # noqa: E731
+        self.h = (self.L.dlcfn_rec_open if flag == "r" else self.L.dlcfn_rec_writer_open)(enc(uri), enc(idx_path))
+        if not self.h:
+            raise IOError(f"cannot open {uri}")
+
+    def __len__(self):
+        return int(self.L.dlcfn_rec_num(self.h))
+
+    def key(self, i: int) -> int:
+        return int(self.L.dlcfn_rec_key(self.h, i))
+
+    def read(self, i: int) -> bytes:
+        n = self.L.dlcfn_rec_read(self.h, i, None, 0)
+        if n < 0:
+            raise IOError(f"bad record {i}")
+        buf = self._ct.create_string_buffer(int(n))
+        self.L.dlcfn_rec_read(self.h, i, buf, n)
+        return buf.raw
+
+    def write(self, key: int, buf: bytes) -> None:
+        if self.L.dlcfn_rec_write(self.h, key, buf, len(buf)) != 0:
+            raise ValueError("record too large")
+
+    def close(self) -> None:
+        if self.h:
+            if self.flag == "r":
+                self.L.dlcfn_rec_close(self.h)
+            elif self.L.dlcfn_rec_writer_close(self.h) != 0:
+                raise IOError("could not finish the record file / index")
+            self.h = None
+
+
+class NativeImageRecordIter:
+    """`ImageRecordIter` on the native pipeline: decoder threads fill fixed-shape uint8 NHWC batches in a ring of pooled
+    host buffers, in order, `prefetch_buffer` batches ahead.  Yields (x uint8 [B,H,W,C], y int64 [B]) views over the
+    ring; a view stays valid for `keep` further `next()` calls (enough for an asynchronous H2D copy that is
+    synchronised one step later).  With CUDA present the ring is page-locked once."""
+
+    def __init__(self, path_imgrec: str, batch_size: int, data_shape=(3, 224, 224), path_imgidx: str | None = None,
+                 shuffle: bool = False, num_parts: int = 1, part_index: int = 0, preprocess_threads: int = 4,
+                 prefetch_buffer: int = 4, seed: int = 0, round_batch: bool = True, rand_crop: bool = False,
+                 rand_mirror: bool = False, label_width: int = 1, keep: int = 2, pin: bool | None = None):
+        self.L, self._ct = _rtlib()
+        self.batch_size, self.shape, self.label_width = batch_size, tuple(data_shape), label_width
+        idx = path_imgidx or os.path.splitext(path_imgrec)[0] + ".idx"
+        self._rec = self.L.dlcfn_rec_open(path_imgrec.encode(), idx.encode() if os.path.exists(idx) else None)
+        if not self._rec:
+            raise IOError(f"cannot open {path_imgrec}")
+        c, h, w = self.shape
+        self._it = self.L.dlcfn_imgiter_create(self._rec, batch_size, h, w, c, label_width, int(shuffle), seed, part_index,
+                                               num_parts, preprocess_threads, prefetch_buffer, int(rand_crop),
+                                               int(rand_mirror), int(round_batch), keep)
+        if not self._it:
+            self.L.dlcfn_rec_close(self._rec)
+            raise IOError("image iterator could not be created (empty shard or bad arguments)")
+        self._pinned = []
+        pin = torch.cuda.is_available() if pin is None else pin
+        if pin and torch.cuda.is_available():
+            from . import storage
+            nbytes = storage.size_class(batch_size * h * w * c)
+            for i in range(self.L.dlcfn_imgiter_num_slots(self._it)):
+                p = self.L.dlcfn_imgiter_slot_data(self._it, i)
+                if int(torch.cuda.cudart().cudaHostRegister(p, nbytes, 0)) == 0:
+                    self._pinned.append(p)
+        self.pad = 0
+        self._first = True
+
+    def __len__(self):
+        return int(self.L.dlcfn_imgiter_num_batches(self._it))
+
+    @property
+    def num_samples(self) -> int:
+        return int(self.L.dlcfn_imgiter_num_samples(self._it))
+
+    def reset(self) -> None:
+        if not self._first:
+            self.L.dlcfn_imgiter_reset(self._it)
+        self._first = False
+
+    def __iter__(self):
+        self.reset()
+        return self
+
+    def __next__(self):
+        self._first = False
+        d, l, nv = self._ct.c_void_p(), self._ct.c_void_p(), self._ct.c_int()
+        if self.L.dlcfn_imgiter_next(self._it, self._ct.byref(d), self._ct.byref(l), self._ct.byref(nv)) == 0:
+            raise StopIteration
+        c, h, w = self.shape
+        B = self.batch_size
+        xb = (self._ct.c_uint8 * (B * h * w * c)).from_address(d.value)
+        lb = (self._ct.c_float * (B * self.label_width)).from_address(l.value)
+        x = torch.frombuffer(xb, dtype=torch.uint8).view(B, h, w, c)
+        lab = torch.frombuffer(lb, dtype=torch.float32).view(B, self.label_width)
+        self.pad = B - nv.value
+        y = lab[:, 0].to(torch.int64) if self.label_width == 1 else lab.clone()
+        return x, y
+
+    @property
+    def errors(self) -> int:
+        return int(self.L.dlcfn_imgiter_errors(self._it))
+
+    def close(self) -> None:
+        if self._it:
+            for p in self._pinned:
+                torch.cuda.cudart().cudaHostUnregister(p)
+            self._pinned = []
+            self.L.dlcfn_imgiter_destroy(self._it)
+            self.L.dlcfn_rec_close(self._rec)
+            self._it = self._rec = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -129,3 +129,21 @@ def test_profiler_trace_and_aggregate(tmp_path):
     assert sum(1 for e in ev if e["name"] == "KVStoreDistDefaultPush" and e["ph"] == "X") == 3
     assert any(e["ph"] == "i" for e in ev) and any(e["ph"] == "C" for e in ev)
     assert not profiler.is_running()
+
+
+def test_train_imagenet_from_record_file_two_ranks(tmp_path):
+    """Real-data path: .rec/.idx -> native decoder ring, sharded over 2 ranks (gloo), random crop + mirror."""
+    import numpy as np
+    from deeplearning_cfn_b200.utils import recordio
+    rec = recordio.MXIndexedRecordIO(str(tmp_path / "train.idx"), str(tmp_path / "train.rec"), "w")
+    rng = np.random.default_rng(1)
+    for i in range(48):
+        rec.write_idx(i, recordio.pack_img(recordio.IRHeader(0, float(i % 10), i, 0), rng.integers(0, 256, (36, 36, 3), dtype=np.uint8)))
+    rec.close()
+    r = run([PY, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "2", PY, "-m", "deeplearning_cfn_b200.examples.train_imagenet",
+             "--network", "resnet", "--num-layers", "20", "--num-classes", "10", "--image-shape", "3,32,32", "--batch-size", "8",
+             "--num-epochs", "2", "--kv-store", "horovod", "--data-train", str(tmp_path / "train.rec"), "--rand-crop", "1",
+             "--rand-mirror", "1", "--data-nthreads", "2", "--disp-batches", "1"])
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "24 samples in this shard, 3 batches/epoch" in out and "Epoch[1] Train-loss" in out and "Speed:" in out

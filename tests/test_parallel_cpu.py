@@ -315,3 +315,74 @@ def test_module_fit_with_dataiter_metric_monitor_and_model_helpers(tmp_path, cap
     model.save_checkpoint(str(tmp_path / "ck"), 3, net, dict(net.named_parameters()), {})
     sym, a2, aux = model.load_checkpoint(str(tmp_path / "ck"), 3)
     assert sym["class"] == "Sequential" and set(a2) == {n for n, _ in net.named_parameters()} and aux == {}
+
+
+def test_native_recordio_pipeline_matches_python_reader(tmp_path):
+    import struct
+    import numpy as np
+    from deeplearning_cfn_b200.utils import recordio
+    # -- framing: the C++ writer splits payloads at embedded magic words (dmlc continuation records), both readers join them
+    w = recordio.NativeRecordIO(str(tmp_path / "f.idx"), str(tmp_path / "f.rec"), "w")
+    magic = struct.pack("<I", recordio.MAGIC)
+    payloads = [b"hello", b"", b"abcd" + magic + b"efgh" + magic + b"zz", magic + b"tail", b"x" * 1001]
+    for i, p in enumerate(payloads):
+        w.write(10 + i, p)
+    w.close()
+    r = recordio.NativeRecordIO(str(tmp_path / "f.idx"), str(tmp_path / "f.rec"), "r")
+    assert len(r) == len(payloads) and [r.key(i) for i in range(len(r))] == [10, 11, 12, 13, 14]
+    assert [r.read(i) for i in range(len(r))] == payloads
+    r.close()
+    r2 = recordio.NativeRecordIO(None, str(tmp_path / "f.rec"), "r")          # no index: scanned from the framing
+    assert len(r2) == len(payloads) and r2.read(2) == payloads[2]
+    r2.close()
+    pr = recordio.MXRecordIO(str(tmp_path / "f.rec"), "r")                    # the python reader joins the parts too
+    assert [pr.read() for _ in payloads] == payloads and pr.read() is None
+    pr.close()
+    # -- image batches: python writer -> native iterator, against the python reader
+    rec = recordio.MXIndexedRecordIO(str(tmp_path / "d.idx"), str(tmp_path / "d.rec"), "w")
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (10, 12, 3), dtype=np.uint8) for _ in range(37)]
+    for i, img in enumerate(imgs):
+        rec.write_idx(i, recordio.pack_img(recordio.IRHeader(0, float(i % 5), i, 0), img))
+    rec.close()
+    it = recordio.NativeImageRecordIter(str(tmp_path / "d.rec"), batch_size=8, data_shape=(3, 8, 8), preprocess_threads=3,
+                                        prefetch_buffer=2, round_batch=True)
+    assert len(it) == 5 and it.num_samples == 37
+    seen, pads = [], []
+    for x, y in it:
+        seen.append((x.clone(), y.clone()))
+        pads.append(it.pad)
+    assert pads == [0, 0, 0, 0, 3]                                   # 37 = 4 x 8 + 5, wrapped to the epoch start
+    for b, (x, y) in enumerate(seen):
+        for j in range(8):
+            i = (b * 8 + j) % 37
+            assert int(y[j]) == i % 5
+            assert np.array_equal(x[j].numpy(), imgs[i][1:9, 2:10, :])           # center crop 10x12 -> 8x8
+    assert it.errors == 0
+    again = [(x.clone(), y.clone()) for x, y in it]                  # second epoch, no shuffle: identical
+    assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(seen, again))
+    it.close()
+    # shards partition the data; shuffling is deterministic per (seed, epoch) and independent of the thread count
+    labels = []
+    for part in range(2):
+        sh = recordio.NativeImageRecordIter(str(tmp_path / "d.rec"), 4, (3, 8, 8), num_parts=2, part_index=part,
+                                            round_batch=False)
+        labels.append(sum(len(y) for _, y in sh))
+        sh.close()
+    assert labels == [16, 16]                                        # 19 and 18 samples, partial batches dropped
+    a = recordio.NativeImageRecordIter(str(tmp_path / "d.rec"), 8, (3, 8, 8), shuffle=True, seed=7, preprocess_threads=1,
+                                       rand_mirror=True, rand_crop=True)
+    b = recordio.NativeImageRecordIter(str(tmp_path / "d.rec"), 8, (3, 8, 8), shuffle=True, seed=7, preprocess_threads=4,
+                                       rand_mirror=True, rand_crop=True)
+    ea, eb = [(x.clone(), y.clone()) for x, y in a], [(x.clone(), y.clone()) for x, y in b]
+    assert all(torch.equal(p[0], q[0]) and torch.equal(p[1], q[1]) for p, q in zip(ea, eb))
+    assert [int(v) for _, y in ea for v in y][:8] != [i % 5 for i in range(8)]            # really shuffled
+    e2 = [(x.clone(), y.clone()) for x, y in a]                      # next epoch: a different order
+    assert not all(torch.equal(p[1], q[1]) for p, q in zip(ea, e2))
+    a.close()
+    b.close()
+    # larger target than source: zero padded, image centred; fewer channels requested than stored
+    big = recordio.NativeImageRecordIter(str(tmp_path / "d.rec"), 2, (1, 16, 16), round_batch=False)
+    x, _ = next(iter(big))
+    assert x.shape == (2, 16, 16, 1) and int(x[0, 0, 0, 0]) == 0 and np.array_equal(x[0, 3:13, 2:14, 0].numpy(), imgs[0][:, :, 0])
+    big.close()

@@ -325,7 +325,7 @@ void KVServer::HandleCommand(Message&& m) {
   {
     std::lock_guard<std::mutex> lk(mu_);
     switch (m.head) {
-      case kStopServer: stop_ = true; exec_stop_ = true; break;
+      case kStopServer: stop_ = true; break;
       case kSyncMode: sync_mode_ = true; break;
       case kSetMultiPrecision: multi_precision_ = true; break;
       case kSetGradientCompression: {
@@ -341,17 +341,22 @@ void KVServer::HandleCommand(Message&& m) {
       default: break;
     }
   }
+  const bool is_stop = m.head == kStopServer;
   if (py_controller_) {
-    // python part + the response that releases the worker run on the Run() thread, in arrival order
+    // python part + the response that releases the worker run on the Run() thread, in arrival order.  The stop flag
+    // is raised by that same task AFTER the response has been sent: raising it here would let Run() return between the
+    // flag and the enqueue and drop the response (the worker that sent kStopServer would wait forever).
     auto msg = std::make_shared<Message>(std::move(m));
-    PostToMain([this, msg] {
+    PostToMain([this, msg, is_stop] {
       py_controller_(msg->head, msg->body.data(), msg->body.size(), py_ctl_user_);
       Respond(*msg);
+      if (is_stop) exec_stop_ = true;
     });
     return;
   }
   Respond(m);
-  if (m.head == kStopServer) {
+  if (is_stop) {
+    exec_stop_ = true;
     std::lock_guard<std::mutex> lk(exec_mu_);
     exec_cv_.notify_all();
   }

@@ -276,7 +276,10 @@ class PSTracker:
         if cmd is None:
             self.port = None
             return
-        probe, self.port = _free_port("", port, port_end)
+        # the reference scans 9091..9999 from the bottom; concurrent jobs on one box would all probe the same port first
+        # and race between this probe and the scheduler's own bind, so start at a per-process offset inside the range
+        start = port + (os.getpid() * 7919) % max(1, (port_end - port) // 2) if port_end - port > 64 else port
+        probe, self.port = _free_port("", start, port_end)
         probe.close()
         env = os.environ.copy()
         env["DMLC_ROLE"] = "scheduler"
@@ -352,7 +355,13 @@ def submit(nworker: int, nserver: int, fun_submit, host_ip: str = "auto", pscmd:
                     break
                 time.sleep(0.1)
         else:
-            tracker.join()
+            rc = tracker.join()
+            if rc not in (0, None) and handle is not None:
+                # the scheduler died (could not bind, crashed): the other nodes can only spin on a dead address
+                logging.error("scheduler exited with code %s - stopping the job", rc)
+                for p in list(getattr(handle, "procs", [])):
+                    if p.poll() is None:
+                        p.kill()
         if handle is not None and hasattr(handle, "wait"):
             handle.wait()
     return tracker, handle

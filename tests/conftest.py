@@ -6,6 +6,26 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def run_job(cmd, env=None, timeout=300, cwd=None):
+    """subprocess.run(capture_output=True, text=True) for commands that start whole jobs (launcher -> scheduler, servers,
+    workers): the command gets its own session and on a timeout the entire process group is killed, so a hung job cannot
+    leave processes behind that slow down or confuse later tests."""
+    import signal
+    import subprocess
+    p = subprocess.Popen(cmd, env=env, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        out, err = p.communicate()
+        return subprocess.CompletedProcess(cmd, -9, out, (err or "") + f"\n[tests] job killed after {timeout} s")
+    return subprocess.CompletedProcess(cmd, p.returncode, out, err)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box with `pytest -m gpu`)")
     config.addinivalue_line("markers", "multigpu: needs >= 2 GPUs")

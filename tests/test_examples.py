@@ -14,7 +14,8 @@ PY = sys.executable
 
 
 def run(cmd, env=None, timeout=600):
-    return subprocess.run(cmd, env=dict(ENV, **(env or {})), capture_output=True, text=True, timeout=timeout)
+    from conftest import run_job
+    return run_job(cmd, env=dict(ENV, **(env or {})), timeout=timeout)
 
 
 def test_readme_flow_mxnet_style_ps_over_stack(tmp_path):

@@ -22,7 +22,8 @@ def _launch(nw, ns, script_args, env=None, timeout=180):
     e.update(env or {})
     cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", str(nw), "-s", str(ns), "--launcher", "local",
            sys.executable] + script_args
-    return subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=timeout)
+    from conftest import run_job
+    return run_job(cmd, env=e, timeout=timeout)
 
 
 # ----------------------------------------------------------------------------- local

@@ -128,8 +128,8 @@ def test_ssh_launcher_over_stack_hostfile(tmp_path, monkeypatch):
     out.mkdir()
     script = tmp_path / "probe.py"
     script.write_text("import os\n"
-                      f"open(r'{out}/'+os.environ['DMLC_ROLE']+os.environ['DMLC_TASK_ID'],'w').write("
-                      "os.environ.get('CUDA_VISIBLE_DEVICES','-')+' '+os.environ['DMLC_NODE_HOST']+' '+os.environ['DEEPLEARNING_WORKERS_COUNT'])\n")
+                      f"open(r'{out}/'+os.environ['DMLC_ROLE']+os.environ.get('DMLC_TASK_ID',''),'w').write("
+                      "os.environ.get('CUDA_VISIBLE_DEVICES','-')+' '+os.environ.get('DMLC_NODE_HOST','-')+' '+os.environ.get('DEEPLEARNING_WORKERS_COUNT','-'))\n")
     env = dict(os.environ, PYTHONPATH=ROOT, **h.export_env())
     r = subprocess.run([sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", h.env["DEEPLEARNING_WORKERS_COUNT"],
                         "-H", h.hostfile, sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=120)

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_gloo_world2_data_parallel_matches_single_process(naive):
     cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "2", sys.executable,
            os.path.join(ROOT, "tests/mp/gloo_trainer_worker.py")]
-    r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT, DLCFN_NAIVE_COLLECTIVES=naive), capture_output=True,
-                       text=True, timeout=300)
+    from conftest import run_job
+    r = run_job(cmd, env=dict(os.environ, PYTHONPATH=ROOT, DLCFN_NAIVE_COLLECTIVES=naive), timeout=300)
     assert r.returncode == 0 and "GLOO_TRAINER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
@@ -33,9 +33,9 @@ def test_allreduce_job_through_tracker_launcher(tmp_path):
         "assert hvd.size() == 2 and torch.allclose(t, torch.full((3,), 1.5)), t\n"
         "print('TRACKER_JOB_OK', hvd.rank(), flush=True)\n"
         "hvd.shutdown()\n")
-    r = subprocess.run([sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "0", "--launcher", "local",
-                        sys.executable, str(script)], env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True,
-                       timeout=180)
+    from conftest import run_job
+    r = run_job([sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "0", "--launcher", "local",
+                 sys.executable, str(script)], env=dict(os.environ, PYTHONPATH=ROOT), timeout=180)
     assert r.returncode == 0 and r.stdout.count("TRACKER_JOB_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
 
 
@@ -134,7 +134,8 @@ def test_sync_replicas_with_backup_worker():
     env = dict(os.environ, PYTHONPATH=root, MXNET_KVSTORE_BIGARRAY_BOUND="40")
     cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "3", "-s", "2", "--launcher", "local",
            sys.executable, os.path.join(root, "tests/mp/sync_replicas_worker.py")]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    from conftest import run_job
+    r = run_job(cmd, env=env, timeout=240)
     assert r.returncode == 0 and r.stdout.count("SYNCREP_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
 
 

@@ -1,5 +1,6 @@
 // KVWorker / KVServer: the KVStoreDist (worker) and KVStoreDistServer (server) logic over Node.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -335,7 +336,7 @@ void KVServer::HandleCommand(Message&& m) {
         gc_threshold_ = c == std::string::npos ? 0.5f : (float)atof(m.body.c_str() + c + 1);
         break;
       }
-      case kSetProfilerParams: profiler_prefix_ = "rank" + std::to_string(node_->my_rank()) + "_" + m.body; break;
+      case kSetProfilerParams: HandleProfilerCommand(m.body); break;
       case kSetOptimizer: ParseOpt(m.body, &opt_); break;
       case kController:
       default: break;
@@ -446,12 +447,64 @@ void KVServer::ApplyUpdate(uint64_t key, Entry& e, size_t begin, size_t n) {
   }
 }
 
+static long long ProfNowUs() {
+  using namespace std::chrono;
+  return duration_cast<microseconds>(steady_clock::now().time_since_epoch()).count();
+}
+
+// body: "config:<file>" | "state:run" | "state:stop" | "dump" (a bare file name is accepted as config)
+void KVServer::HandleProfilerCommand(const std::string& body) {
+  if (body.rfind("state:", 0) == 0) {
+    prof_running_ = body.substr(6) == "run";
+  } else if (body == "dump") {
+    DumpProfile();
+  } else {
+    std::lock_guard<std::mutex> lk(prof_mu_);
+    prof_file_ = body.rfind("config:", 0) == 0 ? body.substr(7) : body;
+    profiler_prefix_ = "rank" + std::to_string(node_->my_rank()) + "_";
+  }
+}
+
+void KVServer::ProfRecord(const char* name, long long t0_us, uint64_t key, size_t bytes) {
+  if (!prof_running_) return;
+  const long long now = ProfNowUs();
+  std::lock_guard<std::mutex> lk(prof_mu_);
+  prof_events_.push_back(ProfEvent{name, t0_us, now - t0_us, key, bytes});
+}
+
+int KVServer::DumpProfile() {
+  std::lock_guard<std::mutex> lk(prof_mu_);
+  std::string dir, base = prof_file_;
+  const size_t slash = base.rfind('/');
+  if (slash != std::string::npos) { dir = base.substr(0, slash + 1); base = base.substr(slash + 1); }
+  const std::string path = dir + "rank" + std::to_string(node_->my_rank()) + "_" + base;
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) return -1;
+  fprintf(f, "{\"traceEvents\": [");
+  for (size_t i = 0; i < prof_events_.size(); ++i) {
+    const ProfEvent& e = prof_events_[i];
+    fprintf(f, "%s{\"name\": \"%s\", \"cat\": \"kvstore_server\", \"ph\": \"X\", \"pid\": %d, \"tid\": 0, \"ts\": %lld, "
+               "\"dur\": %lld, \"args\": {\"key\": %llu, \"bytes\": %zu}}",
+            i ? ", " : "", e.name.c_str(), node_->my_rank(), e.ts_us, e.dur_us, (unsigned long long)e.key, e.bytes);
+  }
+  fprintf(f, "], \"displayTimeUnit\": \"ms\"}\n");
+  fclose(f);
+  return 0;
+}
+
 void KVServer::HandleData(Message&& m) {
   int req_type, dtype;
   UnpairCmd(m.head, &req_type, &dtype);
   uint64_t key = 0;
   if (m.data.empty() || m.data[0].size() < 8) return;
   memcpy(&key, m.data[0].data(), 8);
+  const long long prof_t0 = prof_running_ ? ProfNowUs() : 0;
+  const size_t prof_bytes = m.data.size() > 1 ? m.data[1].size() : 0;
+  const bool prof_push = m.push;
+  struct ProfGuard {
+    KVServer* s; const char* name; long long t0; uint64_t key; size_t bytes;
+    ~ProfGuard() { if (t0) s->ProfRecord(name, t0, key, bytes); }
+  } prof_guard{this, prof_push ? "KVStoreDistServerPush" : "KVStoreDistServerPull", prof_t0, key, prof_bytes};
   std::unique_lock<std::mutex> lk(mu_);
   Entry& e = store_[key];
 

@@ -225,6 +225,16 @@ class KVServer {
   PyUpdater py_updater_ = nullptr; void* py_user_ = nullptr;
   PyController py_controller_ = nullptr; void* py_ctl_user_ = nullptr;
   std::string profiler_prefix_;
+  // server-side profiler (reference kvstore_dist_server.h:276-323: kSetProfilerParams carries config / state / dump
+  // requests from worker rank 0; the file name gets a rank<r>_ prefix).  Events = one Chrome-trace 'X' record per request.
+  struct ProfEvent { std::string name; long long ts_us, dur_us; uint64_t key; size_t bytes; };
+  void HandleProfilerCommand(const std::string& body);
+  void ProfRecord(const char* name, long long t0_us, uint64_t key, size_t bytes);
+  int DumpProfile();
+  std::mutex prof_mu_;
+  std::vector<ProfEvent> prof_events_;
+  std::string prof_file_ = "profile.json";
+  std::atomic<bool> prof_running_{false};
 };
 
 // conversions

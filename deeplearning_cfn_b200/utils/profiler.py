@@ -37,12 +37,19 @@ def set_config(filename: str = "profile.json", profile_all: bool = True, aggrega
     _cfg.update(filename=filename, profile_all=profile_all, aggregate_stats=aggregate_stats)
     if profile_process == "server":
         # the reference forwards the parameters to the servers (kSetProfilerParams); the file gets a rank prefix there
-        from . import rt
-        body = os.path.basename(filename)
-        rt.lib().dlcfn_kv_send_command(rt.CMD_SET_PROFILER, body.encode(), len(body))
+        _server_command("config:" + filename)
 
 
-def set_state(state: str = "stop") -> None:
+def _server_command(body: str) -> None:
+    """kSetProfilerParams to every server (worker side of kvstore_dist.h:96-102); needs a joined dist kvstore."""
+    from . import rt
+    rt.lib().dlcfn_kv_send_command(rt.CMD_SET_PROFILER, body.encode(), len(body))
+
+
+def set_state(state: str = "stop", profile_process: str = "worker") -> None:
+    if profile_process == "server":
+        _server_command("state:" + ("run" if state == "run" else "stop"))
+        return
     _cfg["running"] = state == "run"
 
 
@@ -143,8 +150,12 @@ def dumps(reset: bool = False) -> str:
     return "\n".join(lines)
 
 
-def dump(finished: bool = True, filename: str | None = None) -> str:
-    """Write the Chrome-trace file; non-zero ranks prefix the name with `rank<r>_`."""
+def dump(finished: bool = True, filename: str | None = None, profile_process: str = "worker") -> str:
+    """Write the Chrome-trace file; non-zero ranks prefix the name with `rank<r>_`.  profile_process='server' asks
+    every parameter server to write its own `rank<r>_<file>` (request timeline: push / pull per key)."""
+    if profile_process == "server":
+        _server_command("dump")
+        return ""
     _resolve_device()
     fn = filename or _cfg["filename"]
     r = _rank()

@@ -383,3 +383,20 @@ def test_native_host_reducer_matches_sum(dtype, n, k):
     inplace = xs[0].clone()
     rt.reduce_sum_cpu([inplace] + xs[1:], out=inplace, nthreads=4, bigarray_bound=1000)      # dst aliases srcs[0]
     assert torch.allclose(inplace.float(), torch.stack([x.float() for x in xs]).sum(0), rtol=2e-2, atol=2e-2)
+
+
+def test_remote_server_profiling_writes_rank_prefixed_traces(tmp_path):
+    import json
+    r = _launch(2, 2, [os.path.join(ROOT, "tests/mp/server_profile_worker.py"), str(tmp_path)],
+                env={"MXNET_KVSTORE_BIGARRAY_BOUND": "1000"})
+    assert r.returncode == 0 and r.stdout.count("PROFILED") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith("server_profile.json"))
+    assert files == ["rank0_server_profile.json", "rank1_server_profile.json"]
+    seen = set()
+    for f in files:
+        ev = json.load(open(tmp_path / f))["traceEvents"]
+        names = {e["name"] for e in ev}
+        assert "KVStoreDistServerPush" in names and "KVStoreDistServerPull" in names
+        assert all(e["ph"] == "X" and e["dur"] >= 0 and e["cat"] == "kvstore_server" for e in ev)
+        seen |= {e["args"]["key"] for e in ev}
+    assert len(seen) >= 2          # the small key on one server, the big key's shards on both

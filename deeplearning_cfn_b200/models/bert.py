@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.layernorm import dropout_add_layer_norm
 from ..ops.linear import Linear, linear
 
 
@@ -32,9 +33,10 @@ class BertLayer(nn.Module):
         a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=mask,
                                            dropout_p=self.drop if self.training else 0.0)
         a = a.transpose(1, 2).reshape(B, S, H)
-        x = self.ln1(x + F.dropout(self.proj(a), self.drop, self.training))
+        # residual + dropout + LayerNorm: one fused kernel each way when DLCFN_FUSED_LN=1 (ops/layernorm.py), torch otherwise
+        x = dropout_add_layer_norm(self.proj(a), x, self.ln1.weight, self.ln1.bias, self.drop, self.ln1.eps, self.training)
         h = self.fc2(F.gelu(self.fc1(x)))
-        return self.ln2(x + F.dropout(h, self.drop, self.training))
+        return dropout_add_layer_norm(h, x, self.ln2.weight, self.ln2.bias, self.drop, self.ln2.eps, self.training)
 
 
 class Bert(nn.Module):

@@ -1,0 +1,118 @@
+"""Fused dropout + residual add + LayerNorm (csrc/cuda/layernorm.cu) for post-LN transformer blocks.
+
+    y = LayerNorm(residual + dropout(h, p)) * weight + bias
+
+One kernel forward (reads h and the residual once, writes y, the rounded sum z, one mask bit per element and the row
+statistics) and one backward (reads dy, z, mask; writes the residual gradient, the dropout-branch gradient and per-CTA
+partial sums of dweight / dbias that a small kernel reduces in a fixed order).  The PyTorch-eager form of the same
+sub-graph is ~4 kernels forward and ~8 backward over the same [tokens, hidden] tensors.
+
+EXPERIMENTAL in round 1: written and compiled, numerics tests in tests/test_gpu_experimental.py (run with
+DLCFN_EXPERIMENTAL=1), not yet validated on a GPU - the models only use it when DLCFN_FUSED_LN=1.
+CPU tensors / other dtypes / unsupported widths use the torch expression.
+"""
+from __future__ import annotations
+
+import os
+from ctypes import c_float, c_int, c_longlong, c_ulonglong, c_void_p
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+
+_SUPPORTED_H = (256, 512, 768, 1024, 1536, 2048)
+_counter = [0]          # Philox offset: advanced by the number of 8-element groups of every call
+
+
+def enabled() -> bool:
+    return os.environ.get("DLCFN_FUSED_LN", "0") == "1"
+
+
+def _declare():
+    L = native.lib()
+    if getattr(L, "_ln_declared", False):
+        return L
+    L.dlcfn_dal_bwd_blocks.argtypes = [c_longlong]
+    L.dlcfn_dal_bwd_blocks.restype = c_int
+    L.dlcfn_dropout_add_ln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_longlong, c_int, c_float, c_float, c_ulonglong, c_ulonglong, c_void_p]
+    L.dlcfn_dropout_add_ln_fwd.restype = c_int
+    L.dlcfn_dropout_add_ln_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
+    L.dlcfn_dropout_add_ln_bwd.restype = c_int
+    L._ln_declared = True
+    return L
+
+
+class _DropoutAddLNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, residual, weight, bias, p, eps, seed, offset):
+        L = _declare()
+        H = h.shape[-1]
+        h2 = h.reshape(-1, H)
+        h2 = h2 if h2.is_contiguous() else h2.contiguous()
+        x2 = None
+        if residual is not None:
+            x2 = residual.reshape(-1, H)
+            x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        rows = h2.shape[0]
+        g32 = weight.detach().float().contiguous()
+        b32 = bias.detach().float().contiguous()
+        y = torch.empty_like(h2)
+        z = torch.empty_like(h2)
+        mask = torch.empty(rows * H // 8, dtype=torch.uint8, device=h.device) if p > 0 else None
+        mean = torch.empty(rows, dtype=torch.float32, device=h.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=h.device)
+        native.check(L.dlcfn_dropout_add_ln_fwd(h2.data_ptr(), native._ptr(x2), g32.data_ptr(), b32.data_ptr(), z.data_ptr(),
+                                                y.data_ptr(), native._ptr(mask), mean.data_ptr(), rstd.data_ptr(), rows, H,
+                                                eps, p, seed, offset, native.stream_ptr()), "dropout_add_ln_fwd")
+        native._count()
+        ctx.save_for_backward(z, mask, g32, mean, rstd)
+        ctx.p, ctx.has_res, ctx.wdtype, ctx.shape = p, residual is not None, weight.dtype, h.shape
+        ctx.mask_out = mask
+        return y.view(h.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _declare()
+        z, mask, g32, mean, rstd = ctx.saved_tensors
+        rows, H = z.shape
+        dy2 = dy.reshape(rows, H)
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        dz = torch.empty_like(z)
+        dh = torch.empty_like(z) if (ctx.p > 0 or not ctx.has_res) else None     # p == 0: dh is dz itself
+        nblk = L.dlcfn_dal_bwd_blocks(rows)
+        partial = torch.empty(nblk * 2 * H, dtype=torch.float32, device=z.device)
+        dgamma = torch.empty(H, dtype=torch.float32, device=z.device)
+        dbeta = torch.empty(H, dtype=torch.float32, device=z.device)
+        native.check(L.dlcfn_dropout_add_ln_bwd(dy2.data_ptr(), z.data_ptr(), native._ptr(mask), g32.data_ptr(),
+                                                mean.data_ptr(), rstd.data_ptr(), dz.data_ptr(), native._ptr(dh),
+                                                partial.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, H, ctx.p,
+                                                native.stream_ptr()), "dropout_add_ln_bwd")
+        native._count(2)
+        dh_out = (dh if dh is not None else dz).view(ctx.shape)
+        dres = dz.view(ctx.shape) if ctx.has_res else None
+        return dh_out, dres, dgamma.to(ctx.wdtype), dbeta.to(ctx.wdtype), None, None, None, None
+
+
+def fused_supported(h: torch.Tensor) -> bool:
+    return h.is_cuda and h.dtype == torch.bfloat16 and h.shape[-1] in _SUPPORTED_H
+
+
+def dropout_add_layer_norm(h: torch.Tensor, residual: torch.Tensor | None, weight: torch.Tensor, bias: torch.Tensor,
+                           p: float = 0.0, eps: float = 1e-12, training: bool = True, force: bool | None = None):
+    """LayerNorm(residual + dropout(h, p)) * weight + bias.  `force`: True / False overrides DLCFN_FUSED_LN."""
+    use = enabled() if force is None else force
+    p_eff = float(p) if training else 0.0
+    if use and fused_supported(h) and (residual is None or (residual.dtype == h.dtype and residual.shape == h.shape)):
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        offset = _counter[0]
+        _counter[0] += h.numel() // 8
+        return _DropoutAddLNFn.apply(h, residual, weight, bias, p_eff, float(eps), seed, offset)
+    if use and h.is_cuda and not native.lib_path().exists():
+        raise native.NativeUnavailable("libdlcfn_cuda.so missing")
+    s = F.dropout(h, p_eff, True) if p_eff > 0 else h
+    if residual is not None:
+        s = residual + s
+    return F.layer_norm(s, (h.shape[-1],), weight.to(s.dtype), bias.to(s.dtype), eps)

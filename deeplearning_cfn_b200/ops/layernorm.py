@@ -7,8 +7,10 @@ statistics) and one backward (reads dy, z, mask; writes the residual gradient, t
 partial sums of dweight / dbias that a small kernel reduces in a fixed order).  The PyTorch-eager form of the same
 sub-graph is ~4 kernels forward and ~8 backward over the same [tokens, hidden] tensors.
 
-EXPERIMENTAL in round 1: written and compiled, numerics tests in tests/test_gpu_experimental.py (run with
-DLCFN_EXPERIMENTAL=1), not yet validated on a GPU - the models only use it when DLCFN_FUSED_LN=1.
+EXPERIMENTAL in round 1: written without GPU access; the one GPU run that the remaining budget allowed
+(DLCFN_EXPERIMENTAL=1 pytest tests/test_gpu_experimental.py) showed the FORWARD matching the fp32 reference and the
+BACKWARD input gradient NOT matching (first case [True-8-256]: 3 % of elements within tolerance) - to be debugged with a
+GPU next round.  The models only use these kernels when DLCFN_FUSED_LN=1 (default 0).
 CPU tensors / other dtypes / unsupported widths use the torch expression.
 """
 from __future__ import annotations

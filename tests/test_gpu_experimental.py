@@ -42,7 +42,7 @@ def test_fused_add_layernorm_without_dropout(rows, H, with_res):
     xr = x.detach().float().requires_grad_(True) if with_res else None
     wr, br = w.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
     s = hr + xr if with_res else hr
-    s = s.bfloat16().float() + (s - s.detach())          # the kernel normalises the bf16-rounded sum (straight-through)
+    s = s + (s.detach().bfloat16().float() - s.detach())  # the kernel normalises the bf16-rounded sum (straight-through: value rounded, gradient 1)
     yr = F.layer_norm(s, (H,), wr, br, 1e-12)
     yr.backward(gy.float())
     _frac_close(y, yr, 2e-2, 2e-2)
@@ -81,7 +81,7 @@ def test_fused_dropout_add_layernorm_mask_and_gradients(p):
     y.backward(gy)
     hr, xr = h.detach().float().requires_grad_(True), x.detach().float().requires_grad_(True)
     s = xr + hr * keep / (1 - p)
-    s = s.bfloat16().float() + (s - s.detach())
+    s = s + (s.detach().bfloat16().float() - s.detach())
     yr = F.layer_norm(s, (H,), w.detach().float(), b.detach().float(), 1e-12)
     yr.backward(gy.float())
     _frac_close(y, yr, 2e-2, 2e-2)

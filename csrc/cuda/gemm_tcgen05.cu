@@ -94,6 +94,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast load: the box lands at the same shared-memory offset of every CTA in `cta_mask`, and every destination
+// CTA's mbarrier (same offset) receives the complete_tx for its copy
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// MMA-completion arrive on the mbarrier at the same offset of every CTA in `cta_mask`
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1)
@@ -154,7 +178,14 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// MC = true (EXPERIMENTAL, round 1, not yet run on a GPU; DLCFN_GEMM_MULTICAST=1): the grid is launched as clusters of two
+// CTAs that work on M-adjacent tiles of the same N block.  They share the B tile: each CTA fetches HALF of it and
+// multicasts that half into both CTAs' shared memory, so a CTA pulls A (16 KiB) + B/2 (16 KiB) per k-block from L2
+// instead of 48 KiB - the single-CTA kernel needs ~26 TB/s of L2 bandwidth at full tensor rate, which is what holds it
+// at 81 % pipe utilisation.  A stage of either CTA may only be refilled when BOTH CTAs' MMAs have consumed it (the
+// peer's multicast writes into it), so the smem-empty barriers take two arrivals: each CTA's tcgen05.commit is itself
+// multicast to both.  Everything else (TMEM, epilogue, TMA store) is per CTA and unchanged.
+template <int BLOCK_N, bool A_MN, bool B_MN, bool MC = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN>;
   constexpr int kStages = Cfg::kStages;
@@ -178,7 +209,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
-  const int num_items = num_tiles * p.splits;
+  // MC: work items are PAIRS of M-adjacent tiles, one per cluster; a phantom second tile (odd num_m) loads zeros (TMA
+  // out-of-bounds fill) and stores nothing (clipped), so both CTAs always run the same barrier sequence
+  const int cta_rank = MC ? (int)cluster_ctarank() : 0;
+  const int num_pm = MC ? (num_m + 1) / 2 : num_m;
+  const int num_items = MC ? num_pm * num_n : num_tiles * p.splits;
+  const int item0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -186,7 +223,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     if (p.tma_store) tma_prefetch_desc(&p.tmD);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -202,6 +239,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (MC) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -209,10 +247,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item % num_tiles, split = item / num_tiles;
-        const int m_idx = (tile % num_m) * kBlockM;
-        const int n_idx = (tile / num_m) * BLOCK_N;
+      for (int item = item0; item < num_items; item += item_step) {
+        const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
+        const int m_idx = MC ? ((item % num_pm) * 2 + cta_rank) * kBlockM : (tile % num_m) * kBlockM;
+        const int n_idx = MC ? (item / num_pm) * BLOCK_N : (tile / num_m) * BLOCK_N;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           const int k_idx = kb * kBlockK;
@@ -227,7 +265,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
             for (int j = 0; j < kBlockM / 64; ++j)  // box {64 m, 64 k} per 128B-wide MN atom
               tma_load_2d(sa + j * 8192, &p.tmA, full_bar(stage), m_idx + 64 * j, k_idx);
           }
-          if constexpr (!B_MN) {
+          if constexpr (MC) {
+            // this CTA's half of the shared B tile, multicast to both CTAs of the pair
+            if constexpr (!B_MN) {       // K-major: box {64 k, BLOCK_N/2 n}; the halves are 16 KiB apart (swizzle-atom aligned)
+              tma_load_2d_mc(sb + cta_rank * (Cfg::kBBytes / 2), &p.tmB[0], full_bar(stage), k_idx,
+                             n_idx + cta_rank * (BLOCK_N / 2), (uint16_t)3);
+            } else {                     // MN-major: BLOCK_N/64 boxes {64 n, 64 k}; this CTA issues its half of them
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 128; ++j) {
+                const int jj = cta_rank * (BLOCK_N / 128) + j;
+                tma_load_2d_mc(sb + jj * 8192, &p.tmB[0], full_bar(stage), n_idx + 64 * jj, k_idx, (uint16_t)3);
+              }
+            }
+          } else if constexpr (!B_MN) {
             // rows of B (= output columns n) may live on a peer: pick the owner's tensor map
             const int shard = (p.n_shards > 1) ? n_idx / p.rows_per_shard : 0;
             const int n_loc = n_idx - shard * p.rows_per_shard;
@@ -255,8 +305,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int split = item / num_tiles;
+      for (int item = item0; item < num_items; item += item_step) {
+        const int split = MC ? 0 : item / num_tiles;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -274,7 +324,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
             const uint64_t db = B_MN ? umma_desc(sb + k * 2048, 8192, 1024) : umma_desc(sb + k * 32, 16, 1024);
             tc_mma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (MC: tell the peer too, its multicast writes into this slot)
+          if constexpr (MC) tc_commit_mc(empty_bar(stage), (uint16_t)3);
+          else tc_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
@@ -289,10 +341,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     const bool splitk = p.splits > 1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile = item % num_tiles, split = item / num_tiles;
-      const int m_idx = (tile % num_m) * kBlockM;
-      const int n_idx = (tile / num_m) * BLOCK_N;
+    for (int item = item0; item < num_items; item += item_step) {
+      const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
+      const int m_idx = MC ? ((item % num_pm) * 2 + cta_rank) * kBlockM : (tile % num_m) * kBlockM;
+      const int n_idx = MC ? (item / num_pm) * BLOCK_N : (tile / num_m) * BLOCK_N;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m_idx + q * 32 + lane;
@@ -419,6 +471,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols));
@@ -613,6 +666,44 @@ static int launch(GemmParams& p, int num_sms, cudaStream_t stream) {
   return (int)le;
 }
 
+// EXPERIMENTAL multicast-pair launch (BLOCK_N = 256, local B, no split-K): clusters of 2 CTAs, grid = 2 x pairs
+template <bool A_MN, bool B_MN>
+static int launch_mc(GemmParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<256, A_MN, B_MN>;
+  auto kern = kgemm<256, A_MN, B_MN, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (ae != cudaSuccess) return (int)ae;
+    configured = true;
+  }
+  p.splits = 1;
+  p.kb_per_split = (p.K + kBlockK - 1) / kBlockK;
+  p.ws = nullptr;
+  const int num_m = (p.M + kBlockM - 1) / kBlockM, num_n = (p.N + 255) / 256;
+  const int pair_tiles = ((num_m + 1) / 2) * num_n;
+  int pairs = num_sms / 2;
+  if (pairs > pair_tiles) pairs = pair_tiles;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess)
+    fprintf(stderr, "[dlcfn] kgemm (multicast pair) launch failed: %s (grid %d)\n", cudaGetErrorString(le), 2 * pairs);
+  return (int)le;
+}
+
 }  // namespace dlcfn
 
 using namespace dlcfn;
@@ -667,6 +758,11 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   p.relu = relu;
   static const bool splitk_env = [] { const char* e = getenv("DLCFN_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
   p.split_k_ok = splitk_env ? 1 : 0;
+  // EXPERIMENTAL multicast-pair kernel: opt-in, wide tiles, local B, enough tile pairs to fill the machine, and a
+  // reduction too short for split-K to matter (it is not combined with split-K)
+  static const bool mc_env = [] { const char* e = getenv("DLCFN_GEMM_MULTICAST"); return e && e[0] == '1'; }();
+  const bool use_mc = mc_env && block_n == 256 && n_shards == 1 &&
+                      (long long)(((M + kBlockM - 1) / kBlockM + 1) / 2) * ((N + 255) / 256) >= num_sms / 2;
   int rc;
   if (!a_mn) rc = make_map(&p.tmA, A, M, K, lda, kBlockK, kBlockM);
   else rc = make_map(&p.tmA, A, K, M, lda, 64, kBlockK);
@@ -674,7 +770,7 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   for (int s = 0; s < n_shards; ++s) {
     if (!b_mn) {
       const uint64_t rows = n_shards > 1 ? (uint64_t)rows_per_shard : (uint64_t)N;
-      rc = make_map(&p.tmB[s], b_shards[s], rows, K, ldb, kBlockK, block_n);
+      rc = make_map(&p.tmB[s], b_shards[s], rows, K, ldb, kBlockK, use_mc ? block_n / 2 : block_n);   // MC: half tile per CTA
     } else {
       const uint64_t rows = n_shards > 1 ? (uint64_t)rows_per_shard : (uint64_t)K;
       rc = make_map(&p.tmB[s], b_shards[s], rows, N, ldb, 64, kBlockK);
@@ -692,6 +788,12 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
     // a tile must not straddle two shards
     if (!b_mn && (rows_per_shard % block_n)) return (int)cudaErrorInvalidValue;
     if (b_mn && (rows_per_shard % kBlockK)) return (int)cudaErrorInvalidValue;
+  }
+  if (use_mc) {
+    if (!a_mn && !b_mn) return launch_mc<false, false>(p, num_sms, stream);
+    if (!a_mn && b_mn) return launch_mc<false, true>(p, num_sms, stream);
+    if (a_mn && !b_mn) return launch_mc<true, false>(p, num_sms, stream);
+    return launch_mc<true, true>(p, num_sms, stream);
   }
 #define DLCFN_GEMM_CASE(BN, AM, BM) \
   if (block_n == BN && (bool)a_mn == AM && (bool)b_mn == BM) return launch<BN, AM, BM>(p, num_sms, stream);

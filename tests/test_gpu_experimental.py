@@ -108,3 +108,38 @@ def test_bert_layer_same_loss_with_fused_layernorm(monkeypatch):
     assert abs(out["0"][0] - out["1"][0]) < 0.02 * abs(out["0"][0]) + 0.02
     cos = F.cosine_similarity(out["0"][1].flatten(), out["1"][1].flatten(), dim=0).item()
     assert cos > 0.98, cos
+
+
+_MC_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from deeplearning_cfn_b200.ops import native
+torch.manual_seed(0)
+ok = True
+for (M, N, K, a_mn, b_mn) in [(4096, 4096, 512, 0, 0), (8192, 2048, 1024, 0, 1), (4224, 4096, 320, 1, 1), (19072, 512, 256, 1, 0),
+                              (8192, 8192, 8192, 0, 0)]:
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.5).bfloat16()
+    A = a.t().contiguous() if a_mn else a
+    B = b.t().contiguous() if b_mn else b
+    out = native.gemm_bf16(A, B, a_mn=bool(a_mn), b_mn=bool(b_mn), block_n=256)
+    ref = native.gemm_bf16(A, B, a_mn=bool(a_mn), b_mn=bool(b_mn), block_n=128)     # validated single-CTA kernel
+    torch.cuda.synchronize()
+    want = a.float() @ b.float().t()
+    err = ((out.float() - want).abs().max() / (want.abs().max() + 1e-6)).item()
+    same = torch.equal(out, ref)
+    print(M, N, K, a_mn, b_mn, "rel err %%.4f" %% err, "bitwise equal to the single-CTA kernel:", same, flush=True)
+    ok = ok and err < 2e-2
+print("MC_OK" if ok else "MC_WRONG", flush=True)
+"""
+
+
+def test_multicast_pair_gemm_in_a_subprocess():
+    """The 2-CTA-cluster multicast GEMM (DLCFN_GEMM_MULTICAST=1) against torch and against the validated single-CTA kernel.
+    Runs in a child under a timeout: a protocol bug in a cluster kernel shows up as a hang, not as a wrong number."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["timeout", "120", sys.executable, "-c", _MC_SCRIPT % root],
+                       env=dict(os.environ, DLCFN_GEMM_MULTICAST="1"), capture_output=True, text=True)
+    assert "MC_OK" in r.stdout, f"rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"

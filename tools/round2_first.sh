@@ -8,6 +8,8 @@ echo "== whole GPU suite"
 timeout 900 python -m pytest tests/ -x -q -m gpu --timeout 600 2>&1 | tail -4 | tee gpurun_out/r2_pytest_gpu.log
 echo "== GEMM: tile-width score (BERT shapes now take 128x256 tiles)"
 timeout 200 python tools/gemm_quick_perf.py 2>&1 | tail -10 | tee gpurun_out/r2_gemm_perf.log
+echo "== GEMM with the multicast-pair kernel (experimental; under a timeout: a protocol bug would hang)"
+DLCFN_GEMM_MULTICAST=1 timeout 120 python tools/gemm_quick_perf.py 2>&1 | tail -10 | tee gpurun_out/r2_gemm_perf_multicast.log
 echo "== BERT-large, eager LayerNorm vs fused"
 DLCFN_FUSED_LN=0 timeout 300 python bench.py --model bert-large --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_bert_eager_ln.json
 DLCFN_FUSED_LN=1 timeout 300 python bench.py --model bert-large --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_bert_fused_ln.json

@@ -293,6 +293,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      if constexpr (MC) {
+        // producer tail: every slot's last use has been released by BOTH CTAs, i.e. the peer's multicast commits that
+        // target this CTA's barriers have landed - only then may this CTA run towards its exit
+        for (int s = 0; s < kStages; ++s) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================

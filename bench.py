@@ -164,6 +164,9 @@ def main():
         sync_all()
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         last, losses_read = 0.0, 0
+        e_sampler = ClockSampler(gpu_index=local_rank) if rank == 0 else None      # clocks / throttle reasons of THIS loop
+        if e_sampler:
+            e_sampler.__enter__()
         e_start.record()
         for i in range(args.steps):
             if is_worker:
@@ -186,6 +189,8 @@ def main():
             assert losses_read == args.steps
         e_end.record()
         sync_all()
+        if e_sampler:
+            e_sampler.__exit__(None, None, None)
         e_ms = e_start.elapsed_time(e_end)
         if os.environ.get("DLCFN_BENCH_DIAG") == "1" and is_worker:    # diagnostics only: is the e2e gap time-dependent?
             for tag, (xa, ya) in (("device input after e2e", (x, y)), ("last prefetched batch, no copies in flight", (xb, yb))):
@@ -196,7 +201,8 @@ def main():
                 d1.record()
                 torch.cuda.synchronize()
                 print(f"[diag] {tag}: {d0.elapsed_time(d1) / args.steps:.3f} ms/step", file=sys.stderr, flush=True)
-        e2e = {"ms": e_ms, "loss": last, "h2d": src.bytes_per_batch if is_worker else 0}
+        e2e = {"ms": e_ms, "loss": last, "h2d": src.bytes_per_batch if is_worker else 0,
+               "clocks": e_sampler.summary() if e_sampler else {}}
 
     # ---------------------------------------------------------------- reduce over ranks
     t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(launches)], device=device, dtype=torch.float64)
@@ -248,7 +254,8 @@ def main():
             rec["e2e"] = {"value": round(global_batch * args.steps / (e_ms / 1e3), 2), "unit": "images/sec",
                           "h2d_bytes_per_step": e2e["h2d"] * n_workers if is_worker else 0,
                           "d2h_bytes_per_step": 4 * n_workers, "last_loss": e2e["loss"],
-                          "readback": "loss copied D2H (pinned, async) every step and read on the host one step later"}
+                          "readback": "loss copied D2H (pinned, async) every step and read on the host one step later",
+                          "clocks": {"sm_mhz": e2e["clocks"].get("sm_mhz"), "reasons": e2e["clocks"].get("reasons", [])}}
             if not is_worker:  # rank 0 is a dedicated server: bytes come from the workers
                 rec["e2e"]["h2d_bytes_per_step"] = (args.batch * args.image_size * args.image_size * 3 + args.batch * 8) * n_workers
         if rec is not None:

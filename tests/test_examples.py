@@ -148,3 +148,22 @@ def test_train_imagenet_from_record_file_two_ranks(tmp_path):
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
     assert "24 samples in this shard, 3 batches/epoch" in out and "Epoch[1] Train-loss" in out and "Speed:" in out
+
+
+def test_gluon_style_example_reads_record_files(tmp_path):
+    """image_classification --data-dir with train.rec / val.rec (the reference's ImageNet input form) on the native pipeline."""
+    import numpy as np
+    from deeplearning_cfn_b200.utils import recordio
+    rng = np.random.default_rng(2)
+    for split, n in (("train", 40), ("val", 16)):
+        rec = recordio.MXIndexedRecordIO(str(tmp_path / f"{split}.idx"), str(tmp_path / f"{split}.rec"), "w")
+        for i in range(n):
+            lab = i % 10
+            img = np.clip(rng.integers(0, 40, (36, 36, 3)) + lab * 20, 0, 255).astype(np.uint8)
+            rec.write_idx(i, recordio.pack_img(recordio.IRHeader(0, float(lab), i, 0), img))
+        rec.close()
+    r = run([PY, "-m", "deeplearning_cfn_b200.examples.image_classification", "--dataset", "cifar10", "--model", "resnet20",
+             "--data-dir", str(tmp_path), "--epochs", "1", "--batch-size", "8", "--kvstore", "local", "--log-interval", "1"])
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "Epoch[0] Batch [4]" in out and "validation: accuracy" in out

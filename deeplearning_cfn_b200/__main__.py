@@ -88,7 +88,7 @@ def main(argv=None) -> int:
     # job-plane commands own their argument parsing
     passthrough = {"launch": "launch.launcher", "kill": "launch.kill", "generate-trainer": "launch.tf_ps_scripts",
                    "run-example": "examples.run_example", "bandwidth": "examples.bandwidth_measure",
-                   "benchmark": "examples.benchmark", "mpirun": "launch.mpirun"}
+                   "benchmark": "examples.benchmark", "mpirun": "launch.mpirun", "im2rec": "utils.im2rec"}
     if argv and argv[0] in passthrough:
         import importlib
         mod = importlib.import_module("." + passthrough[argv[0]], __package__)

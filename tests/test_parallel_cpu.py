@@ -387,3 +387,30 @@ def test_native_recordio_pipeline_matches_python_reader(tmp_path):
     x, _ = next(iter(big))
     assert x.shape == (2, 16, 16, 1) and int(x[0, 0, 0, 0]) == 0 and np.array_equal(x[0, 3:13, 2:14, 0].numpy(), imgs[0][:, :, 0])
     big.close()
+
+
+def test_im2rec_list_and_record_roundtrip(tmp_path):
+    import numpy as np
+    from PIL import Image
+    from deeplearning_cfn_b200.utils import im2rec, recordio
+    root = tmp_path / "imgs"
+    rng = np.random.default_rng(0)
+    for cls in ("cat", "dog", "eel"):
+        (root / cls).mkdir(parents=True)
+        for i in range(4):
+            Image.fromarray(rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)).save(root / cls / f"{i}.png")
+    prefix = str(tmp_path / "data")
+    assert im2rec.main([prefix, str(root), "--list", "--train-ratio", "0.75"]) == 0
+    train = list(im2rec.read_list(prefix + "_train.lst"))
+    val = list(im2rec.read_list(prefix + "_val.lst"))
+    assert len(train) == 9 and len(val) == 3 and {int(l[0]) for _, _, l in train + val} == {0, 1, 2}
+    assert im2rec.main([prefix, str(root), "--resize", "16", "--center-crop"]) == 0
+    it = recordio.NativeImageRecordIter(prefix + "_train.rec", 3, (3, 16, 16), round_batch=False)
+    seen = 0
+    for x, y in it:
+        assert x.shape == (3, 16, 16, 3) and set(y.tolist()) <= {0, 1, 2}
+        seen += len(y)
+    assert seen == 9 and it.errors == 0
+    it.close()
+    h, img = recordio.unpack_img(recordio.MXIndexedRecordIO(prefix + "_val.idx", prefix + "_val.rec", "r").read())
+    assert img.shape == (16, 16, 3)

@@ -414,3 +414,32 @@ def test_im2rec_list_and_record_roundtrip(tmp_path):
     it.close()
     h, img = recordio.unpack_img(recordio.MXIndexedRecordIO(prefix + "_val.idx", prefix + "_val.rec", "r").read())
     assert img.shape == (16, 16, 3)
+
+
+def test_trainer_handles_parameters_without_gradient():
+    """A parameter that takes no part in the step (its hook never fires) is gathered as zeros when the bucket is flushed."""
+    from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.used = torch.nn.Linear(6, 4)
+            self.unused = torch.nn.Linear(6, 4)
+
+        def forward(self, x):
+            return self.used(x)
+
+    torch.manual_seed(0)
+    net = Net()
+    tr = DataParallelTrainer(net, mode="local", optimizer="sgd", lr=0.5, wd=0.0, bucket_bytes=64)
+    w_unused = net.unused.weight.detach().clone()
+    w_used = net.used.weight.detach().clone()
+    x, y = torch.randn(8, 6), torch.randint(0, 4, (8,))
+    for _ in range(2):
+        loss = tr.step(x, y)
+    assert torch.isfinite(loss)
+    assert torch.equal(net.unused.weight.detach(), w_unused)          # zero gradient, no weight decay: untouched
+    assert not torch.equal(net.used.weight.detach(), w_used)
+    # and the flat gradient buffer really holds zeros for it (not stale values of an earlier step)
+    gv = tr.flat._grad_view[id(net.unused.weight)]
+    assert float(gv.abs().sum()) == 0.0

@@ -8,7 +8,10 @@ from ctypes import (CFUNCTYPE, POINTER, c_char_p, c_double, c_float, c_int, c_in
                     c_void_p)
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent.parent / "_lib" / "libdlcfn_rt.so"
+import os as _os
+
+# DLCFN_RT_LIB points at an alternative build of the runtime (tools/sanitize_rt.sh: address-sanitizer build)
+_LIB_PATH = Path(_os.environ.get("DLCFN_RT_LIB") or (Path(__file__).resolve().parent.parent / "_lib" / "libdlcfn_rt.so"))
 _lib = None
 _lock = threading.Lock()
 

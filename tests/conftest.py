@@ -17,11 +17,20 @@ def run_job(cmd, env=None, timeout=300, cwd=None):
     try:
         out, err = p.communicate(timeout=timeout)
     except subprocess.TimeoutExpired:
-        try:
-            os.killpg(p.pid, signal.SIGKILL)
-        except ProcessLookupError:
-            pass
-        out, err = p.communicate()
+        # SIGTERM first: launchers that supervise their own children in other process groups (torchrun) take their
+        # workers down on it; then SIGKILL whatever is left of the session
+        for sig, grace in ((signal.SIGTERM, 15), (signal.SIGKILL, None)):
+            try:
+                os.killpg(p.pid, sig)
+            except ProcessLookupError:
+                break
+            try:
+                out, err = p.communicate(timeout=grace)
+                break
+            except subprocess.TimeoutExpired:
+                continue
+        else:
+            out, err = p.communicate()
         return subprocess.CompletedProcess(cmd, -9, out, (err or "") + f"\n[tests] job killed after {timeout} s")
     return subprocess.CompletedProcess(cmd, p.returncode, out, err)
 

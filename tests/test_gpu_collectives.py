@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(nproc, script, port, timeout=600):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mp", script)]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    from conftest import run_job
+    return run_job(cmd, timeout=timeout, cwd=ROOT)
 
 
 def test_collectives_world2():

@@ -686,6 +686,11 @@ class KVStoreDistDevice(KVStore):
                 g.copy_(v[0].reshape(-1))
             else:
                 native.elementwise_sum([x.reshape(-1).to(g.device, g.dtype).contiguous() for x in v], g)
+            if self._compression is not None:
+                # 2-bit wire format with error feedback (K9): what this worker contributes is dequantize(quantize(g +
+                # residual)); the fused server kernel then sums the workers' contributions as usual.  On NVLink the
+                # saved bytes do not matter, the point is the reference's numerical semantics.
+                g.copy_(self._compress_roundtrip(ik, 0, g).reshape(-1))
             hp = dict(self._hp) if self._hp else {"lr": 0.0}
             kind = self._opt_kind
             if kind == "adam":

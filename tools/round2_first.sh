@@ -15,3 +15,5 @@ DLCFN_FUSED_LN=0 timeout 300 python bench.py --model bert-large --steps 10 --war
 DLCFN_FUSED_LN=1 timeout 300 python bench.py --model bert-large --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_bert_fused_ln.json
 echo "== ResNet-50 default bench"
 timeout 400 python bench.py 2>&1 | tail -1 | tee gpurun_out/r2_bench_1gpu.json
+echo "== kernel-time breakdown of the step (torch.profiler)"
+timeout 300 python tools/profile_step.py 256 > gpurun_out/r2_profile_step.log 2>&1; head -40 gpurun_out/profile_resnet50.txt | cut -c1-150

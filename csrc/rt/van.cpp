@@ -168,8 +168,18 @@ int Node::Start(int) {
       if (NowMs() - t0 > 60000) { fprintf(stderr, "dlcfn ps: cannot reach scheduler %s:%d\n", scheduler_.host.c_str(), scheduler_.port); return -1; }
       usleep(50000);
     }
+    // A node that (re)joins a running job is only admitted once the scheduler has declared a node of its role dead
+    // (heartbeat timeout), so the registration is repeated until the node table arrives; the scheduler ignores
+    // duplicates of a registration it already holds.
     std::unique_lock<std::mutex> lk(mu_);
-    cv_.wait(lk, [&] { return ready_.load(); });
+    while (!cv_.wait_for(lk, std::chrono::seconds(2), [&] { return ready_.load(); })) {
+      lk.unlock();
+      Message again;
+      again.control = kAddNode; again.request = true; again.recver = kSchedulerId;
+      again.nodes.push_back(my_);
+      Send(again);
+      lk.lock();
+    }
   }
   if (heartbeat_interval_ > 0 && role_ != kScheduler) heartbeat_thread_ = std::thread(&Node::HeartbeatLoop, this);
   if (resend_) resend_thread_ = std::thread(&Node::ResendLoop, this);
@@ -320,6 +330,8 @@ void Node::SchedulerAddNode(Message&& m) {
   // called with mu_ held
   NodeInfo n = m.nodes[0];
   if (!ready_) {
+    for (const auto& p : pending_)
+      if (p.host == n.host && p.port == n.port && p.role == n.role) return;   // repeated registration
     pending_.push_back(n);
     if ((int)pending_.size() < num_workers_ + num_servers_) return;
     // all registered: deterministic rank assignment in host:port order (van.cc:37-85)
@@ -348,6 +360,18 @@ void Node::SchedulerAddNode(Message&& m) {
     return;
   }
   // late registration: a restarted node takes over the id of a dead node of the same role (van.cc:86-156)
+  for (const auto& kv : nodes_)
+    if (kv.second.host == n.host && kv.second.port == n.port && kv.second.role == n.role) {
+      // already admitted (its table may have been lost / it re-sent before the table arrived): send the table again
+      Message table;
+      table.control = kNodeTable;
+      for (auto& e : nodes_) table.nodes.push_back(e.second);
+      table.recver = kv.first;
+      mu_.unlock();
+      Send(table);
+      mu_.lock();
+      return;
+    }
   const long long now = NowMs() / 1000;
   const int timeout = EnvInt("PS_HEARTBEAT_TIMEOUT", 30);
   int take = -1;

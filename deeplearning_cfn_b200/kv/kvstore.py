@@ -570,8 +570,9 @@ class KVStoreDist(KVStoreLocal):
             return
         self._closed = True
         self._engine.wait_all()
-        if not self._L.dlcfn_ps_is_recovery():
-            self._L.dlcfn_ps_barrier(rt.GROUP_WORKER)
+        # every live worker takes part in the closing barrier - a node that rejoined after a failure skipped the START-UP
+        # barriers (its peers had passed them long before), but at shutdown its peers are waiting for it here
+        self._L.dlcfn_ps_barrier(rt.GROUP_WORKER)
         if self.rank == 0:
             self._send_command_to_servers(rt.CMD_STOP_SERVER, "")
         self._engine.close()

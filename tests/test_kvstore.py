@@ -400,3 +400,11 @@ def test_remote_server_profiling_writes_rank_prefixed_traces(tmp_path):
         assert all(e["ph"] == "X" and e["dur"] >= 0 and e["cat"] == "kvstore_server" for e in ev)
         seen |= {e["args"]["key"] for e in ev}
     assert len(seen) >= 2          # the small key on one server, the big key's shards on both
+
+
+def test_dead_worker_is_replaced_and_the_sync_round_completes():
+    r = _launch(2, 1, [os.path.join(ROOT, "tests/mp/recovery_worker.py")],
+                env={"DMLC_NUM_ATTEMPT": "1", "PS_HEARTBEAT_INTERVAL": "1", "PS_HEARTBEAT_TIMEOUT": "3"}, timeout=120)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "worker 1 crashing" in out and "worker 0 attempt 0 RECOVERY_OK" in out and "worker 1 attempt 1 RECOVERY_OK" in out

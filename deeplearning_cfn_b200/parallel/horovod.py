@@ -106,6 +106,120 @@ def allreduce(tensor: torch.Tensor, average: bool = True, name: str | None = Non
     return out
 
 
+def allreduce_(tensor: torch.Tensor, average: bool = True, name: str | None = None) -> torch.Tensor:
+    """In-place form (hvd.allreduce_)."""
+    tensor.copy_(allreduce(tensor, average, name))
+    return tensor
+
+
+def allgather(tensor: torch.Tensor, name: str | None = None) -> torch.Tensor:
+    """Concatenate every rank's tensor along dim 0; the first dimension may differ between ranks (hvd.allgather)."""
+    if size() == 1:
+        return tensor.clone()
+    n = torch.tensor([tensor.shape[0]], device=tensor.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(size())]
+    dist.all_gather(sizes, n)
+    sizes = [int(s) for s in sizes]
+    mx = max(sizes)
+    pad = tensor
+    if tensor.shape[0] < mx:
+        pad = torch.cat([tensor, tensor.new_zeros((mx - tensor.shape[0],) + tuple(tensor.shape[1:]))])
+    parts = [torch.empty_like(pad) for _ in range(size())]
+    dist.all_gather(parts, pad.contiguous())
+    return torch.cat([p[:k] for p, k in zip(parts, sizes)])
+
+
+def broadcast(tensor: torch.Tensor, root_rank: int = 0, name: str | None = None) -> torch.Tensor:
+    """Out-of-place broadcast of one tensor (hvd.broadcast)."""
+    out = tensor.clone()
+    if size() > 1:
+        dist.broadcast(out, src=root_rank)
+    return out
+
+
+def broadcast_(tensor: torch.Tensor, root_rank: int = 0, name: str | None = None) -> torch.Tensor:
+    if size() > 1:
+        dist.broadcast(tensor, src=root_rank)
+    return tensor
+
+
+def alltoall(tensor: torch.Tensor, splits: list[int] | None = None, name: str | None = None) -> torch.Tensor:
+    """Rank r sends slice j of dim 0 to rank j (hvd.alltoall); `splits` = rows sent to each rank (default: equal)."""
+    w = size()
+    if w == 1:
+        return tensor.clone()
+    if splits is None:
+        assert tensor.shape[0] % w == 0, "dim 0 must divide by the number of ranks when no splits are given"
+        splits = [tensor.shape[0] // w] * w
+    send = torch.tensor(splits, device=tensor.device, dtype=torch.int64)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send) if dist.get_backend() != "gloo" else _gloo_all_to_all_counts(recv, send)
+    recv_splits = [int(v) for v in recv]
+    out = tensor.new_empty((sum(recv_splits),) + tuple(tensor.shape[1:]))
+    if dist.get_backend() == "gloo":
+        _gloo_all_to_all(out, tensor.contiguous(), recv_splits, splits)
+    else:
+        dist.all_to_all_single(out, tensor.contiguous(), recv_splits, splits)
+    return out
+
+
+def _gloo_all_to_all_counts(recv: torch.Tensor, send: torch.Tensor) -> None:
+    gathered = [torch.empty_like(send) for _ in range(size())]
+    dist.all_gather(gathered, send)
+    for j in range(size()):
+        recv[j] = gathered[j][rank()]
+
+
+def _gloo_all_to_all(out: torch.Tensor, inp: torch.Tensor, recv_splits: list[int], send_splits: list[int]) -> None:
+    """gloo has no all_to_all: every rank broadcasts its buffer in turn and the others cut their slice out of it."""
+    all_send = [torch.empty(size(), dtype=torch.int64) for _ in range(size())]
+    dist.all_gather(all_send, torch.tensor(send_splits, dtype=torch.int64))
+    lens = torch.tensor([inp.shape[0]], dtype=torch.int64)
+    all_len = [torch.empty_like(lens) for _ in range(size())]
+    dist.all_gather(all_len, lens)
+    off_out = 0
+    for src in range(size()):
+        buf = inp if src == rank() else inp.new_empty((int(all_len[src]),) + tuple(inp.shape[1:]))
+        dist.broadcast(buf, src=src)
+        start = int(all_send[src][:rank()].sum())
+        k = int(all_send[src][rank()])
+        out[off_out:off_out + k] = buf[start:start + k]
+        off_out += k
+
+
+def barrier() -> None:
+    if size() > 1:
+        dist.barrier()
+
+
+def join() -> int:
+    """hvd.join(): wait for every rank; returns the last rank to arrive (here: always size() - 1)."""
+    barrier()
+    return size() - 1
+
+
+class Compression:
+    """hvd.Compression.none / .fp16 (here bf16): wire dtype of `allreduce` for fp32 tensors."""
+
+    class none:
+        @staticmethod
+        def compress(t):
+            return t, None
+
+        @staticmethod
+        def decompress(t, ctx):
+            return t
+
+    class fp16:
+        @staticmethod
+        def compress(t):
+            return (t.to(torch.bfloat16), t.dtype) if t.dtype == torch.float32 else (t, None)
+
+        @staticmethod
+        def decompress(t, ctx):
+            return t.to(ctx) if ctx is not None else t
+
+
 def broadcast_parameters(params, root_rank: int = 0) -> None:
     """hvd.broadcast_parameters(model.state_dict(), root_rank=0)."""
     if size() == 1:

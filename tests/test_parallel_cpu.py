@@ -443,3 +443,11 @@ def test_trainer_handles_parameters_without_gradient():
     # and the flat gradient buffer really holds zeros for it (not stale values of an earlier step)
     gv = tr.flat._grad_view[id(net.unused.weight)]
     assert float(gv.abs().sum()) == 0.0
+
+
+def test_horovod_style_collectives_over_gloo():
+    from conftest import run_job
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "3", sys.executable,
+           os.path.join(ROOT, "tests/mp/hvd_api_worker.py")]
+    r = run_job(cmd, env=dict(os.environ, PYTHONPATH=ROOT), timeout=240)
+    assert r.returncode == 0 and r.stdout.count("HVD_API_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]

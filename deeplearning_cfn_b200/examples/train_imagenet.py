@@ -90,7 +90,15 @@ def main(argv=None) -> int:
     use_gpu = torch.cuda.is_available()
     dev = torch.device("cuda", torch.cuda.current_device()) if use_gpu else torch.device("cpu")
     size = int(a.image_shape.split(",")[-1])
-    model = get_model(a.network, a.num_classes, size, num_layers=a.num_layers).to(dev)
+    model = get_model(a.network, a.num_classes, size, num_layers=a.num_layers)
+    if a.initializer not in ("default", ""):
+        # fit.py:200-215: 'xavier' -> Xavier(gaussian, in, 2), 'msra' -> MSRAPrelu, else the named mx.init class
+        from deeplearning_cfn_b200.kv import initializer as init_mod
+        spec = {"xavier": ("xavier", dict(rnd_type="gaussian", factor_type="in", magnitude=2)),
+                "msra": ("msraprelu", {}), "orthogonal": ("orthogonal", {}), "normal": ("normal", {}),
+                "uniform": ("uniform", {}), "one": ("one", {}), "zero": ("zero", {})}.get(a.initializer, (a.initializer, {}))
+        init_mod.create(spec[0], **spec[1]).init_module(model)
+    model = model.to(dev)
     dtype = torch.bfloat16 if (use_gpu and a.dtype in ("float16", "bfloat16")) else torch.float32
     if dtype != torch.float32:
         model = to_b200_layout(model, dtype)

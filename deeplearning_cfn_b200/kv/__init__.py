@@ -5,7 +5,7 @@ from .kvstore import (KVStore, KVStoreDist, KVStoreDistDevice, KVStoreError, KVS
 from .kvstore_server import KVStoreServer, init_server_module  # noqa: F401
 from . import trainer  # noqa: F401,E402
 from .trainer import Trainer  # noqa: F401,E402
-from . import metric, model  # noqa: F401,E402
+from . import initializer, metric, model  # noqa: F401,E402
 
 # Same contract as `import mxnet` in the reference (kvstore_server.py:75-85): a process launched with
 # DMLC_ROLE=server|scheduler becomes that node as soon as the kv package is imported, and exits afterwards.

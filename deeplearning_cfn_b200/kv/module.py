@@ -39,8 +39,13 @@ class Module:
         if arg_params or aux_params:
             self.symbol.load_state_dict({**(arg_params or {}), **(aux_params or {})}, strict=not allow_missing)
         elif initializer is not None:
-            for p in self._params:
-                initializer(p)
+            from . import initializer as init_mod
+            init = init_mod.create(initializer) if isinstance(initializer, str) else initializer
+            if hasattr(init, "init_module"):
+                init.init_module(self.symbol)              # by parameter name, like the reference's Initializer.__call__
+            else:
+                for p in self._params:
+                    init(p)
         self.params_initialized = True
 
     def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),),

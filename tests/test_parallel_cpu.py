@@ -451,3 +451,37 @@ def test_horovod_style_collectives_over_gloo():
            os.path.join(ROOT, "tests/mp/hvd_api_worker.py")]
     r = run_job(cmd, env=dict(os.environ, PYTHONPATH=ROOT), timeout=240)
     assert r.returncode == 0 and r.stdout.count("HVD_API_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_initializers_by_name_pattern_and_statistics(tmp_path):
+    from deeplearning_cfn_b200.kv import initializer as init
+    from deeplearning_cfn_b200.kv.module import Module
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(16, 32, 3), torch.nn.BatchNorm2d(32), torch.nn.Flatten(), torch.nn.Linear(32, 10))
+    init.create("xavier", rnd_type="gaussian", factor_type="in", magnitude=2).init_module(net)
+    w = net[0].weight
+    assert abs(float(w.std()) - (2.0 / (16 * 9)) ** 0.5) < 0.01 and float(net[0].bias.abs().sum()) == 0.0
+    assert torch.equal(net[1].weight, torch.ones(32)) and torch.equal(net[1].running_var, torch.ones(32))   # gamma / moving_var
+    assert float(net[1].bias.abs().sum()) == 0.0 and float(net[1].running_mean.abs().sum()) == 0.0
+    init.Uniform(0.5)("fc_weight", net[3].weight.data)
+    assert float(net[3].weight.abs().max()) <= 0.5 and float(net[3].weight.abs().max()) > 0.3
+    o = torch.empty(8, 20)
+    init.Orthogonal(scale=1.0)("w", o)
+    assert torch.allclose(o @ o.t(), torch.eye(8), atol=1e-4)
+    m = init.Mixed([".*bias", ".*"], [init.Constant(0.25), init.Normal(0.02)])
+    b, wt = torch.empty(5), torch.empty(5, 5)
+    m("layer_bias_custom", b)          # Constant's name rule would zero a *bias* name; this one is not a plain 'bias' suffix
+    m("layer_weight", wt)
+    assert torch.equal(b, torch.full((5,), 0.25)) and 0.005 < float(wt.std()) < 0.04
+    with pytest.raises(ValueError):
+        init.create("xavier")("vector_w", torch.empty(7))
+    # Load: from a checkpoint written by model.save_checkpoint, with a default for what is missing
+    from deeplearning_cfn_b200.kv import model as model_mod
+    model_mod.save_checkpoint(str(tmp_path / "ck"), 1, net, {"3.weight": net[3].weight.detach().clone()}, {})
+    net2 = torch.nn.Sequential(torch.nn.Conv2d(16, 32, 3), torch.nn.BatchNorm2d(32), torch.nn.Flatten(), torch.nn.Linear(32, 10))
+    init.Load(str(tmp_path / "ck-0001.params"), default_init=init.Zero()).init_module(net2)
+    assert torch.equal(net2[3].weight, net[3].weight) and float(net2[0].weight.abs().sum()) == 0.0
+    mod = Module(torch.nn.Sequential(torch.nn.Linear(4, 4)))
+    mod.bind([("data", (2, 4))])
+    mod.init_params(initializer="one")
+    assert torch.equal(mod.symbol[0].weight.detach(), torch.ones(4, 4)) and float(mod.symbol[0].bias.abs().sum()) == 0.0

@@ -113,8 +113,61 @@ class Module:
                 for i in batch:
                     self._updater(i, self._params[i].grad, self._params[i].data)
 
-    def get_outputs(self):
+    def get_outputs(self, merge_multi_context: bool = True):
         return [self._outputs]
+
+    # ---- the finer-grained steps of BaseModule (base_module.py: forward / backward / update_metric / get_params ...)
+    def forward(self, data_batch, is_train: bool | None = None) -> None:
+        x, y = _unpack(data_batch)
+        train = self.symbol.training if is_train is None else is_train
+        self.symbol.train(train)
+        self._label = y
+        if train:
+            self.symbol.zero_grad(set_to_none=True)
+            self._outputs = self.symbol(x)
+        else:
+            with torch.no_grad():
+                self._outputs = self.symbol(x)
+
+    def backward(self, out_grads=None) -> None:
+        if out_grads is not None:
+            self._outputs.backward(out_grads[0] if isinstance(out_grads, (list, tuple)) else out_grads)
+        else:
+            self._loss = self.loss(self._outputs, self._label)
+            self._loss.backward()
+
+    def update_metric(self, eval_metric, labels, pre_sliced: bool = False) -> None:
+        eval_metric.update(labels if isinstance(labels, (list, tuple)) else [labels], [self._outputs])
+
+    def get_params(self):
+        """(arg_params, aux_params): learnable parameters and auxiliary states (BatchNorm running statistics)."""
+        arg = {n: p.detach() for n, p in self.symbol.named_parameters()}
+        aux = {n: b.detach() for n, b in self.symbol.named_buffers()}
+        return arg, aux
+
+    def set_params(self, arg_params, aux_params=None, allow_missing: bool = False, force_init: bool = True,
+                   allow_extra: bool = False) -> None:
+        sd = {**(arg_params or {}), **(aux_params or {})}
+        res = self.symbol.load_state_dict(sd, strict=False)
+        if res.missing_keys and not allow_missing:
+            raise RuntimeError(f"missing parameters: {res.missing_keys[:5]}")
+        if res.unexpected_keys and not allow_extra:
+            raise ValueError(f"unexpected parameters: {res.unexpected_keys[:5]}")
+        self.params_initialized = True
+
+    def save_params(self, fname: str) -> None:
+        arg, aux = self.get_params()
+        sd = {f"arg:{k}": v.cpu() for k, v in arg.items()}
+        sd.update({f"aux:{k}": v.cpu() for k, v in aux.items()})
+        torch.save(sd, fname)
+
+    def load_params(self, fname: str) -> None:
+        raw = torch.load(fname, map_location="cpu")
+        self.set_params({k[4:]: v for k, v in raw.items() if k.startswith("arg:")},
+                        {k[4:]: v for k, v in raw.items() if k.startswith("aux:")})
+
+    def install_monitor(self, mon) -> None:
+        mon.install(self.symbol)
 
     def fit(self, train_data, eval_data=None, eval_metric="acc", epoch_end_callback=None, batch_end_callback=None,
             kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), initializer=None,

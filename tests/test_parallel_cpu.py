@@ -485,3 +485,35 @@ def test_initializers_by_name_pattern_and_statistics(tmp_path):
     mod.bind([("data", (2, 4))])
     mod.init_params(initializer="one")
     assert torch.equal(mod.symbol[0].weight.detach(), torch.ones(4, 4)) and float(mod.symbol[0].bias.abs().sum()) == 0.0
+
+
+def test_module_fine_grained_api_and_params_roundtrip(tmp_path):
+    from deeplearning_cfn_b200.kv import metric
+    from deeplearning_cfn_b200.kv.module import Module
+    from deeplearning_cfn_b200.utils.io import DataBatch
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.Linear(8, 3))
+    mod = Module(net)
+    mod.bind([("data", (16, 6))])
+    mod.init_params(initializer="xavier")
+    mod.init_optimizer("local", "sgd", (("learning_rate", 0.1),))
+    x, y = torch.randn(16, 6), torch.randint(0, 3, (16,))
+    m = metric.create("acc")
+    w0 = net[0].weight.detach().clone()
+    mod.forward(DataBatch([x], [y]), is_train=True)
+    mod.update_metric(m, [y])
+    mod.backward()
+    mod.update()
+    assert mod.get_outputs()[0].shape == (16, 3) and m.num_inst == 16 and not torch.equal(net[0].weight.detach(), w0)
+    mod.forward(DataBatch([x], [y]), is_train=False)
+    assert not mod.get_outputs()[0].requires_grad
+    arg, aux = mod.get_params()
+    assert set(arg) == {"0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias"} and "1.running_mean" in aux
+    mod.save_params(str(tmp_path / "p.params"))
+    net2 = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.Linear(8, 3))
+    mod2 = Module(net2)
+    mod2.load_params(str(tmp_path / "p.params"))
+    mod2.forward(DataBatch([x], [y]), is_train=False)
+    assert torch.allclose(mod2.get_outputs()[0], mod.get_outputs()[0])
+    with pytest.raises(ValueError):
+        mod2.set_params({"nope": torch.zeros(1)}, allow_missing=True)

@@ -174,3 +174,111 @@ def dump(finished: bool = True, filename: str | None = None, profile_process: st
 if os.environ.get("MXNET_PROFILER_AUTOSTART", os.environ.get("DLCFN_PROFILER_AUTOSTART", "0")) == "1":
     set_config(filename=os.environ.get("DLCFN_PROFILER_FILE", "profile.json"))
     set_state("run")
+
+
+# ----------------------------------------------------------------------------- user-defined objects (profiler.py:197-450)
+class Domain:
+    """A named group of user ranges / counters / markers; shows up as the trace category."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def new_task(self, name: str) -> "Task":
+        return Task(self, name)
+
+    def new_frame(self, name: str) -> "Frame":
+        return Frame(self, name)
+
+    def new_counter(self, name: str, value: int | None = None) -> "Counter":
+        c = Counter(f"{self.name}::{name}")
+        if value is not None:
+            c.set_value(value)
+        return c
+
+    def new_marker(self, name: str) -> "Marker":
+        return Marker(self, name)
+
+    def __str__(self):
+        return self.name
+
+
+class _Range:
+    _kind = "range"
+
+    def __init__(self, domain: Domain | None, name: str):
+        self.domain, self.name = domain, name
+        self._t = None
+
+    def start(self) -> None:
+        self._t = _now_us()
+        if torch.cuda.is_available() and _cfg["running"]:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def stop(self) -> None:
+        if self._t is None:
+            return
+        if torch.cuda.is_available() and _cfg["running"]:
+            torch.cuda.nvtx.range_pop()
+        if _cfg["running"]:
+            with _lock:
+                _events.append({"name": self.name, "cat": f"{self.domain or 'user'}:{self._kind}", "ph": "X", "pid": _rank(),
+                                "tid": 0, "ts": self._t, "dur": _now_us() - self._t})
+        self._t = None
+
+    def __enter__(self):
+        self.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop()
+        return False
+
+    def __str__(self):
+        return self.name
+
+
+class Task(_Range):
+    """A logical unit of work inside a Domain (may span threads)."""
+    _kind = "task"
+
+
+class Frame(_Range):
+    """A repeated unit of work, e.g. one training iteration."""
+    _kind = "frame"
+
+
+class Event(_Range):
+    """A range that belongs to no domain."""
+    _kind = "event"
+
+    def __init__(self, name: str):
+        super().__init__(None, name)
+
+
+class Marker:
+    """An instant in time inside a Domain: `Marker(domain, 'epoch end').mark('process')`."""
+
+    def __init__(self, domain: Domain, name: str):
+        self.domain, self.name = domain, name
+
+    def mark(self, scope: str = "process") -> None:
+        if not _cfg["running"]:
+            return
+        with _lock:
+            _events.append({"name": self.name, "cat": f"{self.domain}:marker", "ph": "i", "pid": _rank(), "tid": 0,
+                            "ts": _now_us(), "s": {"global": "g", "process": "p", "thread": "t"}.get(scope, "p")})
+
+
+def pause(profile_process: str = "worker") -> None:
+    """Stop recording without closing the trace (profiler.py: pause / resume)."""
+    if profile_process == "server":
+        _server_command("state:stop")
+    else:
+        _cfg["running"] = False
+
+
+def resume(profile_process: str = "worker") -> None:
+    if profile_process == "server":
+        _server_command("state:run")
+    else:
+        _cfg["running"] = True

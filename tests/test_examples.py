@@ -130,6 +130,24 @@ def test_profiler_trace_and_aggregate(tmp_path):
     assert sum(1 for e in ev if e["name"] == "KVStoreDistDefaultPush" and e["ph"] == "X") == 3
     assert any(e["ph"] == "i" for e in ev) and any(e["ph"] == "C" for e in ev)
     assert not profiler.is_running()
+    # user-defined objects: Domain / Task / Frame / Event / Counter / Marker, pause / resume
+    profiler.set_config(filename=str(tmp_path / "user.json"))
+    profiler.set_state("run")
+    dom = profiler.Domain("training")
+    with dom.new_task("epoch"):
+        with dom.new_frame("iteration"):
+            time.sleep(0.001)
+        profiler.pause()
+        with profiler.Event("not recorded"):
+            pass
+        profiler.resume()
+        dom.new_counter("samples", 5).increment(3)
+        dom.new_marker("checkpoint").mark("global")
+    ev = json.load(open(profiler.dump()))["traceEvents"]
+    cats = {e["name"]: e.get("cat") for e in ev}
+    assert cats["epoch"] == "training:task" and cats["iteration"] == "training:frame" and "not recorded" not in cats
+    assert any(e["ph"] == "C" and e["args"].get("training::samples") == 8 for e in ev)
+    assert any(e["ph"] == "i" and e["name"] == "checkpoint" and e["s"] == "g" for e in ev)
 
 
 def test_train_imagenet_from_record_file_two_ranks(tmp_path):

@@ -49,10 +49,10 @@ class RecordDataset:
         return self._n
 
     def iterator(self, batch_size: int, num_parts: int, part_index: int, seed: int):
-        from ..utils.recordio import NativeImageRecordIter
+        from ..utils.recordio import image_record_iter
         key = (batch_size, num_parts, part_index)
         if key not in self._iters:
-            self._iters[key] = NativeImageRecordIter(self.rec_path, batch_size, self.shape, shuffle=self.train,
+            self._iters[key] = image_record_iter(self.rec_path, batch_size, self.shape, shuffle=self.train,
                                                      num_parts=num_parts, part_index=part_index, seed=seed,
                                                      rand_crop=self.train, rand_mirror=self.train, round_batch=False)
         return self._iters[key]

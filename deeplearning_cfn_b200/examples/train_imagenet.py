@@ -134,9 +134,9 @@ def main(argv=None) -> int:
     loader = None
     if a.data_train and not a.benchmark:
         from deeplearning_cfn_b200.utils.data import RecordBatchLoader
-        from deeplearning_cfn_b200.utils.recordio import NativeImageRecordIter
+        from deeplearning_cfn_b200.utils.recordio import image_record_iter
         c, hh, ww = (int(v) for v in a.image_shape.split(","))
-        rec_it = NativeImageRecordIter(a.data_train, a.batch_size, (c, hh, ww), shuffle=True, num_parts=hvd.size(),
+        rec_it = image_record_iter(a.data_train, a.batch_size, (c, hh, ww), shuffle=True, num_parts=hvd.size(),
                                        part_index=rank, preprocess_threads=a.data_nthreads, rand_crop=bool(a.rand_crop),
                                        rand_mirror=bool(a.rand_mirror), round_batch=False, seed=epoch_seed)
         mean = tuple(float(v) / 255.0 for v in a.rgb_mean.split(","))

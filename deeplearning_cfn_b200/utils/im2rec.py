@@ -4,9 +4,11 @@
     python -m deeplearning_cfn_b200 im2rec prefix root --resize 256     # read prefix.lst, write prefix.rec + prefix.idx
 
 One sub-directory per class (sorted -> label ids) like `--recursive` in the reference; `--train-ratio` / `--test-ratio`
-split the list; `--shuffle`; `--resize N` scales the shorter edge to N and `--center-crop` crops the square.  Pixels are
-stored raw (uint8 HWC preceded by their shape) because the native decoder ring (csrc/rt/recordio.cpp) has no JPEG codec to
-link against in this image - files written here are what `NativeImageRecordIter` / `ImageRecordIter` read.
+split the list; `--shuffle`; `--resize N` scales the shorter edge to N and `--center-crop` crops the square.  `--encoding
+.raw` (default) stores uint8 HWC pixels preceded by their shape - what the native decoder ring (csrc/rt/recordio.cpp) reads
+with no codec in the loop (this image has no libjpeg / libpng headers to link it against); `--encoding .jpg --quality Q` /
+`.png` write the reference's encoded payloads, read back through torchvision's codecs by `ImageRecordIter`
+(`recordio.image_record_iter` picks the reader from the file's first record).
 """
 from __future__ import annotations
 
@@ -106,7 +108,7 @@ def load_image(path: str, resize: int = 0, center_crop: bool = False, color: int
 
 
 def write_record(lst_path: str, root: str, resize: int = 0, center_crop: bool = False, color: int = 1,
-                 pack_label: bool = False) -> tuple[str, int]:
+                 pack_label: bool = False, encoding: str = ".raw", quality: int = 95) -> tuple[str, int]:
     base = os.path.splitext(lst_path)[0]
     rec = recordio.MXIndexedRecordIO(base + ".idx", base + ".rec", "w")
     n = 0
@@ -115,10 +117,11 @@ def write_record(lst_path: str, root: str, resize: int = 0, center_crop: bool = 
         if pack_label and len(labels) > 1:
             import struct
             header = recordio.IRHeader(len(labels), 0.0, idx, 0)
-            body = struct.pack(f"<{len(labels)}f", *labels) + struct.pack("<III", *img.shape) + img.tobytes()
-            rec.write_idx(idx, recordio.pack(header, body))
+            enc = recordio.pack_img(recordio.IRHeader(0, 0.0, idx, 0), img, quality, encoding)[recordio._IR.size:]
+            rec.write_idx(idx, recordio.pack(header, struct.pack(f"<{len(labels)}f", *labels) + enc))
         else:
-            rec.write_idx(idx, recordio.pack_img(recordio.IRHeader(0, labels[0] if labels else 0.0, idx, 0), img))
+            rec.write_idx(idx, recordio.pack_img(recordio.IRHeader(0, labels[0] if labels else 0.0, idx, 0), img, quality,
+                                                 encoding))
         n += 1
     rec.close()
     return base + ".rec", n
@@ -137,6 +140,9 @@ def main(argv=None) -> int:
     p.add_argument("--center-crop", action="store_true")
     p.add_argument("--color", type=int, default=1, choices=[0, 1])
     p.add_argument("--pack-label", action="store_true", help="store every label column of the list (multi-label records)")
+    p.add_argument("--encoding", default=".raw", choices=[".raw", ".jpg", ".png"],
+                   help=".raw feeds the native decoder ring; .jpg / .png are the reference's formats (decoded through torchvision)")
+    p.add_argument("--quality", type=int, default=95, help="JPEG quality 1-100 / PNG compression 1-9")
     a = p.parse_args(argv)
     if a.list:
         for f in make_lists(a.prefix, a.root, not a.no_shuffle, a.train_ratio, a.test_ratio, not a.no_recursive):
@@ -148,7 +154,7 @@ def main(argv=None) -> int:
         print(f"no {a.prefix}*.lst found - run with --list first", file=sys.stderr)
         return 1
     for lst in lists:
-        rec, n = write_record(lst, a.root, a.resize, a.center_crop, a.color, a.pack_label)
+        rec, n = write_record(lst, a.root, a.resize, a.center_crop, a.color, a.pack_label, a.encoding, a.quality)
         print(f"{rec}: {n} records")
     return 0
 

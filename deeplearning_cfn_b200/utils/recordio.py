@@ -106,15 +106,52 @@ def unpack(s: bytes):
     return h, s[_IR.size:]
 
 
-def pack_img(header: IRHeader, img: np.ndarray) -> bytes:
-    img = np.ascontiguousarray(img, dtype=np.uint8)
-    return pack(header, struct.pack("<III", *img.shape) + img.tobytes())
+def pack_img(header: IRHeader, img: np.ndarray, quality: int = 95, img_fmt: str = ".raw") -> bytes:
+    """Pack an HWC uint8 image.  img_fmt '.jpg' / '.jpeg' / '.png' store the encoded image as the reference does
+    (`mx.recordio.pack_img(header, img, quality, img_fmt)`; readable by any RecordIO consumer), '.raw' (default) stores
+    uint32 h, w, c + the pixels, which is what the native decoder ring reads without a codec."""
+    img = np.array(img, dtype=np.uint8, order="C")
+    if img.ndim == 2:
+        img = img[:, :, None]
+    fmt = img_fmt.lower()
+    if fmt == ".raw":
+        return pack(header, struct.pack("<III", *img.shape) + img.tobytes())
+    import torchvision.io as tvio
+    chw = torch.from_numpy(img).permute(2, 0, 1).contiguous()
+    if fmt in (".jpg", ".jpeg"):
+        enc = tvio.encode_jpeg(chw, quality=int(quality))
+    elif fmt == ".png":
+        enc = tvio.encode_png(chw, compression_level=max(0, min(9, int(quality))) if quality <= 9 else 6)
+    else:
+        raise ValueError(f"unsupported image format {img_fmt!r}")
+    return pack(header, enc.numpy().tobytes())
 
 
-def unpack_img(s: bytes):
+def image_format(body: bytes) -> str:
+    if body[:3] == b"\xff\xd8\xff":
+        return ".jpg"
+    if body[:8] == b"\x89PNG\r\n\x1a\n":
+        return ".png"
+    return ".raw"
+
+
+def unpack_img(s: bytes, device: str = "cpu"):
+    """(header, HWC uint8 numpy image); JPEG / PNG payloads are decoded (torchvision.io: libjpeg-turbo on the host,
+    nvJPEG with device='cuda'), raw payloads are viewed in place."""
     h, body = unpack(s)
-    hh, ww, cc = struct.unpack("<III", body[:12])
-    return h, np.frombuffer(body, dtype=np.uint8, offset=12).reshape(hh, ww, cc)
+    off = 4 * int(h.flag) if h.flag > 0 else 0           # multi-label records carry `flag` floats first
+    if h.flag > 0:
+        labels = np.frombuffer(body, dtype=np.float32, count=int(h.flag))
+        h = IRHeader(h.flag, labels, h.id, h.id2)
+    body = body[off:]
+    fmt = image_format(body)
+    if fmt == ".raw":
+        hh, ww, cc = struct.unpack("<III", body[:12])
+        return h, np.frombuffer(body, dtype=np.uint8, offset=12, count=hh * ww * cc).reshape(hh, ww, cc)
+    import torchvision.io as tvio
+    data = torch.frombuffer(bytearray(body), dtype=torch.uint8)
+    img = tvio.decode_jpeg(data, device=device) if fmt == ".jpg" else tvio.decode_png(data)
+    return h, img.permute(1, 2, 0).contiguous().cpu().numpy()
 
 
 class ImageRecordIter:
@@ -123,8 +160,10 @@ class ImageRecordIter:
 
     def __init__(self, path_imgrec: str, batch_size: int, data_shape=(3, 224, 224), path_imgidx: str | None = None,
                  shuffle: bool = False, num_parts: int = 1, part_index: int = 0, preprocess_threads: int = 2,
-                 prefetch_buffer: int = 4, seed: int = 0, round_batch: bool = True):
+                 prefetch_buffer: int = 4, seed: int = 0, round_batch: bool = True, rand_crop: bool = False,
+                 rand_mirror: bool = False):
         self.batch_size, self.shape = batch_size, tuple(data_shape)
+        self.rand_crop, self.rand_mirror, self.errors = rand_crop, rand_mirror, 0
         idx_path = path_imgidx or os.path.splitext(path_imgrec)[0] + ".idx"
         self.rec = MXIndexedRecordIO(idx_path, path_imgrec, "r")
         if not self.rec.keys:
@@ -137,6 +176,7 @@ class ImageRecordIter:
         self.reset()
 
     def reset(self) -> None:
+        self.close()                                        # an unfinished epoch's workers stop first
         order = list(self.keys)
         if self.shuffle:
             rng = np.random.default_rng(self.seed + self.epoch)
@@ -148,13 +188,23 @@ class ImageRecordIter:
         it = iter(enumerate(batches))
         done = [0]
 
+        stop = self._stop = threading.Event()
+        q = self._q
+
         def worker():
-            while True:
+            try:
+                work(q, stop)
+            except Exception as e:                          # surfaced by __next__ instead of a silent hang
+                q.put(e)
+
+        def work(q, stop):
+            while not stop.is_set():
                 with self._lock:
                     nxt = next(it, None)
                 if nxt is None:
                     break
-                _, ks = nxt
+                bi, ks = nxt
+                aug = np.random.default_rng((self.seed, self.epoch, bi))     # per batch: independent of thread timing
                 c, h, w = self.shape
                 x = torch.empty((len(ks), h, w, c), dtype=torch.uint8)
                 y = torch.empty(len(ks), dtype=torch.int64)
@@ -162,17 +212,41 @@ class ImageRecordIter:
                     with self._lock:
                         raw = self.rec.read_idx(k)
                     hd, img = unpack_img(raw)
-                    x[j] = torch.from_numpy(img[:h, :w, :c].copy())
-                    y[j] = int(hd.label)
+                    sh, sw = img.shape[0], img.shape[1]
+                    y0, x0 = max(0, (sh - h) // 2), max(0, (sw - w) // 2)          # center crop, zero pad when smaller
+                    if self.rand_crop:
+                        y0, x0 = int(aug.integers(0, max(0, sh - h) + 1)), int(aug.integers(0, max(0, sw - w) + 1))
+                    crop = img[y0:y0 + h, x0:x0 + w, :c]
+                    if self.rand_mirror and aug.integers(0, 2):
+                        crop = crop[:, ::-1]
+                    x[j].zero_()
+                    dy0, dx0 = (h - crop.shape[0]) // 2, (w - crop.shape[1]) // 2
+                    x[j, dy0:dy0 + crop.shape[0], dx0:dx0 + crop.shape[1], :crop.shape[2]] = torch.from_numpy(crop.copy())
+                    y[j] = int(hd.label if np.isscalar(hd.label) else hd.label[0])
                 if torch.cuda.is_available():
                     x, y = x.pin_memory(), y.pin_memory()
-                self._q.put((x, y))
+                while not stop.is_set():
+                    try:
+                        q.put((x, y), timeout=0.1)
+                        break
+                    except queue.Full:
+                        pass
             with self._lock:
                 done[0] += 1
-                if done[0] == self.threads:
-                    self._q.put(None)
-        for _ in range(self.threads):
-            threading.Thread(target=worker, daemon=True).start()
+                last = done[0] == self.threads
+            if last and not stop.is_set():
+                q.put(None)
+        self._workers = [threading.Thread(target=worker, daemon=True) for _ in range(self.threads)]
+        for t in self._workers:
+            t.start()
+
+    def close(self) -> None:
+        """Stop the prefetch threads (an abandoned epoch otherwise keeps reading the file)."""
+        if getattr(self, "_stop", None) is not None:
+            self._stop.set()
+        for t in getattr(self, "_workers", []):
+            t.join(timeout=5)
+        self._workers = []
 
     def __iter__(self):
         return self
@@ -181,10 +255,16 @@ class ImageRecordIter:
         item = self._q.get()
         if item is None:
             raise StopIteration
+        if isinstance(item, Exception):
+            raise item
         return item
 
     def __len__(self):
         return self._n
+
+    @property
+    def num_samples(self) -> int:
+        return len(self.keys)
 
 
 # ----------------------------------------------------------------------------------------- native pipeline (csrc/rt/recordio.cpp)
@@ -282,6 +362,15 @@ class NativeImageRecordIter:
         self._rec = self.L.dlcfn_rec_open(path_imgrec.encode(), idx.encode() if os.path.exists(idx) else None)
         if not self._rec:
             raise IOError(f"cannot open {path_imgrec}")
+        n0 = self.L.dlcfn_rec_read(self._rec, 0, None, 0)
+        if n0 > 0:
+            buf = self._ct.create_string_buffer(int(n0))
+            self.L.dlcfn_rec_read(self._rec, 0, buf, n0)
+            hd, body = unpack(buf.raw)
+            if image_format(body[4 * int(hd.flag) if hd.flag > 0 else 0:]) != ".raw":
+                self.L.dlcfn_rec_close(self._rec)
+                raise ValueError(f"{path_imgrec} holds encoded (JPEG / PNG) images: the native decoder ring reads raw pixel "
+                                 "records (im2rec --encoding .raw); use ImageRecordIter / image_record_iter() for encoded files")
         c, h, w = self.shape
         self._it = self.L.dlcfn_imgiter_create(self._rec, batch_size, h, w, c, label_width, int(shuffle), seed, part_index,
                                                num_parts, preprocess_threads, prefetch_buffer, int(rand_crop),
@@ -350,3 +439,13 @@ class NativeImageRecordIter:
             self.close()
         except Exception:
             pass
+
+
+def image_record_iter(path_imgrec: str, batch_size: int, data_shape=(3, 224, 224), **kw):
+    """The native pipeline when the file holds raw pixel records, the python iterator (torchvision codecs) otherwise."""
+    try:
+        return NativeImageRecordIter(path_imgrec, batch_size, data_shape, **kw)
+    except ValueError:
+        allowed = {"path_imgidx", "shuffle", "num_parts", "part_index", "preprocess_threads", "prefetch_buffer", "seed",
+                   "round_batch", "rand_crop", "rand_mirror"}
+        return ImageRecordIter(path_imgrec, batch_size, data_shape, **{k: v for k, v in kw.items() if k in allowed})

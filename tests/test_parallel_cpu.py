@@ -416,6 +416,59 @@ def test_im2rec_list_and_record_roundtrip(tmp_path):
     assert img.shape == (16, 16, 3)
 
 
+def test_encoded_image_records_jpeg_png(tmp_path):
+    """pack_img(.jpg/.png) writes the reference's encoded payloads; unpack_img detects them by magic number; the native ring
+    refuses them with a clear error and image_record_iter falls back to the codec-backed python iterator."""
+    import numpy as np
+    from PIL import Image
+    from deeplearning_cfn_b200.utils import im2rec, recordio
+    yy, xx = np.mgrid[0:24, 0:32]
+    smooth = np.stack([yy * 8, xx * 6, (yy + xx) * 4], -1).astype(np.uint8)           # JPEG-friendly content
+    hdr = recordio.IRHeader(0, 3.0, 7, 0)
+    h, img = recordio.unpack_img(recordio.pack_img(hdr, smooth, img_fmt=".png"))
+    assert h.label == 3.0 and h.id == 7 and np.array_equal(img, smooth)               # PNG is lossless
+    packed = recordio.pack_img(hdr, smooth, quality=95, img_fmt=".jpg")
+    assert recordio.image_format(recordio.unpack(packed)[1]) == ".jpg"
+    h, img = recordio.unpack_img(packed)
+    assert img.shape == smooth.shape and np.abs(img.astype(int) - smooth.astype(int)).mean() < 4.0
+    assert len(recordio.pack_img(hdr, smooth, quality=30, img_fmt=".jpg")) < len(packed)
+    # a JPEG written by another library (what the reference's im2rec / OpenCV produce) decodes too
+    import io
+    bio = io.BytesIO()
+    Image.fromarray(smooth).save(bio, format="JPEG", quality=90)
+    h, img = recordio.unpack_img(recordio.pack(hdr, bio.getvalue()))
+    assert img.shape == smooth.shape and np.abs(img.astype(int) - smooth.astype(int)).mean() < 5.0
+
+    root = tmp_path / "imgs"
+    for cls in ("a", "b"):
+        (root / cls).mkdir(parents=True)
+        for i in range(3):
+            Image.fromarray(np.roll(smooth, i * 3, 1)).save(root / cls / f"{i}.png")
+    prefix = str(tmp_path / "enc")
+    assert im2rec.main([prefix, str(root), "--list"]) == 0
+    assert im2rec.main([prefix, str(root), "--encoding", ".jpg", "--quality", "90"]) == 0
+    with pytest.raises(ValueError, match="encoded"):
+        recordio.NativeImageRecordIter(prefix + ".rec", 2, (3, 24, 32))
+    it = recordio.image_record_iter(prefix + ".rec", 2, (3, 16, 16), round_batch=False)
+    assert isinstance(it, recordio.ImageRecordIter)
+    n = 0
+    for x, y in it:
+        assert x.shape == (2, 16, 16, 3) and x.dtype == torch.uint8 and set(y.tolist()) <= {0, 1}
+        n += len(y)
+    assert n == 6
+    # the center crop matches the decoded image's middle
+    it2 = recordio.ImageRecordIter(prefix + ".rec", 1, (3, 16, 16), preprocess_threads=1)
+    _, full = recordio.unpack_img(recordio.MXIndexedRecordIO(prefix + ".idx", prefix + ".rec", "r").read_idx(it2.keys[0]))
+    x, _ = next(iter(it2))
+    assert np.array_equal(x[0].numpy(), full[4:20, 8:24])
+    it.close(), it2.close()
+    # raw files still take the native ring
+    assert im2rec.main([prefix, str(root)]) == 0
+    nat = recordio.image_record_iter(prefix + ".rec", 2, (3, 24, 32))
+    assert isinstance(nat, recordio.NativeImageRecordIter)
+    nat.close()
+
+
 def test_trainer_handles_parameters_without_gradient():
     """A parameter that takes no part in the step (its hook never fires) is gathered as zeros when the bucket is flushed."""
     from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer

@@ -192,9 +192,10 @@ def resnet(num_layers: int = 50, num_classes: int = 1000, image_size: int = 224)
 def to_b200_layout(model: nn.Module, dtype: torch.dtype = torch.bfloat16) -> nn.Module:
     """channels_last + `dtype` weights for conv/linear; BatchNorm parameters and statistics stay fp32
     (cuDNN mixed-dtype batch norm) - the worker half of the reference's multi_precision mode."""
+    from ..ops.nn import DepthwiseConv2d
     model = model.to(memory_format=torch.channels_last)
     for m in model.modules():
-        if isinstance(m, (nn.Conv2d, nn.Linear, Linear, nn.Embedding)):
+        if isinstance(m, (nn.Conv2d, nn.Linear, Linear, nn.Embedding, DepthwiseConv2d)):
             m.to(dtype)
         elif isinstance(m, (nn.LayerNorm,)):
             m.to(dtype)

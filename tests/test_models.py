@@ -1,0 +1,79 @@
+"""Model zoo: every family the reference's `--network` / `--model` switches accept builds with the published parameter count,
+runs forward + backward on CPU and keeps its shape contract; one GPU test pushes the depthwise / 1x1 / fused-BN variants
+through the CUDA kernels."""
+import pytest
+import torch
+
+from deeplearning_cfn_b200.models import get_model, to_b200_layout
+
+
+def _params(m):
+    return sum(p.numel() for p in m.parameters())
+
+
+# (name, kwargs, parameters at 1000 classes in millions: the published numbers of the papers / model zoos)
+PUBLISHED = [("resnet-v1", {"num_layers": 50}, 25.56), ("resnet18_v1", {}, 11.69), ("resnext", {"num_layers": 50}, 25.03),
+             ("resnext", {"num_layers": 101}, 44.18), ("resnet", {"num_layers": 50}, 25.55), ("mobilenet", {}, 4.23),
+             ("mobilenetv2", {}, 3.50), ("googlenet", {}, 6.99), ("inception-v4", {}, 42.68), ("inception-resnet-v2", {}, 55.84),
+             ("squeezenet1.0", {}, 1.25), ("squeezenet1.1", {}, 1.24), ("densenet121", {}, 7.98), ("densenet169", {}, 14.15),
+             ("vgg11", {}, 132.86), ("alexnet", {}, None), ("inception-v3", {}, None), ("inception-bn", {}, None)]
+
+
+@pytest.mark.parametrize("name,kw,millions", PUBLISHED, ids=[f"{n}-{k.get('num_layers', '')}" for n, k, _ in PUBLISHED])
+def test_parameter_counts_match_published(name, kw, millions):
+    m = get_model(name, 1000, 224, **kw)
+    n = _params(m) / 1e6
+    assert n > 0.5
+    if millions is not None:
+        assert abs(n - millions) / millions < 0.012, f"{name}: {n:.2f} M parameters, published {millions} M"
+
+
+@pytest.mark.parametrize("name,size", [("resnet-v1", 64), ("resnext", 64), ("mobilenet0.5", 64), ("mobilenetv2_0.5", 64),
+                                       ("googlenet", 64), ("inception-bn", 64), ("squeezenet1.1", 64), ("densenet121", 64),
+                                       ("inception-v4", 139), ("inception-resnet-v2", 139)])
+def test_forward_backward_cpu(name, size):
+    torch.manual_seed(0)
+    m = get_model(name, 7, size)
+    x = torch.randn(2, 3, size, size)
+    y = m(x)
+    assert y.shape == (2, 7) and torch.isfinite(y).all()
+    y.logsumexp(1).sum().backward()
+    missing = [n for n, p in m.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, f"no gradient for {missing[:3]}"
+    m.eval()
+    with torch.no_grad():
+        assert m(x).shape == (2, 7)
+
+
+def test_cifar_variants_and_names():
+    assert type(get_model("resnet-v1", 10, 32, num_layers=20)).__name__ == "ResNetV1"
+    assert type(get_model("resnet", 10, 32, num_layers=20)).__name__ == "ResNetV2"
+    assert type(get_model("resnet50_v2", 10)).__name__ == "ResNetV2"
+    assert type(get_model("resnet101_v1", 10)).__name__ == "ResNetV1"
+    with pytest.raises(ValueError):
+        get_model("resnet-v1", 10, 32, num_layers=21)
+    with pytest.raises(ValueError):
+        get_model("no-such-net")
+    # the 0.25 mobilenet keeps channel counts the NHWC kernels accept (multiples of 8)
+    from deeplearning_cfn_b200.ops.nn import DepthwiseConv2d
+    assert all(d.channels % 8 == 0 for d in get_model("mobilenet0.25", 10).modules() if isinstance(d, DepthwiseConv2d))
+    assert all(d.channels % 8 == 0 for d in get_model("mobilenetv2_0.25", 10).modules() if isinstance(d, DepthwiseConv2d))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mobilenet", "mobilenetv2", "resnext", "densenet121", "inception-bn"])
+def test_zoo_models_on_cuda_kernels_match_fp32_cpu(name):
+    """bf16 channels_last on the dlcfn kernels (depthwise, 1x1 GEMM-capable convs, fused BN+ReLU, NHWC pools) against the
+    same weights in fp32 on the host: logits agree to bf16 accuracy and every parameter receives a finite gradient."""
+    torch.manual_seed(1)
+    ref = get_model(name, 16, 64)
+    m = get_model(name, 16, 64)
+    m.load_state_dict(ref.state_dict())
+    m = to_b200_layout(m.cuda())
+    x = torch.randn(8, 3, 64, 64)
+    y_ref = ref(x)
+    y = m(x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float().cpu()
+    cos = torch.nn.functional.cosine_similarity(y.flatten(), y_ref.flatten(), dim=0).item()
+    assert torch.isfinite(y).all() and cos > 0.95, (cos, (y - y_ref).abs().max().item())
+    m(x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float().logsumexp(1).sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)

@@ -60,6 +60,14 @@ struct __align__(64) GemmParams {
   int kb_per_split;     // k-blocks (of kBlockK) per split
   float* ws;
   int split_k_ok;       // host-side switch (DLCFN_GEMM_SPLITK=0 disables)
+  // implicit-GEMM convolution (kgemm<..., CONV = true>): one operand is an NHWC activation tensor read through an
+  // im2col-mode tensor map (tmA for fprop / dgrad, tmB[0] for wgrad)
+  int cv_Q, cv_P;       // base positions per row / rows per image of the im2col traversal (= the output width / height)
+  int cv_cblocks;       // channels of the im2col'd tensor / 64
+  int cv_S, cv_RS;      // filter width, taps
+  int cv_lower_w, cv_lower_h;   // bounding-box lower corner: -pad (fprop, wgrad), pad - (S-1) (dgrad)
+  int cv_stride;        // traversal stride (convolution stride; 1 for dgrad)
+  int cv_cin;           // dgrad: columns per tap of the weight matrix [Cout][R*S*Cin]
 };
 
 // ------------------------------------------------------------------ PTX -----
@@ -92,6 +100,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// im2col-mode load (NHWC activations, tensor map from cuTensorMapEncodeIm2col): `pixels` consecutive base positions
+// starting at (w, h, n) - wrapping row by row, image by image inside the bounding box - each displaced by the filter-tap
+// offset (off_w, off_h), `channels` channels from c: lands as [pixels][channels] rows, out-of-image elements zero-filled.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 // multicast load: the box lands at the same shared-memory offset of every CTA in `cta_mask`, and every destination
@@ -185,8 +204,18 @@ struct GemmCfg {
 // at 81 % pipe utilisation.  A stage of either CTA may only be refilled when BOTH CTAs' MMAs have consumed it (the
 // peer's multicast writes into it), so the smem-empty barriers take two arrivals: each CTA's tcgen05.commit is itself
 // multicast to both.  Everything else (TMEM, epilogue, TMA store) is per CTA and unchanged.
-template <int BLOCK_N, bool A_MN, bool B_MN, bool MC = false>
+//
+// CONV = true (EXPERIMENTAL, written at the end of round 1 without GPU access; DLCFN_CONV3X3=tcgen05): implicit-GEMM
+// convolution on NHWC tensors.  Only the producer changes - the activation operand is fetched by im2col-mode TMA, which
+// performs the (pixel, tap) -> input-pixel arithmetic, the halo zero-fill and the row / image wrap in hardware:
+//   fprop <A_MN=0,B_MN=0>  Y[NPQ, K]     = im2col(X)[NPQ, RS*C] * W[K, RS*C]^T      k-block -> (tap, 64 channels)
+//   dgrad <A_MN=0,B_MN=1>  dX[NHW, C]    = im2col(dY)[NHW, RS*K] * W'[RS*K, C]      W' = taps reversed, read MN-major
+//   wgrad <A_MN=1,B_MN=1>  dW[K, RS*C]   = dY[NPQ, K]^T * im2col(X)[NPQ, RS*C]      k-block = 64 pixels, split-K
+// MMA issue, TMEM double buffering, epilogue and TMA store are those of the plain GEMM.
+template <int BLOCK_N, bool A_MN, bool B_MN, bool MC = false, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__ GemmParams p) {
+  static_assert(!(MC && CONV), "the multicast-pair variant has no convolution producer");
+  static_assert(!CONV || B_MN || !A_MN, "convolution modes: fprop <0,0>, dgrad <0,1>, wgrad <1,1>");
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -258,7 +287,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          if constexpr (!A_MN) {
+          if constexpr (CONV && !A_MN) {
+            // fprop / dgrad: k-block = (filter tap rs, 64-channel slice); 128 consecutive output pixels from m_idx
+            const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
+            const int r = rs / p.cv_S, sx = rs - r * p.cv_S;
+            const int q0 = m_idx % p.cv_Q, t0 = m_idx / p.cv_Q;
+            const int p0 = t0 % p.cv_P, n0 = t0 / p.cv_P;
+            tma_load_im2col_4d(sa, &p.tmA, full_bar(stage), c0, q0 * p.cv_stride + p.cv_lower_w,
+                               p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)sx, (uint16_t)r);   // box {64 c, 128 pixels}
+          } else if constexpr (!A_MN) {
             tma_load_2d(sa, &p.tmA, full_bar(stage), k_idx, m_idx);  // box {64 k, 128 m}
           } else {
 #pragma unroll
@@ -276,6 +313,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
                 const int jj = cta_rank * (BLOCK_N / 128) + j;
                 tma_load_2d_mc(sb + jj * 8192, &p.tmB[0], full_bar(stage), n_idx + 64 * jj, k_idx, (uint16_t)3);
               }
+            }
+          } else if constexpr (CONV && B_MN && !A_MN) {
+            // dgrad: the 64 contraction rows are output channels c0.. of tap rs; the matching weights are the columns of
+            // the REVERSED tap in W viewed as [Cout][R*S*Cin] (MN-major B: box {64 cin, 64 cout})
+            const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * 8192, &p.tmB[0], full_bar(stage), (p.cv_RS - 1 - rs) * p.cv_cin + n_idx + 64 * j, c0);
+          } else if constexpr (CONV && B_MN && A_MN) {
+            // wgrad: the 64 contraction rows are output pixels k_idx..; output column panel P = (tap, 64-channel slice)
+            const int q0 = k_idx % p.cv_Q, t0 = k_idx / p.cv_Q;
+            const int p0 = t0 % p.cv_P, n0 = t0 / p.cv_P;
+            const int last_panel = p.cv_RS * p.cv_cblocks - 1;
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j) {
+              int panel = n_idx / 64 + j;
+              if (panel > last_panel) panel = last_panel;    // N tail: columns >= N are never stored
+              const int rs = panel / p.cv_cblocks, c0 = (panel - rs * p.cv_cblocks) * 64;
+              const int r = rs / p.cv_S, sx = rs - r * p.cv_S;
+              tma_load_im2col_4d(sb + j * 8192, &p.tmB[0], full_bar(stage), c0, q0 * p.cv_stride + p.cv_lower_w,
+                                 p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)sx, (uint16_t)r);   // box {64 c, 64 pixels}
             }
           } else if constexpr (!B_MN) {
             // rows of B (= output columns n) may live on a peer: pick the owner's tensor map
@@ -620,10 +678,10 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
   return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV = false>
 static int launch(GemmParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN>;
-  auto kern = kgemm<BLOCK_N, A_MN, B_MN>;
+  auto kern = kgemm<BLOCK_N, A_MN, B_MN, false, CONV>;
   static bool configured = false;
   if (!configured) {
     cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -672,6 +730,83 @@ static int launch(GemmParams& p, int num_sms, cudaStream_t stream) {
     cudaFreeAsync(p.ws, stream);
   }
   return (int)le;
+}
+
+
+// ------------------------------------------------------------------------------------------ implicit-GEMM convolution
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeIm2colFn)f;
+  }
+  return fn;
+}
+
+struct Im2colKey {
+  const void* ptr;
+  int n, h, w, c, lower_w, lower_h, upper_w, upper_h, stride, pixels;
+  bool operator==(const Im2colKey& o) const {
+    return ptr == o.ptr && n == o.n && h == o.h && w == o.w && c == o.c && lower_w == o.lower_w && lower_h == o.lower_h &&
+           upper_w == o.upper_w && upper_h == o.upper_h && stride == o.stride && pixels == o.pixels;
+  }
+};
+struct Im2colSlot {
+  Im2colKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int kIm2colCacheSlots = 256;
+
+// NHWC bf16 tensor [n, h, w, c] as an im2col-mode map: 64 channels x `pixels` base positions per load, 128B swizzle.
+// Base positions live in the box [lower, extent - 1 + upper] per spatial dimension and advance by `stride`.
+static int make_map_im2col(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int lower_w, int lower_h, int upper_w,
+                           int upper_h, int stride, int pixels) {
+  static thread_local Im2colSlot* cache = nullptr;
+  if (!cache) {
+    cache = static_cast<Im2colSlot*>(aligned_alloc(64, kIm2colCacheSlots * sizeof(Im2colSlot)));
+    if (cache) memset(cache, 0, kIm2colCacheSlots * sizeof(Im2colSlot));
+  }
+  Im2colKey key;
+  memset(&key, 0, sizeof(key));     // padding bytes take part in nothing, but keep the slot image deterministic
+  key.ptr = ptr; key.n = n; key.h = h; key.w = w; key.c = c; key.lower_w = lower_w; key.lower_h = lower_h;
+  key.upper_w = upper_w; key.upper_h = upper_h; key.stride = stride; key.pixels = pixels;
+  uint64_t hsh = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
+  hsh ^= ((uint64_t)n << 48) ^ ((uint64_t)h << 36) ^ ((uint64_t)w << 24) ^ ((uint64_t)c << 8) ^ ((uint64_t)pixels << 2) ^
+         (uint64_t)(lower_w + 8) ^ ((uint64_t)stride << 5);
+  Im2colSlot* slot = cache ? &cache[(hsh >> 22) % kIm2colCacheSlots] : nullptr;
+  if (slot && slot->valid && slot->key == key) {
+    memcpy(m, &slot->map, sizeof(CUtensorMap));
+    return 0;
+  }
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, lower, upper, 64,
+                   (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[dlcfn] cuTensorMapEncodeIm2col failed (%d): ptr=%p nhwc=%dx%dx%dx%d lower=(%d,%d) upper=(%d,%d) stride=%d "
+            "pixels=%d\n", (int)r, ptr, n, h, w, c, lower_w, lower_h, upper_w, upper_h, stride, pixels);
+    return 10000 + (int)r;
+  }
+  if (slot) {
+    slot->key = key;
+    memcpy(&slot->map, m, sizeof(CUtensorMap));
+    slot->valid = true;
+  }
+  return 0;
 }
 
 // EXPERIMENTAL multicast-pair launch (BLOCK_N = 256, local B, no split-K): clusters of 2 CTAs, grid = 2 x pairs
@@ -814,5 +949,105 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   DLCFN_GEMM_CASE(256, true, false)
   DLCFN_GEMM_CASE(256, true, true)
 #undef DLCFN_GEMM_CASE
+  return (int)cudaErrorInvalidValue;
+}
+
+// Implicit-GEMM convolution, NHWC bf16 (EXPERIMENTAL - see kgemm<..., CONV>).  Square stride, symmetric padding, no dilation.
+//   op 0 fprop:  x [n,h,w,c]   * wt [k,r,s,c] -> out = y [n,p,q,k]            (stride 1 or 2 ...)
+//   op 1 dgrad:  x = dy [n,p,q,k] (pass its dims as n,h,w,c = n,p,q,k), wt [k,r,s,cin] -> out = dx [n,oh,ow,cin]; stride 1 only
+//   op 2 wgrad:  x [n,h,w,c], other = dy [n,p,q,k] -> out = dw [k,r,s,c]
+// `k` is always the filter count (Cout), `cin` the filter depth; channel counts of the im2col'd tensor must be multiples
+// of 64 (one 128-byte swizzle row per k-block), all others multiples of 8.
+DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* out, int out_dtype, int n, int h, int w, int c,
+                              int k, int cin, int r, int s, int pad, int stride, int oh, int ow, int accumulate,
+                              int block_n, int num_sms, cudaStream_t stream) {
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    DLCFN_CHECK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
+  (void)cudaGetLastError();
+  if (op < 0 || op > 2 || n <= 0 || h <= 0 || w <= 0 || r <= 0 || s <= 0 || stride <= 0 || pad < 0) return (int)cudaErrorInvalidValue;
+  if ((c % 64) || (k % 8) || (cin % 8) || r * s > 49) return (int)cudaErrorInvalidValue;
+  if (op == 1 && stride != 1) return (int)cudaErrorInvalidValue;
+  if ((((uintptr_t)x) & 15) || (((uintptr_t)other) & 15) || (((uintptr_t)out) & 15)) return (int)cudaErrorInvalidValue;
+  if (num_sms <= 0) {
+    int dev = 0;
+    DLCFN_CHECK(cudaGetDevice(&dev));
+    DLCFN_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_shards = 1;
+  p.D = out;
+  p.d_is_fp32 = out_dtype == 0;
+  p.accumulate = accumulate;
+  static const bool splitk_env = [] { const char* e = getenv("DLCFN_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
+  p.split_k_ok = splitk_env ? 1 : 0;
+  p.cv_S = s;
+  p.cv_RS = r * s;
+  p.cv_cblocks = c / 64;
+  p.cv_stride = stride;
+  p.cv_cin = cin;
+  int rc;
+  bool a_mn, b_mn;
+  if (op == 0 || op == 2) {
+    // im2col of the forward input: base positions = output pixels
+    const int P = (h + 2 * pad - r) / stride + 1, Q = (w + 2 * pad - s) / stride + 1;
+    if (P != oh || Q != ow || c != cin) return (int)cudaErrorInvalidValue;
+    p.cv_P = P; p.cv_Q = Q;
+    p.cv_lower_w = -pad; p.cv_lower_h = -pad;
+    // the last base position of a row is (Q-1)*stride - pad, which must be the box's upper end w - 1 + upper_w or just
+    // inside it: upper = pad - (s - 1) is the exact end for stride 1 and at most stride - 1 positions further otherwise
+    const int upper_w = pad - (s - 1), upper_h = pad - (r - 1);
+    if (op == 0) {
+      p.M = n * P * Q; p.N = k; p.K = r * s * c;
+      p.ldd = k;
+      rc = make_map_im2col(&p.tmA, x, n, h, w, c, -pad, -pad, upper_w, upper_h, stride, kBlockM);
+      if (rc) return rc;
+      if (block_n != 128 && block_n != 256) block_n = (k >= 256) ? 256 : 128;
+      rc = make_map(&p.tmB[0], other, k, (uint64_t)r * s * c, (uint64_t)r * s * c, kBlockK, block_n);   // W as [k][rs*c], K-major
+      if (rc) return rc;
+      a_mn = false; b_mn = false;
+    } else {
+      p.M = k; p.N = r * s * c; p.K = n * P * Q;
+      p.ldd = (long long)r * s * c;
+      rc = make_map(&p.tmA, other, (uint64_t)n * P * Q, k, k, 64, kBlockK);                       // dy as [npq][k], MN-major A
+      if (rc) return rc;
+      rc = make_map_im2col(&p.tmB[0], x, n, h, w, c, -pad, -pad, upper_w, upper_h, stride, kBlockK);
+      if (rc) return rc;
+      if (block_n != 128 && block_n != 256) block_n = 128;
+      a_mn = true; b_mn = true;
+    }
+  } else {
+    // dgrad: x is dy [n, h, w, c = k]; base positions = input-gradient pixels [oh, ow]
+    if (c != k) return (int)cudaErrorInvalidValue;
+    const int lower_w = pad - (s - 1), lower_h = pad - (r - 1);
+    p.cv_P = oh; p.cv_Q = ow;
+    p.cv_lower_w = lower_w; p.cv_lower_h = lower_h;
+    p.M = n * oh * ow; p.N = cin; p.K = r * s * k;
+    p.ldd = cin;
+    rc = make_map_im2col(&p.tmA, x, n, h, w, c, lower_w, lower_h, lower_w + ow - w, lower_h + oh - h, 1, kBlockM);
+    if (rc) return rc;
+    rc = make_map(&p.tmB[0], other, k, (uint64_t)r * s * cin, (uint64_t)r * s * cin, 64, kBlockK);  // W as [k][rs*cin], MN-major B
+    if (rc) return rc;
+    if (block_n != 128 && block_n != 256) block_n = (cin >= 256) ? 256 : 128;
+    a_mn = false; b_mn = true;
+  }
+  static const bool tma_store_env = [] { const char* e = getenv("DLCFN_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  if (tma_store_env && out_dtype == 1 && !accumulate && p.N >= 64 && (p.ldd & 7) == 0) {
+    rc = make_map(&p.tmD, out, p.M, p.N, p.ldd, 64, 32);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
+#define DLCFN_CONV_CASE(BN, AM, BM) \
+  if (block_n == BN && a_mn == AM && b_mn == BM) return launch<BN, AM, BM, true>(p, num_sms, stream);
+  DLCFN_CONV_CASE(128, false, false)
+  DLCFN_CONV_CASE(256, false, false)
+  DLCFN_CONV_CASE(128, false, true)
+  DLCFN_CONV_CASE(256, false, true)
+  DLCFN_CONV_CASE(128, true, true)
+  DLCFN_CONV_CASE(256, true, true)
+#undef DLCFN_CONV_CASE
   return (int)cudaErrorInvalidValue;
 }

@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops.batchnorm import BatchNormReLU2d
-from ..ops.conv import Conv1x1
+from ..ops.conv import Conv1x1, ConvKxK
 from ..ops.linear import Linear
 from ..ops.pool import MaxPool2d, global_avg_pool
 
@@ -42,7 +42,7 @@ class BottleneckV2(nn.Module):
         self.bn1 = _bn(cin)
         self.conv1 = Conv1x1(cin, mid)
         self.bn2 = _bn(mid)
-        self.conv2 = nn.Conv2d(mid, mid, 3, stride, 1, bias=False)
+        self.conv2 = ConvKxK(mid, mid, 3, stride, 1)
         self.bn3 = _bn(mid)
         self.conv3 = Conv1x1(mid, cout)
         self.sc = None if dim_match else Conv1x1(cin, cout, stride)
@@ -64,9 +64,9 @@ class BasicV2(nn.Module):
     def __init__(self, cin: int, cout: int, stride: int, dim_match: bool):
         super().__init__()
         self.bn1 = _bn(cin)
-        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.conv1 = ConvKxK(cin, cout, 3, stride, 1)
         self.bn2 = _bn(cout)
-        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.conv2 = ConvKxK(cout, cout, 3, 1, 1)
         self.sc = None if dim_match else Conv1x1(cin, cout, stride)
 
     def forward(self, x):

@@ -101,6 +101,8 @@ def _declare(L) -> None:
     L.dlcfn_ps_set_next_pull_mask.restype = None
     L.dlcfn_ps_async_server.argtypes = [vp, sz, sz, sz, sz, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, vp]
     L.dlcfn_gemm_bf16.argtypes = [vp, ll, i, vp, i, i, ll, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp]
+    L.dlcfn_conv_bf16.argtypes = [i, vp, vp, vp, i] + [i] * 15 + [vp]
+    L.dlcfn_conv_bf16.restype = c_int
     for fn in ("dlcfn_elementwise_sum", "dlcfn_cast_scale", "dlcfn_fused_optimizer", "dlcfn_normalize_u8_nhwc",
                "dlcfn_quantize_2bit", "dlcfn_dequantize_2bit", "dlcfn_unique_rows", "dlcfn_symm_create",
                "dlcfn_symm_get_handle", "dlcfn_symm_open_peer", "dlcfn_symm_set_peer_ptr", "dlcfn_symm_finalize",
@@ -254,3 +256,56 @@ def gemm_bf16(a: torch.Tensor, b, *, a_mn: bool = False, b_mn: bool = False, out
                            f"b%16={ptrs[0] % 16} d%16={out.data_ptr() % 16} shards={len(ptrs)} block_n={block_n}")
     _count()
     return out
+
+
+# ------------------------------------------------------------------ implicit-GEMM convolution (EXPERIMENTAL)
+def _nhwc_ok(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def conv_fprop(x: torch.Tensor, weight: torch.Tensor, stride: int, pad: int, block_n: int = 0) -> torch.Tensor:
+    """x [N,C,H,W] channels_last, weight [K,C,R,S] channels_last (memory [K][R][S][C]) -> y [N,K,P,Q] channels_last."""
+    assert _nhwc_ok(x) and _nhwc_ok(weight)
+    N, C, H, W = x.shape
+    K, _, R, S = weight.shape
+    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    y = torch.empty((N, K, P, Q), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    rc = lib().dlcfn_conv_bf16(0, x.data_ptr(), weight.data_ptr(), y.data_ptr(), 1, N, H, W, C, K, C, R, S, pad, stride, P, Q,
+                               0, block_n, 0, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"dlcfn conv fprop failed with CUDA error {rc}: x={tuple(x.shape)} w={tuple(weight.shape)} "
+                           f"stride={stride} pad={pad}")
+    _count()
+    return y
+
+
+def conv_dgrad(dy: torch.Tensor, weight: torch.Tensor, pad: int, in_hw: tuple[int, int], block_n: int = 0) -> torch.Tensor:
+    """Stride-1 input gradient: dy [N,K,P,Q] channels_last, weight [K,C,R,S] channels_last -> dx [N,C,H,W] channels_last."""
+    assert _nhwc_ok(dy) and _nhwc_ok(weight)
+    N, K, P, Q = dy.shape
+    _, C, R, S = weight.shape
+    H, W = in_hw
+    dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+    rc = lib().dlcfn_conv_bf16(1, dy.data_ptr(), weight.data_ptr(), dx.data_ptr(), 1, N, P, Q, K, K, C, R, S, pad, 1, H, W,
+                               0, block_n, 0, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"dlcfn conv dgrad failed with CUDA error {rc}: dy={tuple(dy.shape)} w={tuple(weight.shape)} pad={pad}")
+    _count()
+    return dx
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, kernel: tuple[int, int], stride: int, pad: int,
+               block_n: int = 0) -> torch.Tensor:
+    """dw [K,C,R,S] channels_last = dy^T * im2col(x); split-K over the N*P*Q pixels, deterministic reduction."""
+    assert _nhwc_ok(x) and _nhwc_ok(dy)
+    N, C, H, W = x.shape
+    _, K, P, Q = dy.shape
+    R, S = kernel
+    dw = torch.empty((K, C, R, S), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    rc = lib().dlcfn_conv_bf16(2, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), 1, N, H, W, C, K, C, R, S, pad, stride, P, Q,
+                               0, block_n, 0, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"dlcfn conv wgrad failed with CUDA error {rc}: x={tuple(x.shape)} dy={tuple(dy.shape)} "
+                           f"kernel={kernel} stride={stride} pad={pad}")
+    _count(2)
+    return dw

@@ -77,3 +77,18 @@ def test_zoo_models_on_cuda_kernels_match_fp32_cpu(name):
     assert torch.isfinite(y).all() and cos > 0.95, (cos, (y - y_ref).abs().max().item())
     m(x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float().logsumexp(1).sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)
+
+
+@pytest.mark.parametrize("case", [(1, 64, 7, 9, 128, 3, 1, 1), (2, 64, 9, 9, 72, 3, 2, 1), (1, 128, 5, 5, 64, 1, 1, 0)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_implicit_gemm_conv_producer_index_math(case):
+    """tools/conv_im2col_model.py replays the index arithmetic of the convolution producer warp (k-block -> tap / channel
+    slice, tile -> first pixel, reversed taps for dgrad, column panels for wgrad) on a host model of im2col-mode TMA."""
+    import importlib.util
+    import pathlib
+    spec = importlib.util.spec_from_file_location("conv_im2col_model",
+                                                  pathlib.Path(__file__).resolve().parents[1] / "tools" / "conv_im2col_model.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    errs = mod.check(*case)
+    assert "fprop" in errs and "wgrad" in errs and all(v < 1e-9 for v in errs.values()), errs

@@ -3,7 +3,12 @@
 #   gpurun --timeout 900 -- 'bash tools/round2_first.sh'
 mkdir -p gpurun_out
 echo "== experimental kernels (fused dropout+add+LayerNorm)"
-DLCFN_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -q -m gpu --timeout 200 2>&1 | tail -15 | tee gpurun_out/r2_experimental.log
+DLCFN_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -q -m gpu --timeout 200 -k "layernorm" 2>&1 | tail -15 | tee gpurun_out/r2_experimental_ln.log
+echo "== experimental kernels (implicit-GEMM convolution through im2col TMA): fprop, dgrad, wgrad, module - one process each,"
+echo "   a wrong assumption about the im2col load would hang on the mbarrier, hence the timeouts"
+for k in fprop dgrad wgrad convkxk_module; do
+  DLCFN_EXPERIMENTAL=1 timeout 150 python -m pytest tests/test_gpu_experimental.py -q -m gpu --timeout 100 -k "$k" 2>&1 | tail -12 | tee gpurun_out/r2_experimental_conv_$k.log
+done
 echo "== whole GPU suite"
 timeout 900 python -m pytest tests/ -x -q -m gpu --timeout 600 2>&1 | tail -4 | tee gpurun_out/r2_pytest_gpu.log
 echo "== GEMM: tile-width score (BERT shapes now take 128x256 tiles)"
@@ -15,5 +20,8 @@ DLCFN_FUSED_LN=0 timeout 300 python bench.py --model bert-large --steps 10 --war
 DLCFN_FUSED_LN=1 timeout 300 python bench.py --model bert-large --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_bert_fused_ln.json
 echo "== ResNet-50 default bench"
 timeout 400 python bench.py 2>&1 | tail -1 | tee gpurun_out/r2_bench_1gpu.json
+echo "== ResNet-50 with the 3x3 convolutions on the implicit-GEMM kernel (only meaningful if the conv tests above passed)"
+DLCFN_CONVKXK=tcgen05 timeout 400 python bench.py 2>&1 | tail -1 | tee gpurun_out/r2_bench_1gpu_convkxk.json
+DLCFN_CONVKXK=tcgen05 DLCFN_CONV1X1=tcgen05 timeout 400 python bench.py 2>&1 | tail -1 | tee gpurun_out/r2_bench_1gpu_allconv_tcgen05.json
 echo "== kernel-time breakdown of the step (torch.profiler)"
 timeout 300 python tools/profile_step.py 256 > gpurun_out/r2_profile_step.log 2>&1; head -40 gpurun_out/profile_resnet50.txt | cut -c1-150

@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--num-layers", type=int, default=50)
     ap.add_argument("--bucket-mb", type=float, default=16.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dry-cpu", action="store_true",
+                    help="exercise the whole script on the host with tiny shapes (fp32, wall-clock 'events', no H2D): a check "
+                         "of this file's logic on a box without a GPU - the line it prints is marked and is NOT a measurement")
     ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn", "auto"],
                     help="backend of the 1x1 convolutions (default: ops.conv default / DLCFN_CONV1X1)")
     return ap.parse_args()
@@ -51,6 +54,34 @@ def reference_arm(args):
     return 0
 
 
+class _HostEvent:
+    """--dry-cpu stand-in for torch.cuda.Event (wall clock)."""
+
+    def __init__(self, enable_timing: bool = False):
+        self.t = 0.0
+
+    def record(self, *_a):
+        self.t = time.perf_counter()
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other) -> float:
+        return (other.t - self.t) * 1e3
+
+
+class _HostPrefetcher:
+    """--dry-cpu stand-in for utils.data.DevicePrefetcher: same interface, normalisation through torch on the host."""
+
+    def __init__(self, source, device):
+        self.source = source
+
+    def next(self):
+        import torch
+        img, lab = self.source.next()
+        return ((img.float() / 255.0 - 0.45) / 0.225).permute(0, 3, 1, 2), lab
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -64,14 +95,25 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:
         args.gpus = world
-    if not torch.cuda.is_available():
+    dry = args.dry_cpu
+    if not dry and not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device"}))
         return 1
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    if dry:
+        device = torch.device("cpu")
+        Event, cuda_sync, pin = _HostEvent, (lambda _d=None: None), (lambda t: t)
+        args.image_size, args.num_layers = min(args.image_size, 32), (20 if args.num_layers == 50 else args.num_layers)
+        args.batch, args.seq_len = args.batch or 4, min(args.seq_len, 32)
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local_rank)
+        device = torch.device("cuda", local_rank)
+        Event, cuda_sync, pin = torch.cuda.Event, torch.cuda.synchronize, (lambda t: t.pin_memory())
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=device)
 
     from deeplearning_cfn_b200.models import resnet, to_b200_layout
     from deeplearning_cfn_b200.ops import native
@@ -79,7 +121,9 @@ def main():
     from deeplearning_cfn_b200.utils.clocks import ClockSampler
     from deeplearning_cfn_b200.utils.data import DevicePrefetcher, SyntheticImageSource, synthetic_device_batch
 
-    native.lib()  # fail loudly if the sm_100a library is missing
+    if not dry:
+        native.lib()  # fail loudly if the sm_100a library is missing
+    compute_dtype = torch.float32 if dry else torch.bfloat16
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234)
 
@@ -89,6 +133,8 @@ def main():
         mode, servers, workers = "ps_sync", [0], list(range(1, world))
     if world == 1:
         mode = "local"
+    elif dry:
+        mode = "nccl"          # torch.distributed all-reduce (gloo on the host); the fused kernels need peer HBM
 
     from deeplearning_cfn_b200.ops import conv as conv_ops
     if args.conv1x1:
@@ -99,7 +145,12 @@ def main():
     if is_bert:
         from deeplearning_cfn_b200.models import bert_pretrain_loss, get_model
         args.no_e2e = True
-        model = to_b200_layout(get_model(args.model, max_seq=args.seq_len).to(device), torch.bfloat16).train()
+        if dry:
+            from deeplearning_cfn_b200.models import Bert
+            model = Bert(hidden=64, layers=2, heads=4, ffn=128, max_seq=args.seq_len)
+        else:
+            model = get_model(args.model, max_seq=args.seq_len)
+        model = to_b200_layout(model.to(device), compute_dtype).train()
         model.padded_logits = True     # the fused loss kernel masks the TMA padding columns of the vocabulary
         trainer = DataParallelTrainer(model, mode=mode, optimizer="adam", lr=1e-4, wd=0.01, beta1=0.9, beta2=0.999,
                                       bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
@@ -111,37 +162,40 @@ def main():
         y = (torch.randint(0, 30522, (args.batch, npred), generator=g).to(device),
              torch.randint(0, 2, (args.batch,), generator=g).to(device))
     else:
-        model = to_b200_layout(resnet(args.num_layers, 1000, args.image_size).to(device), torch.bfloat16)
+        model = to_b200_layout(resnet(args.num_layers, 1000, args.image_size).to(device), compute_dtype)
         model.train()
         trainer = DataParallelTrainer(model, mode=mode, optimizer="sgd_mom", lr=0.1, momentum=0.9, wd=1e-4,
                                       bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
                                       worker_ranks=workers)
-        x, y = synthetic_device_batch(args.batch, args.image_size, 1000, device)
+        x, y = synthetic_device_batch(args.batch, args.image_size, 1000, device, dtype=compute_dtype)
     n_workers = len(trainer.workers)
     is_worker = trainer.is_worker
 
     def sync_all():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize(device)
+        cuda_sync(device)
 
     # ---------------------------------------------------------------- device-timed loop
     for _ in range(args.warmup):
         trainer.step(x, y) if is_worker else trainer.step()
     sync_all()
     launches0 = native.launch_count
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start, t_end = Event(enable_timing=True), Event(enable_timing=True)
     sampler = ClockSampler(gpu_index=local_rank) if rank == 0 else None
     if sampler:
         sampler.__enter__()
     t_start.record()
+    step_loss = None
     for _ in range(args.steps):
-        trainer.step(x, y) if is_worker else trainer.step()
+        step_loss = trainer.step(x, y) if is_worker else trainer.step()
     t_end.record()
     sync_all()
     if sampler:
         sampler.__exit__(None, None, None)
     ms = t_start.elapsed_time(t_end)
+    # read after the timed region: the loss of the last timed step (a diverged / NaN run would not be a training step)
+    timed_loss = float(step_loss.detach().float()) if (is_worker and torch.is_tensor(step_loss)) else None
     launches = native.launch_count - launches0
     trainer.check()
 
@@ -149,12 +203,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         src = SyntheticImageSource(args.batch, args.image_size, 1000) if is_worker else None
-        pre = DevicePrefetcher(src, device) if is_worker else None
+        pre = (_HostPrefetcher if dry else DevicePrefetcher)(src, device) if is_worker else None
         # the loss of every step is copied device->host (pinned, async) and READ one step later, when its copy event has
         # completed: the host never runs more than one step ahead, and it never drains the GPU queue either (a hard
         # synchronize per step leaves the GPU idle while the host enqueues the next step's first kernels)
-        host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        host_loss = [pin(torch.zeros(1, dtype=torch.float32)) for _ in range(2)]
+        loss_ev = [Event(), Event()]
         for _ in range(3):
             if is_worker:
                 xb, yb = pre.next()
@@ -162,7 +216,7 @@ def main():
             else:
                 trainer.step()
         sync_all()
-        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start, e_end = Event(enable_timing=True), Event(enable_timing=True)
         last, losses_read = 0.0, 0
         e_sampler = ClockSampler(gpu_index=local_rank) if rank == 0 else None      # clocks / throttle reasons of THIS loop
         if e_sampler:
@@ -224,32 +278,34 @@ def main():
             rec = {"metric": f"{args.model}_pretrain_sequences_per_sec", "value": round(value, 2), "unit": "sequences/sec",
                    "tokens_per_sec": round(value * args.seq_len, 1),
                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (dry run)" if dry else "bf16",
                    "data": "synthetic (random token ids, random-init weights)", "impl": "ours" if args.impl == "ours" else "nccl-baseline",
                    "config": {"model": args.model, "global_batch": global_batch, "per_gpu_batch": args.batch,
                               "seq_len": args.seq_len, "parallelism": par, "optimizer": "adam multi-precision (fp32 master)",
                               "bucket_mb": args.bucket_mb, "l2": "activations larger than L2",
                               "baseline": "none published (the reference has no transformer workload)"},
                    "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", [])},
-                   "gpu_launches": launches}
+                   "gpu_launches": launches, "last_loss": timed_loss}
+            if dry:
+                rec["dry_cpu"] = "host dry run of bench.py with tiny shapes - NOT a measurement"
             print(json.dumps(rec), flush=True)
             rec = None
         else:
           rec = {"metric": "resnet50_train_images_per_sec", "value": round(value, 2), "unit": "images/sec",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": round(value / (BASELINE_IMG_S_PER_GPU * world), 3), "dtype": "bf16",
+               "vs_baseline": round(value / (BASELINE_IMG_S_PER_GPU * world), 3), "dtype": "fp32 (dry run)" if dry else "bf16",
                "data": "synthetic (random images/labels, random-init weights)",
                "impl": "ours" if args.impl == "ours" else "nccl-baseline",
                "config": {"model": f"resnet-{args.num_layers}-v2 (reference symbols/resnet.py)",
                           "global_batch": global_batch, "per_gpu_batch": args.batch, "image": args.image_size,
                           "seq_len": None, "parallelism": par, "optimizer": "sgd-momentum multi-precision (fp32 master)",
                           "bucket_mb": args.bucket_mb, "l2": "inputs+activations larger than L2 (no flush needed)",
-                          "conv1x1": conv_ops.conv1x1_backend(),
+                          "conv1x1": conv_ops.conv1x1_backend(), "convkxk": conv_ops.convkxk_backend(),
                           "baseline": "363.69 img/s per V100 (perf.md:219) x n_gpus"},
                "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                           "reasons": clocks.get("reasons", [])},
-               "gpu_launches": launches}
+               "gpu_launches": launches, "last_loss": timed_loss}
         if e2e and rec is not None:
             rec["e2e"] = {"value": round(global_batch * args.steps / (e_ms / 1e3), 2), "unit": "images/sec",
                           "h2d_bytes_per_step": e2e["h2d"] * n_workers if is_worker else 0,
@@ -259,6 +315,8 @@ def main():
             if not is_worker:  # rank 0 is a dedicated server: bytes come from the workers
                 rec["e2e"]["h2d_bytes_per_step"] = (args.batch * args.image_size * args.image_size * 3 + args.batch * 8) * n_workers
         if rec is not None:
+            if dry:
+                rec["dry_cpu"] = "host dry run of bench.py with tiny shapes - NOT a measurement"
             print(json.dumps(rec), flush=True)
     if world > 1:
         dist.barrier()

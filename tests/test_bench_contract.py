@@ -1,0 +1,74 @@
+"""bench.py / __graft_entry__ contract, checked on the host: `--dry-cpu` runs the whole script (both timed loops, the
+rank reduction, the JSON line) with tiny shapes so that an edit to bench.py cannot first fail on the GPU box."""
+import json
+import os
+import sys
+
+import pytest
+
+from conftest import run_job
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches"}
+
+
+def _last_json(out: str) -> dict:
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, f"bench must print exactly one JSON line, got {len(lines)}:\n{out[-2000:]}"
+    return json.loads(lines[0])
+
+
+def test_bench_dry_run_single_rank_prints_the_contract_line():
+    r = run_job([sys.executable, "bench.py", "--dry-cpu", "--steps", "3", "--warmup", "1"], cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rec = _last_json(r.stdout)
+    assert REQUIRED <= set(rec), REQUIRED - set(rec)
+    assert rec["metric"] == "resnet50_train_images_per_sec" and rec["n_gpus"] == 1 and rec["steps"] == 3 and rec["warmup"] == 1
+    assert rec["higher_is_better"] is True and rec["scaling"] == "weak" and rec["value"] > 0
+    assert abs(rec["value"] - rec["config"]["global_batch"] * 1e3 / rec["ms_per_step"]) / rec["value"] < 0.01
+    assert {"model", "global_batch", "seq_len", "parallelism"} <= set(rec["config"])
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(rec["clocks"])
+    e = rec["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
+    b, s = rec["config"]["per_gpu_batch"], rec["config"]["image"]
+    assert e["h2d_bytes_per_step"] == b * s * s * 3 + b * 8 and e["d2h_bytes_per_step"] == 4      # uint8 pixels + int64 labels
+    assert e["value"] != rec["value"]                       # measured by its own loop
+    assert rec["last_loss"] == rec["last_loss"] and e["last_loss"] == e["last_loss"]            # finite, not NaN
+    assert "dry_cpu" in rec                                  # a host run is labelled as such
+
+
+def test_bench_dry_run_bert_and_reference_arm():
+    r = run_job([sys.executable, "bench.py", "--dry-cpu", "--model", "bert-large", "--steps", "2", "--warmup", "1"], cwd=ROOT,
+                timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rec = _last_json(r.stdout)
+    assert rec["metric"] == "bert-large_pretrain_sequences_per_sec" and rec["vs_baseline"] is None
+    r = run_job([sys.executable, "bench.py", "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"], cwd=ROOT,
+                timeout=120)
+    assert r.returncode == 0
+    rec = _last_json(r.stdout)
+    assert rec["impl"] == "reference" and "unavailable" in rec and "\n" not in rec["unavailable"]
+
+
+def test_bench_dry_run_two_ranks_under_torchrun():
+    """The driver's multi-GPU launch line, on gloo: one JSON line from rank 0, whole-job value, max-over-ranks time."""
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    port = 29500 + (os.getpid() % 400)
+    r = run_job([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                 "127.0.0.1", "--master-port", str(port), "bench.py", "--dry-cpu", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                cwd=ROOT, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rec = _last_json(r.stdout)
+    assert rec["n_gpus"] == 2 and rec["config"]["global_batch"] == 2 * rec["config"]["per_gpu_batch"]
+    assert abs(rec["value"] - rec["config"]["global_batch"] * 1e3 / rec["ms_per_step"]) / rec["value"] < 0.01
+    assert rec["e2e"]["h2d_bytes_per_step"] == 2 * (rec["config"]["per_gpu_batch"] * (rec["config"]["image"] ** 2 * 3 + 8))
+
+
+def test_graft_entry_has_build_and_smoke():
+    sys.path.insert(0, ROOT)
+    try:
+        import __graft_entry__ as g
+    finally:
+        sys.path.pop(0)
+    assert callable(g.build) and callable(g.smoke)

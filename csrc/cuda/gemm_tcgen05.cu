@@ -544,6 +544,247 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   }
 }
 
+
+// ====================================================================================================================
+// CTA-PAIR kernel (EXPERIMENTAL, written at the end of round 1 without GPU access; DLCFN_GEMM_2CTA=1).
+//
+// tcgen05.mma.cta_group::2: the two CTAs of a cluster (the two SMs of a TPC) execute ONE 256 x 256 x 16 MMA per
+// instruction.  CTA r holds rows [128r, 128r+128) of the A tile and columns [128r, 128r+128) of the B tile in ITS shared
+// memory and rows [128r, 128r+128) of the accumulator in ITS tensor memory; the tensor cores of each SM read the B half
+// they do not own from the partner's shared memory.  Per k-block a CTA therefore pulls 16 KiB (A) + 16 KiB (B half) from
+// L2 instead of 16 + 32 KiB, and the shared-memory reads per MMA halve as well - the single-CTA kernel is limited by
+// exactly those two (26 TB/s of L2 reads at full rate, 81 % tensor-pipe utilisation in profiles/gemm_tcgen05_8192_ncu.txt).
+//
+// Protocol (after CUTLASS's sm100 2-SM pipeline, re-derived here):
+//   * both CTAs run a TMA producer; their loads use the .cta_group::2 form whose completion bytes are credited to the
+//     LEADER's (rank 0) full barrier (barrier address with the CTA bit cleared), which expects the bytes of both CTAs
+//   * only the leader runs the MMA issuer; its tcgen05.commit is multicast to both CTAs: to the smem-empty barriers (each
+//     producer refills its own ring) and to the tmem-full barriers (each CTA's epilogue drains its own 128 rows)
+//   * epilogue warps of both CTAs arrive on the LEADER's tmem-empty barrier (mapa + remote arrive), 16 arrivals per stage
+//   * TMEM is allocated / freed with cta_group::2 by warp 1 of both CTAs; cluster barriers bracket the kernel
+constexpr int k2BlockN = 256;
+constexpr int k2HalfN = 128;
+constexpr int k2Stages = 6;
+constexpr int k2ABytes = kBlockM * kBlockK * 2;     // 16 KiB
+constexpr int k2BBytes = k2HalfN * kBlockK * 2;     // 16 KiB (this CTA's half of the B tile)
+constexpr int k2StageBytes = k2ABytes + k2BBytes;
+constexpr int k2StagingBytes = 8 * 4096;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + k2StagingBytes + 1024 + 256;
+constexpr int k2TmemCols = 2 * k2BlockN;            // two accumulator stages = all 512 columns
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at the same shared-memory offset of cluster CTA `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(bar), "r"(rank)
+      : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stg_base = smem_base + k2Stages * k2StageBytes;
+  const uint32_t bar_base = stg_base + k2StagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + 2 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + k2Stages * k2StageBytes + k2StagingBytes +
+                                                    8 * (2 * k2Stages + 4));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = (int)cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_pm = (num_m + 1) / 2;                 // pairs of M tiles; a phantom second tile loads zeros, stores nothing
+  const int num_n = (p.N + k2BlockN - 1) / k2BlockN;
+  const int num_items = num_pm * num_n;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int item0 = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB[0]);
+    tma_prefetch_desc(&p.tmD);
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(full_bar(s), 1);      // used on the leader only: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(empty_bar(s), 1);     // one multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);     // one multicast tcgen05.commit
+      mbar_init(tempty_bar(s), 16);   // used on the leader only: 8 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                 // both CTAs' barriers exist before any remote arrive / multicast commit / pair load
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(k2TmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = item0; item < num_items; item += item_step) {
+        const int m_idx = ((item % num_pm) * 2 + cta_rank) * kBlockM;
+        const int n_idx = (item / num_pm) * k2BlockN + cta_rank * k2HalfN;     // this CTA's half of the B tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int k_idx = kb * kBlockK;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * k2StageBytes;
+          const uint32_t sb = sa + k2ABytes;
+          const uint32_t lbar = full_bar(stage) & 0xFEFFFFFFu;                 // the leader CTA's barrier
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * k2StageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d_pair(sa, &p.tmA, lbar, k_idx, m_idx);                  // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &p.tmA, lbar, m_idx + 64 * j, k_idx);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sb, &p.tmB[0], lbar, k_idx, n_idx);               // box {64 k, 128 n}
+          } else {
+#pragma unroll
+            for (int j = 0; j < k2HalfN / 64; ++j) tma_load_2d_pair(sb + j * 8192, &p.tmB[0], lbar, n_idx + 64 * j, k_idx);
+          }
+          if (++stage == k2Stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(k2BlockN >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = item0; item < num_items; item += item_step) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * k2BlockN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * k2StageBytes;
+          const uint32_t sb = sa + k2ABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = A_MN ? umma_desc(sa + k * 2048, 8192, 1024) : umma_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc(sb + k * 2048, 8192, 1024) : umma_desc(sb + k * 32, 16, 1024);
+            tc_mma_bf16_pair(tmem_d, da, db, idesc, (kb != 0 || k != 0) ? 1u : 0u);
+          }
+          tc_commit_pair(empty_bar(stage));      // both producers may refill this slot
+          if (++stage == k2Stages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_pair(tfull_bar(acc));          // both epilogues may drain this accumulator stage
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9 of both CTAs): bf16 through swizzled staging + TMA store ==========
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kChunks = k2BlockN / 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
+    uint8_t* stg_gen = smem_gen + (stg - smem_base);
+    for (int item = item0; item < num_items; item += item_step) {
+      const int m_idx = ((item % num_pm) * 2 + cta_rank) * kBlockM;
+      const int n_idx = (item / num_pm) * k2BlockN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      uint32_t r[kChunks][32];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c)
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * k2BlockN + (half * kChunks + c) * 32, r[c]);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);     // this warp's quarter of the stage is in registers
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+#pragma unroll
+      for (int bx = 0; bx < kChunks / 2; ++bx) {
+        const int colb = n_idx + (half * kChunks + 2 * bx) * 32;
+        if (colb < p.N) {
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float o[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(r[2 * bx + (j >> 2)][(j & 3) * 8 + t]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                if (colb + j * 8 + t < p.N) o[t] += __ldg(p.bias + colb + j * 8 + t);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
+            }
+            *reinterpret_cast<uint4*>(stg_gen + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmD, stg, colb, m_idx + q * 32);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_read();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // the partner has consumed everything that lives in this CTA's shared / tensor memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(k2TmemCols));
+  }
+}
+
 // Sum the split-K partials, then bias / accumulate / relu / convert.  A CTA is 32 float4 columns x 8 slice lanes:
 // lane group g sums slices g, g+8, g+16, ... (4 loads in flight), the 8 partial sums meet in shared memory and are
 // added in a fixed order, so the result does not depend on scheduling.  (The first version walked all slices
@@ -847,6 +1088,44 @@ static int launch_mc(GemmParams& p, int num_sms, cudaStream_t stream) {
   return (int)le;
 }
 
+
+// EXPERIMENTAL CTA-pair launch (256 x 256 pair tiles, local B, bf16 TMA-store output, no split-K)
+template <bool A_MN, bool B_MN>
+static int launch_pair(GemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = kgemm_pair<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+    if (ae != cudaSuccess) return (int)ae;
+    configured = true;
+  }
+  p.splits = 1;
+  p.kb_per_split = (p.K + kBlockK - 1) / kBlockK;
+  p.ws = nullptr;
+  const int num_m = (p.M + kBlockM - 1) / kBlockM, num_n = (p.N + k2BlockN - 1) / k2BlockN;
+  const int pair_tiles = ((num_m + 1) / 2) * num_n;
+  int pairs = num_sms / 2;
+  if (pairs > pair_tiles) pairs = pair_tiles;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = k2SmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess)
+    fprintf(stderr, "[dlcfn] kgemm_pair launch failed: %s (grid %d, smem %d)\n", cudaGetErrorString(le), 2 * pairs, k2SmemBytes);
+  return (int)le;
+}
+
 }  // namespace dlcfn
 
 using namespace dlcfn;
@@ -906,6 +1185,13 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   static const bool mc_env = [] { const char* e = getenv("DLCFN_GEMM_MULTICAST"); return e && e[0] == '1'; }();
   const bool use_mc = mc_env && block_n == 256 && n_shards == 1 &&
                       (long long)(((M + kBlockM - 1) / kBlockM + 1) / 2) * ((N + 255) / 256) >= num_sms / 2;
+  // EXPERIMENTAL CTA-pair kernel (cta_group::2): opt-in; bf16 TMA-store outputs of GEMMs with enough 256 x 256 pair tiles
+  static const bool pair_env = [] { const char* e = getenv("DLCFN_GEMM_2CTA"); return e && e[0] == '1'; }();
+  static const bool tma_store_env2 = [] { const char* e = getenv("DLCFN_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  const bool use_pair = pair_env && !use_mc && n_shards == 1 && N >= 256 && tma_store_env2 && d_dtype == 1 && !accumulate &&
+                        (ldd & 7) == 0 && (((uintptr_t)D) & 15) == 0 &&
+                        (long long)(((M + kBlockM - 1) / kBlockM + 1) / 2) * ((N + 255) / 256) >= num_sms / 4;
+  if (use_pair) block_n = 256;
   int rc;
   if (!a_mn) rc = make_map(&p.tmA, A, M, K, lda, kBlockK, kBlockM);
   else rc = make_map(&p.tmA, A, K, M, lda, 64, kBlockK);
@@ -913,7 +1199,7 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   for (int s = 0; s < n_shards; ++s) {
     if (!b_mn) {
       const uint64_t rows = n_shards > 1 ? (uint64_t)rows_per_shard : (uint64_t)N;
-      rc = make_map(&p.tmB[s], b_shards[s], rows, K, ldb, kBlockK, use_mc ? block_n / 2 : block_n);   // MC: half tile per CTA
+      rc = make_map(&p.tmB[s], b_shards[s], rows, K, ldb, kBlockK, (use_mc || use_pair) ? block_n / 2 : block_n);   // MC / pair: half tile per CTA
     } else {
       const uint64_t rows = n_shards > 1 ? (uint64_t)rows_per_shard : (uint64_t)K;
       rc = make_map(&p.tmB[s], b_shards[s], rows, N, ldb, 64, kBlockK);
@@ -931,6 +1217,12 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
     // a tile must not straddle two shards
     if (!b_mn && (rows_per_shard % block_n)) return (int)cudaErrorInvalidValue;
     if (b_mn && (rows_per_shard % kBlockK)) return (int)cudaErrorInvalidValue;
+  }
+  if (use_pair) {
+    if (!a_mn && !b_mn) return launch_pair<false, false>(p, num_sms, stream);
+    if (!a_mn && b_mn) return launch_pair<false, true>(p, num_sms, stream);
+    if (a_mn && !b_mn) return launch_pair<true, false>(p, num_sms, stream);
+    return launch_pair<true, true>(p, num_sms, stream);
   }
   if (use_mc) {
     if (!a_mn && !b_mn) return launch_mc<false, false>(p, num_sms, stream);

@@ -239,3 +239,34 @@ def test_convkxk_module_autograd_and_resnet_step():
     assert losses["tcgen05"][1] > losses["cudnn"][1] + 40            # the 3x3 layers really ran on the dlcfn kernel
     cos = F.cosine_similarity(losses["tcgen05"][2].flatten(), losses["cudnn"][2].flatten(), dim=0).item()
     assert cos > 0.98, cos
+
+
+# ----------------------------------------------------------- GEMM variants selected by environment (read once by the .so)
+_GEMM_VARIANT = "2cta" if os.environ.get("DLCFN_GEMM_2CTA") == "1" else ("multicast" if os.environ.get("DLCFN_GEMM_MULTICAST") == "1" else None)
+
+
+@pytest.mark.skipif(_GEMM_VARIANT is None, reason="run with DLCFN_GEMM_2CTA=1 or DLCFN_GEMM_MULTICAST=1 in the environment")
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,epi", [(4096, 4096, 1024, False), (4224, 2048, 512, True), (8192, 1000, 256, False),
+                                       (16384, 512, 64, True), (5000, 3000, 1096, False)])
+def test_gemm_pair_variants_match_fp32(M, N, K, epi, a_mn, b_mn):
+    """Shapes with enough 256-wide tile pairs to take the CTA-pair / multicast kernel: odd tile-row counts (phantom second
+    tile), N tails, K tails, all four operand layouts, bias + relu epilogue."""
+    from deeplearning_cfn_b200.ops import native
+    torch.manual_seed(M + N + K)
+    if a_mn and M % 8:
+        M = (M + 7) // 8 * 8
+    if b_mn and N % 8:
+        N = (N + 7) // 8 * 8
+    a = torch.randn(M, K, device=dev()).bfloat16()
+    b = torch.randn(N, K, device=dev()).bfloat16()
+    bias = torch.randn(N, device=dev()) if epi else None
+    A = a.t().contiguous() if a_mn else a
+    B = b.t().contiguous() if b_mn else b
+    d = native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=epi, block_n=256)
+    ref = a.float() @ b.float().t()
+    if epi:
+        ref = torch.relu(ref + bias)
+    assert d.shape == (M, N)
+    _frac_close(d, ref, 2e-2, 2e-2 * float(ref.abs().max()), frac=0.9999)
+    assert torch.equal(d, native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=epi, block_n=256))

@@ -13,6 +13,10 @@ echo "== whole GPU suite"
 timeout 900 python -m pytest tests/ -x -q -m gpu --timeout 600 2>&1 | tail -4 | tee gpurun_out/r2_pytest_gpu.log
 echo "== GEMM: tile-width score (BERT shapes now take 128x256 tiles)"
 timeout 200 python tools/gemm_quick_perf.py 2>&1 | tail -10 | tee gpurun_out/r2_gemm_perf.log
+echo "== GEMM on the CTA-pair kernel (tcgen05.mma.cta_group::2; experimental, under timeouts)"
+DLCFN_GEMM_2CTA=1 DLCFN_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -q -m gpu --timeout 150 -k "pair_variants" 2>&1 | tail -8 | tee gpurun_out/r2_gemm_2cta_tests.log
+DLCFN_GEMM_2CTA=1 timeout 120 python tools/gemm_quick_perf.py 2>&1 | tail -10 | tee gpurun_out/r2_gemm_perf_2cta.log
+DLCFN_GEMM_MULTICAST=1 DLCFN_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -q -m gpu --timeout 150 -k "pair_variants" 2>&1 | tail -8 | tee gpurun_out/r2_gemm_multicast_tests.log
 echo "== GEMM with the multicast-pair kernel (experimental; under a timeout: a protocol bug would hang)"
 DLCFN_GEMM_MULTICAST=1 timeout 120 python tools/gemm_quick_perf.py 2>&1 | tail -10 | tee gpurun_out/r2_gemm_perf_multicast.log
 echo "== BERT-large, eager LayerNorm vs fused"

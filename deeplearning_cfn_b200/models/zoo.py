@@ -51,9 +51,15 @@ def conv_relu(cin: int, cout: int, k=1, s=1, p=0) -> nn.Sequential:
     return nn.Sequential(nn.Conv2d(cin, cout, k, s, p), nn.ReLU(inplace=True))
 
 
-def _init(model: nn.Module) -> None:
+def _init(model: nn.Module, xavier: bool = False) -> None:
+    """MSRA-style init for the BatchNorm networks, Xavier (magnitude 2, the reference's default initializer of fit.py) for the
+    plain conv+ReLU ones, which diverge at lr 0.1 with the former."""
     for m in model.modules():
-        if isinstance(m, nn.Conv2d):
+        if isinstance(m, nn.Conv2d) and xavier:
+            nn.init.xavier_uniform_(m.weight, gain=2 ** 0.5)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.Conv2d):
             nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
             if m.bias is not None:
                 nn.init.zeros_(m.bias)
@@ -221,7 +227,7 @@ class GoogLeNet(nn.Module):
                 cin = c[0] + c[2] + c[4] + c[5]
         self.features = nn.Sequential(*layers)
         self.fc = Linear(cin, num_classes)
-        _init(self)
+        _init(self, xavier=True)
 
     def forward(self, x):
         return self.fc(global_avg_pool(self.features(x)))
@@ -411,7 +417,7 @@ class SqueezeNet(nn.Module):
             raise ValueError("SqueezeNet version must be '1.0' or '1.1'")
         self.features = nn.Sequential(*f, nn.Dropout(0.5))
         self.classifier = conv_relu(512, num_classes, 1)
-        _init(self)
+        _init(self, xavier=True)
 
     def forward(self, x):
         return torch.flatten(global_avg_pool(self.classifier(self.features(x))), 1)

@@ -196,6 +196,9 @@ def main():
     ms = t_start.elapsed_time(t_end)
     # read after the timed region: the loss of the last timed step (a diverged / NaN run would not be a training step)
     timed_loss = float(step_loss.detach().float()) if (is_worker and torch.is_tensor(step_loss)) else None
+    if timed_loss is not None and timed_loss != timed_loss or timed_loss in (float("inf"), float("-inf")):
+        print(f"[bench] WARNING: loss of the last timed step is {timed_loss}", file=sys.stderr, flush=True)
+        timed_loss = None             # keep the output line strict JSON (no NaN literal)
     launches = native.launch_count - launches0
     trainer.check()
 
@@ -255,6 +258,9 @@ def main():
                 d1.record()
                 torch.cuda.synchronize()
                 print(f"[diag] {tag}: {d0.elapsed_time(d1) / args.steps:.3f} ms/step", file=sys.stderr, flush=True)
+        if last != last or last in (float("inf"), float("-inf")):
+            print(f"[bench] WARNING: end-to-end loss is {last}", file=sys.stderr, flush=True)
+            last = None
         e2e = {"ms": e_ms, "loss": last, "h2d": src.bytes_per_batch if is_worker else 0,
                "clocks": e_sampler.summary() if e_sampler else {}}
 

@@ -52,3 +52,32 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "multigpu" in item.keywords and ngpu < 2:
             item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs"))
+
+
+@pytest.fixture(autouse=True)
+def _seed_from_environment(request):
+    """The reference's `@with_seed()` (MX/tests/python/unittest/common.py): when DLCFN_TEST_SEED / MXNET_TEST_SEED is set
+    (tools/flakiness_checker.py sets it per trial) every test starts from that seed and a failure names it; without it tests
+    keep their own fixed seeds."""
+    seed = os.environ.get("DLCFN_TEST_SEED") or os.environ.get("MXNET_TEST_SEED")
+    if seed is None:
+        yield
+        return
+    import random
+    import numpy as np
+    import torch
+    s = int(seed)
+    random.seed(s)
+    np.random.seed(s % (1 << 32))
+    torch.manual_seed(s)
+    yield
+    rep = getattr(request.node, "rep_call", None)
+    if rep is not None and rep.failed:
+        print(f"\n[tests] {request.node.nodeid} failed with DLCFN_TEST_SEED={s}")
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_makereport(item, call):
+    outcome = yield
+    rep = outcome.get_result()
+    setattr(item, "rep_" + rep.when, rep)

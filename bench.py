@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--dry-cpu", action="store_true",
                     help="exercise the whole script on the host with tiny shapes (fp32, wall-clock 'events', no H2D): a check "
                          "of this file's logic on a box without a GPU - the line it prints is marked and is NOT a measurement")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="experimental: replay the device-timed step as one CUDA graph (parallel/graph.py); off by default")
     ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn", "auto"],
                     help="backend of the 1x1 convolutions (default: ops.conv default / DLCFN_CONV1X1)")
     return ap.parse_args()
@@ -177,8 +179,15 @@ def main():
         cuda_sync(device)
 
     # ---------------------------------------------------------------- device-timed loop
+    run_step = trainer.step
+    graphed = None
+    if args.cuda_graph:
+        graphed = trainer.capture(x if is_worker else None, y if is_worker else None)
+        run_step = graphed
+        if rank == 0:
+            print(f"[bench] {graphed!r}", file=sys.stderr, flush=True)
     for _ in range(args.warmup):
-        trainer.step(x, y) if is_worker else trainer.step()
+        run_step(x, y) if is_worker else run_step()
     sync_all()
     launches0 = native.launch_count
     t_start, t_end = Event(enable_timing=True), Event(enable_timing=True)
@@ -188,7 +197,7 @@ def main():
     t_start.record()
     step_loss = None
     for _ in range(args.steps):
-        step_loss = trainer.step(x, y) if is_worker else trainer.step()
+        step_loss = run_step(x, y) if is_worker else run_step()
     t_end.record()
     sync_all()
     if sampler:
@@ -308,6 +317,7 @@ def main():
                           "seq_len": None, "parallelism": par, "optimizer": "sgd-momentum multi-precision (fp32 master)",
                           "bucket_mb": args.bucket_mb, "l2": "inputs+activations larger than L2 (no flush needed)",
                           "conv1x1": conv_ops.conv1x1_backend(), "convkxk": conv_ops.convkxk_backend(),
+                          "cuda_graph": bool(graphed is not None and graphed.graphed),
                           "baseline": "363.69 img/s per V100 (perf.md:219) x n_gpus"},
                "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                           "reasons": clocks.get("reasons", [])},

@@ -275,6 +275,13 @@ class DataParallelTrainer:
         self.synchronize_and_update()
         return loss
 
+    def capture(self, x=None, y=None, warmup: int = 3):
+        """The whole step as one CUDA graph (parallel/graph.py, experimental): `step = trainer.capture(x, y)`, then
+        `loss = step(x, y)` per batch.  Falls back to the eager step (and says why in `step.reason`) on CPU tensors, under
+        the debugging engine and for optimizers whose learning rate is recomputed on the host every step."""
+        from .graph import GraphedStep
+        return GraphedStep(self, x, y, warmup)
+
     def set_learning_rate(self, lr: float) -> None:
         self.hp["lr"] = lr
 

@@ -570,3 +570,30 @@ def test_module_fine_grained_api_and_params_roundtrip(tmp_path):
     assert torch.allclose(mod2.get_outputs()[0], mod.get_outputs()[0])
     with pytest.raises(ValueError):
         mod2.set_params({"nope": torch.zeros(1)}, allow_missing=True)
+
+
+def test_graphed_step_falls_back_to_eager_where_a_graph_cannot_be_used():
+    """trainer.capture on CPU parameters returns a pass-through that says why and trains exactly like trainer.step."""
+    from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer
+    from deeplearning_cfn_b200.parallel.graph import GraphedStep, _flatten, _map
+
+    def make():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    x, y = torch.randn(6, 8), torch.randint(0, 4, (6,))
+    a = DataParallelTrainer(make(), mode="local", optimizer="sgd_mom", lr=0.1)
+    b = DataParallelTrainer(make(), mode="local", optimizer="sgd_mom", lr=0.1)
+    step = a.capture(x, y)
+    assert isinstance(step, GraphedStep) and not step.graphed and "CUDA" in step.reason and "eager" in repr(step)
+    for _ in range(3):
+        la, lb = step(x, y), b.step(x, y)
+        assert torch.equal(la, lb)
+    assert a.step_count == b.step_count == 3
+    for pa, pb in zip(a.model.parameters(), b.model.parameters()):
+        assert torch.equal(pa, pb)
+    # nested inputs (BERT passes tuples) are cloned / flattened structurally
+    nested = ((x, x + 1), [y])
+    cl = _map(nested, lambda t: t.clone())
+    assert isinstance(cl[0], tuple) and isinstance(cl[1], list) and cl[0][1].data_ptr() != nested[0][1].data_ptr()
+    assert [t.shape for t in _flatten(nested, [])] == [x.shape, x.shape, y.shape]
+    assert GraphedStep._signature_inputs(x, y) != GraphedStep._signature_inputs(x[:3], y[:3])

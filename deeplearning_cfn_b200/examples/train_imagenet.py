@@ -70,6 +70,9 @@ def parse(argv=None):
     d.add_argument("--rgb-mean", type=str, default="123.68,116.779,103.939")
     d.add_argument("--rgb-std", type=str, default="58.393,57.12,57.375")
     d.add_argument("--num-batches", type=int, default=0, help="stop an epoch after this many batches (benchmark runs)")
+    d.add_argument("--cuda-graph", type=int, default=0,
+                   help="1: replay the training step as one CUDA graph (experimental; the counterpart of the reference's bulk "
+                        "execution, MXNET_EXEC_BULK_EXEC_TRAIN) - pays off for launch-bound small batches")
     return p.parse_args(argv)
 
 
@@ -144,23 +147,28 @@ def main(argv=None) -> int:
         loader = RecordBatchLoader(rec_it, dev, mean, std, dtype if use_gpu else torch.float32)
         logging.info("training data: %s, %d samples in this shard, %d batches/epoch", a.data_train, rec_it.num_samples, len(rec_it))
     speed = Speedometer(a.batch_size, a.disp_batches)
+    step_fn = None
     for epoch in range(begin, a.num_epochs):
         if epoch in steps:
             lr *= a.lr_factor
             tr.set_learning_rate(lr)
             logging.info("Update[%d]: Change learning rate to %0.5e", epoch, lr)
         tic = time.time()
+        if a.cuda_graph and step_fn is None:
+            step_fn = tr.capture(x, y)
+            logging.info("training step: %r", step_fn)
+        run = step_fn if step_fn is not None else tr.step
         if loader is not None:       # real data: native record pipeline, sharded by rank
             for i, (xb, yb) in enumerate(loader):
                 if a.num_batches and i >= a.num_batches:
                     break
                 with profiler.scope("batch", "train", device=use_gpu):
-                    loss = tr.step(xb, yb)
+                    loss = run(xb, yb)
                 speed(epoch, i, None)
         else:
             for i in range(epoch_batches):
                 with profiler.scope("batch", "train", device=use_gpu):
-                    loss = tr.step(x, y)
+                    loss = run(x, y)
                 speed(epoch, i, None)
         if use_gpu:
             torch.cuda.synchronize()

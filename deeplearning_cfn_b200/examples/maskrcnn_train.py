@@ -102,6 +102,9 @@ def main(argv=None) -> int:
     size = int(cfg["PREPROC.MAX_SIZE"])
     model = ctor(weights=None, weights_backbone=None, num_classes=int(cfg["DATA.NUM_CLASS"]), norm_layer=norm,
                  min_size=size, max_size=size, trainable_backbone_layers=3).to(dev).train()
+    from deeplearning_cfn_b200.ops import roi as roi_ops
+    if roi_ops.patch_torchvision():          # DLCFN_ROI_OPS=dlcfn: ROIAlign / NMS on the dlcfn kernels (experimental)
+        logging.info("ROIAlign and NMS run on the dlcfn kernels")
     from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer
     # data-parallel engine: fp32 detector, fused all-reduce of fp32 gradient buckets, fused SGD-momentum
     tr = DataParallelTrainer(model, mode="auto", optimizer="sgd_mom", lr=float(cfg["TRAIN.BASE_LR"]), momentum=0.9,

@@ -597,3 +597,42 @@ def test_graphed_step_falls_back_to_eager_where_a_graph_cannot_be_used():
     assert isinstance(cl[0], tuple) and isinstance(cl[1], list) and cl[0][1].data_ptr() != nested[0][1].data_ptr()
     assert [t.shape for t in _flatten(nested, [])] == [x.shape, x.shape, y.shape]
     assert GraphedStep._signature_inputs(x, y) != GraphedStep._signature_inputs(x[:3], y[:3])
+
+
+def test_roi_align_and_nms_semantics_match_torchvision():
+    """ops/roi.py: the plain-torch statements of ROIAlign / NMS (what the CUDA kernels implement) against torchvision on
+    the host, incl. adaptive sampling, aligned / legacy modes, boxes leaving the map, list-of-boxes input, batched NMS."""
+    import torchvision.ops as tvo
+    from deeplearning_cfn_b200.ops import roi
+    torch.manual_seed(0)
+    x = torch.randn(2, 5, 12, 9, dtype=torch.float64)
+    rois = torch.tensor([[0, 1.2, 0.7, 6.8, 9.9], [1, -3.0, -2.0, 4.0, 5.0], [1, 3.3, 2.2, 30.0, 40.0], [0, 2.0, 2.0, 2.0, 2.0],
+                         [1, 0.0, 0.0, 8.5, 11.5]], dtype=torch.float64)
+    for aligned in (False, True):
+        for sr in (2, -1):
+            for scale in (1.0, 0.5):
+                ref = tvo.roi_align(x, rois, (3, 4), scale, sr, aligned)
+                got = roi.roi_align_ref(x, rois, (3, 4), scale, sr, aligned)
+                assert torch.allclose(got, ref, atol=1e-5), (aligned, sr, scale, (got - ref).abs().max())
+    lst = [rois[rois[:, 0] == 0][:, 1:], rois[rois[:, 0] == 1][:, 1:]]
+    a = roi.roi_align(x, lst, 3, 1.0, 2, True)                       # CPU tensors: torchvision path, list input
+    b = roi.roi_align_ref(x, lst, 3, 1.0, 2, True)
+    assert a.shape == (5, 5, 3, 3) and torch.allclose(a, b, atol=1e-5)
+    # gradient of the reference statement = torchvision's backward
+    xr = x.clone().requires_grad_(True)
+    xt = x.clone().requires_grad_(True)
+    gy = torch.randn(5, 5, 3, 4, dtype=torch.float64)
+    roi.roi_align_ref(xr, rois, (3, 4), 1.0, 2, True).backward(gy)
+    tvo.roi_align(xt, rois, (3, 4), 1.0, 2, True).backward(gy)
+    assert torch.allclose(xr.grad, xt.grad, atol=1e-5)
+
+    g = torch.Generator().manual_seed(1)
+    xy = torch.rand(300, 2, generator=g) * 50
+    boxes = torch.cat([xy, xy + 2 + torch.rand(300, 2, generator=g) * 20], 1)
+    scores = torch.rand(300, generator=g)
+    for thr in (0.3, 0.5, 0.7):
+        assert torch.equal(roi.nms_ref(boxes, scores, thr), tvo.nms(boxes, scores, thr))
+        assert torch.equal(roi.nms(boxes, scores, thr), tvo.nms(boxes, scores, thr))
+    cls = torch.randint(0, 4, (300,), generator=g)
+    assert torch.equal(roi.batched_nms(boxes, scores, cls, 0.5), tvo.batched_nms(boxes, scores, cls, 0.5))
+    assert roi.nms(boxes[:0], scores[:0], 0.5).numel() == 0 and roi.backend() == "torchvision"

@@ -28,7 +28,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
-    ap.add_argument("--mode", default=None, help="allreduce (default) | ps_sync | ps_dedicated | nccl | nccl_ps")
+    ap.add_argument("--mode", default=None, help="allreduce (default) | ps_sync | ps_dedicated | nccl | nccl_ps | hier (multi-node: fused node-local + NCCL rails)")
     ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert-large", "bert-base"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 256 images / 16 sequences)")
     ap.add_argument("--seq-len", type=int, default=512)
@@ -288,7 +288,8 @@ def main():
         value = global_batch * args.steps / (ms / 1e3)
         clocks = sampler.summary() if sampler else {}
         par = {"local": "single", "allreduce": f"dp{world}-fused-allreduce", "ps_sync": f"ps-sync-{len(trainer.servers)}s{n_workers}w",
-               "nccl": f"dp{world}-nccl-allreduce", "nccl_ps": f"dp{world}-nccl-reduce-bcast"}[trainer.mode]
+               "nccl": f"dp{world}-nccl-allreduce", "nccl_ps": f"dp{world}-nccl-reduce-bcast", "gloo": f"dp{world}-gloo-allreduce",
+               "hier": f"dp{world}-hier-{getattr(trainer, 'num_nodes', 1)}x{trainer.node_size}"}[trainer.mode]
         if is_bert:
             rec = {"metric": f"{args.model}_pretrain_sequences_per_sec", "value": round(value, 2), "unit": "sequences/sec",
                    "tokens_per_sec": round(value * args.seq_len, 1),

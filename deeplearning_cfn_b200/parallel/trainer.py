@@ -15,6 +15,12 @@ Modes (the reference's three communication shapes + their NCCL baselines):
   nccl       baseline: torch.distributed NCCL all-reduce per bucket + the same fused optimizer.
   nccl_ps    baseline with the reference KVStoreNCCL shape (kvstore_nccl.h:221-405): ncclReduce to the
              bucket's root, optimizer on the root, ncclBcast.
+  hier       multi-node data parallelism (the reference's actual deployment: N nodes x G GPUs behind CloudFormation):
+             per bucket, (1) the node-local fused all-reduce kernel over NVLink / NVSwitch, (2) every local rank l
+             all-reduces ITS 1/G slice of the bucket with the ranks l of the other nodes (G concurrent "rail" rings over
+             the inter-node fabric, NCCL), (3) node-local broadcasts hand the slices back.  Inter-node traffic per GPU is
+             1/G of the bucket.  On CPU tensors the node-local steps run over gloo groups (tests).  Node size =
+             LOCAL_WORLD_SIZE (torchrun) or DLCFN_VIRTUAL_NODE_SIZE (several virtual nodes on one box, for testing).
   local      single GPU / CPU, no communication.
 """
 from __future__ import annotations
@@ -53,6 +59,9 @@ class DataParallelTrainer:
         self.on_gpu = self.device.type == "cuda"
         if mode == "auto":
             mode = "local" if self.world == 1 else ("allreduce" if self.on_gpu else "gloo")
+            per_node = int(os.environ.get("DLCFN_VIRTUAL_NODE_SIZE") or os.environ.get("LOCAL_WORLD_SIZE") or self.world)
+            if self.on_gpu and 0 < per_node < self.world and self.world % per_node == 0:
+                mode = "hier"         # the job spans several nodes: peer HBM only reaches the GPUs of one NVSwitch domain
         if self.world == 1 and mode != "local":
             mode = "local"
         if mode == "local":
@@ -65,9 +74,17 @@ class DataParallelTrainer:
         self.loss_fn = loss_fn or softmax_cross_entropy     # fused loss kernels on CUDA, torch on CPU
         self.step_count = 0
 
-        fused = mode in ("allreduce", "ps_sync")
+        self.node_size, self.node_group, self.rail_group = self.world, None, None
+        if mode == "hier":
+            self._init_node_topology()
+            if self.node_size >= self.world:        # a single node: the plain fused all-reduce is the same thing
+                mode = self.mode = "allreduce" if self.on_gpu else "gloo"
+        fused = mode in ("allreduce", "ps_sync") or (mode == "hier" and self.on_gpu)
         self.heap = heap
-        if fused and heap is None:
+        if mode == "hier" and self.on_gpu and heap is None:
+            nbytes = sum((p.numel() * p.element_size() + 127) // 128 * 128 for p in model.parameters() if p.requires_grad)
+            self.heap = SymmetricHeap(2 * nbytes + _HEAP_SLACK, group=self.node_group)
+        if fused and self.heap is None:
             nbytes = 0
             for p in model.parameters():
                 if p.requires_grad:
@@ -105,7 +122,51 @@ class DataParallelTrainer:
                     p.register_post_accumulate_grad_hook(self._make_hook(b))
 
     # ------------------------------------------------------------------ setup
+    def _init_node_topology(self) -> None:
+        """Ranks are laid out node by node (torchrun's order): node = rank // G, local rank = rank % G.  Two families of
+        groups: the G ranks of a node, and for every local rank l the "rail" {l, G + l, 2G + l, ...} across nodes."""
+        G = int(os.environ.get("DLCFN_VIRTUAL_NODE_SIZE") or os.environ.get("LOCAL_WORLD_SIZE") or self.world)
+        if G <= 0 or self.world % G:
+            raise ValueError(f"world size {self.world} is not a multiple of the node size {G}")
+        self.node_size = G
+        self.num_nodes = self.world // G
+        self.node_index, self.local_rank = self.rank // G, self.rank % G
+        if G >= self.world:
+            return
+        for n in range(self.num_nodes):                # every rank creates every group, in the same order
+            grp = dist.new_group([n * G + l for l in range(G)])
+            if n == self.node_index:
+                self.node_group = grp
+        for l in range(G):
+            grp = dist.new_group([n * G + l for n in range(self.num_nodes)])
+            if l == self.local_rank:
+                self.rail_group = grp
+
+    def _rail_slice(self, b: Bucket, l: int) -> tuple[int, int]:
+        """Element range (relative to the bucket) that local rank l carries across nodes; 16-byte granules."""
+        vec = 16 // b.group.esize
+        nvec = (b.numel + vec - 1) // vec
+        per = (nvec + self.node_size - 1) // self.node_size
+        return min(l * per * vec, b.numel), min((l + 1) * per * vec, b.numel)
+
     def _broadcast_initial(self, root: int) -> None:
+        if self.mode == "hier":
+            # global root -> its rail (one rank per node), then every node fans out from that local rank
+            l0, n0 = root % self.node_size, root // self.node_size
+            for g in self.flat.groups:
+                if self.local_rank == l0:
+                    dist.broadcast(g.weight, src=root, group=self.rail_group)
+                if self.heap is not None:
+                    torch.cuda.synchronize(self.device)
+                    self.heap.broadcast_(g.weight_off, g.numel * g.esize, l0, nblocks=self.comm_blocks or 32)
+                else:
+                    dist.broadcast(g.weight, src=self.node_index * self.node_size + l0, group=self.node_group)
+            if self.heap is not None:
+                torch.cuda.synchronize(self.device)
+            for buf in self.model.buffers():
+                if buf.dtype.is_floating_point and buf.numel() > 0:
+                    dist.broadcast(buf, src=root)
+            return
         if self.mode in ("allreduce", "ps_sync"):
             for g in self.flat.groups:
                 self.heap.broadcast_(g.weight_off, g.numel * g.esize, root, nblocks=self.comm_blocks or 32)
@@ -197,6 +258,34 @@ class DataParallelTrainer:
                                    self.opt_kind, lr=self._lr(), wd=hp["wd"], momentum=hp["momentum"],
                                    beta1=hp["beta1"], beta2=hp["beta2"], eps=hp["eps"], rescale=self.grad_scale,
                                    clip=hp["clip"], nblocks=self.comm_blocks, stream=self.comm_stream)
+        elif self.mode == "hier":
+            lo, hi = self._rail_slice(b, self.local_rank)
+            bview = g.grad[b.start:b.end]
+            if self.heap is not None:
+                off = g.grad_off + b.start * g.esize
+                # (1) node-local sum, scaled by 1 / world: the fused kernel over NVLink
+                self.heap.allreduce_(off, b.numel, g.dtype, self.grad_scale, nblocks=self.comm_blocks, stream=self.comm_stream)
+                with torch.cuda.stream(self.comm_stream):
+                    # (2) this rank's slice across the nodes (G concurrent rails)
+                    if hi > lo:
+                        dist.all_reduce(bview[lo:hi], op=dist.ReduceOp.SUM, group=self.rail_group)
+                # (3) the slices come back node-locally; the flag barrier inside each broadcast orders it after its
+                #     root's rail all-reduce (same stream on the root)
+                for l in range(self.node_size):
+                    slo, shi = self._rail_slice(b, l)
+                    if shi > slo:
+                        self.heap.broadcast_(off + slo * g.esize, (shi - slo) * g.esize, l, nblocks=self.comm_blocks or 16,
+                                             stream=self.comm_stream)
+            else:                                   # host tensors (tests): the same three steps over gloo groups
+                dist.all_reduce(bview, op=dist.ReduceOp.SUM, group=self.node_group)
+                bview.mul_(self.grad_scale)
+                if hi > lo:
+                    dist.all_reduce(bview[lo:hi], op=dist.ReduceOp.SUM, group=self.rail_group)
+                base = self.node_index * self.node_size
+                for l in range(self.node_size):
+                    slo, shi = self._rail_slice(b, l)
+                    if shi > slo:
+                        dist.broadcast(bview[slo:shi], src=base + l, group=self.node_group)
         elif self.mode in ("nccl", "gloo"):
             view = g.grad[b.start:b.end]
             if self.comm_stream is not None:
@@ -259,7 +348,7 @@ class DataParallelTrainer:
             self._works.clear()
             if self.comm_stream is not None:
                 torch.cuda.current_stream().wait_stream(self.comm_stream)
-        if self.mode in ("allreduce", "nccl", "gloo", "local"):
+        if self.mode in ("allreduce", "hier", "nccl", "gloo", "local"):
             for gi, g in enumerate(self.flat.groups):
                 st = self.state[gi]
                 self._apply_opt(g.grad, st, g.weight if g.dtype != torch.float32 else None)

@@ -34,7 +34,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.deterministic = True
     ok = True
-    res = {m: run(m, dev, rank) for m in ("nccl", "allreduce", "ps_sync", "nccl_ps")}
+    modes = tuple(os.environ.get("DLCFN_TEST_MODES", "nccl,allreduce,ps_sync,nccl_ps").split(","))
+    res = {m: run(m, dev, rank) for m in modes}
     base, base_loss = res["nccl"]
     for m, (w, losses) in res.items():
         # identical across ranks?

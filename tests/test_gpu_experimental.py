@@ -352,3 +352,19 @@ def test_nms_kernel_matches_torchvision(n):
         assert torch.equal(roi.batched_nms(boxes, scores, cls, 0.5).cpu(), tvo.batched_nms(boxes.cpu(), scores.cpu(), cls.cpu(), 0.5))
     finally:
         roi.set_backend("torchvision")
+
+
+# -------------------------------------------------------------------------- hierarchical (multi-node) trainer mode on GPUs
+@pytest.mark.multigpu
+def test_hier_mode_virtual_nodes_agree_with_nccl():
+    """`hier` with virtual nodes on one box: node-local fused all-reduce + NCCL rails + node-local broadcasts must train like
+    the flat NCCL all-reduce.  2 GPUs -> 2 nodes x 1 GPU (degenerate node-local steps), >= 4 GPUs -> 2 nodes x 2 GPUs."""
+    import sys
+    from conftest import run_job
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 4 if torch.cuda.device_count() >= 4 else 2
+    env = dict(os.environ, DLCFN_TEST_MODES="nccl,hier", DLCFN_VIRTUAL_NODE_SIZE=str(n // 2))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(root, "tests", "mp", "trainer_worker.py")]
+    r = run_job(cmd, env=env, timeout=600, cwd=root)
+    assert r.returncode == 0 and "TRAINER_OK" in r.stdout and "hier:" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

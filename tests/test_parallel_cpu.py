@@ -21,6 +21,15 @@ def test_gloo_world2_data_parallel_matches_single_process(naive):
     assert r.returncode == 0 and "GLOO_TRAINER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_hierarchical_multinode_mode_matches_flat_allreduce():
+    """2 virtual nodes x 2 ranks on gloo: node-local sum -> per-rail all-reduce of the slices -> node-local broadcast."""
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "4", sys.executable,
+           os.path.join(ROOT, "tests/mp/hier_trainer_worker.py")]
+    from conftest import run_job
+    r = run_job(cmd, env=dict(os.environ, PYTHONPATH=ROOT, DLCFN_VIRTUAL_NODE_SIZE="2", OMP_NUM_THREADS="2"), timeout=600)
+    assert r.returncode == 0 and "HIER_TRAINER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_allreduce_job_through_tracker_launcher(tmp_path):
     """launch -n 2 -s 0: no servers -> all-reduce tracker; workers find each other through it."""
     script = tmp_path / "w.py"

@@ -27,6 +27,7 @@ timeout 400 python bench.py 2>&1 | tail -1 | tee gpurun_out/r2_bench_1gpu.json
 echo "== ResNet-50 with the 3x3 convolutions on the implicit-GEMM kernel (only meaningful if the conv tests above passed)"
 DLCFN_CONVKXK=tcgen05 timeout 400 python bench.py 2>&1 | tail -1 | tee gpurun_out/r2_bench_1gpu_convkxk.json
 DLCFN_CONVKXK=tcgen05 DLCFN_CONV1X1=tcgen05 timeout 400 python bench.py 2>&1 | tail -1 | tee gpurun_out/r2_bench_1gpu_allconv_tcgen05.json
+echo "== (multi-GPU calls only) hierarchical multi-node mode with virtual nodes: gpurun --gpus 2|4 -- 'DLCFN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -k hier_mode -q'"
 echo "== ROIAlign / NMS kernels (Mask R-CNN head, experimental)"
 DLCFN_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -q -m gpu --timeout 200 -k "roi_align or nms_kernel" 2>&1 | tail -6 | tee gpurun_out/r2_roi_tests.log
 echo "== the step as one CUDA graph (experimental): numerics test, then the bench at batch 256 and at a launch-bound batch 32"

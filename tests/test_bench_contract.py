@@ -72,3 +72,16 @@ def test_graft_entry_has_build_and_smoke():
     finally:
         sys.path.pop(0)
     assert callable(g.build) and callable(g.smoke)
+
+
+def test_no_undefined_names_in_code_that_only_runs_on_a_gpu():
+    """GPU-only branches, gated experimental tests and tools never execute on the CPU test tier: a static pass over every
+    module (tools/lint_names.py) keeps typos in them from first surfacing on the GPU box."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import lint_names
+    finally:
+        sys.path.pop(0)
+    files = lint_names.collect([os.path.join(ROOT, x) for x in ("deeplearning_cfn_b200", "tests", "tools", "bench.py", "__graft_entry__.py")])
+    problems = [p for f in files for p in lint_names.check_file(f)]
+    assert len(files) > 100 and not problems, "\n".join(problems)

@@ -85,3 +85,12 @@ def test_no_undefined_names_in_code_that_only_runs_on_a_gpu():
     files = lint_names.collect([os.path.join(ROOT, x) for x in ("deeplearning_cfn_b200", "tests", "tools", "bench.py", "__graft_entry__.py")])
     problems = [p for f in files for p in lint_names.check_file(f)]
     assert len(files) > 100 and not problems, "\n".join(problems)
+
+
+def test_ctypes_tables_match_the_c_signatures():
+    """tools/check_abi.py: parameter count / class and pointer-or-64-bit return types of every ctypes binding against the
+    exported C functions of both native libraries (a wrong table only misbehaves at run time - for CUDA, on the GPU box)."""
+    r = run_job([sys.executable, os.path.join(ROOT, "tools", "check_abi.py")], cwd=ROOT, timeout=300)
+    assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    compared = int(r.stdout.strip().splitlines()[-1].split(" exported functions parsed, ")[1].split(" ")[0])
+    assert compared >= 100

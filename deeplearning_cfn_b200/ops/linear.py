@@ -30,8 +30,12 @@ class _LinearFn(torch.autograd.Function):
         bias_f32 = None
         if bias is not None:
             bias_f32 = bias if bias.dtype == torch.float32 else bias.float()
-        y = native.gemm_bf16(x2, weight, bias=bias_f32, out_dtype=torch.bfloat16)
-        return y.view(*x.shape[:-1], weight.shape[0])
+        # the result is allocated in its final shape and handed to the GEMM as a 2-D alias: returning `y.view(...)` would
+        # make the Function's output a view, which autograd forbids to modify in place (classifier stacks follow their
+        # Linear layers with nn.ReLU(inplace=True))
+        y = torch.empty((*x.shape[:-1], weight.shape[0]), dtype=torch.bfloat16, device=x.device)
+        native.gemm_bf16(x2, weight, bias=bias_f32, out=y.view(-1, weight.shape[0]))
+        return y
 
     @staticmethod
     def backward(ctx, dy):

@@ -157,7 +157,7 @@ class _RoiAlignFn(torch.autograd.Function):
             dy = dy.to(dt)
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
-        dx32 = torch.zeros((N, C, H, W), dtype=torch.float32, device=dy.device, memory_format=torch.channels_last)
+        dx32 = torch.zeros((N, H, W, C), dtype=torch.float32, device=dy.device).permute(0, 3, 1, 2)   # channels_last view
         native.check(L.dlcfn_roi_align_bwd(dy.data_ptr(), rois.data_ptr(), dx32.data_ptr(), 0 if dt == torch.float32 else 1,
                                            N, H, W, C, rois.shape[0], PH, PW, scale, sr, aligned, native.stream_ptr()),
                      "roi_align_bwd")

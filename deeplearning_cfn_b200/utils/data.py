@@ -107,13 +107,19 @@ class RecordBatchLoader:
                                    "x": torch.empty(x_u8.shape, dtype=torch.bfloat16, device=self.device),
                                    "ev": torch.cuda.Event()})
             s = self._bufs[self._k % 2]
+            n = x_u8.shape[0]
+            if n > s["u8"].shape[0] or x_u8.shape[1:] != s["u8"].shape[1:]:      # a larger / differently shaped batch: new staging set
+                s.update(u8=torch.empty(x_u8.shape, dtype=torch.uint8, device=self.device),
+                         y=torch.empty(y.shape, dtype=torch.int64, device=self.device),
+                         x=torch.empty(x_u8.shape, dtype=torch.bfloat16, device=self.device))
+            u8, yd, xd = s["u8"][:n], s["y"][:n], s["x"][:n]                      # the last batch of an epoch may be short
             self._k += 1
             self.copy_stream.wait_stream(torch.cuda.current_stream())     # the slot's previous consumer has been enqueued
             with torch.cuda.stream(self.copy_stream):
-                s["u8"].copy_(x_u8, non_blocking=True)                     # ring slot is page-locked: true async DMA
-                s["y"].copy_(y.pin_memory() if not y.is_pinned() else y, non_blocking=True)
+                u8.copy_(x_u8, non_blocking=True)                          # ring slot is page-locked: true async DMA
+                yd.copy_(y.pin_memory() if not y.is_pinned() else y, non_blocking=True)
                 s["ev"].record(self.copy_stream)
             s["ev"].synchronize()      # the ring slot may be recycled `keep` batches later; the copy is short
             torch.cuda.current_stream().wait_event(s["ev"])
-            native.normalize_u8_nhwc(s["u8"], s["x"], self.mean, self.std)
-            yield s["x"].permute(0, 3, 1, 2), s["y"]
+            native.normalize_u8_nhwc(u8, xd, self.mean, self.std)
+            yield xd.permute(0, 3, 1, 2), yd

@@ -175,3 +175,19 @@ def test_elementwise_compression_and_sparse_wrappers():
         sparse.group_adagrad_update(None, torch.randn(50, 16), w, torch.zeros(50), lr=0.1)
     assert {"dlcfn_elementwise_sum", "dlcfn_cast_scale", "dlcfn_fused_optimizer", "dlcfn_quantize_2bit", "dlcfn_dequantize_2bit",
             "dlcfn_normalize_u8_nhwc", "dlcfn_sparse_row_update", "dlcfn_group_adagrad_update"} <= set(log)
+
+
+def test_kvstore_compression_on_device_gradients_uses_the_2bit_kernels():
+    """`local` store, 2-bit compression, gradients that live "on the GPU": quantize / dequantize go through the kernels
+    (csrc/cuda/compress.cu) with a per-(key, device) residual, the reduce falls back to the host reducer."""
+    import deeplearning_cfn_b200.kv as kv
+    with mock_gpu() as log:
+        store = kv.create("local")
+        store.set_gradient_compression({"type": "2bit", "threshold": 0.5})
+        store.init(3, torch.zeros(100))
+        store.push(3, [torch.randn(100), torch.randn(100).to(BF)])
+        out = torch.empty(100)
+        store.pull(3, out=out)
+        assert out.shape == (100,) and len(store._residuals) == 2
+        assert all(r.dtype == torch.float32 and r.numel() == 100 for r in store._residuals.values())
+    assert log.count("dlcfn_quantize_2bit") == 2 and log.count("dlcfn_dequantize_2bit") == 2

@@ -18,18 +18,60 @@ from . import optimizer as opt
 from .kvstore import KVStore, create
 
 
+def decide_slices(batch_size: int, work_load_list: list) -> list[slice]:
+    """Batch rows per device, proportional to its workload (reference executor_group.py:281-305 `_split_input_slice`:
+    rounded shares, the last device takes what is left; an empty slice is an error)."""
+    total = float(sum(work_load_list))
+    sizes = [int(round(batch_size * w / total)) for w in work_load_list]
+    sizes[-1] = batch_size - sum(sizes[:-1])
+    out, start = [], 0
+    for n in sizes:
+        if n <= 0:
+            raise ValueError(f"batch of {batch_size} rows cannot be sliced over {len(work_load_list)} devices: too many slices")
+        out.append(slice(start, start + n))
+        start += n
+    return out
+
+
 class Module:
+    """`context` may be ONE device or a LIST of devices.  With a list the module is the reference's
+    DataParallelExecutorGroup (module/executor_group.py:143-572): one replica of the network per device, every batch sliced
+    by `work_load_list`, forward / backward per slice, gradients of parameter i pushed as a per-device list (the kvstore
+    reduces them), then either the updated weight is pulled into every replica (update_on_kvstore) or the summed gradient
+    is pulled back and every device runs its own updater with state index `i * num_device + k` (model.py:157-176)."""
+
     def __init__(self, symbol: torch.nn.Module, data_names=("data",), label_names=("softmax_label",), context=None,
-                 loss=None):
+                 loss=None, work_load_list=None):
         self.symbol = symbol
-        self.device = torch.device(context) if context is not None else next(symbol.parameters()).device
+        ctxs = list(context) if isinstance(context, (list, tuple)) else ([context] if context is not None else [])
+        ctxs = [torch.device(c) for c in ctxs]
+        self.device = ctxs[0] if ctxs else next(symbol.parameters()).device
+        self._contexts = ctxs if len(ctxs) > 1 else [self.device]
+        self._work_load = list(work_load_list) if work_load_list is not None else [1] * len(self._contexts)
+        if len(self._work_load) != len(self._contexts):
+            raise ValueError("work_load_list needs one entry per context")
         self.loss = loss or (lambda out, y: softmax_cross_entropy(out, y, reduction="sum"))
         self.binded = self.params_initialized = self.optimizer_initialized = False
         self._kv: KVStore | None = None
         self._update_on_kvstore = False
-        self._params = [p for p in symbol.parameters() if p.requires_grad]
+        if len(self._contexts) > 1:
+            import copy
+            self._replicas = [symbol.to(self._contexts[0])] + [copy.deepcopy(symbol).to(c) for c in self._contexts[1:]]
+        else:
+            self._replicas = [symbol]
+        self._rparams = [[p for p in r.parameters() if p.requires_grad] for r in self._replicas]
+        self._params = self._rparams[0]
         self._batch_size = None
         self._outputs = None
+
+    @property
+    def multi_device(self) -> bool:
+        return len(self._replicas) > 1
+
+    def _sync_replicas_from_first(self) -> None:
+        sd = self.symbol.state_dict()
+        for r in self._replicas[1:]:
+            r.load_state_dict(sd)
 
     def bind(self, data_shapes, label_shapes=None, for_training: bool = True, **_):
         self._batch_size = data_shapes[0][1][0] if isinstance(data_shapes[0], tuple) else data_shapes[0]
@@ -46,11 +88,14 @@ class Module:
             else:
                 for p in self._params:
                     init(p)
+        self._sync_replicas_from_first()
         self.params_initialized = True
 
     def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),),
                        force_init: bool = False):
         assert self.binded and self.params_initialized
+        if kvstore is None and self.multi_device:
+            kvstore = "device" if self.device.type == "cuda" else "local"     # several devices always aggregate (model.py:77-90)
         kv = create(kvstore) if isinstance(kvstore, str) else kvstore
         params = dict(optimizer_params)
         batch = self._batch_size or 1
@@ -68,19 +113,61 @@ class Module:
             if self._update_on_kvstore:
                 kv.set_optimizer(self._optimizer)
             for i, p in enumerate(self._params):
-                kv.pull(i, out=p.data, priority=-i)
+                kv.pull(i, out=[rp[i].data for rp in self._rparams] if self.multi_device else p.data, priority=-i)
         self.optimizer_initialized = True
+
+    def _forward_slices(self, x, y, train: bool):
+        """Slice the batch over the replicas, run each slice on its device; outputs merged on the first device."""
+        slices = decide_slices(x.shape[0], self._work_load)
+        outs, labels = [], []
+        for r, (net, ctx, sl) in enumerate(zip(self._replicas, self._contexts, slices)):
+            xr = x[sl].to(ctx, non_blocking=True)
+            labels.append(y[sl].to(ctx, non_blocking=True) if y is not None else None)
+            if train:
+                net.zero_grad(set_to_none=True)
+                outs.append(net(xr))
+            else:
+                with torch.no_grad():
+                    outs.append(net(xr))
+        self._slice_outputs, self._slice_labels = outs, labels
+        self._outputs = torch.cat([o.detach().to(self.device) for o in outs])      # merge_multi_context
+        return outs, labels
 
     def forward_backward(self, data_batch):
         x, y = data_batch
+        if self.multi_device:
+            outs, labels = self._forward_slices(x, y, True)
+            losses = [self.loss(o, l) for o, l in zip(outs, labels)]
+            for l in losses:
+                l.backward()
+            self._loss = sum(l.detach().to(self.device) for l in losses)
+            return
         self.symbol.zero_grad(set_to_none=True)
         self._outputs = self.symbol(x)
         self._loss = self.loss(self._outputs, y)
         self._loss.backward()
 
     @torch.no_grad()
+    def _update_multi_device(self):
+        """model.py:145-176 with several executors: push the per-device gradient list of every parameter."""
+        kv, nd = self._kv, len(self._replicas)
+        for i in range(len(self._params)):
+            grads = [rp[i].grad for rp in self._rparams]
+            if any(g is None for g in grads):
+                continue
+            kv.push(i, grads, priority=-i)
+            if self._update_on_kvstore:
+                kv.pull(i, out=[rp[i].data for rp in self._rparams], priority=-i)
+            else:
+                kv.pull(i, out=grads, priority=-i)                       # every device receives the sum
+                for k, rp in enumerate(self._rparams):
+                    self._updater(i * nd + k, rp[i].grad, rp[i].data)
+
+    @torch.no_grad()
     def update(self):
         kv = self._kv
+        if self.multi_device:
+            return self._update_multi_device()
         if kv is not None and "nccl" in kv.type:
             return self._update_params_on_kvstore_nccl()
         for i, p in enumerate(self._params):
@@ -114,14 +201,21 @@ class Module:
                     self._updater(i, self._params[i].grad, self._params[i].data)
 
     def get_outputs(self, merge_multi_context: bool = True):
+        """[merged output] - or, with merge_multi_context=False on several devices, [[output of device 0, device 1, ...]]."""
+        if not merge_multi_context and self.multi_device:
+            return [list(self._slice_outputs)]
         return [self._outputs]
 
     # ---- the finer-grained steps of BaseModule (base_module.py: forward / backward / update_metric / get_params ...)
     def forward(self, data_batch, is_train: bool | None = None) -> None:
         x, y = _unpack(data_batch)
         train = self.symbol.training if is_train is None else is_train
-        self.symbol.train(train)
+        for r in self._replicas:
+            r.train(train)
         self._label = y
+        if self.multi_device:
+            self._forward_slices(x, y, train)
+            return
         if train:
             self.symbol.zero_grad(set_to_none=True)
             self._outputs = self.symbol(x)
@@ -130,6 +224,17 @@ class Module:
                 self._outputs = self.symbol(x)
 
     def backward(self, out_grads=None) -> None:
+        if self.multi_device:
+            if out_grads is not None:
+                g = out_grads[0] if isinstance(out_grads, (list, tuple)) else out_grads
+                for o, sl in zip(self._slice_outputs, decide_slices(g.shape[0], self._work_load)):
+                    o.backward(g[sl].to(o.device))
+            else:
+                losses = [self.loss(o, l) for o, l in zip(self._slice_outputs, self._slice_labels)]
+                for l in losses:
+                    l.backward()
+                self._loss = sum(l.detach().to(self.device) for l in losses)
+            return
         if out_grads is not None:
             self._outputs.backward(out_grads[0] if isinstance(out_grads, (list, tuple)) else out_grads)
         else:
@@ -153,6 +258,7 @@ class Module:
             raise RuntimeError(f"missing parameters: {res.missing_keys[:5]}")
         if res.unexpected_keys and not allow_extra:
             raise ValueError(f"unexpected parameters: {res.unexpected_keys[:5]}")
+        self._sync_replicas_from_first()
         self.params_initialized = True
 
     def save_params(self, fname: str) -> None:
@@ -186,7 +292,8 @@ class Module:
         for epoch in range(begin_epoch, num_epoch):
             tic = time.time()
             train_metric.reset()
-            self.symbol.train()
+            for r in self._replicas:
+                r.train()
             if hasattr(train_data, "reset"):
                 train_data.reset()
             it = train_data() if callable(train_data) else train_data

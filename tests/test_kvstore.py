@@ -408,3 +408,52 @@ def test_dead_worker_is_replaced_and_the_sync_round_completes():
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
     assert "worker 1 crashing" in out and "worker 0 attempt 0 RECOVERY_OK" in out and "worker 1 attempt 1 RECOVERY_OK" in out
+
+
+@pytest.mark.parametrize("update_on_kvstore_store", ["local", "device"])
+def test_module_with_several_contexts_matches_single_device(update_on_kvstore_store):
+    """Module(context=[...]) = the reference's DataParallelExecutorGroup, faked like the reference's own unit tests with
+    several CPU contexts: batch sliced by work_load_list, per-device gradients reduced through the kvstore, every replica
+    updated identically - and the trajectory equals the single-context module on the whole batch."""
+    import torch
+    from deeplearning_cfn_b200.kv.module import Module, decide_slices
+
+    assert decide_slices(10, [1, 1, 1]) == [slice(0, 3), slice(3, 6), slice(6, 10)]
+    assert decide_slices(8, [3, 1]) == [slice(0, 6), slice(6, 8)]
+    with pytest.raises(ValueError):
+        decide_slices(2, [1, 1, 1, 1])
+
+    def net():
+        torch.manual_seed(0)
+        return torch.nn.Sequential(torch.nn.Linear(6, 12), torch.nn.Tanh(), torch.nn.Linear(12, 3))
+    g = torch.Generator().manual_seed(1)
+    batches = [(torch.randn(10, 6, generator=g), torch.randint(0, 3, (10,), generator=g)) for _ in range(4)]
+    opt = (("learning_rate", 0.1), ("momentum", 0.9))
+    single = Module(net(), context="cpu")
+    single.fit(batches, num_epoch=2, kvstore="local", optimizer="sgd", optimizer_params=opt, batch_size=10)
+    multi = Module(net(), context=["cpu", "cpu", "cpu"], work_load_list=[2, 1, 1])
+    assert multi.multi_device and len(multi._replicas) == 3
+    multi.fit(batches, num_epoch=2, kvstore=update_on_kvstore_store, optimizer="sgd", optimizer_params=opt, batch_size=10)
+    for a, b in zip(single.symbol.parameters(), multi.symbol.parameters()):
+        assert torch.allclose(a, b, atol=1e-5), float((a - b).abs().max())
+    for rp in multi._rparams[1:]:                        # replicas stay bit-identical to each other
+        for a, b in zip(multi._rparams[0], rp):
+            assert torch.equal(a, b)
+    # merged outputs cover the whole batch; per-device outputs on request
+    multi.forward(batches[0], is_train=False)
+    assert multi.get_outputs()[0].shape == (10, 3)
+    parts = multi.get_outputs(merge_multi_context=False)[0]
+    assert [p.shape[0] for p in parts] == [5, 2, 3]
+    assert torch.allclose(torch.cat(parts), multi.get_outputs()[0])
+    acc = multi.score(batches, "acc")[0][1]
+    assert 0.0 <= acc <= 1.0
+    # no kvstore named: several devices still aggregate
+    m2 = Module(net(), context=["cpu", "cpu"])
+    m2.bind([("data", (10, 6))])
+    m2.init_params()
+    m2.init_optimizer(kvstore=None, optimizer="sgd", optimizer_params=opt)
+    assert m2._kv is not None and m2._kv.type == "local"
+    m2.forward_backward(batches[0])
+    m2.update()
+    for a, b in zip(*m2._rparams):
+        assert torch.equal(a, b)

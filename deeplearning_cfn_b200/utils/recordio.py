@@ -449,3 +449,39 @@ def image_record_iter(path_imgrec: str, batch_size: int, data_shape=(3, 224, 224
         allowed = {"path_imgidx", "shuffle", "num_parts", "part_index", "preprocess_threads", "prefetch_buffer", "seed",
                    "round_batch", "rand_crop", "rand_mirror"}
         return ImageRecordIter(path_imgrec, batch_size, data_shape, **{k: v for k, v in kw.items() if k in allowed})
+
+
+def rec2idx(rec_path: str, idx_path: str | None = None) -> int:
+    """Rebuild the `.idx` of a `.rec` file (reference MX/tools/rec2idx.py): one `key\toffset` line per record, the key
+    taken from the record's image header (`id`) when it has one, the ordinal otherwise.  Returns the record count."""
+    idx_path = idx_path or os.path.splitext(rec_path)[0] + ".idx"
+    r = MXRecordIO(rec_path, "r")
+    n = 0
+    with open(idx_path, "w") as f:
+        while True:
+            pos = r.tell()
+            buf = r.read()
+            if buf is None:
+                break
+            key = n
+            if len(buf) >= _IR.size:
+                try:
+                    hid = int(unpack(buf)[0].id)
+                    key = hid if hid >= 0 else n
+                except Exception:
+                    key = n
+            f.write(f"{key}\t{pos}\n")
+            n += 1
+    r.close()
+    return n
+
+
+def main(argv=None) -> int:
+    import argparse
+    ap = argparse.ArgumentParser(prog="rec2idx", description="Create the index file of a RecordIO file")
+    ap.add_argument("record", help="path to the .rec file")
+    ap.add_argument("index", nargs="?", default=None, help="path of the .idx file to write (default: next to the .rec)")
+    a = ap.parse_args(argv)
+    n = rec2idx(a.record, a.index)
+    print(f"{a.record}: {n} records indexed")
+    return 0

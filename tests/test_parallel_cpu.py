@@ -645,3 +645,38 @@ def test_roi_align_and_nms_semantics_match_torchvision():
     cls = torch.randint(0, 4, (300,), generator=g)
     assert torch.equal(roi.batched_nms(boxes, scores, cls, 0.5), tvo.batched_nms(boxes, scores, cls, 0.5))
     assert roi.nms(boxes[:0], scores[:0], 0.5).numel() == 0 and roi.backend() == "torchvision"
+
+
+def test_rec2idx_and_parse_log_tools(tmp_path, capsys):
+    import numpy as np
+    from deeplearning_cfn_b200.__main__ import main as cli
+    from deeplearning_cfn_b200.utils import parse_log, recordio
+    rec_path = str(tmp_path / "d.rec")
+    w = recordio.MXRecordIO(rec_path, "w")
+    for i in range(5):
+        w.write(recordio.pack_img(recordio.IRHeader(0, float(i), 10 + i, 0), np.full((4, 4, 3), i, dtype=np.uint8)))
+    w.close()
+    assert cli(["rec2idx", rec_path]) == 0
+    r = recordio.MXIndexedRecordIO(str(tmp_path / "d.idx"), rec_path, "r")
+    assert sorted(r.keys) == [10, 11, 12, 13, 14]
+    h, img = recordio.unpack_img(r.read_idx(13))
+    assert h.label == 3.0 and int(img[0, 0, 0]) == 3
+    it = recordio.NativeImageRecordIter(rec_path, 5, (3, 4, 4), round_batch=False)     # the rebuilt index feeds the native reader
+    x, y = next(iter(it))
+    assert sorted(y.tolist()) == [0, 1, 2, 3, 4]
+    it.close()
+
+    log = tmp_path / "train.log"
+    log.write_text("\n".join([
+        "INFO Epoch[0] Batch [20] Speed: 1000.0 samples/sec accuracy=0.1",
+        "INFO Epoch[0] Batch [40] Speed: 3000.0 samples/sec accuracy=0.2",
+        "INFO Epoch[0] Train-accuracy=0.250000", "INFO Epoch[0] Time cost=12.500", "INFO Epoch[0] Validation-accuracy=0.300000",
+        "INFO Epoch[1] Train-accuracy=0.500000", "INFO Epoch[1] Train-top_k_accuracy_5=0.9", "INFO Epoch[1] Time cost=11.000",
+        "noise line", "INFO Epoch[1] Validation-accuracy=nan"]))
+    cols, rows = parse_log.parse(open(log))
+    assert cols == ["epoch", "train-accuracy", "train-top_k_accuracy_5", "val-accuracy", "val-top_k_accuracy_5", "time", "speed"]
+    assert rows[0][:2] == [0, 0.25] and rows[0][3] == 0.3 and rows[0][5] == 12.5 and rows[0][6] == 2000.0
+    assert rows[1][1] == 0.5 and rows[1][2] == 0.9 and rows[1][6] is None
+    assert cli(["parse-log", str(log), "--metric-names", "accuracy"]) == 0
+    out = capsys.readouterr().out
+    assert "| epoch | train-accuracy | val-accuracy | time | speed |" in out and "| 0 | 0.25 | 0.3 | 12.5 | 2000 |" in out

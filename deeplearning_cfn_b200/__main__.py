@@ -3,7 +3,7 @@
 Control plane (counterparts of `aws cloudformation ...` as used by mask-rcnn-stack.sh:62-92):
     create-stack / launch-cluster, list-stacks, describe-stacks, delete-stack, prepare-bucket, node-exec
 Job plane:
-    launch (tools/launch.py compatible), kill, generate-trainer, run-example, bandwidth, benchmark, im2rec, rec2idx, parse-log
+    launch (tools/launch.py compatible), kill, generate-trainer, run-example, bandwidth, benchmark, im2rec, rec2idx, parse-log, diagnose
 """
 from __future__ import annotations
 
@@ -89,7 +89,7 @@ def main(argv=None) -> int:
     passthrough = {"launch": "launch.launcher", "kill": "launch.kill", "generate-trainer": "launch.tf_ps_scripts",
                    "run-example": "examples.run_example", "bandwidth": "examples.bandwidth_measure",
                    "benchmark": "examples.benchmark", "mpirun": "launch.mpirun", "im2rec": "utils.im2rec",
-                   "parse-log": "utils.parse_log", "rec2idx": "utils.recordio"}
+                   "parse-log": "utils.parse_log", "rec2idx": "utils.recordio", "diagnose": "utils.diagnose"}
     if argv and argv[0] in passthrough:
         import importlib
         mod = importlib.import_module("." + passthrough[argv[0]], __package__)

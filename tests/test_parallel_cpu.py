@@ -680,3 +680,13 @@ def test_rec2idx_and_parse_log_tools(tmp_path, capsys):
     assert cli(["parse-log", str(log), "--metric-names", "accuracy"]) == 0
     out = capsys.readouterr().out
     assert "| epoch | train-accuracy | val-accuracy | time | speed |" in out and "| 0 | 0.25 | 0.3 | 12.5 | 2000 |" in out
+
+
+def test_diagnose_report(capsys):
+    from deeplearning_cfn_b200.__main__ import main as cli
+    assert cli(["diagnose", "--json"]) == 0
+    import json
+    info = json.loads(capsys.readouterr().out)
+    assert info["package"]["cuda_library"]["present"] and info["package"]["cuda_library"]["loads"] is True
+    assert info["package"]["runtime_library"]["loads"] is True and "gloo" in info["torch"]["distributed_backends"]
+    assert {"platform", "python", "torch", "gpus", "tools", "environment"} <= set(info)

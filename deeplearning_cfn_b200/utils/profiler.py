@@ -20,7 +20,8 @@ from collections import defaultdict
 
 import torch
 
-_cfg = {"filename": "profile.json", "profile_all": False, "aggregate_stats": True, "running": False}
+_cfg = {"filename": "profile.json", "profile_all": True, "aggregate_stats": True, "running": False,
+        "profile_symbolic": True, "profile_imperative": True, "profile_api": True, "profile_memory": True}
 _lock = threading.Lock()
 _events: list = []
 _device_pending: list = []
@@ -33,8 +34,13 @@ def _rank() -> int:
 
 
 def set_config(filename: str = "profile.json", profile_all: bool = True, aggregate_stats: bool = True,
-               profile_process: str = "worker", **_ignored) -> None:
-    _cfg.update(filename=filename, profile_all=profile_all, aggregate_stats=aggregate_stats)
+               profile_process: str = "worker", profile_symbolic: bool = True, profile_imperative: bool = True,
+               profile_memory: bool = True, profile_api: bool = True, **_ignored) -> None:
+    """The reference's switches (profiler.py:33-68): `profile_all` records every category; otherwise operators are
+    recorded when `profile_symbolic` / `profile_imperative` is set, kvstore / API ranges with `profile_api`, storage
+    counters with `profile_memory`.  User-defined Domains / Tasks / Markers are always recorded."""
+    _cfg.update(filename=filename, profile_all=profile_all, aggregate_stats=aggregate_stats, profile_symbolic=profile_symbolic,
+                profile_imperative=profile_imperative, profile_memory=profile_memory, profile_api=profile_api)
     if profile_process == "server":
         # the reference forwards the parameters to the servers (kSetProfilerParams); the file gets a rank prefix there
         _server_command("config:" + filename)
@@ -57,6 +63,19 @@ def is_running() -> bool:
     return _cfg["running"]
 
 
+def category_enabled(category: str) -> bool:
+    if _cfg["profile_all"]:
+        return True
+    c = category.lower()
+    if c in ("operator", "train", "symbolic", "imperative"):
+        return _cfg["profile_symbolic"] or _cfg["profile_imperative"]
+    if c in ("kvstore", "api", "collective", "io"):
+        return _cfg["profile_api"]
+    if c in ("memory", "storage"):
+        return _cfg["profile_memory"]
+    return True             # user domains
+
+
 def _now_us() -> float:
     return (time.perf_counter() - _t0) * 1e6
 
@@ -64,7 +83,7 @@ def _now_us() -> float:
 @contextlib.contextmanager
 def scope(name: str, category: str = "operator", device: bool = False, stream=None):
     """Record one range.  device=True additionally brackets it with CUDA events on `stream`."""
-    if not _cfg["running"]:
+    if not _cfg["running"] or not category_enabled(category):
         yield
         return
     use_nvtx = torch.cuda.is_available()
@@ -172,7 +191,10 @@ def dump(finished: bool = True, filename: str | None = None, profile_process: st
 
 
 if os.environ.get("MXNET_PROFILER_AUTOSTART", os.environ.get("DLCFN_PROFILER_AUTOSTART", "0")) == "1":
-    set_config(filename=os.environ.get("DLCFN_PROFILER_FILE", "profile.json"))
+    # MXNET_PROFILER_MODE (env_var.md:154-165): 0 = operators of symbolic execution only, 1 = everything
+    _all = os.environ.get("MXNET_PROFILER_MODE", "1") != "0"
+    set_config(filename=os.environ.get("DLCFN_PROFILER_FILE", "profile.json"), profile_all=_all, profile_symbolic=True,
+               profile_imperative=_all, profile_api=_all, profile_memory=_all)
     set_state("run")
 
 

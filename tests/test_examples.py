@@ -185,3 +185,26 @@ def test_gluon_style_example_reads_record_files(tmp_path):
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
     assert "Epoch[0] Batch [4]" in out and "validation: accuracy" in out
+
+
+def test_profiler_category_switches_and_mode_env(tmp_path):
+    """set_config(profile_all=False, profile_api=False): kvstore / API ranges are dropped, operators and user domains stay;
+    MXNET_PROFILER_AUTOSTART=1 with MXNET_PROFILER_MODE=0 starts a symbolic-operators-only profile at import."""
+    from deeplearning_cfn_b200.utils import profiler
+    profiler.set_config(filename=str(tmp_path / "cat.json"), profile_all=False, profile_api=False, profile_symbolic=True)
+    profiler.set_state("run")
+    with profiler.scope("KVStoreReduce", "kvstore"):
+        pass
+    with profiler.scope("conv0", "operator"):
+        pass
+    with profiler.Domain("mine").new_task("t"):
+        pass
+    names = {e["name"] for e in json.load(open(profiler.dump()))["traceEvents"]}
+    assert "conv0" in names and "t" in names and "KVStoreReduce" not in names
+    profiler.set_config(filename=str(tmp_path / "x.json"))          # back to the defaults for later tests
+    code = ("from deeplearning_cfn_b200.utils import profiler as p\n"
+            "print(p.is_running(), p.category_enabled('operator'), p.category_enabled('kvstore'))\n")
+    env = dict(os.environ, MXNET_PROFILER_AUTOSTART="1", MXNET_PROFILER_MODE="0", DLCFN_PROFILER_FILE=str(tmp_path / "auto.json"),
+               PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.stdout.split() == ["True", "True", "False"], r.stdout + r.stderr

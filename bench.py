@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--dry-cpu", action="store_true",
                     help="exercise the whole script on the host with tiny shapes (fp32, wall-clock 'events', no H2D): a check "
                          "of this file's logic on a box without a GPU - the line it prints is marked and is NOT a measurement")
+    ap.add_argument("--device-batches", type=int, default=4,
+                    help="distinct device-resident input batches rotated by the device-timed loop (the same synthetic images the "
+                         "end-to-end loop streams from the host); 1 = train on one fixed batch")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="experimental: replay the device-timed step as one CUDA graph (parallel/graph.py); off by default")
     ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn", "auto"],
@@ -163,6 +166,7 @@ def main():
         x = (ids, torch.zeros_like(ids), torch.randint(0, args.seq_len, (args.batch, npred), generator=g).to(device))
         y = (torch.randint(0, 30522, (args.batch, npred), generator=g).to(device),
              torch.randint(0, 2, (args.batch,), generator=g).to(device))
+        dev_batches = [(x, y)]
     else:
         model = to_b200_layout(resnet(args.num_layers, 1000, args.image_size).to(device), compute_dtype)
         model.train()
@@ -170,6 +174,26 @@ def main():
                                       bucket_bytes=int(args.bucket_mb * (1 << 20)), server_ranks=servers,
                                       worker_ranks=workers)
         x, y = synthetic_device_batch(args.batch, args.image_size, 1000, device, dtype=compute_dtype)
+        # The device-timed loop rotates the SAME synthetic uint8 image batches that the end-to-end loop streams from pinned host
+        # memory (normalised once, resident on the device), so `value` and `e2e.value` differ by the input pipeline only.  A
+        # single batch trained on for the whole run collapses the activations of a randomly initialised network within a few
+        # steps, which round 1 measured as a 7 % shorter step than on fresh batches with identical kernels.
+        if args.device_batches > 1:
+            from deeplearning_cfn_b200.utils.data import IMAGENET_MEAN, IMAGENET_STD
+            _src = SyntheticImageSource(args.batch, args.image_size, 1000, distinct=args.device_batches, pin=False)
+            dev_batches = []
+            for img, lab in zip(_src.images, _src.labels):
+                if dry:
+                    xb = ((img.float() / 255.0 - 0.45) / 0.225).permute(0, 3, 1, 2)
+                else:
+                    u8 = img.to(device)
+                    nx = torch.empty(u8.shape, dtype=torch.bfloat16, device=device)
+                    native.normalize_u8_nhwc(u8, nx, IMAGENET_MEAN, IMAGENET_STD)
+                    xb = nx.permute(0, 3, 1, 2)            # NHWC storage viewed as NCHW = channels_last
+                dev_batches.append((xb, lab.to(device)))
+            del _src
+        else:
+            dev_batches = [(x, y)]
     n_workers = len(trainer.workers)
     is_worker = trainer.is_worker
 
@@ -186,8 +210,9 @@ def main():
         run_step = graphed
         if rank == 0:
             print(f"[bench] {graphed!r}", file=sys.stderr, flush=True)
-    for _ in range(args.warmup):
-        run_step(x, y) if is_worker else run_step()
+    nb = len(dev_batches)
+    for i in range(args.warmup):
+        run_step(*dev_batches[i % nb]) if is_worker else run_step()
     sync_all()
     launches0 = native.launch_count
     t_start, t_end = Event(enable_timing=True), Event(enable_timing=True)
@@ -196,8 +221,8 @@ def main():
         sampler.__enter__()
     t_start.record()
     step_loss = None
-    for _ in range(args.steps):
-        step_loss = run_step(x, y) if is_worker else run_step()
+    for i in range(args.steps):
+        step_loss = run_step(*dev_batches[(args.warmup + i) % nb]) if is_worker else run_step()
     t_end.record()
     sync_all()
     if sampler:
@@ -311,7 +336,7 @@ def main():
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": round(value / (BASELINE_IMG_S_PER_GPU * world), 3), "dtype": "fp32 (dry run)" if dry else "bf16",
-               "data": "synthetic (random images/labels, random-init weights)",
+               "data": "synthetic (random uint8 images normalised on the device, random labels, random-init weights)",
                "impl": "ours" if args.impl == "ours" else "nccl-baseline",
                "config": {"model": f"resnet-{args.num_layers}-v2 (reference symbols/resnet.py)",
                           "global_batch": global_batch, "per_gpu_batch": args.batch, "image": args.image_size,
@@ -319,6 +344,7 @@ def main():
                           "bucket_mb": args.bucket_mb, "l2": "inputs+activations larger than L2 (no flush needed)",
                           "conv1x1": conv_ops.conv1x1_backend(), "convkxk": conv_ops.convkxk_backend(),
                           "cuda_graph": bool(graphed is not None and graphed.graphed),
+                          "device_batches": len(dev_batches),
                           "baseline": "363.69 img/s per V100 (perf.md:219) x n_gpus"},
                "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                           "reasons": clocks.get("reasons", [])},

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <functional>
 #include <map>
+#include <set>
 #include <memory>
 #include <deque>
 #include <mutex>
@@ -117,6 +118,7 @@ class Node {
   std::map<int, NodeInfo> nodes_;        // id -> info
   std::map<int, int> send_fd_;           // id -> fd
   std::map<int, std::unique_ptr<std::mutex>> send_mu_;
+  std::set<int> stale_fd_;                // peers whose connection must be replaced by the next Send
   std::vector<NodeInfo> pending_;        // scheduler: registrations before assignment
   std::vector<int> pending_fd_;
   std::map<int, int> registered_fd_;     // scheduler: id -> fd of the registration connection

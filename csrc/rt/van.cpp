@@ -194,10 +194,21 @@ void Node::Finalize(bool do_barrier) {
   stop_ = true;
   ::shutdown(listen_fd_, SHUT_RDWR);
   ::close(listen_fd_);
+  // Outgoing connections: a reader thread may be inside send() on one of them right now (ACKs, barrier replies).
+  // Pass 1 only SHUTS the sockets down - safe against a concurrent send(), and it fails a sender that is blocked on a
+  // peer that stopped reading.  Pass 2 closes each descriptor while holding that peer's send mutex, so the number cannot
+  // be recycled under a sender (found by ThreadSanitizer: close() here raced with send() in ReadLoop -> Send).
+  std::vector<std::pair<int, std::mutex*>> peers;
   {
     std::lock_guard<std::mutex> lk(mu_);
-    for (auto& kv : send_fd_) { ::shutdown(kv.second, SHUT_RDWR); ::close(kv.second); }
-    send_fd_.clear();
+    for (auto& kv : send_fd_) ::shutdown(kv.second, SHUT_RDWR);
+    for (auto& kv : send_mu_) peers.emplace_back(kv.first, kv.second.get());
+  }
+  for (auto& pm : peers) {
+    std::lock_guard<std::mutex> ls(*pm.second);
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = send_fd_.find(pm.first);
+    if (it != send_fd_.end()) { ::close(it->second); send_fd_.erase(it); }
   }
   if (accept_thread_.joinable()) accept_thread_.join();
   if (heartbeat_thread_.joinable()) heartbeat_thread_.join();
@@ -221,16 +232,21 @@ int Node::ConnectTo(const NodeInfo& n) {
   return fd;
 }
 
+// Called with the peer's send mutex held (Send): the only place that opens, replaces or closes a peer's descriptor.
 int Node::FdFor(int id) {
   std::lock_guard<std::mutex> lk(mu_);
   auto it = send_fd_.find(id);
+  if (it != send_fd_.end() && stale_fd_.erase(id)) {     // the id was handed to a restarted node: drop the old connection
+    ::close(it->second);
+    send_fd_.erase(it);
+    it = send_fd_.end();
+  }
   if (it != send_fd_.end()) return it->second;
   auto n = nodes_.find(id);
   if (n == nodes_.end()) return -1;
   int fd = ConnectTo(n->second);
   if (fd < 0) return -1;
   send_fd_[id] = fd;
-  if (!send_mu_.count(id)) send_mu_[id].reset(new std::mutex());
   return fd;
 }
 
@@ -255,14 +271,19 @@ int Node::Send(Message& msg) {
     std::lock_guard<std::mutex> lk(rs_mu_);
     unacked_[msg.sig] = Pending{msg, NowMs(), 0};
   }
-  int fd = FdFor(msg.recver);
-  if (fd < 0) return -1;
   std::mutex* m = nullptr;
   {
     std::lock_guard<std::mutex> lk(mu_);
-    m = send_mu_[msg.recver].get();
+    auto& slot = send_mu_[msg.recver];
+    if (!slot) slot.reset(new std::mutex());
+    m = slot.get();
   }
+  // one sender per peer at a time, and the descriptor is resolved INSIDE that critical section: nobody can close or
+  // replace it between the lookup and the send (lock order: peer send mutex -> mu_)
   std::lock_guard<std::mutex> lk(*m);
+  if (stop_) return -1;                              // late ACK / reply from a detached reader after Finalize
+  int fd = FdFor(msg.recver);
+  if (fd < 0) return -1;
   if (!SendRaw(fd, msg)) {
     std::lock_guard<std::mutex> lk2(mu_);
     ::close(fd);
@@ -384,7 +405,7 @@ void Node::SchedulerAddNode(Message&& m) {
   nodes_[take] = n;
   last_seen_[take] = now;
   auto it = send_fd_.find(take);
-  if (it != send_fd_.end()) { ::close(it->second); send_fd_.erase(it); }
+  if (it != send_fd_.end()) { ::shutdown(it->second, SHUT_RDWR); stale_fd_.insert(take); }   // closed by the next Send (FdFor)
   Message table;
   table.control = kNodeTable;
   for (auto& kv : nodes_) table.nodes.push_back(kv.second);
@@ -412,8 +433,8 @@ void Node::HandleControl(Message&& m, int) {
       for (auto& n : m.nodes) {
         auto old = nodes_.find(n.id);
         if (old != nodes_.end() && (old->second.host != n.host || old->second.port != n.port)) {
-          auto it = send_fd_.find(n.id);   // peer moved (recovery): reconnect lazily
-          if (it != send_fd_.end()) { ::close(it->second); send_fd_.erase(it); }
+          auto it = send_fd_.find(n.id);   // peer moved (recovery): the next Send replaces the connection (FdFor)
+          if (it != send_fd_.end()) { ::shutdown(it->second, SHUT_RDWR); stale_fd_.insert(n.id); }
         }
         nodes_[n.id] = n;
         if (my_.id < 0 && n.host == my_.host && n.port == my_.port && n.role == my_.role) my_ = n;
@@ -434,16 +455,20 @@ void Node::HandleControl(Message&& m, int) {
           c = 0;
           ids = IdsOfGroup(m.barrier_group);
         }
+        // Everybody else is released BEFORE the scheduler's own main thread: at the closing barrier that thread goes on
+        // to stop the node and close its connections, and a release still waiting to be sent from this reader thread
+        // would be lost - its receiver would sit in the barrier forever (the close() / send() race ThreadSanitizer reported).
+        bool self = false;
         for (int id : ids) {
-          if (id == kSchedulerId) {
-            std::lock_guard<std::mutex> lk(mu_);
-            barrier_done_ = true;
-            cv_.notify_all();
-            continue;
-          }
+          if (id == kSchedulerId) { self = true; continue; }
           Message r;
           r.control = kBarrier; r.request = false; r.recver = id; r.barrier_group = m.barrier_group;
           Send(r);
+        }
+        if (self) {
+          std::lock_guard<std::mutex> lk(mu_);
+          barrier_done_ = true;
+          cv_.notify_all();
         }
       } else {
         std::lock_guard<std::mutex> lk(mu_);

@@ -18,20 +18,25 @@ n=$(ls $out/tsan.* 2>/dev/null | wc -l)
 echo "TSAN report files: $n"
 grep -h "SUMMARY: ThreadSanitizer" $out/tsan.* 2>/dev/null | sort | uniq -c | sort -rn | head -30
 
-# ---- a whole parameter-server job with every role under TSAN.  The launchers start their children through `sh -c`, and a
-# shell with libtsan preloaded crashes at start-up, so the five processes are started by hand here.
-echo "== parameter-server job under TSAN (scheduler + 2 servers + 2 workers, dist_sync then dist_async)"
-for mode in dist_sync dist_async; do
-  port=$((9600 + RANDOM % 300))
-  export DMLC_PS_ROOT_URI=127.0.0.1 DMLC_PS_ROOT_PORT=$port DMLC_NUM_WORKER=2 DMLC_NUM_SERVER=2 PYTHONPATH=$PWD
-  export TSAN_OPTIONS="halt_on_error=0:exitcode=0:report_signal_unsafe=0:log_path=$out/job_$mode:history_size=4"
-  rm -f $out/job_$mode.*
-  pids=""
-  DMLC_ROLE=scheduler timeout 300 python -c "import deeplearning_cfn_b200.kv" > $out/sched_$mode.log 2>&1 & pids="$pids $!"
-  for i in 0 1; do DMLC_ROLE=server timeout 300 python -c "import deeplearning_cfn_b200.kv" > $out/server${i}_$mode.log 2>&1 & pids="$pids $!"; done
-  for i in 0 1; do DMLC_ROLE=worker timeout 300 python tests/mp/dist_kvstore_worker.py $mode > $out/worker${i}_$mode.log 2>&1 & pids="$pids $!"; done
-  rc=0
+# ---- whole parameter-server jobs with every role under TSAN.  The launchers start their children through `sh -c`, and a
+# shell with libtsan preloaded crashes at start-up, so the processes are started by hand here.
+run_job() { # tag, workers, script [args...]   (environment of the caller is inherited: PS_RESEND, PS_DROP_MSG, ...)
+  local tag=$1 nw=$2 script=$3; shift 3
+  local port=$((9600 + RANDOM % 300)) pids="" rc=0
+  export DMLC_PS_ROOT_URI=127.0.0.1 DMLC_PS_ROOT_PORT=$port DMLC_NUM_WORKER=$nw DMLC_NUM_SERVER=2 PYTHONPATH=$PWD
+  export TSAN_OPTIONS="halt_on_error=0:exitcode=0:report_signal_unsafe=0:log_path=$out/job_$tag:history_size=4"
+  rm -f $out/job_$tag.*
+  DMLC_ROLE=scheduler timeout 300 python -c "import deeplearning_cfn_b200.kv" > $out/sched_$tag.log 2>&1 & pids="$pids $!"
+  for i in 0 1; do DMLC_ROLE=server timeout 300 python -c "import deeplearning_cfn_b200.kv" > $out/server${i}_$tag.log 2>&1 & pids="$pids $!"; done
+  for i in $(seq 1 $nw); do DMLC_ROLE=worker timeout 300 python $script "$@" > $out/worker${i}_$tag.log 2>&1 & pids="$pids $!"; done
   for p in $pids; do wait $p || rc=$?; done
-  echo "$mode: exit $rc; $(grep -h "_OK" $out/worker*_$mode.log | tr '\n' ' ')"
-  grep -h "SUMMARY: ThreadSanitizer" $out/job_$mode.* 2>/dev/null | grep -v "libtorch\|python3\|libgomp\|memintrinsics" | sort | uniq -c | sort -rn | head -20
-done
+  echo "$tag: exit $rc; $(grep -h "_OK\|PROFILED" $out/worker*_$tag.log | tr '\n' ' ')"
+  grep -h "SUMMARY: ThreadSanitizer" $out/job_$tag.* 2>/dev/null | grep -v "libtorch\|python3\|libgomp\|memintrinsics" | sort | uniq -c | sort -rn | head -20
+}
+set +e
+echo "== parameter-server jobs under TSAN (scheduler + 2 servers + workers)"
+run_job dist_sync 2 tests/mp/dist_kvstore_worker.py dist_sync
+run_job dist_async 2 tests/mp/dist_kvstore_worker.py dist_async
+PS_RESEND=1 PS_RESEND_TIMEOUT=200 PS_DROP_MSG=10 PS_HEARTBEAT_INTERVAL=1 run_job resend_drop_heartbeat 2 tests/mp/dist_kvstore_worker.py dist_sync
+MXNET_KVSTORE_BIGARRAY_BOUND=40 run_job sync_replicas_python_callbacks 3 tests/mp/sync_replicas_worker.py
+run_job server_profiling 2 tests/mp/server_profile_worker.py $out/prof

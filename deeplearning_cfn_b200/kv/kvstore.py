@@ -389,6 +389,22 @@ class KVStoreDist(KVStoreLocal):
         if self.rank == 0 and self._sync:
             self._send_command_to_servers(rt.CMD_SYNC_MODE, "")   # kvstore.cc:55-58
         self._closed = False
+        # The reference's destructor (kvstore_dist.h:62-76) runs when the process ends even if the script never drops the
+        # store.  `__del__` is not reliable for objects that are still referenced at interpreter shutdown (a module-level
+        # `kv = create(...)`), and a worker that skips the closing barrier leaves servers and peers waiting - so the
+        # protocol is also run from an atexit hook that holds only a weak reference.
+        import atexit
+        import weakref
+        ref = weakref.ref(self)
+
+        def _close_at_exit(ref=ref):
+            store = ref()
+            if store is not None:
+                try:
+                    store.close()
+                except Exception:       # noqa: BLE001 - nothing useful can be done this late
+                    pass
+        atexit.register(_close_at_exit)
 
     @property
     def rank(self) -> int:

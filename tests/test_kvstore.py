@@ -457,3 +457,24 @@ def test_module_with_several_contexts_matches_single_device(update_on_kvstore_st
     m2.update()
     for a, b in zip(*m2._rparams):
         assert torch.equal(a, b)
+
+
+def test_package_import_turns_servers_into_nodes_and_store_closes_at_exit(tmp_path):
+    """The reference contract of `import mxnet` + the KVStoreDist destructor: the user script imports only the top-level
+    package before doing unrelated work, never calls close(), keeps the store in a module global - servers and scheduler
+    still become their nodes at the import, and the job still ends (closing barrier + server stop run at interpreter exit)."""
+    script = tmp_path / "user_script.py"
+    script.write_text(
+        "import sys\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "import deeplearning_cfn_b200                      # servers / scheduler never get past this line\n"
+        "import os, torch\n"
+        "assert os.environ['DMLC_ROLE'] == 'worker', os.environ['DMLC_ROLE']\n"
+        "import deeplearning_cfn_b200.kv as kv\n"
+        "store = kv.create('dist_sync')\n"
+        "store.init(1, torch.zeros(4)); store.push(1, torch.ones(4) * (store.rank + 1))\n"
+        "out = torch.zeros(4); store.pull(1, out=out)\n"
+        "print('USER_SCRIPT_DONE', store.rank, out.tolist(), flush=True)\n")
+    r = _launch(2, 2, [str(script)])
+    assert r.returncode == 0 and r.stdout.count("USER_SCRIPT_DONE") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "[3.0, 3.0, 3.0, 3.0]" in r.stdout

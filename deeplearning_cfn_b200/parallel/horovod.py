@@ -35,6 +35,18 @@ def init(backend: str | None = None) -> None:
         env["MASTER_ADDR"], env["MASTER_PORT"] = info["master_addr"], str(info["master_port"])
         env.setdefault("LOCAL_RANK", str(info["rank"]))
         _state["tracker"], _state["tracker_rank"] = c, info["rank"]
+    if "RANK" not in env and env.get("DMLC_ROLE") == "worker" and "DMLC_PS_ROOT_URI" in env:
+        # Worker of a parameter-server job (`launch -n W -s S script`): the PS rendezvous is the only thing that knows the
+        # ranks.  Join it (the servers and the scheduler are waiting for every worker anyway), take rank / world from it and
+        # build the process group next to the scheduler's port.  The store is kept: `shutdown()` runs its closing protocol
+        # (barrier, rank 0 stops the servers), without which the job would never end.
+        from .. import kv as _kv
+        store = _kv.create("dist_sync")
+        env["RANK"], env["WORLD_SIZE"] = str(store.rank), str(store.num_workers)
+        env.setdefault("LOCAL_RANK", str(store.rank))
+        env.setdefault("MASTER_ADDR", env["DMLC_PS_ROOT_URI"])
+        env.setdefault("MASTER_PORT", str(20000 + (int(env.get("DMLC_PS_ROOT_PORT", "9091")) * 7) % 20000))
+        _state["ps_store"] = store
     world = int(env.get("WORLD_SIZE", "1"))
     use_cuda = torch.cuda.is_available()
     if use_cuda:
@@ -57,6 +69,8 @@ def shutdown() -> None:
         _state["tracker"] = None
     if dist.is_initialized():
         dist.destroy_process_group()
+    if _state.get("ps_store") is not None:
+        _state.pop("ps_store").close()
     _state["initialized"] = False
 
 

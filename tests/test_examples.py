@@ -208,3 +208,19 @@ def test_profiler_category_switches_and_mode_env(tmp_path):
                PYTHONPATH=ROOT)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert r.stdout.split() == ["True", "True", "False"], r.stdout + r.stderr
+
+
+def test_train_imagenet_under_the_parameter_server_launcher(tmp_path):
+    """`launch -n 2 -s 2 python train_imagenet.py --benchmark 1 --kv-store dist_sync` (README.md:253-258 of the reference's
+    example directory): scheduler and servers become their nodes at package import, the workers take rank / world from the
+    PS rendezvous, train in lock step and the job ends by itself."""
+    from conftest import run_job
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "2", "--launcher", "local", sys.executable, "-m",
+           "deeplearning_cfn_b200.examples.train_imagenet", "--network", "resnet", "--num-layers", "20", "--benchmark", "1",
+           "--batch-size", "4", "--image-shape", "3,32,32", "--num-classes", "10", "--num-batches", "3", "--num-epochs", "1",
+           "--kv-store", "dist_sync", "--disp-batches", "1"]
+    r = run_job(cmd, env=dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2"), timeout=420)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    losses = sorted(set(l.split("Train-loss=")[1].strip() for l in out.splitlines() if "Train-loss=" in l))
+    assert "Node[0]" in out and "Node[1]" in out and len(losses) == 1, out[-2000:]      # both ranks, identical loss

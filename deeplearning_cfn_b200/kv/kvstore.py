@@ -375,6 +375,12 @@ class KVStoreDist(KVStoreLocal):
 
     def __init__(self, name: str):
         super().__init__(name)
+        missing = [v for v in ("DMLC_PS_ROOT_URI", "DMLC_PS_ROOT_PORT", "DMLC_NUM_WORKER", "DMLC_NUM_SERVER") if v not in os.environ]
+        if missing:
+            # the reference aborts in ps::Postoffice with a CHECK on the same variables; without them the node would wait
+            # forever for a scheduler on the default address
+            raise KVStoreError(f"a `{name}` kvstore is a node of a parameter-server job: start the script through the launcher "
+                               f"(`python -m deeplearning_cfn_b200 launch -n W -s S ...`), which sets {', '.join(missing)}")
         self._L = rt.lib()
         if self._L.dlcfn_ps_start() != 0:
             raise KVStoreError("cannot join the parameter-server job (is the scheduler up? DMLC_PS_ROOT_URI/PORT)")

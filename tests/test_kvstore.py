@@ -478,3 +478,10 @@ def test_package_import_turns_servers_into_nodes_and_store_closes_at_exit(tmp_pa
     r = _launch(2, 2, [str(script)])
     assert r.returncode == 0 and r.stdout.count("USER_SCRIPT_DONE") == 2, r.stdout[-2000:] + r.stderr[-3000:]
     assert "[3.0, 3.0, 3.0, 3.0]" in r.stdout
+
+
+def test_dist_store_outside_a_launcher_fails_with_a_clear_error(monkeypatch):
+    for v in ("DMLC_PS_ROOT_URI", "DMLC_PS_ROOT_PORT", "DMLC_NUM_WORKER", "DMLC_NUM_SERVER"):
+        monkeypatch.delenv(v, raising=False)
+    with pytest.raises(kv.KVStoreError, match="launcher"):
+        kv.create("dist_sync")

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import sys
 import pickle
 
 import torch
@@ -405,6 +406,10 @@ class KVStoreDist(KVStoreLocal):
 
         def _close_at_exit(ref=ref):
             store = ref()
+            # an unhandled exception is ending this worker: do not enter the closing barrier (its peers are not there -
+            # they are blocked on this worker's missing push), just leave with the error code so the launcher ends the job
+            if getattr(sys, "last_exc", None) is not None or getattr(sys, "last_type", None) is not None:
+                return
             if store is not None:
                 try:
                     store.close()

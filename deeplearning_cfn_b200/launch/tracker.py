@@ -221,6 +221,13 @@ class AllreduceTracker:
     def alive(self) -> bool:
         return self.thread is not None and self.thread.is_alive()
 
+    def stop(self) -> None:
+        """End the rendezvous service (the launcher calls this when a rank died: nobody will send its `shutdown`)."""
+        try:
+            self.sock.close()          # accept() in the service thread fails, the thread ends (daemon)
+        except OSError:
+            pass
+
 
 class TrackerClient:
     """Worker side of the AllreduceTracker protocol."""
@@ -307,7 +314,29 @@ class PSTracker:
 
     def stop(self) -> None:
         if self.alive():
-            self.proc.terminate()
+            kill_tree(self.proc)
+
+
+def kill_tree(proc) -> None:
+    """Kill a launched process AND its descendants: the launchers start commands through a shell, so the Popen handle is
+    the shell and the node itself is its child - killing only the handle would orphan a node that is blocked in a barrier."""
+    if proc is None or proc.poll() is not None:
+        return
+    victims = []
+    try:
+        import psutil
+        victims = psutil.Process(proc.pid).children(recursive=True)
+    except Exception:       # noqa: BLE001 - psutil missing or the process just ended
+        victims = []
+    for v in victims:
+        try:
+            v.kill()
+        except Exception:   # noqa: BLE001
+            pass
+    try:
+        proc.kill()
+    except OSError:
+        pass
 
 
 def get_host_ip(host_ip: str | None = None) -> str:
@@ -347,21 +376,50 @@ def submit(nworker: int, nserver: int, fun_submit, host_ip: str = "auto", pscmd:
         tracker = PSTracker(ip, pscmd, envs=envs)
         envs.update(tracker.slave_envs())
     handle = fun_submit(nworker, nserver, envs)
+
+    def first_failure():
+        """(name, code) of a launched process that ended with a non-zero code after its retries, else None."""
+        for k, rc in list(getattr(handle, "returncodes", {}).items()):
+            if rc not in (0, None):
+                return k, rc
+        return None
+
+    def stop_job(why: str) -> None:
+        # A synchronous job cannot make progress without one of its members (the reference documents that a dead worker
+        # stalls everyone, distributed_training.md:101, and its local launcher then waits forever): end it instead.
+        logging.error("%s - stopping the job", why)
+        for p in list(getattr(handle, "procs", [])):
+            kill_tree(p)
+        tracker.stop()
+
     if wait:
         if isinstance(tracker, AllreduceTracker):
             # the job is over when every launched process has exited or every rank sent `shutdown`
             while tracker.alive():
                 if handle is not None and hasattr(handle, "all_done") and handle.all_done():
                     break
+                bad = first_failure()
+                if bad:
+                    stop_job(f"{bad[0]} exited with code {bad[1]}")
+                    break
                 time.sleep(0.1)
         else:
-            rc = tracker.join()
+            rc = None
+            while True:
+                rc = tracker.join(timeout=0.2)
+                if rc is not None or not tracker.alive():
+                    break
+                bad = first_failure()
+                if bad:
+                    stop_job(f"{bad[0]} exited with code {bad[1]}")
+                    rc = tracker.join(timeout=10)
+                    rc = None          # reported through the handle's return codes
+                    break
             if rc not in (0, None) and handle is not None:
                 # the scheduler died (could not bind, crashed): the other nodes can only spin on a dead address
                 logging.error("scheduler exited with code %s - stopping the job", rc)
                 for p in list(getattr(handle, "procs", [])):
-                    if p.poll() is None:
-                        p.kill()
+                    kill_tree(p)
         if handle is not None and hasattr(handle, "wait"):
             handle.wait()
     return tracker, handle

@@ -485,3 +485,29 @@ def test_dist_store_outside_a_launcher_fails_with_a_clear_error(monkeypatch):
         monkeypatch.delenv(v, raising=False)
     with pytest.raises(kv.KVStoreError, match="launcher"):
         kv.create("dist_sync")
+
+
+def test_job_ends_when_a_worker_crashes(tmp_path):
+    """A synchronous job cannot continue without one of its workers: the failing worker leaves with its error (it does not
+    enter the closing barrier), the launcher kills the remaining process trees, ends the scheduler and reports failure -
+    instead of the survivors waiting in a push forever."""
+    import time
+    script = tmp_path / "crash.py"
+    script.write_text(
+        "import sys, torch\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "import deeplearning_cfn_b200.kv as kv\n"
+        "s = kv.create('dist_sync')\n"
+        "s.init(1, torch.zeros(4))\n"
+        "if s.rank == 1:\n"
+        "    raise RuntimeError('worker 1 dies')\n"
+        "s.push(1, torch.ones(4)); out = torch.zeros(4); s.pull(1, out=out)\n"
+        "print('SURVIVOR_DONE', flush=True)\n")
+    t0 = time.time()
+    r = _launch(2, 1, [str(script)], timeout=120)
+    took = time.time() - t0
+    assert r.returncode != 0 and took < 90, (r.returncode, took, r.stdout[-1000:] + r.stderr[-2000:])
+    assert "worker 1 dies" in r.stderr and "stopping the job" in r.stderr and "SURVIVOR_DONE" not in r.stdout
+    import psutil
+    left = [p for p in psutil.process_iter(["cmdline"]) if str(script) in " ".join(p.info["cmdline"] or [])]
+    assert not left, [p.pid for p in left]

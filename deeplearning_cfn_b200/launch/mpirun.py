@@ -98,11 +98,23 @@ def main(argv=None) -> int:
     threads = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(n)]
     for t in threads:
         t.start()
-    for t in threads:
-        t.join()
+    # like mpirun: the first rank that exits non-zero terminates the job (its peers would otherwise sit in a collective
+    # until the transport times out - with NCCL that is many minutes)
+    import time
+    from .tracker import kill_tree
+    aborted = None
+    while any(t.is_alive() for t in threads):
+        first_bad = next((r for r, rc in enumerate(rcs) if rc not in (None, 0)), None)
+        if first_bad is not None and aborted is None:
+            aborted = first_bad
+            time.sleep(0.5)                      # let ranks that are failing for the same reason report it themselves
+            for p in list(procs):
+                kill_tree(p)
+        time.sleep(0.05)
     bad = [r for r, rc in enumerate(rcs) if rc != 0]
     if bad:
-        print(f"mpirun: ranks {bad} exited non-zero: {[rcs[r] for r in bad]}", file=sys.stderr)
+        why = f" (rank {aborted} exited first with code {rcs[aborted]}; the job was terminated)" if aborted is not None else ""
+        print(f"mpirun: ranks {bad} exited non-zero: {[rcs[r] for r in bad]}{why}", file=sys.stderr)
         return 1
     return 0
 

@@ -230,3 +230,16 @@ def test_kill_matches_only_the_named_program(tmp_path):
         q.kill()
         if p.poll() is None:
             p.kill()
+
+
+def test_mpirun_terminates_the_job_when_a_rank_fails(tmp_path):
+    """Like mpirun: the first rank that exits non-zero ends the job - a peer blocked in a collective is killed, not waited for."""
+    import time
+    from conftest import run_job
+    script = tmp_path / "r.py"
+    script.write_text("import os, sys, time\nif os.environ['RANK'] == '1':\n    sys.exit(3)\ntime.sleep(600)\n")
+    t0 = time.time()
+    r = run_job([sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "3", sys.executable, str(script)],
+                env=dict(os.environ, PYTHONPATH=ROOT), timeout=120)
+    assert r.returncode == 1 and time.time() - t0 < 60
+    assert "rank 1 exited first with code 3" in r.stderr

@@ -149,7 +149,7 @@ def main(argv=None) -> int:
     speed = Speedometer(a.batch_size, a.disp_batches)
     step_fn = None
     for epoch in range(begin, a.num_epochs):
-        if epoch in steps:
+        if epoch in steps and epoch > begin:          # steps up to `begin` are already in the resumed rate (fit.py:29-55)
             lr *= a.lr_factor
             tr.set_learning_rate(lr)
             logging.info("Update[%d]: Change learning rate to %0.5e", epoch, lr)

@@ -224,3 +224,21 @@ def test_train_imagenet_under_the_parameter_server_launcher(tmp_path):
     assert r.returncode == 0, out[-3000:]
     losses = sorted(set(l.split("Train-loss=")[1].strip() for l in out.splitlines() if "Train-loss=" in l))
     assert "Node[0]" in out and "Node[1]" in out and len(losses) == 1, out[-2000:]      # both ranks, identical loss
+
+
+def test_train_imagenet_resume_rederives_the_learning_rate_once(tmp_path):
+    """--load-epoch N: the rate starts at lr * factor^(steps <= N) and the steps already passed are not applied again
+    (fit.py:29-55 of the reference: `begin_epoch` removes them from the scheduler)."""
+    from conftest import run_job
+    base = [sys.executable, "-m", "deeplearning_cfn_b200.examples.train_imagenet", "--network", "resnet", "--num-layers", "20",
+            "--benchmark", "1", "--batch-size", "4", "--image-shape", "3,32,32", "--num-classes", "10", "--num-batches", "2",
+            "--gpus", "", "--model-prefix", str(tmp_path / "ck"), "--save-period", "1", "--lr-step-epochs", "1,2,3", "--lr", "0.1"]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = run_job(base + ["--num-epochs", "2"], env=env, timeout=300)
+    assert r.returncode == 0 and os.path.exists(tmp_path / "ck-0002.params"), (r.stdout + r.stderr)[-2000:]
+    r = run_job(base + ["--num-epochs", "4", "--load-epoch", "2"], env=env, timeout=300)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-2000:]
+    changes = [l.split("Change learning rate to ")[1].strip() for l in out.splitlines() if "Change learning rate to" in l]
+    assert changes == ["1.00000e-04"], changes          # resumed at 1e-3 (two steps passed), one more step at epoch 3
+    assert os.path.exists(tmp_path / "ck-0004.params")

@@ -79,7 +79,8 @@ def main(argv=None) -> int:
     if dtype != torch.float32 and use_gpu:
         net = to_b200_layout(net, dtype)
     if opt.resume:
-        net.load_state_dict(torch.load(opt.resume, map_location="cpu"))
+        from deeplearning_cfn_b200.utils.callback import load_params_file
+        load_params_file(opt.resume, net)          # periodic checkpoints and the -best file use different key layouts
 
     # ---- distributed identity comes from the kvstore (rank / num_workers), as in the reference
     bucketed = opt.engine == "bucketed"

@@ -77,6 +77,15 @@ def load_checkpoint(prefix: str, epoch: int, model: torch.nn.Module | None = Non
     return arg, aux
 
 
+def load_params_file(fname: str, model: torch.nn.Module, strict: bool = True):
+    """Load a parameter file into `model` whichever way it was written: the checkpoint format (`arg:` / `aux:` prefixes,
+    save_checkpoint / Module.save_params) or a plain state dict (`net.save_parameters`, the `-best.params` of the gluon example)."""
+    raw = torch.load(fname, map_location="cpu")
+    if raw and all(isinstance(k, str) and k[:4] in ("arg:", "aux:") for k in raw):
+        raw = {k[4:]: v for k, v in raw.items()}
+    return model.load_state_dict(raw, strict=strict)
+
+
 def latest_checkpoint(prefix: str) -> int | None:
     d, b = os.path.split(os.path.abspath(prefix))
     if not os.path.isdir(d):

@@ -242,3 +242,25 @@ def test_train_imagenet_resume_rederives_the_learning_rate_once(tmp_path):
     changes = [l.split("Change learning rate to ")[1].strip() for l in out.splitlines() if "Change learning rate to" in l]
     assert changes == ["1.00000e-04"], changes          # resumed at 1e-3 (two steps passed), one more step at epoch 3
     assert os.path.exists(tmp_path / "ck-0004.params")
+
+
+def test_image_classification_resume_accepts_periodic_and_best_checkpoints(tmp_path):
+    """--resume takes the file written every --save-frequency (arg:/aux: keys) as well as the -best file (plain state dict)."""
+    from conftest import run_job
+    base = [sys.executable, "-m", "deeplearning_cfn_b200.examples.image_classification", "--dataset", "dummy", "--model", "resnet18_v1",
+            "--batch-size", "4", "--gpus", "", "--num-samples", "8", "--prefix", str(tmp_path / "m"), "--save-frequency", "1",
+            "--kvstore", "local"]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = run_job(base + ["--epochs", "1"], env=env, timeout=300)
+    assert r.returncode == 0 and os.path.exists(tmp_path / "m-0001.params"), (r.stdout + r.stderr)[-2000:]
+    import torch
+    from deeplearning_cfn_b200.models import get_model
+    from deeplearning_cfn_b200.utils.callback import load_params_file
+    raw = torch.load(tmp_path / "m-0001.params", map_location="cpu")
+    assert all(k[:4] in ("arg:", "aux:") for k in raw)
+    torch.save({k[4:]: v for k, v in raw.items()}, tmp_path / "plain.params")      # what net.save_parameters / -best.params hold
+    for f in ("m-0001.params", "plain.params"):
+        r = run_job(base + ["--epochs", "2", "--start-epoch", "1", "--resume", str(tmp_path / f)], env=env, timeout=300)
+        assert r.returncode == 0, f + (r.stdout + r.stderr)[-2000:]
+    res = load_params_file(str(tmp_path / "m-0001.params"), get_model("resnet18_v1", 1000, 224), strict=False)
+    assert not res.unexpected_keys and get_model is not None

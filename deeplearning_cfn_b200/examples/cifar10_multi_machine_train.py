@@ -91,6 +91,13 @@ def main(argv=None) -> int:
 
     use_gpu = torch.cuda.is_available() and os.environ.get("CUDA_VISIBLE_DEVICES", "x") != ""
     dev = torch.device("cuda", 0) if use_gpu else torch.device("cpu")
+    if not use_gpu:
+        # CPU workers that share a host share its cores: with every process running a full intra-op thread pool a step of
+        # this small network takes 50x longer than with the pools sized to the share (measured: 376 ms vs 8 ms backward)
+        host_of = lambda h: h[0] if isinstance(h, (tuple, list)) else str(h).split(":")[0]      # noqa: E731
+        mine = host_of(workers[a.task_index])
+        local = sum(1 for h in list(workers) + list(ps) if host_of(h) == mine)
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, local)))
     torch.manual_seed(0)
     net = Cifar10CNN(10, 24).to(dev)
     store = kv.create("dist_async")
@@ -147,7 +154,7 @@ def main(argv=None) -> int:
                 dt = time.time() - t0
                 t0 = time.time()
                 eps = a.log_frequency * a.batch_size / dt
-                print(f"{datetime.now()}: step {step}, loss = {float(loss) / a.batch_size:.2f} ({eps:.1f} examples/sec; "
+                print(f"{datetime.now()}: step {step}, loss = {float(loss.detach()) / a.batch_size:.2f} ({eps:.1f} examples/sec; "
                       f"{dt / a.log_frequency:.3f} sec/batch)", flush=True)
             if is_chief and time.time() - last_save >= a.save_checkpoint_secs:
                 torch.save({"model": net.state_dict(), "global_step": step, "moving_average": [e.cpu() for e in ema]}, ckpt)

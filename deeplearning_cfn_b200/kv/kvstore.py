@@ -382,6 +382,9 @@ class KVStoreDist(KVStoreLocal):
             # forever for a scheduler on the default address
             raise KVStoreError(f"a `{name}` kvstore is a node of a parameter-server job: start the script through the launcher "
                                f"(`python -m deeplearning_cfn_b200 launch -n W -s S ...`), which sets {', '.join(missing)}")
+        if not torch.cuda.is_available():
+            from ..utils.cpu import share_cpu_threads
+            share_cpu_threads()                      # co-located CPU workers / servers split the cores
         self._L = rt.lib()
         if self._L.dlcfn_ps_start() != 0:
             raise KVStoreError("cannot join the parameter-server job (is the scheduler up? DMLC_PS_ROOT_URI/PORT)")

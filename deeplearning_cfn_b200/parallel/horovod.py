@@ -53,11 +53,18 @@ def init(backend: str | None = None) -> None:
         lr = int(env.get("LOCAL_RANK", "0"))
         ndev = torch.cuda.device_count()
         torch.cuda.set_device(lr % ndev)
+    if not use_cuda:
+        _share_cpu_threads(env, world)
     if world > 1 and not dist.is_initialized():
         env.setdefault("MASTER_ADDR", "127.0.0.1")
         env.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"))
     _state["initialized"] = True
+
+
+def _share_cpu_threads(env, world: int) -> None:
+    from ..utils.cpu import share_cpu_threads
+    share_cpu_threads(world, env)
 
 
 def shutdown() -> None:

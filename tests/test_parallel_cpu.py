@@ -690,3 +690,19 @@ def test_diagnose_report(capsys):
     assert info["package"]["cuda_library"]["present"] and info["package"]["cuda_library"]["loads"] is True
     assert info["package"]["runtime_library"]["loads"] is True and "gloo" in info["torch"]["distributed_backends"]
     assert {"platform", "python", "torch", "gpus", "tools", "environment"} <= set(info)
+
+
+def test_cpu_thread_budget_is_split_between_colocated_processes(monkeypatch):
+    from deeplearning_cfn_b200.utils import cpu
+    before = torch.get_num_threads()
+    try:
+        cores = os.cpu_count() or 1
+        assert cpu.share_cpu_threads(1, {}) is None                                        # alone: untouched
+        assert cpu.share_cpu_threads(4, {"OMP_NUM_THREADS": "3"}) is None                  # user pinned it
+        assert cpu.share_cpu_threads(4, {"DLCFN_KEEP_THREADS": "1"}) is None
+        assert cpu.share_cpu_threads(2, {}) == max(1, cores // 2) == torch.get_num_threads()
+        assert cpu.share_cpu_threads(8, {"LOCAL_WORLD_SIZE": "4"}) == max(1, cores // 4)   # 2 nodes x 4 ranks
+        env = {"DMLC_JOB_CLUSTER": "local", "DMLC_NUM_WORKER": "2", "DMLC_NUM_SERVER": "2"}
+        assert cpu.share_cpu_threads(1, env) == max(1, cores // 4)                          # local launcher: workers + servers
+    finally:
+        torch.set_num_threads(before)

@@ -46,6 +46,8 @@ class KVStoreServer:
         self.updater(key, g, w)
 
     def run(self) -> None:
+        from ..utils.cpu import share_cpu_threads
+        share_cpu_threads()                 # python updaters on a server use torch ops: split the cores with local peers
         if self.L.dlcfn_ps_start() != 0:
             raise RuntimeError("parameter-server node could not start")
         role = self.L.dlcfn_ps_role()

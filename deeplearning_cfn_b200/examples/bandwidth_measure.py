@@ -140,6 +140,10 @@ def measure(r: Runner, sizes: list[int], num_batches: int, check: bool) -> tuple
 def main(argv=None) -> int:
     a = parse(argv)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        # like the reference tool (measure.py:62-75 builds its kvstore over mx.gpu(i) contexts) this measures device stores
+        raise SystemExit("bandwidth_measure: no CUDA device on this host - the tool measures the GPU communication paths "
+                         "(`--kv-store device|nccl|dist_sync...` between GPUs); use `diagnose` to see what the box has")
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

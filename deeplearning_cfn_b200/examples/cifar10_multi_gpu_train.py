@@ -56,7 +56,7 @@ def main(argv=None) -> int:
                 t.zero_grad(set_to_none=True)
                 l = F.cross_entropy(t(xb), yb, reduction="sum")
                 l.backward()
-                losses.append(float(l))
+                losses.append(float(l.detach()))
             for i, n in enumerate(names):
                 store.push(i, [pl[n].grad for pl in plists], priority=-i)      # list of per-device gradients
                 store.pull(i, out=[pl[n].data for pl in plists], priority=-i)

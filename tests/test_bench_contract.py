@@ -94,3 +94,14 @@ def test_ctypes_tables_match_the_c_signatures():
     assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
     compared = int(r.stdout.strip().splitlines()[-1].split(" exported functions parsed, ")[1].split(" ")[0])
     assert compared >= 100
+
+
+def test_gpu_tier_test_bodies_run_on_the_stand_in_gpu():
+    """DLCFN_MOCK_GPU_DRYRUN=1 executes the bodies of the GPU-marked experimental and model-zoo tests on the host (stubbed
+    kernels, numeric assertions ignored): a typo, a wrong argument count or a bad constructor in a test that only ever runs
+    on the GPU box shows up here."""
+    env = dict(os.environ, DLCFN_MOCK_GPU_DRYRUN="1", DLCFN_EXPERIMENTAL="1", PYTHONPATH=ROOT)
+    r = run_job([sys.executable, "-m", "pytest", "tests/test_gpu_experimental.py", "tests/test_models.py", "-m", "gpu", "-q", "--no-header",
+                 "-p", "no:cacheprovider"], cwd=ROOT, env=env, timeout=900)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:] + r.stderr[-1000:]

@@ -7,6 +7,10 @@ import torch
 from deeplearning_cfn_b200.models import get_model, to_b200_layout
 
 
+def dev():
+    return torch.device("cuda", 0)
+
+
 def _params(m):
     return sum(p.numel() for p in m.parameters())
 
@@ -69,13 +73,13 @@ def test_zoo_models_on_cuda_kernels_match_fp32_cpu(name):
     ref = get_model(name, 16, 64)
     m = get_model(name, 16, 64)
     m.load_state_dict(ref.state_dict())
-    m = to_b200_layout(m.cuda())
+    m = to_b200_layout(m.to(dev()))
     x = torch.randn(8, 3, 64, 64)
     y_ref = ref(x)
-    y = m(x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float().cpu()
+    y = m(x.to(dev()).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float().cpu()
     cos = torch.nn.functional.cosine_similarity(y.flatten(), y_ref.flatten(), dim=0).item()
     assert torch.isfinite(y).all() and cos > 0.95, (cos, (y - y_ref).abs().max().item())
-    m(x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float().logsumexp(1).sum().backward()
+    m(x.to(dev()).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float().logsumexp(1).sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)
 
 

@@ -706,3 +706,84 @@ def test_cpu_thread_budget_is_split_between_colocated_processes(monkeypatch):
         assert cpu.share_cpu_threads(1, env) == max(1, cores // 4)                          # local launcher: workers + servers
     finally:
         torch.set_num_threads(before)
+
+
+def test_recordio_framing_property_python_and_native_agree(tmp_path):
+    """Property test (hypothesis): arbitrary payloads - empty, unaligned lengths, payloads that CONTAIN the record magic at
+    aligned and unaligned offsets (the dmlc writer splits those into continuation records) - written by either writer are
+    read back identically by either reader."""
+    import struct
+    from hypothesis import given, settings, strategies as st
+    from deeplearning_cfn_b200.utils import recordio
+    magic = struct.pack("<I", recordio.MAGIC)
+    chunk = st.one_of(st.binary(min_size=0, max_size=40), st.just(magic), st.just(magic * 2), st.just(b"\x00" * 3 + magic))
+    payload = st.lists(chunk, min_size=0, max_size=6).map(b"".join)
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(payload, min_size=1, max_size=6))
+    def run(payloads):
+        counter[0] += 1
+        for writer in ("python", "native"):
+            path = str(tmp_path / f"p{counter[0]}_{writer}.rec")
+            if writer == "python":
+                w = recordio.MXRecordIO(path, "w")
+                for b in payloads:
+                    w.write(b)
+                w.close()
+            else:
+                w = recordio.NativeRecordIO(None, path, "w")
+                for i, b in enumerate(payloads):
+                    w.write(i, b)
+                w.close()
+            r = recordio.MXRecordIO(path, "r")
+            got = []
+            while True:
+                b = r.read()
+                if b is None:
+                    break
+                got.append(b)
+            r.close()
+            assert got == payloads, (writer, "python reader")
+            n = recordio.NativeRecordIO(None, path, "r")
+            assert len(n) == len(payloads) and [n.read(i) for i in range(len(n))] == payloads, (writer, "native reader")
+            n.close()
+    run()
+
+
+def test_slicing_helpers_partition_their_ranges():
+    """Properties of the three slicing rules: executor-group batch slices, inter-node rail slices of a bucket, server shards
+    of a bucket - each is an exact partition, rail / shard boundaries fall on 16-byte granules."""
+    from types import SimpleNamespace
+    from hypothesis import given, settings, strategies as st
+    from deeplearning_cfn_b200.kv.module import decide_slices
+    from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 512), st.lists(st.integers(1, 5), min_size=1, max_size=8))
+    def batch(n, loads):
+        try:
+            sl = decide_slices(n, loads)
+        except ValueError:
+            assert n < 2 * len(loads) + sum(loads)        # only tiny batches may fail to give every device a row
+            return
+        assert sl[0].start == 0 and sl[-1].stop == n and all(a.stop == b.start for a, b in zip(sl, sl[1:]))
+        assert all(s.stop > s.start for s in sl)
+    batch()
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 1 << 16).map(lambda k: k * 64), st.sampled_from([1, 2, 4, 8]), st.sampled_from([2, 4]))
+    def rails(numel, node_size, esize):
+        fake = SimpleNamespace(node_size=node_size)
+        b = SimpleNamespace(numel=numel, group=SimpleNamespace(esize=esize))
+        cuts = [DataParallelTrainer._rail_slice(fake, b, l) for l in range(node_size)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == numel and all(a[1] == c[0] for a, c in zip(cuts, cuts[1:]))
+        assert all((lo * esize) % 16 == 0 for lo, _ in cuts)
+        fake2 = SimpleNamespace(rank=0, servers=list(range(node_size)))
+        shards = []
+        for r in range(node_size):
+            fake2.rank = r
+            shards.append(DataParallelTrainer._shard(fake2, b))
+        assert shards[0][0] == 0 and max(h for _, h in shards) >= numel and all(a[1] == c[0] or c == (numel, numel) or a[1] >= numel
+                                                                                for a, c in zip(shards, shards[1:]))
+    rails()

@@ -511,3 +511,50 @@ def test_job_ends_when_a_worker_crashes(tmp_path):
     import psutil
     left = [p for p in psutil.process_iter(["cmdline"]) if str(script) in " ".join(p.info["cmdline"] or [])]
     assert not left, [p.pid for p in left]
+
+
+def test_scheduler_survives_garbage_connections(tmp_path):
+    """Fuzz the scheduler's port (random bytes, a frame header announcing 2^40 bytes, connect-and-close, truncated frames)
+    before the job's nodes arrive: it must drop those connections and still run the job."""
+    import random
+    import signal
+    import socket
+    import struct
+    import subprocess
+    import time
+    port = 9300 + os.getpid() % 200
+    env = dict(os.environ, PYTHONPATH=ROOT, DMLC_PS_ROOT_URI="127.0.0.1", DMLC_PS_ROOT_PORT=str(port), DMLC_NUM_WORKER="1",
+               DMLC_NUM_SERVER="1")
+    procs = []
+
+    def spawn(role, cmd):
+        p = subprocess.Popen(cmd, env=dict(env, DMLC_ROLE=role), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                             start_new_session=True)
+        procs.append(p)
+        return p
+    try:
+        sched = spawn("scheduler", [sys.executable, "-c", "import deeplearning_cfn_b200.kv"])
+        for _ in range(150):
+            try:
+                socket.create_connection(("127.0.0.1", port), timeout=1).close()
+                break
+            except OSError:
+                time.sleep(0.2)
+        rng = random.Random(0)
+        for i in range(40):
+            s = socket.create_connection(("127.0.0.1", port), timeout=2)
+            data = [rng.randbytes(rng.randint(1, 200)), struct.pack("<IQ", 0xDEADBEEF, 1 << 40) + rng.randbytes(50), b"",
+                    rng.randbytes(12) + rng.randbytes(rng.randint(0, 5000))][i % 4]
+            s.sendall(data)
+            s.close()
+        time.sleep(0.3)
+        assert sched.poll() is None, sched.communicate()[0][-2000:]
+        server = spawn("server", [sys.executable, "-c", "import deeplearning_cfn_b200.kv"])
+        worker = spawn("worker", [sys.executable, os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_sync"])
+        out, _ = worker.communicate(timeout=120)
+        assert worker.returncode == 0 and "SYNC_OK" in out, out[-2000:]
+        assert server.wait(timeout=60) == 0 and sched.wait(timeout=60) == 0
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                os.killpg(p.pid, signal.SIGKILL)

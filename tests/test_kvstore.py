@@ -543,8 +543,11 @@ def test_scheduler_survives_garbage_connections(tmp_path):
         rng = random.Random(0)
         for i in range(40):
             s = socket.create_connection(("127.0.0.1", port), timeout=2)
+            body = rng.randbytes(rng.randint(0, 300))
             data = [rng.randbytes(rng.randint(1, 200)), struct.pack("<IQ", 0xDEADBEEF, 1 << 40) + rng.randbytes(50), b"",
-                    rng.randbytes(12) + rng.randbytes(rng.randint(0, 5000))][i % 4]
+                    rng.randbytes(12) + rng.randbytes(rng.randint(0, 5000)),
+                    struct.pack("<IQ", 0xD1CF2026, len(body)) + body,                     # well-framed, undecodable message
+                    struct.pack("<IQ", 0xD1CF2026, 1000) + body[:10]][i % 6]              # frame cut short
             s.sendall(data)
             s.close()
         time.sleep(0.3)

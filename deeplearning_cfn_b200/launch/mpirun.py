@@ -68,6 +68,12 @@ def rank_map(hosts: list[Host], n: int) -> list[tuple[Host, int, int]]:
 
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv or argv[0] in ("-h", "--help"):
+        print("usage: mpirun [-np N] [--hostfile FILE (host slots=G per line)] [-x NAME[=VALUE]]... [--output-filename DIR]\n"
+              "              [-bind-to X] [-map-by X] [-mca K V] [--allow-run-as-root] command [args...]\n"
+              "starts N ranks (local or over the node transport) with RANK / LOCAL_RANK / WORLD_SIZE / LOCAL_WORLD_SIZE /\n"
+              "MASTER_ADDR / MASTER_PORT and OMPI_COMM_WORLD_* set; the first rank that fails terminates the job")
+        return 0 if argv else 2
     n, hostfile, outdir, exports, cmd = parse(argv)
     if not cmd:
         raise SystemExit("mpirun: no command")

@@ -1,5 +1,6 @@
 // Node = Postoffice + Van + Resender of the dlcfn parameter-server transport (see ps.h).
 #include "ps.h"
+#include <new>
 
 #include <arpa/inet.h>
 #include <netdb.h>
@@ -53,6 +54,10 @@ struct Reader {
 
 std::string Pack(const Message& m) {
   Writer w;
+  size_t total = 128 + m.body.size();                 // one allocation: a gradient blob must not be re-copied as the buffer grows
+  for (const auto& n : m.nodes) total += 32 + n.host.size();
+  for (const auto& d : m.data) total += 8 + d.size();
+  w.buf.reserve(total);
   w.i32(m.sender); w.i32(m.recver); w.i32(m.control); w.i32(m.barrier_group); w.i32(m.app_id);
   w.i32(m.customer_id); w.i32(m.timestamp);
   w.i32((m.request ? 1 : 0) | (m.push ? 2 : 0) | (m.simple_app ? 4 : 0));
@@ -64,8 +69,8 @@ std::string Pack(const Message& m) {
   return std::move(w.buf);
 }
 
-bool Unpack(const std::string& s, Message* m) {
-  Reader r{s.data(), s.data() + s.size()};
+bool Unpack(const char* begin, size_t size, Message* m) {
+  Reader r{begin, begin + size};
   m->sender = r.i32(); m->recver = r.i32(); m->control = r.i32(); m->barrier_group = r.i32(); m->app_id = r.i32();
   m->customer_id = r.i32(); m->timestamp = r.i32();
   int flags = r.i32();
@@ -251,16 +256,18 @@ int Node::FdFor(int id) {
 }
 
 bool Node::SendRaw(int fd, const Message& m) {
-  std::string payload = Pack(m);
-  uint32_t hdr[2] = {kFrameMagic, 0};
-  uint64_t n = payload.size();
-  std::string frame;
-  frame.reserve(16 + payload.size());
-  frame.append(reinterpret_cast<const char*>(hdr), 4);
-  frame.append(reinterpret_cast<const char*>(&n), 8);
-  frame.append(payload);
-  if (!SendAll(fd, frame.data(), frame.size())) return false;
-  bytes_sent_ += (long long)frame.size();
+  const std::string payload = Pack(m);
+  char hdr[12];
+  const uint32_t magic = kFrameMagic;
+  const uint64_t n = payload.size();
+  memcpy(hdr, &magic, 4);
+  memcpy(hdr + 4, &n, 8);
+  // header and payload go out as two writes under the peer's send mutex (MSG_MORE keeps them in one segment train)
+  // instead of being copied into a third buffer first
+  ssize_t k = ::send(fd, hdr, 12, MSG_NOSIGNAL | MSG_MORE);
+  if (k != 12) return false;
+  if (!SendAll(fd, payload.data(), payload.size())) return false;
+  bytes_sent_ += (long long)payload.size() + 12;
   return true;
 }
 
@@ -317,11 +324,12 @@ void Node::ReadLoop(int fd) {
     uint32_t magic; uint64_t n;
     memcpy(&magic, hdr, 4); memcpy(&n, hdr + 4, 8);
     if (magic != kFrameMagic || n > (1ull << 34)) break;
-    std::string payload(n, '\0');
-    if (!RecvAll(fd, &payload[0], n)) break;
+    std::unique_ptr<char[]> payload(new (std::nothrow) char[n ? n : 1]);     // not zero-filled: recv overwrites all of it
+    if (!payload) break;
+    if (!RecvAll(fd, payload.get(), n)) break;
     bytes_recv_ += (long long)n + 12;
     Message m;
-    if (!Unpack(payload, &m)) continue;
+    if (!Unpack(payload.get(), n, &m)) continue;
     if (role_ == kScheduler && m.sender > 0) {
       std::lock_guard<std::mutex> lk(mu_);
       last_seen_[m.sender] = NowMs() / 1000;

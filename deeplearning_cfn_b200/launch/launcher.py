@@ -59,7 +59,10 @@ def main(argv=None) -> int:
         raise SystemExit("no command given")
     args.env_server = _kv_list(args.env_server)
     args.env_worker = _kv_list(args.env_worker)
-    cmd = " ".join(args.command)
+    # one word = a shell command line as in the reference's README (`launch.py -n 2 "python train.py --lr 0.1"`); several
+    # words = an argv, quoted so that empty arguments (`--gpus ""`) and arguments with spaces survive the shell
+    import shlex
+    cmd = args.command[0] if len(args.command) == 1 else shlex.join(args.command)
     kind = args.launcher
     if kind == "ssh" and args.hostfile is None:
         kind = "local"   # reference behaviour: no hostfile -> run everything here (launch.py:98-118)

@@ -137,7 +137,9 @@ int KVWorker::Push(int key, const void* data, size_t n, int dtype, int req_type,
       uint64_t meta[1] = {p.len};
       m.data.emplace_back(reinterpret_cast<const char*>(meta), 8);
     } else {
-      m.data.emplace_back(reinterpret_cast<const char*>(data) + p.offset * es, p.len * es);
+      // dense values leave straight from the caller's buffer (borrowed blob): no copy into the message, none into the frame
+      m.blob = reinterpret_cast<const char*>(data) + p.offset * es;
+      m.blob_len = p.len * es;
     }
     node_->Send(m);
   }
@@ -282,7 +284,7 @@ void KVServer::Respond(const Message& req, const std::string* payload) {
   r.recver = req.sender;
   r.request = false; r.push = req.push; r.simple_app = req.simple_app;
   r.timestamp = req.timestamp; r.head = req.head;
-  if (payload) r.data.push_back(*payload);
+  if (payload) { r.blob = payload->data(); r.blob_len = payload->size(); }   // borrowed: Send is synchronous
   node_->Send(r);
 }
 

@@ -63,6 +63,11 @@ struct Message {
   std::string body;
   std::vector<NodeInfo> nodes;            // control payload
   std::vector<std::string> data;          // blobs: keys / vals / lens
+  // Optional LAST data element that is only borrowed: sent from the caller's memory after `data` (the receiver sees one
+  // more element).  Valid until Send() returns; Send() copies it into `data` first when the message must be kept for
+  // retransmission.
+  const char* blob = nullptr;
+  size_t blob_len = 0;
 };
 
 class Node {

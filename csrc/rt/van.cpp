@@ -57,15 +57,16 @@ std::string Pack(const Message& m) {
   size_t total = 128 + m.body.size();                 // one allocation: a gradient blob must not be re-copied as the buffer grows
   for (const auto& n : m.nodes) total += 32 + n.host.size();
   for (const auto& d : m.data) total += 8 + d.size();
-  w.buf.reserve(total);
+  w.buf.reserve(total);      // (a borrowed blob is not copied in: only its length is written, SendRaw sends the bytes)
   w.i32(m.sender); w.i32(m.recver); w.i32(m.control); w.i32(m.barrier_group); w.i32(m.app_id);
   w.i32(m.customer_id); w.i32(m.timestamp);
   w.i32((m.request ? 1 : 0) | (m.push ? 2 : 0) | (m.simple_app ? 4 : 0));
   w.i32(m.head); w.u64(m.sig); w.str(m.body);
   w.i32((int)m.nodes.size());
   for (const auto& n : m.nodes) { w.i32(n.role); w.i32(n.id); w.i32(n.port); w.i32(n.is_recovery ? 1 : 0); w.str(n.host); }
-  w.i32((int)m.data.size());
+  w.i32((int)m.data.size() + (m.blob ? 1 : 0));
   for (const auto& d : m.data) w.str(d);
+  if (m.blob) w.u64(m.blob_len);
   return std::move(w.buf);
 }
 
@@ -259,7 +260,7 @@ bool Node::SendRaw(int fd, const Message& m) {
   const std::string payload = Pack(m);
   char hdr[12];
   const uint32_t magic = kFrameMagic;
-  const uint64_t n = payload.size();
+  const uint64_t n = payload.size() + (m.blob ? m.blob_len : 0);
   memcpy(hdr, &magic, 4);
   memcpy(hdr + 4, &n, 8);
   // header and payload go out as two writes under the peer's send mutex (MSG_MORE keeps them in one segment train)
@@ -267,12 +268,18 @@ bool Node::SendRaw(int fd, const Message& m) {
   ssize_t k = ::send(fd, hdr, 12, MSG_NOSIGNAL | MSG_MORE);
   if (k != 12) return false;
   if (!SendAll(fd, payload.data(), payload.size())) return false;
-  bytes_sent_ += (long long)payload.size() + 12;
+  if (m.blob && m.blob_len && !SendAll(fd, m.blob, m.blob_len)) return false;
+  bytes_sent_ += (long long)n + 12;
   return true;
 }
 
 int Node::Send(Message& msg) {
   msg.sender = my_.id;
+  if (resend_ && msg.blob) {            // the resender keeps messages for retransmission: own the bytes
+    msg.data.emplace_back(msg.blob, msg.blob_len);
+    msg.blob = nullptr;
+    msg.blob_len = 0;
+  }
   if (resend_ && msg.control == kNone && msg.sig == 0) {
     msg.sig = ((uint64_t)(uint32_t)my_.id << 40) | sig_counter_++;
     std::lock_guard<std::mutex> lk(rs_mu_);

@@ -55,6 +55,17 @@ void ToFloat(const void* src, int dtype, size_t n, float* dst) {
   if (dtype == kBF16) for (size_t i = 0; i < n; ++i) dst[i] = Bf16ToF(p[i]);
   else for (size_t i = 0; i < n; ++i) dst[i] = F16ToF(p[i]);
 }
+// dst[i] += src[i] with the conversion fused in (no temporary)
+void AccumulateFloat(const void* src, int dtype, size_t n, float* dst) {
+  if (dtype == kF32) {
+    const char* p = (const char*)src;
+    for (size_t i = 0; i < n; ++i) { float v; memcpy(&v, p + 4 * i, 4); dst[i] += v; }
+    return;
+  }
+  const uint16_t* p = (const uint16_t*)src;
+  if (dtype == kBF16) for (size_t i = 0; i < n; ++i) dst[i] += Bf16ToF(p[i]);
+  else for (size_t i = 0; i < n; ++i) dst[i] += F16ToF(p[i]);
+}
 void FromFloat(const float* src, int dtype, size_t n, void* dst) {
   if (dtype == kF32) { memcpy(dst, src, n * 4); return; }
   uint16_t* p = (uint16_t*)dst;
@@ -553,11 +564,17 @@ void KVServer::HandleData(Message&& m) {
 
   const bool first = e.waiting.empty() || !sync_mode_;
   if (e.merged.size() != e.store.size()) e.merged.assign(e.store.size(), 0.f);
-  if (first) std::fill(e.merged.begin(), e.merged.end(), 0.f);
+  if (first && req_type != kDefaultPushPull) std::fill(e.merged.begin(), e.merged.end(), 0.f);
   if (req_type == kDefaultPushPull) {
-    std::vector<float> tmp(n);
-    ToFloat(m.data[1].data(), dtype, n, tmp.data());
-    for (size_t i = 0; i < n && i < e.merged.size(); ++i) e.merged[i] += tmp[i];
+    // the first pusher's values are converted straight into the merge buffer, later ones are added with the conversion
+    // fused in: one pass over the data instead of fill + temporary + convert + add
+    const size_t cnt = std::min(n, e.merged.size());
+    if (first) {
+      ToFloat(m.data[1].data(), dtype, cnt, e.merged.data());
+      if (cnt < e.merged.size()) std::fill(e.merged.begin() + cnt, e.merged.end(), 0.f);
+    } else {
+      AccumulateFloat(m.data[1].data(), dtype, cnt, e.merged.data());
+    }
   } else if (req_type == kCompressedPushPull) {
     // 2-bit codes, 16 per 32-bit word: 11 -> +thr, 10 -> -thr (gradient_compression-inl.h:96-140)
     const uint32_t* words = reinterpret_cast<const uint32_t*>(m.data[1].data());

@@ -109,7 +109,16 @@ def main(argv=None) -> int:
         for k, (_, d) in EXAMPLES.items():
             print(f"{k:24s} {d}")
         return 0
-    return run_example(a.name, a.stack_name, a.home, a.gpus, extra, a.dry_run)
+    from ..cluster.stack import StackError
+    try:
+        return run_example(a.name, a.stack_name, a.home, a.gpus, extra, a.dry_run)
+    except StackError as e:
+        print(f"error: {e} (create it with `python -m deeplearning_cfn_b200 create-stack --stack-name {a.stack_name or 'NAME'} ...`)",
+              file=sys.stderr)
+        return 1
+    except KeyError as e:
+        print(f"error: unknown example {e}; `run-example --list` shows the bundled ones", file=sys.stderr)
+        return 1
 
 
 if __name__ == "__main__":

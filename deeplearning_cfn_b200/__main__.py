@@ -93,7 +93,11 @@ def main(argv=None) -> int:
     if argv and argv[0] in passthrough:
         import importlib
         mod = importlib.import_module("." + passthrough[argv[0]], __package__)
-        return int(mod.main(argv[1:]) or 0)
+        try:
+            return int(mod.main(argv[1:]) or 0)
+        except FileNotFoundError as e:          # a missing hostfile / log / list file is a usage error, not a crash
+            print(f"{argv[0]}: error: {e.strerror}: {e.filename}", file=sys.stderr)
+            return 1
 
     ap = argparse.ArgumentParser(prog="dlcfn")
     sub = ap.add_subparsers(dest="cmd", required=True)

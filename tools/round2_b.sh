@@ -8,6 +8,7 @@ run() { local name=$1 t=$2; shift 2; echo "== $name"; timeout "$t" "$@" 2> "gpur
 export PYTHONUNBUFFERED=1
 run bench_1gpu_b 400 python bench.py
 if has conv; then
+  echo "== per-layer 3x3 probe"; timeout 300 python tools/conv3x3_probe.py 2>&1 | tail -9 | tee gpurun_out/r2_conv3x3_probe.log
   DLCFN_CONVKXK=tcgen05 run bench_convkxk 400 python bench.py --no-e2e
   DLCFN_CONVKXK=tcgen05 DLCFN_CONV1X1=tcgen05 run bench_allconv_tcgen05 400 python bench.py --no-e2e
 fi

@@ -177,6 +177,7 @@ class ImageRecordIter:
 
     def reset(self) -> None:
         self.close()                                        # an unfinished epoch's workers stop first
+        self._done = False
         order = list(self.keys)
         if self.shuffle:
             rng = np.random.default_rng(self.seed + self.epoch)
@@ -249,13 +250,19 @@ class ImageRecordIter:
         self._workers = []
 
     def __iter__(self):
+        if getattr(self, "_done", False):        # a finished epoch: iterating again starts the next one (like the native reader)
+            self.reset()
         return self
 
     def __next__(self):
+        if getattr(self, "_done", False):
+            raise StopIteration
         item = self._q.get()
         if item is None:
+            self._done = True
             raise StopIteration
         if isinstance(item, Exception):
+            self._done = True
             raise item
         return item
 

@@ -470,7 +470,12 @@ def test_encoded_image_records_jpeg_png(tmp_path):
     _, full = recordio.unpack_img(recordio.MXIndexedRecordIO(prefix + ".idx", prefix + ".rec", "r").read_idx(it2.keys[0]))
     x, _ = next(iter(it2))
     assert np.array_equal(x[0].numpy(), full[4:20, 8:24])
-    it.close(), it2.close()
+    # a finished epoch: iterating again starts the next epoch instead of blocking on an empty queue
+    it3 = recordio.ImageRecordIter(prefix + ".rec", 2, (3, 16, 16), shuffle=True, seed=3)
+    e1 = [y.tolist() for _, y in it3]
+    e2 = [y.tolist() for _, y in it3]
+    assert len(e1) == len(e2) == 3 and sorted(sum(e1, [])) == sorted(sum(e2, [])) and len(it3) == 3
+    it.close(), it2.close(), it3.close()
     # raw files still take the native ring
     assert im2rec.main([prefix, str(root)]) == 0
     nat = recordio.image_record_iter(prefix + ".rec", 2, (3, 24, 32))

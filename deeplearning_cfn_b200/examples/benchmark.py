@@ -42,10 +42,12 @@ def gpu_steps(max_gpus: int) -> list[int]:
     return out
 
 
-def command(net: str, layers: int, batch: int, size: int, kv: str, n: int, num_batches: int) -> list[str]:
+def command(net: str, layers: int, batch: int, size: int, kv: str, n: int, num_batches: int, cpu: bool = False) -> list[str]:
     train = [sys.executable, "-m", "deeplearning_cfn_b200.examples.train_imagenet", "--benchmark", "1", "--network", net,
              "--num-layers", str(layers), "--batch-size", str(batch), "--image-shape", f"3,{size},{size}", "--kv-store", kv,
-             "--num-epochs", "1", "--num-batches", str(num_batches), "--disp-batches", "5"]
+             "--num-epochs", "1", "--num-batches", str(num_batches), "--disp-batches", str(max(1, min(5, num_batches // 2)))]
+    if cpu:
+        train += ["--gpus", ""]
     if n == 1:
         return train
     return [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", str(n)] + train
@@ -82,7 +84,8 @@ def svg_chart(series: dict, xs: list[int], path: str, title: str) -> None:
 def main(argv=None) -> int:
     a = parse(argv)
     os.makedirs(a.out_dir, exist_ok=True)
-    xs = gpu_steps(a.gpu_count * max(1, a.worker_count))
+    cpu = a.gpu_count <= 0            # a box without GPUs: sweep the number of CPU ranks per worker instead
+    xs = gpu_steps(max(1, a.gpu_count) * max(1, a.worker_count))
     for spec in a.networks:
         _, net, batch, size = spec.split(":")
         layers = 50
@@ -93,12 +96,15 @@ def main(argv=None) -> int:
         for kv in a.kv_stores:
             speeds = []
             for n in xs:
-                cmd = command(net, layers, int(batch), int(size), kv if n > 1 else "device", n, a.num_batches)
+                cmd = command(net, layers, int(batch), int(size), kv if n > 1 else "device", n, a.num_batches, cpu)
                 if a.dry_run:
                     print(" ".join(cmd))
                     speeds.append(0.0)
                     continue
                 r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    print(f"{net}-{layers} kv={kv} ranks={n}: run failed (exit {r.returncode})\n" + (r.stdout + r.stderr)[-800:],
+                          file=sys.stderr, flush=True)
                 per_rank = scrape(r.stdout + r.stderr)
                 total = per_rank * n
                 speeds.append(total)

@@ -264,3 +264,16 @@ def test_image_classification_resume_accepts_periodic_and_best_checkpoints(tmp_p
         assert r.returncode == 0, f + (r.stdout + r.stderr)[-2000:]
     res = load_params_file(str(tmp_path / "m-0001.params"), get_model("resnet18_v1", 1000, 224), strict=False)
     assert not res.unexpected_keys and get_model is not None
+
+
+def test_scaling_sweep_tool_runs_on_a_box_without_gpus(tmp_path):
+    """benchmark.py (`--networks mode:net:batch:size --worker_count --gpu_count`): with --gpu_count 0 the sweep is over CPU
+    ranks; it writes <net>.csv and the speed-up chart like the reference tool."""
+    from conftest import run_job
+    r = run_job([sys.executable, "-m", "deeplearning_cfn_b200", "benchmark", "--networks", "native:resnet-20:4:32", "--gpu_count", "0",
+                 "--worker_count", "2", "--kv-stores", "local", "--num-batches", "4", "--out-dir", str(tmp_path)],
+                env=dict(os.environ, PYTHONPATH=ROOT), timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    rows = open(tmp_path / "resnet.csv").read().strip().splitlines()
+    assert rows[0] == "network,layers,kv_store,gpus,images_per_sec" and len(rows) == 3
+    assert all(float(l.split(",")[-1]) > 0 for l in rows[1:]) and (tmp_path / "resnet_speedup.svg").exists()

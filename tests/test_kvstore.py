@@ -561,3 +561,47 @@ def test_scheduler_survives_garbage_connections(tmp_path):
         for p in procs:
             if p.poll() is None:
                 os.killpg(p.pid, signal.SIGKILL)
+
+
+def test_dead_server_is_reported_through_heartbeats(tmp_path):
+    """Failure detection (reference: PS_HEARTBEAT_INTERVAL / PS_HEARTBEAT_TIMEOUT, `kv.get_num_dead_node`): SIGKILL one of two
+    servers after the rendezvous; a worker asking the scheduler sees exactly one dead node in the server group."""
+    import signal
+    import subprocess
+    import time
+    port = 9500 + os.getpid() % 150
+    env = dict(os.environ, PYTHONPATH=ROOT, DMLC_PS_ROOT_URI="127.0.0.1", DMLC_PS_ROOT_PORT=str(port), DMLC_NUM_WORKER="1",
+               DMLC_NUM_SERVER="2", PS_HEARTBEAT_INTERVAL="1", PS_HEARTBEAT_TIMEOUT="3")
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, time, torch\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "import deeplearning_cfn_b200.kv as kv\n"
+        "s = kv.create('dist_async')\n"
+        "s.init(1, torch.zeros(4))\n"
+        "assert s.get_num_dead_node(2, 3) == 0\n"
+        "print('WORKER_READY', flush=True)\n"
+        "t0, seen = time.time(), 0\n"
+        "while time.time() - t0 < 40 and not seen:\n"
+        "    seen = s.get_num_dead_node(2, 3)\n"
+        "    time.sleep(0.5)\n"
+        "print('DEAD_SERVERS', seen, flush=True)\n"
+        "os._exit(0)\n")                      # no closing barrier: one server is gone
+
+    def spawn(role, cmd):
+        return subprocess.Popen(cmd, env=dict(env, DMLC_ROLE=role), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                start_new_session=True)
+    procs = [spawn("scheduler", [sys.executable, "-c", "import deeplearning_cfn_b200.kv"])]
+    procs += [spawn("server", [sys.executable, "-c", "import deeplearning_cfn_b200.kv"]) for _ in range(2)]
+    worker = spawn("worker", [sys.executable, str(script)])
+    procs.append(worker)
+    try:
+        line = worker.stdout.readline()
+        assert "WORKER_READY" in line, line + worker.stdout.read()[-2000:]
+        os.killpg(procs[2].pid, signal.SIGKILL)
+        out, _ = worker.communicate(timeout=90)
+        assert "DEAD_SERVERS 1" in out, out[-2000:]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                os.killpg(p.pid, signal.SIGKILL)

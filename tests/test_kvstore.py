@@ -605,3 +605,48 @@ def test_dead_server_is_reported_through_heartbeats(tmp_path):
         for p in procs:
             if p.poll() is None:
                 os.killpg(p.pid, signal.SIGKILL)
+
+
+def test_job_ends_when_a_server_is_killed(tmp_path):
+    """SIGKILL one server of a running dist_sync job: the launcher notices the exit code, kills the remaining process trees and
+    returns non-zero within seconds; nothing of the job is left behind."""
+    import signal
+    import subprocess
+    import time
+    import psutil
+    script = tmp_path / "loop.py"
+    script.write_text(
+        "import sys, time, torch\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "import deeplearning_cfn_b200.kv as kv\n"
+        "s = kv.create('dist_sync')\n"
+        "s.init(1, torch.zeros(4))\n"
+        "print('WORKER_READY', flush=True)\n"
+        "for _ in range(400):\n"
+        "    s.push(1, torch.ones(4)); out = torch.zeros(4); s.pull(1, out=out); time.sleep(0.2)\n")
+    p = subprocess.Popen([sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "2", "--launcher", "local",
+                          sys.executable, str(script)], env=dict(os.environ, PYTHONPATH=ROOT), stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        servers, deadline = [], time.time() + 60
+        while time.time() < deadline and len(servers) < 2:
+            time.sleep(1.0)
+            servers = []
+            for c in psutil.Process(p.pid).children(recursive=True):
+                try:
+                    if c.environ().get("DMLC_ROLE") == "server" and "python" in c.name():
+                        servers.append(c)
+                except (psutil.Error, OSError):
+                    pass
+        assert len(servers) == 2
+        time.sleep(3.0)                              # let the job get going
+        servers[0].kill()
+        out, _ = p.communicate(timeout=60)
+        assert p.returncode != 0 and "stopping the job" in out, out[-2000:]
+        time.sleep(1.0)
+        left = [c.pid for c in psutil.process_iter(["cmdline", "status"])
+                if str(script) in " ".join(c.info["cmdline"] or []) and c.info["status"] != psutil.STATUS_ZOMBIE]
+        assert not left, left
+    finally:
+        if p.poll() is None:
+            os.killpg(p.pid, signal.SIGKILL)

@@ -650,3 +650,27 @@ def test_job_ends_when_a_server_is_killed(tmp_path):
     finally:
         if p.poll() is None:
             os.killpg(p.pid, signal.SIGKILL)
+
+
+def test_module_fit_with_dist_sync_store_under_the_launcher(tmp_path):
+    """The symbolic recipe (`Module.fit(kvstore='dist_sync')`, update on the servers, push / pull with priority -index) as a
+    2-worker job: different data per rank, identical weights afterwards, the job ends without an explicit close()."""
+    script = tmp_path / "fit.py"
+    script.write_text(
+        "import sys, torch\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "import deeplearning_cfn_b200.kv as kv\n"
+        "from deeplearning_cfn_b200.kv.module import Module\n"
+        "torch.manual_seed(0)\n"
+        "net = torch.nn.Sequential(torch.nn.Linear(6, 12), torch.nn.ReLU(), torch.nn.Linear(12, 3))\n"
+        "store = kv.create('dist_sync')\n"
+        "g = torch.Generator().manual_seed(1 + store.rank)\n"
+        "batches = [(torch.randn(8, 6, generator=g), torch.randint(0, 3, (8,), generator=g)) for _ in range(5)]\n"
+        "m = Module(net, context='cpu')\n"
+        "m.fit(batches, num_epoch=2, kvstore=store, optimizer='sgd', optimizer_params=(('learning_rate', 0.1), ('momentum', 0.9)),\n"
+        "      batch_size=8)\n"
+        "w = torch.cat([p.detach().reshape(-1) for p in net.parameters()])\n"
+        "print(f'MODULE_DIST_OK {float(w.sum()):.6f} {float(w.abs().sum()):.6f}', flush=True)\n")
+    r = _launch(2, 1, [str(script)], timeout=240)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("MODULE_DIST_OK")]
+    assert r.returncode == 0 and len(lines) == 2 and lines[0] == lines[1], r.stdout[-2000:] + r.stderr[-2000:]

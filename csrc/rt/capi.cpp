@@ -70,6 +70,7 @@ RT_API void dlcfn_kv_wait(int ts) { if (g_worker) g_worker->Wait(ts); }
 RT_API void dlcfn_kv_send_command(int head, const char* body, size_t len) {
   if (g_worker) g_worker->SendCommand(head, std::string(body ? body : "", len));
 }
+RT_API void dlcfn_kv_set_key_unit(int key, size_t unit) { if (g_worker) g_worker->SetKeyUnit(key, unit); }
 RT_API void dlcfn_kv_set_bigarray_bound(size_t n) { if (g_worker) g_worker->bigarray_bound = n; }
 // partition introspection: fills up to `cap` entries of (server, offset, len); returns the count
 RT_API int dlcfn_kv_partition(int key, size_t num_elems, int* servers, size_t* offsets, size_t* lens, int cap) {

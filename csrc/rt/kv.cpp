@@ -79,6 +79,11 @@ KVWorker::KVWorker(Node* node) : node_(node) {
   if (b) bigarray_bound = (size_t)atoll(b);
 }
 
+void KVWorker::SetKeyUnit(int key, size_t unit) {
+  std::lock_guard<std::mutex> lk(unit_mu_);
+  key_unit_[key] = unit;
+}
+
 std::vector<KVWorker::Part> KVWorker::Partition(int key, size_t n) const {
   const int S = node_->num_servers();
   std::vector<Part> parts;
@@ -88,14 +93,23 @@ std::vector<KVWorker::Part> KVWorker::Partition(int key, size_t n) const {
     auto range = node_->ServerKeyRange(server);
     parts.push_back(Part{server, range.first + (uint64_t)key, 0, n});
   } else {
-    // big array: contiguous even split over all servers (kvstore_dist.h:557-570)
+    // big array: contiguous even split over all servers (kvstore_dist.h:557-570), boundaries rounded to the key's unit
+    size_t unit = 16;
+    {
+      std::lock_guard<std::mutex> lk(unit_mu_);
+      auto it = key_unit_.find(key);
+      if (it != key_unit_.end() && it->second > 0) unit = it->second;
+    }
     size_t off = 0;
     for (int s = 0; s < S; ++s) {
-      size_t len = (size_t)std::llround((double)n / S * (s + 1)) - (size_t)std::llround((double)n / S * s);
-      if (s == S - 1) len = n - off;
+      size_t end = (size_t)std::llround((double)n / S * (s + 1));
+      end = (end + unit / 2) / unit * unit;
+      if (s == S - 1 || end > n) end = n;
+      if (end < off) end = off;
+      const size_t len = end - off;
       auto range = node_->ServerKeyRange(s);
-      parts.push_back(Part{s, range.first + (uint64_t)key, off, len});
-      off += len;
+      if (len > 0) parts.push_back(Part{s, range.first + (uint64_t)key, off, len});
+      off = end;
     }
   }
   return parts;
@@ -141,8 +155,7 @@ int KVWorker::Push(int key, const void* data, size_t n, int dtype, int req_type,
       m.data.push_back(std::move(ids));
       m.data.emplace_back(reinterpret_cast<const char*>(meta), 16);
     } else if (req_type == kCompressedPushPull) {
-      // word-aligned slice of the packed buffer (parts of big arrays start at multiples of 16 by construction
-      // when n % (16*S) == 0; otherwise the caller keeps the key small)
+      // word-aligned slice of the packed buffer: Partition() keeps every boundary on a multiple of 16 elements
       size_t w0 = p.offset / 16, w1 = (p.offset + p.len + 15) / 16;
       m.data.emplace_back(reinterpret_cast<const char*>(data) + w0 * 4, (w1 - w0) * 4);
       uint64_t meta[1] = {p.len};

@@ -167,6 +167,11 @@ class KVWorker {
   // sharding rule of KVStoreDist::EncodeDefaultKey (kvstore_dist.h:532-574)
   struct Part { int server; uint64_t ps_key; size_t offset, len; };
   std::vector<Part> Partition(int key, size_t num_elems) const;
+  // Split boundaries of a big array are multiples of the key's unit: 16 elements (one packed word of the 2-bit wire
+  // format) and, for keys with more than one dimension, whole rows (row-sparse push / pull address rows by local id) -
+  // every request type of a key therefore sees the same shards (upstream splits row-sparse keys on shape[0],
+  // kvstore_dist.h:571-600).  Set once per key before its first push.
+  void SetKeyUnit(int key, size_t unit);
   int Push(int key, const void* data, size_t num_elems, int dtype, int req_type = kDefaultPushPull,
            const int64_t* row_ids = nullptr, size_t num_rows = 0, size_t row_len = 0);
   int Pull(int key, void* out, size_t num_elems, int dtype, int req_type = kDefaultPushPull,
@@ -175,6 +180,8 @@ class KVWorker {
   void SendCommand(int head, const std::string& body);  // to every server, waits for the replies
   void OnMessage(Message&& m);
   size_t bigarray_bound = 1000000;
+  std::unordered_map<int, size_t> key_unit_;
+  mutable std::mutex unit_mu_;
 
  private:
   struct Track { int expected = 0, received = 0; void* out = nullptr; int dtype = 0;

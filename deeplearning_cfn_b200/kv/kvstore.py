@@ -22,6 +22,7 @@ Back-ends
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 import sys
 import pickle
@@ -489,6 +490,10 @@ class KVStoreDist(KVStoreLocal):
             if t.dtype not in _DT:
                 raise KVStoreError(f"unsupported dtype {t.dtype}")
             self._shapes[ik] = (tuple(t.shape), t.dtype)
+            # shard boundaries of a big key: whole 16-element words of the 2-bit wire format and, for >1-D keys, whole rows
+            # (row-sparse requests address rows by shard-local id) - same split for every request type of the key
+            row_len = int(torch.tensor(t.shape[1:]).prod()) if t.dim() > 1 else 1
+            self._L.dlcfn_kv_set_key_unit(ik, math.lcm(16, max(row_len, 1)))
             if self.rank == 0:   # only rank 0's value initialises the servers (kvstore_dist.h:196-208)
                 h = self._host(ik, t)
                 h.copy_(t.reshape(-1))
@@ -511,6 +516,8 @@ class KVStoreDist(KVStoreLocal):
                 self._compression = None          # compress AFTER the local reduce, once (kvstore_dist.h:378-410)
             merged = self._reduce(ik, v)          # local multi-device reduce first (comm_->Reduce)
             self._compression = comp
+            if merged.dtype != dtype:             # the wire carries the key's init dtype (a bf16 gradient of an fp32 key
+                merged = merged.to(dtype)         # would otherwise be reinterpreted byte-wise by the native push)
             h = self._host(ik, merged)
             n = merged.numel()
 
@@ -525,6 +532,9 @@ class KVStoreDist(KVStoreLocal):
                     ts = self._L.dlcfn_kv_push_2bit(ik, words.data_ptr(), n)
                     self._L.dlcfn_kv_wait(ts)
             else:
+                # the staging buffer is borrowed by a queued push of the same key until that push has been sent: wait for it
+                # before overwriting (the reference copies into comm_buf inside the engine op, kvstore_dist.h:335-342)
+                self._engine.wait_for_var(self._var(ik))
                 h.copy_(merged.reshape(-1))
 
                 def do_push(ik=ik, h=h, dtype=dtype):

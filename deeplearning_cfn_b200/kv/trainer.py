@@ -81,6 +81,23 @@ class Trainer:
             for i, p in enumerate(self._params):       # first pull: every worker starts from rank 0's values
                 kvs.pull(i, out=p.data, priority=-i)
         self._kv_initialized = True
+        self._shipped = self._optimizer_signature()
+
+    def _optimizer_signature(self):
+        o = self._optimizer
+        return (float(o.rescale_grad), float(o.learning_rate), float(getattr(o, "wd", 0.0)))
+
+    def _sync_optimizer_to_kvstore(self) -> None:
+        """With update_on_kvstore the optimizer lives on the servers: a change of rescale_grad (batch size), learning rate
+        or weight decay made on the worker's copy is re-sent (upstream raises in _check_and_rescale_grad; the native
+        servers keep their per-key states across a config update, so re-sending is safe).  Every worker calls step() /
+        set_learning_rate() with the same values, which keeps the set_optimizer barrier symmetric."""
+        if not (self._update_on_kvstore and self._kvstore is not None):
+            return
+        sig = self._optimizer_signature()
+        if sig != self._shipped:
+            self._kvstore.set_optimizer(self._optimizer)
+            self._shipped = sig
 
     @property
     def learning_rate(self) -> float:
@@ -91,9 +108,11 @@ class Trainer:
 
     # ------------------------------------------------------------------ step
     def step(self, batch_size: int, ignore_stale_grad: bool = False) -> None:
+        # rescale_grad BEFORE the store is initialised: _init_kvstore ships the optimizer to the servers (trainer.py:192-197)
+        self._optimizer.rescale_grad = self._scale / batch_size
         if not self._kv_initialized:
             self._init_kvstore()
-        self._optimizer.rescale_grad = self._scale / batch_size
+        self._sync_optimizer_to_kvstore()
         self._allreduce_grads()
         self._update(ignore_stale_grad)
 

@@ -70,6 +70,7 @@ def _declare(L) -> None:
     L.dlcfn_kv_wait.argtypes = [c_int]
     L.dlcfn_kv_send_command.argtypes = [c_int, c_char_p, c_size_t]
     L.dlcfn_kv_set_bigarray_bound.argtypes = [c_size_t]
+    L.dlcfn_kv_set_key_unit.argtypes = [c_int, c_size_t]
     L.dlcfn_kv_partition.argtypes = [c_int, c_size_t, POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t), c_int]
     L.dlcfn_kv_partition.restype = c_int
     L.dlcfn_kv_server_set_updater.argtypes = [UPDATER_FN, c_void_p]

@@ -164,6 +164,19 @@ def test_dist_sync_seven_workers_seven_servers():
     assert r.returncode == 0 and r.stdout.count("SYNC_OK") == 7, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("ns", [2, 3])
+def test_dist_store_regressions_big_keys_dtype_and_staging(ns):
+    # advisor round 1: 2-bit shards not on word boundaries, row-sparse rows across the split, bf16 grad on an fp32 key,
+    # staging buffer reused under a queued push
+    r = _launch(2, ns, [os.path.join(ROOT, "tests/mp/dist_regress_worker.py"), "store"])
+    assert r.returncode == 0 and r.stdout.count("REGRESS_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_dist_trainer_rescale_grad_and_lr_reach_the_servers():
+    r = _launch(2, 1, [os.path.join(ROOT, "tests/mp/dist_regress_worker.py"), "trainer"])
+    assert r.returncode == 0 and r.stdout.count("TRAINER_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_dist_async():
     r = _launch(3, 2, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_async"])
     assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]

@@ -25,9 +25,14 @@ BASELINE_IMG_S_PER_GPU = 363.69  # BASELINE.md row 13 (V100, batch 128, fp32) - 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "torch-stock"],
+                    help="ours | reference (the unmodified reference: unavailable offline) | nccl (ours with NCCL collectives) | "
+                         "torch-stock (stock nn.Module ResNet-50 + torch.optim.SGD + DDP, baseline/torch_stock.py: no repo code)")
+    ap.add_argument("--stock", type=int, default=int(os.environ.get("DLCFN_BENCH_STOCK", "1")),
+                    help="after the own measurement, run the stock-PyTorch arm (baseline/torch_stock.py) in a child process per rank "
+                         "and add `vs_stock` to the JSON line (ResNet only; 0 = skip)")
     ap.add_argument("--mode", default=None, help="allreduce (default) | ps_sync | ps_dedicated | nccl | nccl_ps | hier (multi-node: fused node-local + NCCL rails)")
     ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert-large", "bert-base"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 256 images / 16 sequences)")
@@ -87,10 +92,47 @@ class _HostPrefetcher:
         return ((img.float() / 255.0 - 0.45) / 0.225).permute(0, 3, 1, 2), lab
 
 
+def stock_argv(args):
+    here = os.path.dirname(os.path.abspath(__file__))
+    argv = [sys.executable, os.path.join(here, "baseline", "torch_stock.py"), "--gpus", str(args.gpus), "--steps", str(args.steps),
+            "--warmup", str(args.warmup), "--batch", str(args.batch or 256), "--image-size", str(args.image_size),
+            "--device-batches", str(args.device_batches)]
+    if args.no_e2e:
+        argv.append("--no-e2e")
+    return argv
+
+
+def run_stock_child(args, rank):
+    """The stock-PyTorch arm in a child process of every rank (its own NCCL group on MASTER_PORT + 17): nothing of this
+    repository is imported there.  Returns rank 0's parsed JSON record, or None."""
+    import subprocess
+    env = dict(os.environ)
+    if "MASTER_PORT" in env:
+        env["MASTER_PORT"] = str(int(env["MASTER_PORT"]) + 17)
+    env.pop("TORCHELASTIC_RUN_ID", None)
+    try:
+        r = subprocess.run(stock_argv(args), env=env, capture_output=True, text=True, timeout=600)
+    except (subprocess.TimeoutExpired, OSError) as e:      # the headline must not depend on the comparison arm
+        print(f"[bench] stock arm failed: {e}", file=sys.stderr, flush=True)
+        return None
+    if rank != 0:
+        return None
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except ValueError:
+                pass
+    print(f"[bench] stock arm printed no record (rc {r.returncode}): {r.stderr[-800:]}", file=sys.stderr, flush=True)
+    return None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.impl == "torch-stock":
+        os.execv(sys.executable, stock_argv(args))
 
     import torch
     import torch.distributed as dist
@@ -308,6 +350,12 @@ def main():
         ms, e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
     else:
         e_ms = float(t[1])
+    stock = None
+    if args.stock and not dry and not is_bert and args.impl == "ours" and servers is None:
+        del dev_batches
+        torch.cuda.empty_cache()
+        sync_all()
+        stock = run_stock_child(args, rank)
     if rank == 0:
         global_batch = args.batch * n_workers
         value = global_batch * args.steps / (ms / 1e3)
@@ -357,6 +405,15 @@ def main():
                           "clocks": {"sm_mhz": e2e["clocks"].get("sm_mhz"), "reasons": e2e["clocks"].get("reasons", [])}}
             if not is_worker:  # rank 0 is a dedicated server: bytes come from the workers
                 rec["e2e"]["h2d_bytes_per_step"] = (args.batch * args.image_size * args.image_size * 3 + args.batch * 8) * n_workers
+        if rec is not None and stock is not None and stock.get("value"):
+            # same box, same process tree, run back to back: stock nn.Module ResNet-50-v2 + torch.optim.SGD (+ DDP/NCCL), cuDNN
+            # convolutions and BatchNorm, no code of this repository (baseline/torch_stock.py)
+            rec["vs_stock"] = round(rec["value"] / stock["value"], 4)
+            rec["stock"] = {"value": stock["value"], "ms_per_step": stock.get("ms_per_step"), "impl": "torch-stock",
+                            "clocks": stock.get("clocks")}
+            if "e2e" in rec and stock.get("e2e", {}).get("value"):
+                rec["e2e"]["vs_stock"] = round(rec["e2e"]["value"] / stock["e2e"]["value"], 4)
+                rec["stock"]["e2e_value"] = stock["e2e"]["value"]
         if rec is not None:
             if dry:
                 rec["dry_cpu"] = "host dry run of bench.py with tiny shapes - NOT a measurement"

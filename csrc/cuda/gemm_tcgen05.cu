@@ -68,6 +68,14 @@ struct __align__(64) GemmParams {
   int cv_lower_w, cv_lower_h;   // bounding-box lower corner: -pad (fprop, wgrad), pad - (S-1) (dgrad)
   int cv_stride;        // traversal stride (convolution stride; 1 for dgrad)
   int cv_cin;           // dgrad: columns per tap of the weight matrix [Cout][R*S*Cin]
+  // filter-tap table: tap t of the reduction reads the im2col'd tensor displaced by (cv_tap_ow[t], cv_tap_oh[t]) from the
+  // base position; dgrad multiplies it with weight tap cv_tap_wi[t] (fprop / wgrad walk the taps in storage order).  A
+  // strided dgrad is decomposed by output parity: every class has its own (shorter) tap list.
+  int cv_ntaps;
+  unsigned char cv_tap_ow[52], cv_tap_oh[52], cv_tap_wi[52];
+  // output-row remap (strided dgrad): GEMM row m = (n, i, j) of the [cv_P x cv_Q] class grid is pixel
+  // (i * out_step + out_h0, j * out_step + out_w0) of the [out_H x out_W] gradient image
+  int out_remap, out_H, out_W, out_step, out_h0, out_w0;
 };
 
 // ------------------------------------------------------------------ PTX -----
@@ -290,11 +298,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
           if constexpr (CONV && !A_MN) {
             // fprop / dgrad: k-block = (filter tap rs, 64-channel slice); 128 consecutive output pixels from m_idx
             const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
-            const int r = rs / p.cv_S, sx = rs - r * p.cv_S;
             const int q0 = m_idx % p.cv_Q, t0 = m_idx / p.cv_Q;
             const int p0 = t0 % p.cv_P, n0 = t0 / p.cv_P;
             tma_load_im2col_4d(sa, &p.tmA, full_bar(stage), c0, q0 * p.cv_stride + p.cv_lower_w,
-                               p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)sx, (uint16_t)r);   // box {64 c, 128 pixels}
+                               p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)p.cv_tap_ow[rs],
+                               (uint16_t)p.cv_tap_oh[rs]);   // box {64 c, 128 pixels}
           } else if constexpr (!A_MN) {
             tma_load_2d(sa, &p.tmA, full_bar(stage), k_idx, m_idx);  // box {64 k, 128 m}
           } else {
@@ -315,12 +323,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
               }
             }
           } else if constexpr (CONV && B_MN && !A_MN) {
-            // dgrad: the 64 contraction rows are output channels c0.. of tap rs; the matching weights are the columns of
-            // the REVERSED tap in W viewed as [Cout][R*S*Cin] (MN-major B: box {64 cin, 64 cout})
+            // dgrad: the 64 contraction rows are output channels c0.. of list entry rs; the matching weights are the columns
+            // of filter tap cv_tap_wi[rs] in W viewed as [Cout][R*S*Cin] (MN-major B: box {64 cin, 64 cout})
             const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * 8192, &p.tmB[0], full_bar(stage), (p.cv_RS - 1 - rs) * p.cv_cin + n_idx + 64 * j, c0);
+              tma_load_2d(sb + j * 8192, &p.tmB[0], full_bar(stage), (int)p.cv_tap_wi[rs] * p.cv_cin + n_idx + 64 * j, c0);
           } else if constexpr (CONV && B_MN && A_MN) {
             // wgrad: the 64 contraction rows are output pixels k_idx..; output column panel P = (tap, 64-channel slice)
             const int q0 = k_idx % p.cv_Q, t0 = k_idx / p.cv_Q;
@@ -331,9 +339,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
               int panel = n_idx / 64 + j;
               if (panel > last_panel) panel = last_panel;    // N tail: columns >= N are never stored
               const int rs = panel / p.cv_cblocks, c0 = (panel - rs * p.cv_cblocks) * 64;
-              const int r = rs / p.cv_S, sx = rs - r * p.cv_S;
               tma_load_im2col_4d(sb + j * 8192, &p.tmB[0], full_bar(stage), c0, q0 * p.cv_stride + p.cv_lower_w,
-                                 p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)sx, (uint16_t)r);   // box {64 c, 64 pixels}
+                                 p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)p.cv_tap_ow[rs],
+                                 (uint16_t)p.cv_tap_oh[rs]);   // box {64 c, 64 pixels}
             }
           } else if constexpr (!B_MN) {
             // rows of B (= output columns n) may live on a peer: pick the owner's tensor map
@@ -415,6 +423,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       tc_fence_after();
       const int row = m_idx + q * 32 + lane;
       const bool row_ok = row < p.M;
+      long long row_pix = row;         // output pixel (row of the [pixels, N] output matrix) this GEMM row is stored to
+      if (CONV && p.out_remap) {
+        const int jj = row % p.cv_Q, tt = row / p.cv_Q;
+        const int ii = tt % p.cv_P, nn = tt / p.cv_P;
+        row_pix = ((long long)nn * p.out_H + (long long)ii * p.out_step + p.out_h0) * p.out_W + (long long)jj * p.out_step + p.out_w0;
+      }
       // all of this warp's accumulator columns in flight at once, one wait
       uint32_t r[kChunks][32];
 #pragma unroll
@@ -482,7 +496,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
               if (col0 + j < p.N) f[j] += __ldg(bias + col0 + j);
           }
           if (d_fp32) {
-            float* d = reinterpret_cast<float*>(dbase) + (size_t)row * ldd + col0;
+            float* d = reinterpret_cast<float*>(dbase) + (size_t)(splitk ? (long long)row : row_pix) * ldd + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (col0 + j + 3 < p.N) {
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
               }
             }
           } else {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dbase) + (size_t)row * ldd + col0;
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dbase) + (size_t)row_pix * ldd + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (col0 + j + 7 < p.N) {
@@ -1193,8 +1207,9 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   static const bool mc_env = [] { const char* e = getenv("DLCFN_GEMM_MULTICAST"); return e && e[0] == '1'; }();
   const bool use_mc = mc_env && block_n == 256 && n_shards == 1 &&
                       (long long)(((M + kBlockM - 1) / kBlockM + 1) / 2) * ((N + 255) / 256) >= num_sms / 2;
-  // EXPERIMENTAL CTA-pair kernel (cta_group::2): opt-in; bf16 TMA-store outputs of GEMMs with enough 256 x 256 pair tiles
-  static const bool pair_env = [] { const char* e = getenv("DLCFN_GEMM_2CTA"); return e && e[0] == '1'; }();
+  // CTA-pair kernel (cta_group::2, validated on B200 in round 2: 983 vs 629 TFLOP/s single-CTA at 16384x1024x1024): default
+  // for bf16 TMA-store outputs of GEMMs with enough 256 x 256 pair tiles; DLCFN_GEMM_2CTA=0 disables
+  static const bool pair_env = [] { const char* e = getenv("DLCFN_GEMM_2CTA"); return !(e && e[0] == '0'); }();
   static const bool tma_store_env2 = [] { const char* e = getenv("DLCFN_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
   const bool use_pair = pair_env && !use_mc && n_shards == 1 && N >= 256 && tma_store_env2 && d_dtype == 1 && !accumulate &&
                         (ldd & 7) == 0 && (((uintptr_t)D) & 15) == 0 &&
@@ -1252,12 +1267,27 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   return (int)cudaErrorInvalidValue;
 }
 
-// Implicit-GEMM convolution, NHWC bf16 (EXPERIMENTAL - see kgemm<..., CONV>).  Square stride, symmetric padding, no dilation.
-//   op 0 fprop:  x [n,h,w,c]   * wt [k,r,s,c] -> out = y [n,p,q,k]            (stride 1 or 2 ...)
-//   op 1 dgrad:  x = dy [n,p,q,k] (pass its dims as n,h,w,c = n,p,q,k), wt [k,r,s,cin] -> out = dx [n,oh,ow,cin]; stride 1 only
+// Implicit-GEMM convolution, NHWC bf16 (kgemm<..., CONV>).  Square stride, symmetric padding, no dilation.
+//   op 0 fprop:  x [n,h,w,c]   * wt [k,r,s,c] -> out = y [n,p,q,k]            (any stride)
+//   op 1 dgrad:  x = dy [n,p,q,k] (pass its dims as n,h,w,c = n,p,q,k), wt [k,r,s,cin] -> out = dx [n,oh,ow,cin]; any stride:
+//                a strided dgrad runs one implicit GEMM per output-parity class (the taps that reach pixels of that
+//                parity), each storing to its strided positions of dx; classes no tap reaches are zero-filled
 //   op 2 wgrad:  x [n,h,w,c], other = dy [n,p,q,k] -> out = dw [k,r,s,c]
 // `k` is always the filter count (Cout), `cin` the filter depth; channel counts of the im2col'd tensor must be multiples
 // of 64 (one 128-byte swizzle row per k-block), all others multiples of 8.
+static int conv_launch(GemmParams& p, int block_n, bool a_mn, bool b_mn, int num_sms, cudaStream_t stream) {
+#define DLCFN_CONV_CASE(BN, AM, BM) \
+  if (block_n == BN && a_mn == AM && b_mn == BM) return launch<BN, AM, BM, true>(p, num_sms, stream);
+  DLCFN_CONV_CASE(128, false, false)
+  DLCFN_CONV_CASE(256, false, false)
+  DLCFN_CONV_CASE(128, false, true)
+  DLCFN_CONV_CASE(256, false, true)
+  DLCFN_CONV_CASE(128, true, true)
+  DLCFN_CONV_CASE(256, true, true)
+#undef DLCFN_CONV_CASE
+  return (int)cudaErrorInvalidValue;
+}
+
 DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* out, int out_dtype, int n, int h, int w, int c,
                               int k, int cin, int r, int s, int pad, int stride, int oh, int ow, int accumulate,
                               int block_n, int num_sms, cudaStream_t stream) {
@@ -1269,7 +1299,6 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
   (void)cudaGetLastError();
   if (op < 0 || op > 2 || n <= 0 || h <= 0 || w <= 0 || r <= 0 || s <= 0 || stride <= 0 || pad < 0) return (int)cudaErrorInvalidValue;
   if ((c % 64) || (k % 8) || (cin % 8) || r * s > 49) return (int)cudaErrorInvalidValue;
-  if (op == 1 && stride != 1) return (int)cudaErrorInvalidValue;
   if ((((uintptr_t)x) & 15) || (((uintptr_t)other) & 15) || (((uintptr_t)out) & 15)) return (int)cudaErrorInvalidValue;
   if (num_sms <= 0) {
     int dev = 0;
@@ -1289,17 +1318,24 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
   p.cv_cblocks = c / 64;
   p.cv_stride = stride;
   p.cv_cin = cin;
+  static const bool tma_store_env = [] { const char* e = getenv("DLCFN_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
   int rc;
-  bool a_mn, b_mn;
   if (op == 0 || op == 2) {
-    // im2col of the forward input: base positions = output pixels
+    // im2col of the forward input: base positions = output pixels, taps in storage order
     const int P = (h + 2 * pad - r) / stride + 1, Q = (w + 2 * pad - s) / stride + 1;
     if (P != oh || Q != ow || c != cin) return (int)cudaErrorInvalidValue;
     p.cv_P = P; p.cv_Q = Q;
     p.cv_lower_w = -pad; p.cv_lower_h = -pad;
+    p.cv_ntaps = r * s;
+    for (int t = 0; t < r * s; ++t) {
+      p.cv_tap_ow[t] = (unsigned char)(t % s);
+      p.cv_tap_oh[t] = (unsigned char)(t / s);
+      p.cv_tap_wi[t] = (unsigned char)t;
+    }
     // the last base position of a row is (Q-1)*stride - pad, which must be the box's upper end w - 1 + upper_w or just
     // inside it: upper = pad - (s - 1) is the exact end for stride 1 and at most stride - 1 positions further otherwise
     const int upper_w = pad - (s - 1), upper_h = pad - (r - 1);
+    bool a_mn, b_mn;
     if (op == 0) {
       p.M = n * P * Q; p.N = k; p.K = r * s * c;
       p.ldd = k;
@@ -1319,35 +1355,82 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
       if (block_n != 128 && block_n != 256) block_n = 128;
       a_mn = true; b_mn = true;
     }
-  } else {
-    // dgrad: x is dy [n, h, w, c = k]; base positions = input-gradient pixels [oh, ow]
-    if (c != k) return (int)cudaErrorInvalidValue;
-    const int lower_w = pad - (s - 1), lower_h = pad - (r - 1);
-    p.cv_P = oh; p.cv_Q = ow;
-    p.cv_lower_w = lower_w; p.cv_lower_h = lower_h;
-    p.M = n * oh * ow; p.N = cin; p.K = r * s * k;
-    p.ldd = cin;
-    rc = make_map_im2col(&p.tmA, x, n, h, w, c, lower_w, lower_h, lower_w + ow - w, lower_h + oh - h, 1, kBlockM);
-    if (rc) return rc;
-    rc = make_map(&p.tmB[0], other, k, (uint64_t)r * s * cin, (uint64_t)r * s * cin, 64, kBlockK);  // W as [k][rs*cin], MN-major B
-    if (rc) return rc;
-    if (block_n != 128 && block_n != 256) block_n = (cin >= 256) ? 256 : 128;
-    a_mn = false; b_mn = true;
+    if (tma_store_env && out_dtype == 1 && !accumulate && p.N >= 64 && (p.ldd & 7) == 0) {
+      rc = make_map(&p.tmD, out, p.M, p.N, p.ldd, 64, 32);
+      if (rc) return rc;
+      p.tma_store = 1;
+    }
+    return conv_launch(p, block_n, a_mn, b_mn, num_sms, stream);
   }
-  static const bool tma_store_env = [] { const char* e = getenv("DLCFN_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
-  if (tma_store_env && out_dtype == 1 && !accumulate && p.N >= 64 && (p.ldd & 7) == 0) {
-    rc = make_map(&p.tmD, out, p.M, p.N, p.ldd, 64, 32);
-    if (rc) return rc;
-    p.tma_store = 1;
+  // ---------------------------------------------------------------- dgrad: x is dy [n, h, w, c = k]; out = dx [n, oh, ow, cin]
+  if (c != k) return (int)cudaErrorInvalidValue;
+  if ((h + 0) != (oh + 2 * pad - r) / stride + 1 || w != (ow + 2 * pad - s) / stride + 1) return (int)cudaErrorInvalidValue;
+  rc = make_map(&p.tmB[0], other, k, (uint64_t)r * s * cin, (uint64_t)r * s * cin, 64, kBlockK);  // W as [k][rs*cin], MN-major B
+  if (rc) return rc;
+  if (block_n != 128 && block_n != 256) block_n = (cin >= 256) ? 256 : 128;
+  p.ldd = cin;
+  p.N = cin;
+  p.cv_stride = 1;                 // base positions walk dy's grid with unit steps in every class
+  // per output-parity class (ph, pw): taps with (ph + pad - r') % stride == 0 reach it, displaced by (ph + pad - r') / stride
+  auto taps_1d = [&](int phase, int taps, int* idx, int* disp) {
+    int cnt = 0;
+    for (int t = 0; t < taps; ++t) {
+      const int v = phase + pad - t;
+      if (((v % stride) + stride) % stride != 0) continue;
+      idx[cnt] = t;
+      disp[cnt] = (v >= 0) ? v / stride : -((-v) / stride);     // exact division
+      ++cnt;
+    }
+    return cnt;
+  };
+  bool any_empty = false;
+  for (int ph = 0; ph < stride && ph < oh; ++ph)
+    for (int pw = 0; pw < stride && pw < ow; ++pw) {
+      int ti[8], td[8];
+      if (r > 8 || s > 8) return (int)cudaErrorInvalidValue;
+      if (taps_1d(ph, r, ti, td) == 0 || taps_1d(pw, s, ti, td) == 0) any_empty = true;
+    }
+  if (any_empty && !accumulate)
+    DLCFN_CHECK(cudaMemsetAsync(out, 0, (size_t)n * oh * ow * cin * (out_dtype == 0 ? 4 : 2), stream));
+  for (int ph = 0; ph < stride && ph < oh; ++ph) {
+    for (int pw = 0; pw < stride && pw < ow; ++pw) {
+      int ri[8], rd[8], si[8], sd[8];
+      const int nr = taps_1d(ph, r, ri, rd), ns = taps_1d(pw, s, si, sd);
+      if (nr == 0 || ns == 0) continue;
+      const int Hp = (oh - ph + stride - 1) / stride, Wp = (ow - pw + stride - 1) / stride;
+      int dmin_h = rd[0], dmin_w = sd[0];
+      for (int t = 1; t < nr; ++t) dmin_h = rd[t] < dmin_h ? rd[t] : dmin_h;
+      for (int t = 1; t < ns; ++t) dmin_w = sd[t] < dmin_w ? sd[t] : dmin_w;
+      GemmParams q = p;
+      q.cv_ntaps = nr * ns;
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < ns; ++b) {
+          const int t = a * ns + b;
+          q.cv_tap_oh[t] = (unsigned char)(rd[a] - dmin_h);
+          q.cv_tap_ow[t] = (unsigned char)(sd[b] - dmin_w);
+          q.cv_tap_wi[t] = (unsigned char)(ri[a] * s + si[b]);
+        }
+      q.cv_P = Hp; q.cv_Q = Wp;
+      q.cv_lower_w = dmin_w; q.cv_lower_h = dmin_h;
+      q.M = n * Hp * Wp;
+      q.K = nr * ns * k;
+      // base positions per row = w + upper - lower = Wp
+      rc = make_map_im2col(&q.tmA, x, n, h, w, c, dmin_w, dmin_h, dmin_w + Wp - w, dmin_h + Hp - h, 1, kBlockM);
+      if (rc) return rc;
+      if (stride == 1) {
+        if (tma_store_env && out_dtype == 1 && !accumulate && q.N >= 64 && (q.ldd & 7) == 0) {
+          rc = make_map(&q.tmD, out, q.M, q.N, q.ldd, 64, 32);
+          if (rc) return rc;
+          q.tma_store = 1;
+        }
+      } else {
+        q.out_remap = 1;
+        q.split_k_ok = 0;          // the split-K reduce kernel stores plain rows
+        q.out_H = oh; q.out_W = ow; q.out_step = stride; q.out_h0 = ph; q.out_w0 = pw;
+      }
+      rc = conv_launch(q, block_n, false, true, num_sms, stream);
+      if (rc) return rc;
+    }
   }
-#define DLCFN_CONV_CASE(BN, AM, BM) \
-  if (block_n == BN && a_mn == AM && b_mn == BM) return launch<BN, AM, BM, true>(p, num_sms, stream);
-  DLCFN_CONV_CASE(128, false, false)
-  DLCFN_CONV_CASE(256, false, false)
-  DLCFN_CONV_CASE(128, false, true)
-  DLCFN_CONV_CASE(256, false, true)
-  DLCFN_CONV_CASE(128, true, true)
-  DLCFN_CONV_CASE(256, true, true)
-#undef DLCFN_CONV_CASE
-  return (int)cudaErrorInvalidValue;
+  return 0;
 }

@@ -1,22 +1,25 @@
-"""Convolutions on the hand-written tcgen05 GEMM (csrc/cuda/gemm_tcgen05.cu): 1x1 as a plain GEMM (validated, below) and
-KxK as an implicit GEMM through im2col-mode TMA (`ConvKxK`, EXPERIMENTAL, at the end of this file).
+"""Convolutions on the hand-written tcgen05 kernels (csrc/cuda/gemm_tcgen05.cu).
 
-In NHWC a 1x1 convolution IS a GEMM: the activation [N,H,W,Cin] is the row-major matrix [N*H*W, Cin] as it sits in
-memory, the filter [Cout,Cin,1,1] is [Cout,Cin] K-major, and the output matrix [N*H*W, Cout] is the NHWC output.
-No im2col, no layout change, no workspace:
-    fprop  Y[M,Cout]  = X[M,Cin]  * W[Cout,Cin]^T
-    dgrad  dX[M,Cin]  = dY[M,Cout] * W[Cout,Cin]       (W read MN-major by TMA)
-    wgrad  dW[Cout,Cin] = dY[M,Cout]^T * X[M,Cin]      (both operands MN-major)
-A stride-s 1x1 convolution (ResNet projection shortcuts) first gathers the s-strided pixels with one NHWC kernel
-(ops.nn.subsample), then runs the same three GEMMs on the smaller matrix.
+Every convolution whose channel counts fit the 128-byte TMA rows runs on the repo's own sm_100a code, forward and backward:
+
+* 1x1 / stride 1: in NHWC the activation [N,H,W,Cin] IS the row-major matrix [N*H*W, Cin], the filter [Cout,Cin,1,1] is
+  [Cout,Cin] K-major, and the output matrix [N*H*W, Cout] is the NHWC output - three plain GEMMs, no im2col, no layout
+  change, no workspace:
+      fprop  Y[M,Cout]    = X[M,Cin]  * W[Cout,Cin]^T
+      dgrad  dX[M,Cin]    = dY[M,Cout] * W[Cout,Cin]       (W read MN-major by TMA)
+      wgrad  dW[Cout,Cin] = dY[M,Cout]^T * X[M,Cin]        (both operands MN-major, split-K)
+* everything else (KxK, and strided 1x1 projection shortcuts): implicit GEMM - the producer warp asks the TMA unit for
+  "128 consecutive output pixels, filter tap (r, s), channels c0..c0+63" (im2col-mode tensor map) and receives the operand
+  tile with the halo zero-filled; no im2col buffer, no gather kernel.  fprop and wgrad take any stride; dgrad of a strided
+  convolution is decomposed by output parity (stride^2 implicit GEMMs over the taps that reach each class, stored to the
+  strided positions of dX).
 
 Reference: M1 convolution via cuDNN / im2col+cuBLAS (MX/src/operator/nn/convolution.cu:90-160,
-nn/cudnn/cudnn_convolution-inl.h:638-793, nn/im2col.cuh:79-132).  2/3 of ResNet-50's convolution layers are 1x1.
+nn/cudnn/cudnn_convolution-inl.h:638-793, nn/im2col.cuh:79-132).
 
-The backend is selectable because cuDNN's sm_100 kernels are the yardstick: `set_conv1x1_backend(...)` or
-DLCFN_CONV1X1 = `tcgen05` (every 1x1 convolution on the dlcfn GEMM), `cudnn` (none; the measured default: 25.36 ms
-per ResNet-50 step vs 25.61 `auto` vs 26.46 `tcgen05`), or `auto` (the strided projection shortcuts only: gather + GEMM +
-scatter); tools/conv1x1_probe.py measures both per layer shape.
+The backends stay selectable because cuDNN's sm_100 kernels are the yardstick: `set_conv1x1_backend(...)` /
+`set_convkxk_backend(...)` or DLCFN_CONV1X1 / DLCFN_CONVKXK = `tcgen05` (default) | `cudnn`; tools/conv_probe.py measures
+both per layer shape and per op.
 """
 from __future__ import annotations
 
@@ -27,10 +30,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import native
-from .linear import _LinearFn
-from .nn import subsample
 
-_BACKEND = os.environ.get("DLCFN_CONV1X1", "cudnn").lower()
+_BACKEND = os.environ.get("DLCFN_CONV1X1", "tcgen05").lower()
 
 
 def set_conv1x1_backend(name: str) -> None:
@@ -44,25 +45,96 @@ def conv1x1_backend() -> str:
     return _BACKEND
 
 
-def _eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
-    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and
-            weight.shape[2] == 1 and weight.shape[3] == 1 and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0)
+class ConvOps:
+    """The three kernels of one convolution (square stride, symmetric padding, no bias) on the dlcfn tcgen05 path.
+    `x` [N,C,H,W] and `weight` [K,C,R,S] are channels_last bf16 CUDA tensors."""
+
+    def __init__(self, x: torch.Tensor, weight: torch.Tensor, stride: int = 1, pad: int = 0):
+        self.x, self.w, self.stride, self.pad = x, weight, int(stride), int(pad)
+        K, C, R, S = weight.shape
+        self.gemm = (R == 1 and S == 1 and self.stride == 1 and self.pad == 0)
+        N, _, H, W = x.shape
+        self.P, self.Q = (H + 2 * self.pad - R) // self.stride + 1, (W + 2 * self.pad - S) // self.stride + 1
+
+    @staticmethod
+    def eligible(x: torch.Tensor, weight: torch.Tensor, stride, padding, dilation=(1, 1), groups: int = 1) -> bool:
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4):
+            return False
+        K, C, R, S = weight.shape
+        if not (groups == 1 and tuple(dilation) == (1, 1) and stride[0] == stride[1] and padding[0] == padding[1] and x.shape[1] == C):
+            return False
+        if R == 1 and S == 1 and stride[0] == 1 and padding[0] == 0:
+            return C % 8 == 0 and K % 8 == 0
+        # implicit GEMM: the im2col'd tensors (x for fprop / wgrad, dy for dgrad) need whole 64-channel TMA rows
+        return C % 64 == 0 and K % 64 == 0 and R <= 7 and S <= 7
+
+    def _mat(self, t: torch.Tensor) -> torch.Tensor:
+        n, c, h, w = t.shape
+        return t.permute(0, 2, 3, 1).reshape(n * h * w, c)          # a view: NHWC memory is already this matrix
+
+    def fprop(self) -> torch.Tensor:
+        x, w = self.x, self.w
+        if self.gemm:
+            N, C, H, W = x.shape
+            y = torch.empty((N, w.shape[0], H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+            native.gemm_bf16(self._mat(x), w.reshape(w.shape[0], C), out=self._mat(y))
+            return y
+        return native.conv_fprop(x, w, self.stride, self.pad)
+
+    def dgrad(self, dy: torch.Tensor) -> torch.Tensor:
+        x, w = self.x, self.w
+        if self.gemm:
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+            native.gemm_bf16(self._mat(dy), w.reshape(w.shape[0], w.shape[1]), b_mn=True, out=self._mat(dx))
+            return dx
+        return native.conv_dgrad(dy, w, self.pad, (x.shape[2], x.shape[3]), stride=self.stride)
+
+    def wgrad(self, dy: torch.Tensor) -> torch.Tensor:
+        x, w = self.x, self.w
+        if self.gemm:
+            dw = torch.empty((w.shape[0], w.shape[1]), dtype=torch.bfloat16, device=x.device)
+            native.gemm_bf16(self._mat(dy), self._mat(x), a_mn=True, b_mn=True, out=dw)
+            return dw.view(w.shape)           # [K,C,1,1]: contiguous and channels_last at once
+        return native.conv_wgrad(x, dy, (w.shape[2], w.shape[3]), self.stride, self.pad)
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        w = weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.pad = stride, pad
+        return ConvOps(x, w, stride, pad).fprop()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        ops = ConvOps(x, w, ctx.stride, ctx.pad)
+        dx = ops.dgrad(dy) if ctx.needs_input_grad[0] else None
+        dw = ops.wgrad(dy) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None
+
+
+def conv2d(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding: int = 0) -> torch.Tensor:
+    """x [N,C,H,W] channels_last bf16, weight [K,C,R,S] -> [N,K,P,Q] channels_last, all three passes on the tcgen05 kernels."""
+    return _ConvFn.apply(x, weight, int(stride), int(padding))
+
+
+def _eligible(x: torch.Tensor, weight: torch.Tensor, stride: int = 1) -> bool:
+    return weight.shape[2] == 1 and weight.shape[3] == 1 and ConvOps.eligible(x, weight, (stride, stride), (0, 0))
 
 
 def conv1x1(x: torch.Tensor, weight: torch.Tensor, stride: int = 1) -> torch.Tensor:
     """x [N,Cin,H,W] (channels_last), weight [Cout,Cin,1,1] -> [N,Cout,ceil(H/s),ceil(W/s)] channels_last."""
-    if not _eligible(x, weight):
+    if not _eligible(x, weight, stride):
         if x.is_cuda and not native.lib_path().exists():
             raise native.NativeUnavailable("CUDA conv1x1 requested but libdlcfn_cuda.so is missing")
         return F.conv2d(x, weight.to(x.dtype), None, stride)
-    if not x.is_contiguous(memory_format=torch.channels_last):
-        x = x.contiguous(memory_format=torch.channels_last)
-    x = subsample(x, stride)
-    N, C, H, W = x.shape
-    O = weight.shape[0]
-    x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)          # a view: NHWC memory is already this matrix
-    y2 = _LinearFn.apply(x2, weight.reshape(O, C), None)       # [N*H*W, O]
-    return y2.view(N, H, W, O).permute(0, 3, 1, 2)            # channels_last view of the GEMM output
+    return conv2d(x, weight, stride, 0)
 
 
 class Conv1x1(nn.Conv2d):
@@ -76,24 +148,16 @@ class Conv1x1(nn.Conv2d):
 
     def forward(self, x):
         use = _BACKEND == "tcgen05" or (_BACKEND == "auto" and self.stride[0] > 1)
-        if use and _eligible(x, self.weight):
-            return conv1x1(x, self.weight, self.stride[0])
+        if use and _eligible(x, self.weight, self.stride[0]):
+            return conv2d(x, self.weight, self.stride[0], 0)
         return super().forward(x)
 
     def extra_repr(self):
         return super().extra_repr() + f", backend={_BACKEND}"
 
 
-# ------------------------------------------------------------------------------ KxK implicit GEMM (EXPERIMENTAL)
-# Written at the end of round 1 with no GPU left to run it on: compiled (SASS shows UTMALDG.4D.IM2COL), off by default,
-# validated by tests/test_gpu_experimental.py under DLCFN_EXPERIMENTAL=1.  `DLCFN_CONVKXK=tcgen05` / set_convkxk_backend
-# switch ConvKxK modules over; cuDNN stays the default and the yardstick.
-#
-# The activation tensor never goes through an im2col buffer: the producer warp of the GEMM kernel asks the TMA unit for
-# "128 consecutive output pixels, filter tap (r, s), channels c0..c0+63" and receives the [128 x 64] operand tile with the
-# halo already zero-filled (cuTensorMapEncodeIm2col).  fprop, the stride-1 dgrad (same kernel on dY with the taps reversed,
-# weights read MN-major) and wgrad (split-K over the N*P*Q pixels) all run on it; a strided dgrad falls back to cuDNN.
-_KXK_BACKEND = os.environ.get("DLCFN_CONVKXK", "cudnn").lower()
+# ------------------------------------------------------------------------------ KxK implicit GEMM
+_KXK_BACKEND = os.environ.get("DLCFN_CONVKXK", "tcgen05").lower()
 
 
 def set_convkxk_backend(name: str) -> None:
@@ -108,43 +172,12 @@ def convkxk_backend() -> str:
 
 
 def _kxk_eligible(x: torch.Tensor, weight: torch.Tensor, stride, padding, dilation, groups) -> bool:
-    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4):
-        return False
-    K, C, R, S = weight.shape
-    return (groups == 1 and tuple(dilation) == (1, 1) and stride[0] == stride[1] and padding[0] == padding[1] and
-            C % 64 == 0 and K % 8 == 0 and R * S <= 49 and x.shape[1] == C)
-
-
-class _ConvKxKFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, stride, pad):
-        if not x.is_contiguous(memory_format=torch.channels_last):
-            x = x.contiguous(memory_format=torch.channels_last)
-        w = weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
-        ctx.save_for_backward(x, w)
-        ctx.stride, ctx.pad = stride, pad
-        return native.conv_fprop(x, w, stride, pad)
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, w = ctx.saved_tensors
-        if not dy.is_contiguous(memory_format=torch.channels_last):
-            dy = dy.contiguous(memory_format=torch.channels_last)
-        dx = dw = None
-        if ctx.needs_input_grad[0]:
-            if ctx.stride == 1 and w.shape[0] % 64 == 0:
-                dx = native.conv_dgrad(dy, w, ctx.pad, (x.shape[2], x.shape[3]))
-            else:       # strided dgrad (zero-interleaved gradient) or Cout not a multiple of 64: cuDNN for now
-                dx = torch.ops.aten.convolution_backward(dy, x, w, None, [ctx.stride] * 2, [ctx.pad] * 2, [1, 1], False, [0, 0],
-                                                         1, [True, False, False])[0]
-        if ctx.needs_input_grad[1]:
-            dw = native.conv_wgrad(x, dy, (w.shape[2], w.shape[3]), ctx.stride, ctx.pad)
-        return dx, dw, None, None
+    return ConvOps.eligible(x, weight, stride, padding, dilation, groups)
 
 
 def conv_kxk(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding: int = 0) -> torch.Tensor:
     """x [N,C,H,W] channels_last bf16, weight [K,C,R,S] -> [N,K,P,Q] channels_last on the tcgen05 implicit GEMM."""
-    return _ConvKxKFn.apply(x, weight, int(stride), int(padding))
+    return conv2d(x, weight, stride, padding)
 
 
 class ConvKxK(nn.Conv2d):

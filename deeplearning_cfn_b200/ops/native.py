@@ -279,18 +279,21 @@ def conv_fprop(x: torch.Tensor, weight: torch.Tensor, stride: int, pad: int, blo
     return y
 
 
-def conv_dgrad(dy: torch.Tensor, weight: torch.Tensor, pad: int, in_hw: tuple[int, int], block_n: int = 0) -> torch.Tensor:
-    """Stride-1 input gradient: dy [N,K,P,Q] channels_last, weight [K,C,R,S] channels_last -> dx [N,C,H,W] channels_last."""
+def conv_dgrad(dy: torch.Tensor, weight: torch.Tensor, pad: int, in_hw: tuple[int, int], block_n: int = 0,
+               stride: int = 1) -> torch.Tensor:
+    """Input gradient: dy [N,K,P,Q] channels_last, weight [K,C,R,S] channels_last -> dx [N,C,H,W] channels_last.  A strided
+    convolution's gradient runs as one implicit GEMM per output-parity class (csrc/cuda/gemm_tcgen05.cu:dlcfn_conv_bf16)."""
     assert _nhwc_ok(dy) and _nhwc_ok(weight)
     N, K, P, Q = dy.shape
     _, C, R, S = weight.shape
     H, W = in_hw
     dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
-    rc = lib().dlcfn_conv_bf16(1, dy.data_ptr(), weight.data_ptr(), dx.data_ptr(), 1, N, P, Q, K, K, C, R, S, pad, 1, H, W,
+    rc = lib().dlcfn_conv_bf16(1, dy.data_ptr(), weight.data_ptr(), dx.data_ptr(), 1, N, P, Q, K, K, C, R, S, pad, stride, H, W,
                                0, block_n, 0, stream_ptr())
     if rc != 0:
-        raise RuntimeError(f"dlcfn conv dgrad failed with CUDA error {rc}: dy={tuple(dy.shape)} w={tuple(weight.shape)} pad={pad}")
-    _count()
+        raise RuntimeError(f"dlcfn conv dgrad failed with CUDA error {rc}: dy={tuple(dy.shape)} w={tuple(weight.shape)} pad={pad} "
+                           f"stride={stride} in_hw={in_hw}")
+    _count(stride * stride)
     return dx
 
 

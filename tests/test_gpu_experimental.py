@@ -145,102 +145,6 @@ def test_multicast_pair_gemm_in_a_subprocess():
     assert "MC_OK" in r.stdout, f"rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
 
 
-# ------------------------------------------------------------------------------------------ implicit-GEMM convolution
-def _conv_case(N, C, H, W, K, R, stride, pad, seed=0):
-    torch.manual_seed(seed)
-    x = torch.randn(N, C, H, W, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last)
-    w = (torch.randn(K, C, R, R, device=dev()) / (C * R * R) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
-    return x, w
-
-
-# (N, C, H, W, K, R, stride, pad): ResNet-50 conv2 shapes at small batch, M / N / K tails, row / image wrap inside one tile
-_CONV_SHAPES = [(1, 64, 7, 9, 128, 3, 1, 1), (1, 192, 5, 5, 64, 5, 1, 2), (2, 64, 56, 56, 64, 3, 1, 1), (3, 128, 28, 28, 128, 3, 1, 1), (4, 256, 14, 14, 256, 3, 1, 1),
-                (8, 512, 7, 7, 512, 3, 1, 1), (1, 64, 9, 13, 72, 3, 1, 1), (5, 64, 5, 5, 200, 3, 1, 1),
-                (2, 128, 56, 56, 128, 3, 2, 1), (2, 64, 15, 15, 64, 3, 2, 1), (2, 64, 12, 12, 96, 5, 1, 2),
-                (2, 64, 10, 10, 64, 1, 1, 0), (2, 64, 16, 16, 128, 1, 2, 0), (2, 64, 8, 8, 64, 3, 1, 0)]
-
-
-@pytest.mark.parametrize("shape", _CONV_SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_conv_fprop_matches_fp32(shape):
-    from deeplearning_cfn_b200.ops import native
-    N, C, H, W, K, R, stride, pad = shape
-    x, w = _conv_case(*shape)
-    y = native.conv_fprop(x, w, stride, pad)
-    yr = F.conv2d(x.float(), w.float(), None, stride, pad)
-    assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
-    _frac_close(y, yr, 2e-2, 2e-2)
-
-
-@pytest.mark.parametrize("shape", [s for s in _CONV_SHAPES if s[6] == 1 and s[4] % 64 == 0], ids=lambda s: "x".join(map(str, s)))
-def test_conv_dgrad_matches_fp32(shape):
-    from deeplearning_cfn_b200.ops import native
-    N, C, H, W, K, R, stride, pad = shape
-    x, w = _conv_case(*shape)
-    P, Q = (H + 2 * pad - R) + 1, (W + 2 * pad - R) + 1
-    dy = torch.randn(N, K, P, Q, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last)
-    dx = native.conv_dgrad(dy, w, pad, (H, W))
-    dxr = torch.nn.grad.conv2d_input((N, C, H, W), w.float(), dy.float(), 1, pad)
-    assert dx.shape == dxr.shape
-    _frac_close(dx, dxr, 2e-2, 2e-2 * float(dxr.abs().max()))
-
-
-@pytest.mark.parametrize("shape", _CONV_SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_conv_wgrad_matches_fp32(shape):
-    from deeplearning_cfn_b200.ops import native
-    N, C, H, W, K, R, stride, pad = shape
-    x, w = _conv_case(*shape)
-    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
-    dy = torch.randn(N, K, P, Q, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last)
-    dw = native.conv_wgrad(x, dy, (R, R), stride, pad)
-    dwr = torch.nn.grad.conv2d_weight(x.float(), (K, C, R, R), dy.float(), stride, pad)
-    assert dw.shape == dwr.shape and dw.is_contiguous(memory_format=torch.channels_last)
-    _frac_close(dw, dwr, 2e-2, 2e-2 * float(dwr.abs().max()))
-    assert torch.equal(dw, native.conv_wgrad(x, dy, (R, R), stride, pad))          # split-K reduction is deterministic
-
-
-def test_convkxk_module_autograd_and_resnet_step():
-    """ConvKxK on the tcgen05 backend inside autograd, against the same module on cuDNN; then one ResNet-50 training step
-    with every 1x1 and 3x3 convolution on the dlcfn kernels."""
-    from deeplearning_cfn_b200.ops import conv
-    torch.manual_seed(0)
-    m = conv.ConvKxK(64, 128, 3, 2, 1).to(dev()).to(torch.bfloat16).to(memory_format=torch.channels_last)
-    x = torch.randn(4, 64, 28, 28, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    outs = {}
-    for be in ("cudnn", "tcgen05"):
-        conv.set_convkxk_backend(be)
-        try:
-            m.zero_grad(); x.grad = None
-            y = m(x)
-            y.float().square().mean().backward()
-            outs[be] = (y.detach().float(), x.grad.float().clone(), m.weight.grad.float().clone())
-        finally:
-            conv.set_convkxk_backend("cudnn")
-    for a, b in zip(outs["tcgen05"], outs["cudnn"]):
-        _frac_close(a, b, 3e-2, 3e-2 * float(b.abs().max()))
-
-    from deeplearning_cfn_b200.models import resnet, to_b200_layout
-    from deeplearning_cfn_b200.ops import native
-    net = to_b200_layout(resnet(50, 16, 64).to(dev()))
-    xb = torch.randn(8, 3, 64, 64, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last)
-    losses = {}
-    for be in ("cudnn", "tcgen05"):
-        conv.set_convkxk_backend(be)
-        conv.set_conv1x1_backend(be)
-        try:
-            net.zero_grad()
-            n0 = native.launch_count
-            loss = net(xb).float().logsumexp(1).mean()
-            loss.backward()
-            losses[be] = (float(loss), native.launch_count - n0, net.fc1.weight.grad.float().clone())
-        finally:
-            conv.set_convkxk_backend("cudnn")
-            conv.set_conv1x1_backend("cudnn")
-    assert abs(losses["tcgen05"][0] - losses["cudnn"][0]) < 0.05 * abs(losses["cudnn"][0]) + 0.05
-    assert losses["tcgen05"][1] > losses["cudnn"][1] + 40            # the 3x3 layers really ran on the dlcfn kernel
-    cos = F.cosine_similarity(losses["tcgen05"][2].flatten(), losses["cudnn"][2].flatten(), dim=0).item()
-    assert cos > 0.98, cos
-
-
 # ----------------------------------------------------------- GEMM variants selected by environment (read once by the .so)
 _GEMM_VARIANT = "2cta" if os.environ.get("DLCFN_GEMM_2CTA") == "1" else ("multicast" if os.environ.get("DLCFN_GEMM_MULTICAST") == "1" else None)
 

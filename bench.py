@@ -352,7 +352,8 @@ def main():
         e_ms = float(t[1])
     stock = None
     if args.stock and not dry and not is_bert and args.impl == "ours" and servers is None:
-        del dev_batches
+        n_dev_batches = len(dev_batches)
+        dev_batches = [None] * n_dev_batches            # release the device-resident inputs before the child allocates its own
         torch.cuda.empty_cache()
         sync_all()
         stock = run_stock_child(args, rank)

@@ -432,6 +432,22 @@ DLCFN_API int dlcfn_bn_forward_ex(const void* x, const void* x2, void* z, void* 
   return (int)cudaGetLastError();
 }
 
+// Training forward whose statistics pass already happened in the epilogue of the producing convolution
+// (gemm_tcgen05.cu, GemmParams::stats): `part` = [part_rows][2][C] partial sums / sums of squares of x.  2 launches.
+DLCFN_API int dlcfn_bn_forward_pre(const void* x, void* y, long long M, int C, const float* gamma, const float* beta,
+                                   float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
+                                   float eps, int relu, const float* part, int part_rows, float* workspace,
+                                   cudaStream_t stream) {
+  (void)cudaGetLastError();
+  if (!bn_supported(M, C) || part == nullptr || part_rows <= 0) return (int)cudaErrorInvalidValue;
+  BnGeom g = bn_geom(M, C);
+  float* scale_shift = workspace + (size_t)g.grid * 2 * C;
+  kbn_fwd_finalize<<<(C + 31) / 32, dim3(32, kFinY), 0, stream>>>(part, part_rows, C, M, eps, momentum, gamma, beta, mean,
+                                                        invstd, running_mean, running_var, scale_shift);
+  kbn_apply<<<g.grid, g.threads, 0, stream>>>((const uint4*)x, (uint4*)y, M, g.CV, g.RL, scale_shift, relu);
+  return (int)cudaGetLastError();
+}
+
 // inference / frozen-statistics forward: one pass
 DLCFN_API int dlcfn_bn_inference(const void* x, void* y, long long M, int C, const float* gamma,
                                  const float* beta, const float* running_mean, const float* running_var,

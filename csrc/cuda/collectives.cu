@@ -497,6 +497,16 @@ DLCFN_API int dlcfn_symm_check_error(void* ctx, cudaStream_t stream, int* out_er
   return 0;
 }
 
+// Non-blocking form: copies the error word into PINNED host memory on `stream` and returns; the caller reads it after the
+// stream has passed this point (DataParallelTrainer polls it every few steps without draining the GPU queue).
+DLCFN_API int dlcfn_symm_poll_error_async(void* ctx, int* host_pinned, cudaStream_t stream) {
+  (void)cudaGetLastError();
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (host_pinned == nullptr) return (int)cudaErrorInvalidValue;
+  DLCFN_CHECK(cudaMemcpyAsync(host_pinned, c->dev.err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  return 0;
+}
+
 DLCFN_API int dlcfn_symm_destroy(void* ctx) {
   (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
@@ -598,31 +608,43 @@ DLCFN_API int dlcfn_broadcast(void* ctx, size_t off_bytes, size_t bytes, int roo
 
 // One synchronous parameter-server step, launched by EVERY rank (servers and workers alike).
 // shard_lo/shard_hi are element indices (multiples of 16B/sizeof(T)) into the flat buffers.
-static uint32_t g_next_pull_mask = 0;
-// one-shot modifier for the next dlcfn_ps_sync_step: restrict the ranks that receive the updated weights
-DLCFN_API void dlcfn_ps_set_next_pull_mask(uint32_t mask) { g_next_pull_mask = mask; }
+// algo 1 routes the push through multimem.ld_reduce and the pull through multimem.st (needs a multicast mapping);
+// pull_mask != 0 restricts the ranks that receive the updated weights (dedicated servers keep no model replica).
+DLCFN_API int dlcfn_ps_sync_step_ex(void* ctx, size_t grad_off, size_t weight_off, size_t total_count,
+                                    size_t shard_lo, size_t shard_hi, uint32_t worker_mask, uint32_t pull_mask,
+                                    float* master, float* s1, float* s2, int dtype, int opt_kind, float lr, float wd,
+                                    float momentum, float beta1, float beta2, float eps, float rescale,
+                                    float clip, int channel, int nblocks, int algo, cudaStream_t stream);
 
 DLCFN_API int dlcfn_ps_sync_step(void* ctx, size_t grad_off, size_t weight_off, size_t total_count,
                                  size_t shard_lo, size_t shard_hi, uint32_t worker_mask, float* master,
                                  float* s1, float* s2, int dtype, int opt_kind, float lr, float wd,
                                  float momentum, float beta1, float beta2, float eps, float rescale,
                                  float clip, int channel, int nblocks, cudaStream_t stream) {
+  return dlcfn_ps_sync_step_ex(ctx, grad_off, weight_off, total_count, shard_lo, shard_hi, worker_mask, 0u, master, s1, s2,
+                               dtype, opt_kind, lr, wd, momentum, beta1, beta2, eps, rescale, clip, channel, nblocks, 0, stream);
+}
+
+DLCFN_API int dlcfn_ps_sync_step_ex(void* ctx, size_t grad_off, size_t weight_off, size_t total_count,
+                                    size_t shard_lo, size_t shard_hi, uint32_t worker_mask, uint32_t pull_mask,
+                                    float* master, float* s1, float* s2, int dtype, int opt_kind, float lr, float wd,
+                                    float momentum, float beta1, float beta2, float eps, float rescale,
+                                    float clip, int channel, int nblocks, int algo, cudaStream_t stream) {
   (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries
   SymmCtx* c = (SymmCtx*)ctx;
   const int N = dtype == 1 ? 8 : 4;
   if (!c->finalized || (grad_off & 15) || (weight_off & 15) || (shard_lo % N) || dtype < 0 || dtype > 1)
     return (int)cudaErrorInvalidValue;
   if (worker_mask == 0 || channel < 0 || channel >= kSigChannels) return (int)cudaErrorInvalidValue;
-  int use_mc = 0;
-  if (nblocks >= 10000) { use_mc = c->dev.mc != nullptr; nblocks -= 10000; }   // python encodes algo in nblocks
+  if (algo == 1 && c->dev.mc == nullptr) return (int)cudaErrorNotSupported;
+  const int use_mc = algo == 1 ? 1 : 0;
   PSArgs a;
   a.grad_off = grad_off;
   a.weight_off = weight_off;
   a.lo = shard_lo / N;
   a.hi = (shard_hi + N - 1) / N;
   a.worker_mask = worker_mask;
-  a.pull_mask = g_next_pull_mask;
-  g_next_pull_mask = 0;
+  a.pull_mask = pull_mask;
   a.master = master;
   a.s1 = s1;
   a.s2 = s2;

@@ -76,6 +76,11 @@ struct __align__(64) GemmParams {
   // output-row remap (strided dgrad): GEMM row m = (n, i, j) of the [cv_P x cv_Q] class grid is pixel
   // (i * out_step + out_h0, j * out_step + out_w0) of the [out_H x out_W] gradient image
   int out_remap, out_H, out_W, out_step, out_h0, out_w0;
+  // pipeline shape chosen by the host: ring depth, weights-stationary mode (B panel of bres_bytes resident in shared memory)
+  int stages, b_resident, bres_bytes;
+  int stg_bufs;         // staging tiles per epilogue warp: 2 = a warp fills one tile while TMA still reads the other
+  // fused BatchNorm statistics of the stored bf16 outputs: partial rows [4 * grid][2][N] (sum, sum of squares), or null
+  float* stats;
 };
 
 // ------------------------------------------------------------------ PTX -----
@@ -152,6 +157,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk store have finished reading shared memory (double-buffered staging tiles)
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -194,50 +201,67 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // ---------------------------------------------------------------- kernel ----
+constexpr int kMaxStages = 12;
+constexpr int kStagingBytes = 8 * 4096;             // one 32-row x 128-byte store tile per epilogue warp
+constexpr int kBarrierBytes = 256;                  // full[12] empty[12] tfull[2] tempty[2] bfull[1] + tmem slot
+constexpr int kSmemLimit = 227 * 1024;
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;   // 16 / 32 KiB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;   // 8 / 16 / 32 KiB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int kTmemCols = 2 * BLOCK_N;           // two accumulator stages
-  static constexpr int kStagingBytes = 8 * 4096;          // one 32-row x 128-byte store tile per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);   // streaming-B default
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;             // two accumulator stages
+  static constexpr int kEpiWarps = (BLOCK_N == 64) ? 4 : 8;                           // 64 columns per warp at least
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + kBarrierBytes;
 };
 
-// MC = true (EXPERIMENTAL, round 1, not yet run on a GPU; DLCFN_GEMM_MULTICAST=1): the grid is launched as clusters of two
-// CTAs that work on M-adjacent tiles of the same N block.  They share the B tile: each CTA fetches HALF of it and
-// multicasts that half into both CTAs' shared memory, so a CTA pulls A (16 KiB) + B/2 (16 KiB) per k-block from L2
-// instead of 48 KiB - the single-CTA kernel needs ~26 TB/s of L2 bandwidth at full tensor rate, which is what holds it
-// at 81 % pipe utilisation.  A stage of either CTA may only be refilled when BOTH CTAs' MMAs have consumed it (the
-// peer's multicast writes into it), so the smem-empty barriers take two arrivals: each CTA's tcgen05.commit is itself
-// multicast to both.  Everything else (TMEM, epilogue, TMA store) is per CTA and unchanged.
+// MC = true (DLCFN_GEMM_MULTICAST=1, validated on B200 in round 2, not faster than the pair kernel): the grid is launched as
+// clusters of two CTAs that work on M-adjacent tiles of the same N block.  They share the B tile: each CTA fetches HALF of it
+// and multicasts that half into both CTAs' shared memory.  A stage of either CTA may only be refilled when BOTH CTAs' MMAs
+// have consumed it (the peer's multicast writes into it), so the smem-empty barriers take two arrivals: each CTA's
+// tcgen05.commit is itself multicast to both.  Everything else (TMEM, epilogue, TMA store) is per CTA and unchanged.
 //
-// CONV = true (EXPERIMENTAL, written at the end of round 1 without GPU access; DLCFN_CONV3X3=tcgen05): implicit-GEMM
-// convolution on NHWC tensors.  Only the producer changes - the activation operand is fetched by im2col-mode TMA, which
-// performs the (pixel, tap) -> input-pixel arithmetic, the halo zero-fill and the row / image wrap in hardware:
+// CONV = true: implicit-GEMM convolution on NHWC tensors.  Only the producer changes - the activation operand is fetched by
+// im2col-mode TMA, which performs the (pixel, tap) -> input-pixel arithmetic, the halo zero-fill and the row / image wrap in
+// hardware:
 //   fprop <A_MN=0,B_MN=0>  Y[NPQ, K]     = im2col(X)[NPQ, RS*C] * W[K, RS*C]^T      k-block -> (tap, 64 channels)
 //   dgrad <A_MN=0,B_MN=1>  dX[NHW, C]    = im2col(dY)[NHW, RS*K] * W'[RS*K, C]      W' = taps reversed, read MN-major
 //   wgrad <A_MN=1,B_MN=1>  dW[K, RS*C]   = dY[NPQ, K]^T * im2col(X)[NPQ, RS*C]      k-block = 64 pixels, split-K
 // MMA issue, TMEM double buffering, epilogue and TMA store are those of the plain GEMM.
+//
+// p.b_resident (weights-stationary, chosen by the host when the whole [BLOCK_N x K] weight panel fits beside the A ring):
+// the B operand of an N tile is loaded ONCE per CTA into its own shared-memory region and every M tile of that panel reuses
+// it; the ring then carries A only (more stages).  The convolutions of a CNN are tall-skinny (M = N*P*Q pixels, K = R*S*C
+// <= a few thousand): without this every 128-pixel tile re-fetches the same weights through the L2->SM crossbar, which is
+// the bound of the small-channel layers (profiles/r2/conv_ncu_*.md).
+//
+// p.stats (fused BatchNorm statistics): the epilogue also accumulates, per output column (= channel), the sum and the sum
+// of squares of the bf16-rounded outputs it stores, and writes them as partial rows [4 * grid][2][N] in the format of
+// batchnorm.cu:kbn_fwd_finalize - the BatchNorm that follows the convolution skips its statistics pass over the tensor.
 template <int BLOCK_N, bool A_MN, bool B_MN, bool MC = false, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__ GemmParams p) {
   static_assert(!(MC && CONV), "the multicast-pair variant has no convolution producer");
   static_assert(!CONV || B_MN || !A_MN, "convolution modes: fprop <0,0>, dgrad <0,1>, wgrad <1,1>");
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN>;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiWarps = Cfg::kEpiWarps;
+  const int stages = p.stages;
+  const bool bres = !MC && p.b_resident != 0;
+  const uint32_t stage_bytes = Cfg::kABytes + (bres ? 0 : Cfg::kBBytes);
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B atoms need 1024 B alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t stg_base = smem_base + kStages * Cfg::kStageBytes;   // 1024-aligned (stage sizes are multiples of 16 KiB)
-  const uint32_t bar_base = stg_base + Cfg::kStagingBytes;
+  const uint32_t bres_base = smem_base + stages * stage_bytes;        // 1024-aligned (all sizes are multiples of 8 KiB)
+  const uint32_t stg_base = bres_base + (uint32_t)p.bres_bytes;
+  const uint32_t bar_base = stg_base + (uint32_t)p.stg_bufs * kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + Cfg::kStagingBytes +
-                                                    8 * (2 * kStages + 4));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * kMaxStages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kMaxStages + 5));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -258,14 +282,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     tma_prefetch_desc(&p.tmA);
     for (int s = 0; s < p.n_shards; ++s) tma_prefetch_desc(&p.tmB[s]);
     if (p.tma_store) tma_prefetch_desc(&p.tmD);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), MC ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiThreads);
+      mbar_init(tempty_bar(s), kEpiWarps * 32);
     }
+    mbar_init(bfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -282,19 +307,71 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // one k-block of the B operand for output columns n_idx.. -> shared memory at sb (not used by the MC variant)
+      auto load_b = [&](uint32_t sb, int kb, int n_idx, uint32_t bar) {
+        const int k_idx = kb * kBlockK;
+        if constexpr (CONV && B_MN && !A_MN) {
+          // dgrad: the 64 contraction rows are output channels c0.. of list entry rs; the matching weights are the columns
+          // of filter tap cv_tap_wi[rs] in W viewed as [Cout][R*S*Cin] (MN-major B: box {64 cin, 64 cout})
+          const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(sb + j * 8192, &p.tmB[0], bar, (int)p.cv_tap_wi[rs] * p.cv_cin + n_idx + 64 * j, c0);
+        } else if constexpr (CONV && B_MN && A_MN) {
+          // wgrad: the 64 contraction rows are output pixels k_idx..; output column panel P = (tap, 64-channel slice)
+          const int q0 = k_idx % p.cv_Q, t0 = k_idx / p.cv_Q;
+          const int p0 = t0 % p.cv_P, n0 = t0 / p.cv_P;
+          const int last_panel = p.cv_ntaps * p.cv_cblocks - 1;
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j) {
+            int panel = n_idx / 64 + j;
+            if (panel > last_panel) panel = last_panel;    // N tail: columns >= N are never stored
+            const int rs = panel / p.cv_cblocks, c0 = (panel - rs * p.cv_cblocks) * 64;
+            tma_load_im2col_4d(sb + j * 8192, &p.tmB[0], bar, c0, q0 * p.cv_stride + p.cv_lower_w,
+                               p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)p.cv_tap_ow[rs],
+                               (uint16_t)p.cv_tap_oh[rs]);   // box {64 c, 64 pixels}
+          }
+        } else if constexpr (!B_MN) {
+          // rows of B (= output columns n) may live on a peer: pick the owner's tensor map
+          const int shard = (p.n_shards > 1) ? n_idx / p.rows_per_shard : 0;
+          const int n_loc = n_idx - shard * p.rows_per_shard;
+          tma_load_2d(sb, &p.tmB[shard], bar, k_idx, n_loc);  // box {64 k, BLOCK_N n}
+        } else {
+          // MN-major B is stored [K, N]: the CONTRACTION rows may live on a peer
+          const int shard = (p.n_shards > 1) ? k_idx / p.rows_per_shard : 0;
+          const int k_loc = k_idx - shard * p.rows_per_shard;
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(sb + j * 8192, &p.tmB[shard], bar, n_idx + 64 * j, k_loc);
+        }
+      };
       int stage = 0;
       uint32_t phase = 0;
+      int cur_n = -1;                       // b_resident: the N tile whose weights are in shared memory
+      int acc = 0, prev_acc = 0;            // mirror of the MMA issuer's accumulator-stage sequence
+      uint32_t acc_phase = 0, prev_acc_phase = 0;
       for (int item = item0; item < num_items; item += item_step) {
         const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
         const int m_idx = MC ? ((item % num_pm) * 2 + cta_rank) * kBlockM : (tile % num_m) * kBlockM;
         const int n_idx = MC ? (item / num_pm) * BLOCK_N : (tile / num_m) * BLOCK_N;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        if (bres) {
+          if (n_idx != cur_n) {
+            // every MMA that reads the old panel has completed once the previous item's accumulator is committed
+            if (cur_n >= 0) mbar_wait(tfull_bar(prev_acc), prev_acc_phase);
+            mbar_expect_tx(bfull_bar, (uint32_t)num_kb * Cfg::kBBytes);
+            for (int kb = 0; kb < num_kb; ++kb) load_b(bres_base + (uint32_t)kb * Cfg::kBBytes, kb, n_idx, bfull_bar);
+            cur_n = n_idx;
+          }
+          prev_acc = acc; prev_acc_phase = acc_phase;
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int k_idx = kb * kBlockK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          mbar_expect_tx(full_bar(stage), stage_bytes);
           if constexpr (CONV && !A_MN) {
             // fprop / dgrad: k-block = (filter tap rs, 64-channel slice); 128 consecutive output pixels from m_idx
             const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
@@ -322,49 +399,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
                 tma_load_2d_mc(sb + jj * 8192, &p.tmB[0], full_bar(stage), n_idx + 64 * jj, k_idx, (uint16_t)3);
               }
             }
-          } else if constexpr (CONV && B_MN && !A_MN) {
-            // dgrad: the 64 contraction rows are output channels c0.. of list entry rs; the matching weights are the columns
-            // of filter tap cv_tap_wi[rs] in W viewed as [Cout][R*S*Cin] (MN-major B: box {64 cin, 64 cout})
-            const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
-#pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * 8192, &p.tmB[0], full_bar(stage), (int)p.cv_tap_wi[rs] * p.cv_cin + n_idx + 64 * j, c0);
-          } else if constexpr (CONV && B_MN && A_MN) {
-            // wgrad: the 64 contraction rows are output pixels k_idx..; output column panel P = (tap, 64-channel slice)
-            const int q0 = k_idx % p.cv_Q, t0 = k_idx / p.cv_Q;
-            const int p0 = t0 % p.cv_P, n0 = t0 / p.cv_P;
-            const int last_panel = p.cv_RS * p.cv_cblocks - 1;
-#pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j) {
-              int panel = n_idx / 64 + j;
-              if (panel > last_panel) panel = last_panel;    // N tail: columns >= N are never stored
-              const int rs = panel / p.cv_cblocks, c0 = (panel - rs * p.cv_cblocks) * 64;
-              tma_load_im2col_4d(sb + j * 8192, &p.tmB[0], full_bar(stage), c0, q0 * p.cv_stride + p.cv_lower_w,
-                                 p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)p.cv_tap_ow[rs],
-                                 (uint16_t)p.cv_tap_oh[rs]);   // box {64 c, 64 pixels}
-            }
-          } else if constexpr (!B_MN) {
-            // rows of B (= output columns n) may live on a peer: pick the owner's tensor map
-            const int shard = (p.n_shards > 1) ? n_idx / p.rows_per_shard : 0;
-            const int n_loc = n_idx - shard * p.rows_per_shard;
-            tma_load_2d(sb, &p.tmB[shard], full_bar(stage), k_idx, n_loc);  // box {64 k, BLOCK_N n}
-          } else {
-            // MN-major B is stored [K, N]: the CONTRACTION rows may live on a peer
-            const int shard = (p.n_shards > 1) ? k_idx / p.rows_per_shard : 0;
-            const int k_loc = k_idx - shard * p.rows_per_shard;
-#pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * 8192, &p.tmB[shard], full_bar(stage), n_idx + 64 * j, k_loc);
+          } else if (!bres) {
+            load_b(sb, kb, n_idx, full_bar(stage));
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
       if constexpr (MC) {
         // producer tail: every slot's last use has been released by BOTH CTAs, i.e. the peer's multicast commits that
         // target this CTA's barriers have landed - only then may this CTA run towards its exit
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < stages; ++s) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -379,17 +425,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int cur_n = -1;
+      uint32_t bphase = 0;
       for (int item = item0; item < num_items; item += item_step) {
-        const int split = MC ? 0 : item / num_tiles;
+        const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        if (bres) {
+          const int n_idx = (tile / num_m) * BLOCK_N;
+          if (n_idx != cur_n) {            // the producer has (re)loaded the weight panel
+            mbar_wait(bfull_bar, bphase);
+            bphase ^= 1u;
+            cur_n = n_idx;
+          }
+        }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = bres ? bres_base + (uint32_t)kb * Cfg::kBBytes : sa + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // K-major: advance 16 elements = 32 B inside the swizzle atom; SBO = 8 rows * 128 B
@@ -401,20 +457,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
           // smem slot reusable once these MMAs have read it (MC: tell the peer too, its multicast writes into this slot)
           if constexpr (MC) tc_commit_mc(empty_bar(stage), (uint16_t)3);
           else tc_commit(empty_bar(stage));
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue (and, b_resident, -> the producer's panel swap)
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..9) =====================
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue (warps 2..2+kEpiWarps) =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp owns
-    constexpr int kChunks = BLOCK_N / 64;   // 32-column chunks per warp
+    const int half = (warp - 2) >> 2;   // which part of the tile's columns this warp owns (8 warps: halves; 4 warps: all)
+    constexpr int kChunks = BLOCK_N / (32 * (kEpiWarps / 4));   // 32-column chunks per warp
+    constexpr int kBoxes = kChunks / 2;                         // 64-column TMA store boxes per warp
     const bool splitk = p.splits > 1;
+    const bool do_stats = p.stats != nullptr && p.tma_store && !splitk;
+    float st_s[kBoxes][2], st_q[kBoxes][2];   // fused BN statistics: this lane's two columns of every box
+#pragma unroll
+    for (int b = 0; b < kBoxes; ++b) { st_s[b][0] = st_s[b][1] = 0.f; st_q[b][0] = st_q[b][1] = 0.f; }
+    int st_n = -1;
+    auto flush_stats = [&]() {
+      if (st_n < 0) return;
+      float* row = p.stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N;
+#pragma unroll
+      for (int b = 0; b < kBoxes; ++b) {
+        const int col = st_n + (half * kChunks + 2 * b) * 32 + 2 * lane;
+        if (col + 1 < p.N) {
+          *reinterpret_cast<float2*>(row + col) = make_float2(st_s[b][0], st_s[b][1]);
+          *reinterpret_cast<float2*>(row + p.N + col) = make_float2(st_q[b][0], st_q[b][1]);
+        } else if (col < p.N) {
+          row[col] = st_s[b][0];
+          row[p.N + col] = st_q[b][0];
+        }
+        st_s[b][0] = st_s[b][1] = 0.f; st_q[b][0] = st_q[b][1] = 0.f;
+      }
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool stg2 = p.stg_bufs == 2;
+    uint32_t stg_sel = 0;               // which of this warp's staging tiles the next box goes through
     for (int item = item0; item < num_items; item += item_step) {
       const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
       const int m_idx = MC ? ((item % num_pm) * 2 + cta_rank) * kBlockM : (tile % num_m) * kBlockM;
@@ -446,15 +526,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       const long long ldd = splitk ? (long long)p.N : p.ldd;
       void* dbase = splitk ? (void*)(p.ws + (size_t)split * p.M * p.N) : p.D;
       if (p.tma_store && !splitk) {
+        if (do_stats && n_idx != st_n) {
+          flush_stats();
+          st_n = n_idx;
+        }
         // bf16 output through shared memory: lane = row writes its 64 columns (128 B) as 8 16-byte chunks at the
         // 128B-swizzled position (chunk ^ (row & 7)) - conflict-free - and one lane hands the tile to TMA.
-        const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
-        uint8_t* stg_gen = smem_gen + (stg - smem_base);
 #pragma unroll
-        for (int bx = 0; bx < kChunks / 2; ++bx) {
+        for (int bx = 0; bx < kBoxes; ++bx) {
           const int colb = n_idx + (half * kChunks + 2 * bx) * 32;   // first column of this 64-wide box
           if (colb < p.N) {
-            if (lane == 0) tma_store_wait_read();                    // previous store out of this buffer has been read
+            const uint32_t stg = stg_base + ((uint32_t)(warp - 2) * (stg2 ? 2u : 1u) + (stg2 ? stg_sel : 0u)) * 4096u;
+            uint8_t* stg_gen = smem_gen + (stg - smem_base);
+            stg_sel ^= 1u;
+            if (lane == 0) {                                         // the previous store out of THIS buffer has been read
+              if (stg2) tma_store_wait_read1();
+              else tma_store_wait_read();
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -478,6 +566,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
             if (lane == 0) {
               tma_store_2d(&p.tmD, stg, colb, m_idx + q * 32);       // rows >= M / cols >= N are clipped by the map
               tma_store_commit();
+            }
+            if (do_stats) {
+              // column sums over this warp's 32 rows, read back from the staging tile (the values BatchNorm will see):
+              // lane l owns columns 2l, 2l+1 = one 4-byte word per row, a conflict-free 128-byte row read per step.
+              // Rows >= M hold exact zeros (their A rows are TMA zero-fill) and add nothing.
+              const int chunk = lane >> 2, within = (lane & 3) * 4;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(stg_gen + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
+                const float a = bf16_lo(w), b = bf16_hi(w);
+                st_s[bx][0] += a; st_q[bx][0] = fmaf(a, a, st_q[bx][0]);
+                st_s[bx][1] += b; st_q[bx][1] = fmaf(b, b, st_q[bx][1]);
+              }
             }
           }
         }
@@ -546,6 +647,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
         }
       }
     }
+    if (do_stats) flush_stats();
     if (p.tma_store && lane == 0) tma_store_wait_read();   // staging smem must outlive the last bulk store's reads
   }
 
@@ -578,11 +680,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
 //   * TMEM is allocated / freed with cta_group::2 by warp 1 of both CTAs; cluster barriers bracket the kernel
 constexpr int k2BlockN = 256;
 constexpr int k2HalfN = 128;
-constexpr int k2Stages = 6;
+constexpr int k2Stages = 5;            // 5 x 32 KiB ring + two staging tiles per epilogue warp (64 KiB)
 constexpr int k2ABytes = kBlockM * kBlockK * 2;     // 16 KiB
 constexpr int k2BBytes = k2HalfN * kBlockK * 2;     // 16 KiB (this CTA's half of the B tile)
 constexpr int k2StageBytes = k2ABytes + k2BBytes;
-constexpr int k2StagingBytes = 8 * 4096;
+constexpr int k2StagingBytes = 2 * 8 * 4096;
 constexpr int k2SmemBytes = k2Stages * k2StageBytes + k2StagingBytes + 1024 + 256;
 constexpr int k2TmemCols = 2 * k2BlockN;            // two accumulator stages = all 512 columns
 
@@ -739,8 +841,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
     constexpr int kChunks = k2BlockN / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
-    uint8_t* stg_gen = smem_gen + (stg - smem_base);
+    uint32_t stg_sel = 0;           // two staging tiles per warp: fill one while TMA still reads the other
     for (int item = item0; item < num_items; item += item_step) {
       const int m_idx = ((item % num_pm) * 2 + cta_rank) * kBlockM;
       const int n_idx = (item / num_pm) * k2BlockN;
@@ -759,7 +860,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
       for (int bx = 0; bx < kChunks / 2; ++bx) {
         const int colb = n_idx + (half * kChunks + 2 * bx) * 32;
         if (colb < p.N) {
-          if (lane == 0) tma_store_wait_read();
+          const uint32_t stg = stg_base + ((uint32_t)(warp - 2) * 2u + stg_sel) * 4096u;
+          uint8_t* stg_gen = smem_gen + (stg - smem_base);
+          stg_sel ^= 1u;
+          if (lane == 0) tma_store_wait_read1();
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -939,7 +1043,7 @@ static int launch(GemmParams& p, int num_sms, cudaStream_t stream) {
   auto kern = kgemm<BLOCK_N, A_MN, B_MN, false, CONV>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (ae != cudaSuccess) {
       fprintf(stderr, "[dlcfn] cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(ae));
       return (int)ae;
@@ -962,17 +1066,55 @@ static int launch(GemmParams& p, int num_sms, cudaStream_t stream) {
       p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // every slice owns >= 1 k-block
     }
   }
+  // pipeline shape: weights-stationary when B is a weight panel (A is the activation operand: fprop / dgrad forms), the whole
+  // [BLOCK_N x K] panel fits beside at least 4 A stages, and every CTA works on more than one M tile of it
+  static const bool bres_env = [] { const char* e = getenv("DLCFN_GEMM_BRES"); return !(e && e[0] == '0'); }();
+  // short reductions are epilogue-paced: two staging tiles per warp let a warp convert the next box while TMA drains the last
+  p.stg_bufs = (p.tma_store && num_kb <= 12) ? 2 : 1;
+  const int fixed = p.stg_bufs * kStagingBytes + 1024 + kBarrierBytes;
+  p.b_resident = 0;
+  p.bres_bytes = 0;
+  const long long panel = (long long)num_kb * Cfg::kBBytes;
+  if (bres_env && !A_MN && p.n_shards == 1 && p.splits == 1 && tiles >= 2 * num_sms &&
+      panel + 4 * Cfg::kABytes + fixed <= kSmemLimit) {
+    p.b_resident = 1;
+    p.bres_bytes = (int)panel;
+  }
+  const int stage_bytes = Cfg::kABytes + (p.b_resident ? 0 : Cfg::kBBytes);
+  int stages = (kSmemLimit - fixed - p.bres_bytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (!p.b_resident && stages > Cfg::kStages + 2) stages = Cfg::kStages + 2;
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + p.bres_bytes + fixed;
   if (p.splits > 1) {
+    // stream-ordered workspace from the device's default pool; the pool keeps its memory across synchronisation points
+    // (the default release threshold 0 hands everything back to the driver at every sync: 1+ ms per re-allocation)
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    DLCFN_CHECK(cudaGetDevice(&dev));
+    if (pool_dev != dev) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_dev = dev;
+    }
     void* ws = nullptr;
     DLCFN_CHECK(cudaMallocAsync(&ws, (size_t)p.splits * p.M * p.N * sizeof(float), stream));
     p.ws = (float*)ws;
   }
   int grid = tiles * p.splits;
   if (grid > num_sms) grid = num_sms;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  if (p.stats != nullptr) {
+    // rows of CTAs / N tiles that never meet stay zero
+    if (p.splits > 1 || !p.tma_store) return (int)cudaErrorInvalidValue;
+    DLCFN_CHECK(cudaMemsetAsync(p.stats, 0, (size_t)4 * num_sms * 2 * p.N * sizeof(float), stream));
+  }
+  kern<<<grid, kGemmThreads, smem_bytes, stream>>>(p);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess)
-    fprintf(stderr, "[dlcfn] kgemm launch failed: %s (grid %d, smem %d)\n", cudaGetErrorString(le), grid, Cfg::kSmemBytes);
+    fprintf(stderr, "[dlcfn] kgemm launch failed: %s (grid %d, smem %d)\n", cudaGetErrorString(le), grid, smem_bytes);
   if (p.splits > 1) {
     if (le == cudaSuccess) {
       const long long nvec = (long long)p.M * p.N / 4;
@@ -1008,9 +1150,11 @@ static EncodeIm2colFn get_encode_im2col() {
 struct Im2colKey {
   const void* ptr;
   int n, h, w, c, lower_w, lower_h, upper_w, upper_h, stride, pixels;
+  long long xs_w, xs_h, xs_n;
   bool operator==(const Im2colKey& o) const {
     return ptr == o.ptr && n == o.n && h == o.h && w == o.w && c == o.c && lower_w == o.lower_w && lower_h == o.lower_h &&
-           upper_w == o.upper_w && upper_h == o.upper_h && stride == o.stride && pixels == o.pixels;
+           upper_w == o.upper_w && upper_h == o.upper_h && stride == o.stride && pixels == o.pixels && xs_w == o.xs_w &&
+           xs_h == o.xs_h && xs_n == o.xs_n;
   }
 };
 struct Im2colSlot {
@@ -1023,7 +1167,10 @@ constexpr int kIm2colCacheSlots = 256;
 // NHWC bf16 tensor [n, h, w, c] as an im2col-mode map: 64 channels x `pixels` base positions per load, 128B swizzle.
 // Base positions live in the box [lower, extent - 1 + upper] per spatial dimension and advance by `stride`.
 static int make_map_im2col(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int lower_w, int lower_h, int upper_w,
-                           int upper_h, int stride, int pixels) {
+                           int upper_h, int stride, int pixels, long long xs_w = 0, long long xs_h = 0, long long xs_n = 0) {
+  if (xs_w <= 0) xs_w = c;
+  if (xs_h <= 0) xs_h = (long long)w * xs_w;
+  if (xs_n <= 0) xs_n = (long long)h * xs_h;
   static thread_local Im2colSlot* cache = nullptr;
   if (!cache) {
     cache = static_cast<Im2colSlot*>(aligned_alloc(64, kIm2colCacheSlots * sizeof(Im2colSlot)));
@@ -1033,6 +1180,7 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, int n, int h, int w,
   memset(&key, 0, sizeof(key));     // padding bytes take part in nothing, but keep the slot image deterministic
   key.ptr = ptr; key.n = n; key.h = h; key.w = w; key.c = c; key.lower_w = lower_w; key.lower_h = lower_h;
   key.upper_w = upper_w; key.upper_h = upper_h; key.stride = stride; key.pixels = pixels;
+  key.xs_w = xs_w; key.xs_h = xs_h; key.xs_n = xs_n;
   uint64_t hsh = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
   hsh ^= ((uint64_t)n << 48) ^ ((uint64_t)h << 36) ^ ((uint64_t)w << 24) ^ ((uint64_t)c << 8) ^ ((uint64_t)pixels << 2) ^
          (uint64_t)(lower_w + 8) ^ ((uint64_t)stride << 5);
@@ -1044,7 +1192,7 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, int n, int h, int w,
   EncodeIm2colFn enc = get_encode_im2col();
   if (!enc) return (int)cudaErrorNotSupported;
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t gstr[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)xs_w * 2, (cuuint64_t)xs_h * 2, (cuuint64_t)xs_n * 2};
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
@@ -1086,6 +1234,10 @@ static int launch_mc(GemmParams& p, int num_sms, cudaStream_t stream) {
   p.splits = 1;
   p.kb_per_split = (p.K + kBlockK - 1) / kBlockK;
   p.ws = nullptr;
+  p.stages = Cfg::kStages;
+  p.b_resident = 0;
+  p.bres_bytes = 0;
+  p.stg_bufs = 1;
   const int num_m = (p.M + kBlockM - 1) / kBlockM, num_n = (p.N + 255) / 256;
   const int pair_tiles = ((num_m + 1) / 2) * num_n;
   int pairs = num_sms / 2;
@@ -1157,10 +1309,31 @@ using namespace dlcfn;
 //   [s*rows_per_shard, (s+1)*rows_per_shard) of B's ROW dimension as stored
 //   (K-major: output columns n; MN-major: contraction index k).  n_shards == 1: plain local GEMM.
 // lda / ldb: row strides in elements of the stored matrices.  d_dtype: 0 fp32, 1 bf16.
+// stats (nullable): fp32 [dlcfn_gemm_stats_rows()][2][N] partial column sums / sums of squares of the stored bf16 output
+// (fused BatchNorm statistics, see kgemm); needs the bf16 TMA-store output form.
+DLCFN_API int dlcfn_gemm_stats_rows() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return 4 * sms;
+}
+
+DLCFN_API int dlcfn_gemm_bf16_ex(const void* A, long long lda, int a_mn, const void* const* b_shards, int n_shards,
+                                 int rows_per_shard, long long ldb, int b_mn, void* D, long long ldd, int d_dtype,
+                                 const float* bias, int M, int N, int K, int accumulate, int relu, int block_n,
+                                 int num_sms, float* stats, cudaStream_t stream);
+
 DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void* const* b_shards, int n_shards,
                               int rows_per_shard, long long ldb, int b_mn, void* D, long long ldd, int d_dtype,
                               const float* bias, int M, int N, int K, int accumulate, int relu, int block_n,
                               int num_sms, cudaStream_t stream) {
+  return dlcfn_gemm_bf16_ex(A, lda, a_mn, b_shards, n_shards, rows_per_shard, ldb, b_mn, D, ldd, d_dtype, bias, M, N, K,
+                            accumulate, relu, block_n, num_sms, nullptr, stream);
+}
+
+DLCFN_API int dlcfn_gemm_bf16_ex(const void* A, long long lda, int a_mn, const void* const* b_shards, int n_shards,
+                                 int rows_per_shard, long long ldb, int b_mn, void* D, long long ldd, int d_dtype,
+                                 const float* bias, int M, int N, int K, int accumulate, int relu, int block_n,
+                                 int num_sms, float* stats, cudaStream_t stream) {
   // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread.  Autograd
   // worker threads for device 0 have none until the first runtime call (torch skips cudaSetDevice
   // when the ordinal already matches), so bind the primary context once per thread.
@@ -1178,7 +1351,9 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
     DLCFN_CHECK(cudaGetDevice(&dev));
     DLCFN_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (block_n != 128 && block_n != 256) {
+  if (block_n == 64 && a_mn) block_n = 128;      // the 64-wide tile exists for the activation-operand forms only
+  if (block_n != 64 && block_n != 128 && block_n != 256 && N <= 64 && !a_mn && n_shards == 1) block_n = 64;
+  if (block_n != 64 && block_n != 128 && block_n != 256) {
     // 128x256 tiles feed the tensor pipe better (measured 1.35 vs 1.0 PFLOP/s at 8192^3) but halve the tile count.
     // Score each width by  pipe rate x useful fraction of the padded tile grid x occupancy of the last wave  and take
     // the better one; e.g. M=8192, N=1024: 256 wide tiles = 1.73 waves (86 %) x 1.35 beats 512 narrow tiles (86 %) x 1.0.
@@ -1200,18 +1375,19 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   p.d_is_fp32 = d_dtype == 0;
   p.accumulate = accumulate;
   p.relu = relu;
+  p.stats = stats;
   static const bool splitk_env = [] { const char* e = getenv("DLCFN_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
-  p.split_k_ok = splitk_env ? 1 : 0;
+  p.split_k_ok = (splitk_env && stats == nullptr) ? 1 : 0;
   // EXPERIMENTAL multicast-pair kernel: opt-in, wide tiles, local B, enough tile pairs to fill the machine, and a
   // reduction too short for split-K to matter (it is not combined with split-K)
   static const bool mc_env = [] { const char* e = getenv("DLCFN_GEMM_MULTICAST"); return e && e[0] == '1'; }();
-  const bool use_mc = mc_env && block_n == 256 && n_shards == 1 &&
+  const bool use_mc = mc_env && stats == nullptr && block_n == 256 && n_shards == 1 &&
                       (long long)(((M + kBlockM - 1) / kBlockM + 1) / 2) * ((N + 255) / 256) >= num_sms / 2;
   // CTA-pair kernel (cta_group::2, validated on B200 in round 2: 983 vs 629 TFLOP/s single-CTA at 16384x1024x1024): default
   // for bf16 TMA-store outputs of GEMMs with enough 256 x 256 pair tiles; DLCFN_GEMM_2CTA=0 disables
   static const bool pair_env = [] { const char* e = getenv("DLCFN_GEMM_2CTA"); return !(e && e[0] == '0'); }();
   static const bool tma_store_env2 = [] { const char* e = getenv("DLCFN_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
-  const bool use_pair = pair_env && !use_mc && n_shards == 1 && N >= 256 && tma_store_env2 && d_dtype == 1 && !accumulate &&
+  const bool use_pair = pair_env && stats == nullptr && !use_mc && n_shards == 1 && N >= 256 && tma_store_env2 && d_dtype == 1 && !accumulate &&
                         (ldd & 7) == 0 && (((uintptr_t)D) & 15) == 0 &&
                         (long long)(((M + kBlockM - 1) / kBlockM + 1) / 2) * ((N + 255) / 256) >= num_sms / 4;
   if (use_pair) block_n = 256;
@@ -1236,6 +1412,7 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
     if (rc) return rc;
     p.tma_store = 1;
   }
+  if (stats != nullptr && !p.tma_store) return (int)cudaErrorInvalidValue;
   if (n_shards > 1) {
     // a tile must not straddle two shards
     if (!b_mn && (rows_per_shard % block_n)) return (int)cudaErrorInvalidValue;
@@ -1255,6 +1432,8 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
   }
 #define DLCFN_GEMM_CASE(BN, AM, BM) \
   if (block_n == BN && (bool)a_mn == AM && (bool)b_mn == BM) return launch<BN, AM, BM>(p, num_sms, stream);
+  DLCFN_GEMM_CASE(64, false, false)
+  DLCFN_GEMM_CASE(64, false, true)
   DLCFN_GEMM_CASE(128, false, false)
   DLCFN_GEMM_CASE(128, false, true)
   DLCFN_GEMM_CASE(128, true, false)
@@ -1278,8 +1457,10 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
 static int conv_launch(GemmParams& p, int block_n, bool a_mn, bool b_mn, int num_sms, cudaStream_t stream) {
 #define DLCFN_CONV_CASE(BN, AM, BM) \
   if (block_n == BN && a_mn == AM && b_mn == BM) return launch<BN, AM, BM, true>(p, num_sms, stream);
+  DLCFN_CONV_CASE(64, false, false)
   DLCFN_CONV_CASE(128, false, false)
   DLCFN_CONV_CASE(256, false, false)
+  DLCFN_CONV_CASE(64, false, true)
   DLCFN_CONV_CASE(128, false, true)
   DLCFN_CONV_CASE(256, false, true)
   DLCFN_CONV_CASE(128, true, true)
@@ -1288,9 +1469,26 @@ static int conv_launch(GemmParams& p, int block_n, bool a_mn, bool b_mn, int num
   return (int)cudaErrorInvalidValue;
 }
 
+// _ex: `xs_w / xs_h / xs_n` (elements; 0 = dense NHWC) are the strides of the im2col'd tensor's w / h / n dimensions - an
+// OVERLAPPING view is allowed: ResNet's stem reads its 16-channel space-to-depth image as [n, 115, 112, 64] with xs_w = 16,
+// i.e. a "pixel" of 64 channels = 4 adjacent columns x 16 channels, which turns the 4x4 filter into 4 (r) x 1 taps of whole
+// 128-byte rows.  `stats`: fused BatchNorm statistics of the fprop output (see dlcfn_gemm_bf16_ex).
+DLCFN_API int dlcfn_conv_bf16_ex(int op, const void* x, const void* other, void* out, int out_dtype, int n, int h, int w, int c,
+                                 int k, int cin, int r, int s, int pad, int stride, int oh, int ow, int accumulate,
+                                 int block_n, int num_sms, long long xs_w, long long xs_h, long long xs_n, float* stats,
+                                 cudaStream_t stream);
+
 DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* out, int out_dtype, int n, int h, int w, int c,
                               int k, int cin, int r, int s, int pad, int stride, int oh, int ow, int accumulate,
                               int block_n, int num_sms, cudaStream_t stream) {
+  return dlcfn_conv_bf16_ex(op, x, other, out, out_dtype, n, h, w, c, k, cin, r, s, pad, stride, oh, ow, accumulate, block_n,
+                            num_sms, 0, 0, 0, nullptr, stream);
+}
+
+DLCFN_API int dlcfn_conv_bf16_ex(int op, const void* x, const void* other, void* out, int out_dtype, int n, int h, int w, int c,
+                                 int k, int cin, int r, int s, int pad, int stride, int oh, int ow, int accumulate,
+                                 int block_n, int num_sms, long long xs_w, long long xs_h, long long xs_n, float* stats,
+                                 cudaStream_t stream) {
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) {
     DLCFN_CHECK(cudaFree(nullptr));
@@ -1313,6 +1511,9 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
   p.accumulate = accumulate;
   static const bool splitk_env = [] { const char* e = getenv("DLCFN_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
   p.split_k_ok = splitk_env ? 1 : 0;
+  if (stats != nullptr && op != 0) return (int)cudaErrorInvalidValue;
+  p.stats = stats;
+  if (stats != nullptr) p.split_k_ok = 0;
   p.cv_S = s;
   p.cv_RS = r * s;
   p.cv_cblocks = c / 64;
@@ -1339,9 +1540,9 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
     if (op == 0) {
       p.M = n * P * Q; p.N = k; p.K = r * s * c;
       p.ldd = k;
-      rc = make_map_im2col(&p.tmA, x, n, h, w, c, -pad, -pad, upper_w, upper_h, stride, kBlockM);
+      rc = make_map_im2col(&p.tmA, x, n, h, w, c, -pad, -pad, upper_w, upper_h, stride, kBlockM, xs_w, xs_h, xs_n);
       if (rc) return rc;
-      if (block_n != 128 && block_n != 256) block_n = (k >= 256) ? 256 : 128;
+      if (block_n != 64 && block_n != 128 && block_n != 256) block_n = (k >= 256) ? 256 : (k > 64 ? 128 : 64);
       rc = make_map(&p.tmB[0], other, k, (uint64_t)r * s * c, (uint64_t)r * s * c, kBlockK, block_n);   // W as [k][rs*c], K-major
       if (rc) return rc;
       a_mn = false; b_mn = false;
@@ -1350,9 +1551,11 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
       p.ldd = (long long)r * s * c;
       rc = make_map(&p.tmA, other, (uint64_t)n * P * Q, k, k, 64, kBlockK);                       // dy as [npq][k], MN-major A
       if (rc) return rc;
-      rc = make_map_im2col(&p.tmB[0], x, n, h, w, c, -pad, -pad, upper_w, upper_h, stride, kBlockK);
+      rc = make_map_im2col(&p.tmB[0], x, n, h, w, c, -pad, -pad, upper_w, upper_h, stride, kBlockK, xs_w, xs_h, xs_n);
       if (rc) return rc;
-      if (block_n != 128 && block_n != 256) block_n = 128;
+      // every (tile, k-slice) work item streams its whole slice of BOTH operands through the L2 -> SM crossbar, which is the
+      // bound of these kernels: wide tiles halve the re-reads of dy (profiles/r2/conv_ncu_before.md)
+      if (block_n != 128 && block_n != 256) block_n = (p.N >= 512) ? 256 : 128;
       a_mn = true; b_mn = true;
     }
     if (tma_store_env && out_dtype == 1 && !accumulate && p.N >= 64 && (p.ldd & 7) == 0) {
@@ -1360,6 +1563,7 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
       if (rc) return rc;
       p.tma_store = 1;
     }
+    if (stats != nullptr && !p.tma_store) return (int)cudaErrorInvalidValue;
     return conv_launch(p, block_n, a_mn, b_mn, num_sms, stream);
   }
   // ---------------------------------------------------------------- dgrad: x is dy [n, h, w, c = k]; out = dx [n, oh, ow, cin]
@@ -1367,7 +1571,7 @@ DLCFN_API int dlcfn_conv_bf16(int op, const void* x, const void* other, void* ou
   if ((h + 0) != (oh + 2 * pad - r) / stride + 1 || w != (ow + 2 * pad - s) / stride + 1) return (int)cudaErrorInvalidValue;
   rc = make_map(&p.tmB[0], other, k, (uint64_t)r * s * cin, (uint64_t)r * s * cin, 64, kBlockK);  // W as [k][rs*cin], MN-major B
   if (rc) return rc;
-  if (block_n != 128 && block_n != 256) block_n = (cin >= 256) ? 256 : 128;
+  if (block_n != 64 && block_n != 128 && block_n != 256) block_n = (cin >= 256) ? 256 : (cin > 64 ? 128 : 64);
   p.ldd = cin;
   p.N = cin;
   p.cv_stride = 1;                 // base positions walk dy's grid with unit steps in every class

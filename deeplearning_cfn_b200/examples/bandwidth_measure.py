@@ -71,6 +71,8 @@ class Runner:
             self.w = torch.empty(cap, dtype=dtype, device=self.dev)
 
     def fill(self, n: int, it: int, at: int = 0) -> None:
+        if at + n > self.g.numel():
+            raise IndexError(f"array [{at}, {at + n}) does not fit the {self.g.numel()}-element arena")
         self.g[at:at + n] = float(self.rank + 1 + it % 3)
 
     def expected(self, n: int, it: int) -> float:
@@ -81,6 +83,8 @@ class Runner:
         the reduced values."""
         k = self.kind
         b = at * self.esz
+        if at % 64 or at + n > self.g.numel():           # a region past the arena would be reduced out of bounds on the peers
+            raise IndexError(f"array [{at}, {at + n}) does not fit the {self.g.numel()}-element arena (offsets are multiples of 64)")
         if k == "allreduce":
             self.heap.allreduce_(self.goff + b, n, self.dtype, 1.0)
             return self.g[at:at + n]

@@ -22,6 +22,7 @@ from ..ops.conv import Conv1x1, ConvKxK
 from ..ops.linear import Linear
 from ..ops.pool import MaxPool2d, global_avg_pool
 
+_FUSED_STEM = __import__("os").environ.get("DLCFN_FUSED_STEM", "1") != "0"
 _EPS = 2e-5
 _MOM = 0.1  # torch momentum = 1 - mxnet bn_mom(0.9)
 
@@ -54,8 +55,9 @@ class BottleneckV2(nn.Module):
             x, a = self.bn1.forward_add(x[0], x[1])
         else:
             a = self.bn1(x)  # BN + ReLU fused
-        y = self.conv1(a)
-        y = self.conv2(self.bn2(y))
+        # stats=True: the convolution's epilogue accumulates the BatchNorm statistics of its output (ops/conv.py)
+        y = self.conv1(a, stats=True)
+        y = self.conv2(self.bn2(y), stats=True)
         y = self.conv3(self.bn3(y))
         return y, (x if self.sc is None else self.sc(a))
 
@@ -74,7 +76,7 @@ class BasicV2(nn.Module):
             x, a = self.bn1.forward_add(x[0], x[1])
         else:
             a = self.bn1(x)
-        y = self.conv2(self.bn2(self.conv1(a)))
+        y = self.conv2(self.bn2(self.conv1(a, stats=True)))
         return y, (x if self.sc is None else self.sc(a))
 
 
@@ -140,6 +142,89 @@ class StemConv(nn.Conv2d):
         return F.conv2d(x8, w8, self.bias, self.stride, self.padding)
 
 
+def _stem_w4(w: torch.Tensor) -> torch.Tensor:
+    """[O,3,7,7] -> the 4x4 filter over the 16-channel space-to-depth image, [O,16,4,4] channels_last:
+    w4[o, c*4 + i*2 + j, a, b] = w[o, c, 2a+i, 2b+j] (zero where 2a+i or 2b+j = 7, channels 12..15 zero)."""
+    O, C = w.shape[0], 3
+    w8 = F.pad(w, (0, 1, 0, 1))
+    w4 = w8.reshape(O, C, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(O, C * 4, 4, 4)
+    return F.pad(w4, (0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last)
+
+
+def _stem_w4_adjoint(dw4: torch.Tensor) -> torch.Tensor:
+    """Gradient of `_stem_w4`: [O,16,4,4] -> [O,3,7,7]."""
+    O = dw4.shape[0]
+    d = dw4[:, :12].reshape(O, 3, 2, 2, 4, 4).permute(0, 1, 4, 2, 5, 3).reshape(O, 3, 8, 8)
+    return d[:, :, :7, :7].contiguous()
+
+
+_TAP_MASKS: dict = {}
+
+
+def _stem_tap_masks(H: int, W: int, P: int, Q: int, device):
+    """A[r, p] = 1 iff output row p's filter row r reads a real image row (2p + r - 3 in [0, H)); B likewise for columns."""
+    key = (H, W, P, Q, str(device))
+    if key not in _TAP_MASKS:
+        def mask(extent, outs):
+            m = torch.zeros(7, outs)
+            for t in range(7):
+                lo, hi = max(0, (3 - t + 1) // 2), min(outs - 1, (extent + 2 - t) // 2)
+                m[t, lo:hi + 1] = 1.0
+            return m.to(device)
+        _TAP_MASKS[key] = (mask(H, P), mask(W, Q))
+    return _TAP_MASKS[key]
+
+
+class _FusedStemFn(torch.autograd.Function):
+    """bn_data (BatchNorm over the 3 image channels, gamma fixed) + 7x7 / stride 2 / pad 3 convolution, all on dlcfn kernels:
+    pad 3->8 channels, fused BatchNorm, space-to-depth (one kernel each), then the 4x4 / stride-1 convolution over the
+    16-channel s2d image as an implicit GEMM whose "pixels" are 4 adjacent columns (ops/native.py:_stem_view).
+
+    Backward needs no input gradient (the image): the filter gradient is one split-K implicit GEMM, and the only thing the
+    BatchNorm wants - d beta[c] = sum over real pixels of the convolution's input gradient - is, by linearity,
+        sum_{k,r,s} w[k,c,r,s] * T[k,r,s],     T[k,r,s] = sum_n sum_{(p,q): pixel (2p+r-3, 2q+s-3) inside the image} dy[n,k,p,q]
+    i.e. rectangle sums of the batch-summed output gradient: one reduction over dy instead of a dgrad and a BatchNorm
+    backward over the 224x224 image (reference: MX/src/operator/nn/batch_norm.cu backward with fix_gamma)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bn_bias, bn: "DataBatchNorm", want_stats: bool):
+        from ..ops import native
+        from ..ops.batchnorm import batch_norm_relu
+        from ..ops.pool import pad3to8, stem_space_to_depth
+        x8 = pad3to8(x)
+        g8 = F.pad(bn.weight.detach(), (0, 5), value=1.0)
+        b8 = F.pad(bn_bias.detach(), (0, 5))
+        rm8, rv8 = F.pad(bn.running_mean, (0, 5)), F.pad(bn.running_var, (0, 5), value=1.0)
+        y8 = batch_norm_relu(x8, g8, b8, rm8, rv8, bn.training, bn.momentum, bn.eps, relu=False)
+        if bn.training:
+            bn.running_mean.copy_(rm8[:3])
+            bn.running_var.copy_(rv8[:3])
+        s2d = stem_space_to_depth(y8)
+        stats = native.new_stats(w.shape[0], x.device) if want_stats else None
+        y = native.stem_conv_fprop(s2d, _stem_w4(w.detach()), stats)
+        ctx.save_for_backward(s2d, w)
+        ctx.hw = (x.shape[2], x.shape[3])
+        if stats is not None:
+            ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats=None):
+        from ..ops import native
+        s2d, w = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dw = _stem_w4_adjoint(native.stem_conv_wgrad(s2d, dy)).to(w.dtype) if ctx.needs_input_grad[1] else None
+        dbeta = None
+        if ctx.needs_input_grad[2]:
+            H, W = ctx.hw
+            D = native.batch_sum(dy)                                        # [K, P, Q] fp32 (strides of dy[0]): one pass over dy
+            A, B = _stem_tap_masks(H, W, D.shape[1], D.shape[2], D.device)  # [7, P], [7, Q] 0/1: outputs whose tap hits a real pixel
+            T = torch.einsum("rp,kpq,sq->krs", A, D, B)                     # rectangle sums as two small contractions
+            dbeta = torch.einsum("kcrs,krs->c", w.float(), T)
+        return None, dw, dbeta, None, None
+
+
 class ResNetV2(nn.Module):
     def __init__(self, num_layers: int = 50, num_classes: int = 1000, image_size: int = 224):
         super().__init__()
@@ -178,8 +263,19 @@ class ResNetV2(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
+    def _fused_stem_ok(self, x) -> bool:
+        c = self.stem[0]
+        return (len(self.stem) == 3 and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] == 3 and not x.requires_grad and
+                c.kernel_size == (7, 7) and c.stride == (2, 2) and c.padding == (3, 3) and c.out_channels % 64 == 0 and
+                c.weight.dtype == torch.bfloat16 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and
+                x.is_contiguous(memory_format=torch.channels_last) and _FUSED_STEM)
+
     def forward(self, x):
-        x = self.stem(self.bn_data(x))
+        if self._fused_stem_ok(x):
+            y = _FusedStemFn.apply(x, self.stem[0].weight, self.bn_data.bias, self.bn_data, self.training)
+            x = self.stem[2](self.stem[1](y))  # bn0 takes (y, statistics from the convolution epilogue), then max-pool
+        else:
+            x = self.stem(self.bn_data(x))
         x = self.body(x)                       # (branch, shortcut) of the last unit, still un-summed
         _, x = self.bn1.forward_add(x[0], x[1])
         return self.fc1(global_avg_pool(x))

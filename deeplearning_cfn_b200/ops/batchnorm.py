@@ -40,6 +40,9 @@ def _declare():
     L.dlcfn_bn_backward_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.dlcfn_bn_backward_ex.restype = c_int
+    L.dlcfn_bn_forward_pre.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    L.dlcfn_bn_forward_pre.restype = c_int
     L._bn_declared = True
     return L
 
@@ -61,7 +64,9 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
 
 class _BNReLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, stats=None):
+        """`stats` (optional): partial sums [rows, 2, C] of x written by the epilogue of the convolution that produced x
+        (ops/conv.py, fused statistics): the statistics pass over x is skipped."""
         L = _declare()
         x = _nhwc(x)
         N, C, H, W = x.shape
@@ -70,11 +75,19 @@ class _BNReLUFn(torch.autograd.Function):
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         ws = torch.empty(L.dlcfn_bn_workspace_floats(M, C), dtype=torch.float32, device=x.device)
-        native.check(L.dlcfn_bn_forward(x.data_ptr(), y.data_ptr(), M, C, native._ptr(gamma), native._ptr(beta),
-                                        mean.data_ptr(), invstd.data_ptr(), native._ptr(running_mean),
-                                        native._ptr(running_var), momentum, eps, int(relu), ws.data_ptr(),
-                                        native.stream_ptr()), "bn_forward")
-        native._count(3)
+        if stats is not None:
+            assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[1] == 2 and stats.shape[2] == C
+            native.check(L.dlcfn_bn_forward_pre(x.data_ptr(), y.data_ptr(), M, C, native._ptr(gamma), native._ptr(beta),
+                                                mean.data_ptr(), invstd.data_ptr(), native._ptr(running_mean),
+                                                native._ptr(running_var), momentum, eps, int(relu), stats.data_ptr(),
+                                                stats.shape[0], ws.data_ptr(), native.stream_ptr()), "bn_forward_pre")
+            native._count(2)
+        else:
+            native.check(L.dlcfn_bn_forward(x.data_ptr(), y.data_ptr(), M, C, native._ptr(gamma), native._ptr(beta),
+                                            mean.data_ptr(), invstd.data_ptr(), native._ptr(running_mean),
+                                            native._ptr(running_var), momentum, eps, int(relu), ws.data_ptr(),
+                                            native.stream_ptr()), "bn_forward")
+            native._count(3)
         ctx.save_for_backward(x, gamma, beta, mean, invstd)
         ctx.relu = relu
         return y
@@ -95,7 +108,7 @@ class _BNReLUFn(torch.autograd.Function):
                                          native._ptr(dbeta), 0, int(ctx.relu), ws.data_ptr(), native.stream_ptr()),
                      "bn_backward")
         native._count(3)
-        return dx, dgamma, dbeta, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
 class _AddBNReLUFn(torch.autograd.Function):
@@ -160,11 +173,11 @@ def add_batch_norm_relu(a, b, gamma, beta, running_mean, running_var, training: 
 
 
 def batch_norm_relu(x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float,
-                    relu: bool = True):
+                    relu: bool = True, stats=None):
     C = x.shape[1]
     if fused_supported(x, C) and (gamma is None or gamma.dtype == torch.float32):
         if training:
-            return _BNReLUFn.apply(x, gamma, beta, running_mean, running_var, momentum, eps, relu)
+            return _BNReLUFn.apply(x, gamma, beta, running_mean, running_var, momentum, eps, relu, stats)
         L = _declare()
         x = _nhwc(x)
         N, _, H, W = x.shape
@@ -188,9 +201,13 @@ class BatchNormReLU2d(nn.BatchNorm2d):
         super().__init__(num_features, eps=eps, momentum=momentum)
         self.relu = relu
 
-    def forward(self, x):
+    def forward(self, x, stats=None):
+        """`x` may be the (y, stats) pair of a convolution called with `stats=True` (ops/conv.py): the statistics of y were
+        accumulated in that convolution's epilogue."""
+        if isinstance(x, tuple):
+            x, stats = x
         return batch_norm_relu(x, self.weight, self.bias, self.running_mean, self.running_var, self.training,
-                               self.momentum, self.eps, self.relu)
+                               self.momentum, self.eps, self.relu, stats)
 
     def forward_add(self, a, b):
         """(a + b, bn_relu(a + b)) - the residual add fused into this layer's statistics pass."""

@@ -72,14 +72,20 @@ class ConvOps:
         n, c, h, w = t.shape
         return t.permute(0, 2, 3, 1).reshape(n * h * w, c)          # a view: NHWC memory is already this matrix
 
-    def fprop(self) -> torch.Tensor:
+    def fprop(self, stats: torch.Tensor | None = None) -> torch.Tensor:
+        """`stats`: [rows, 2, K] buffer (native.new_stats) that receives the per-channel partial sums / sums of squares of the
+        bf16 output, accumulated in the kernel's epilogue (fused BatchNorm statistics)."""
         x, w = self.x, self.w
         if self.gemm:
             N, C, H, W = x.shape
             y = torch.empty((N, w.shape[0], H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-            native.gemm_bf16(self._mat(x), w.reshape(w.shape[0], C), out=self._mat(y))
+            native.gemm_bf16(self._mat(x), w.reshape(w.shape[0], C), out=self._mat(y), stats=stats)
             return y
-        return native.conv_fprop(x, w, self.stride, self.pad)
+        return native.conv_fprop(x, w, self.stride, self.pad, stats=stats)
+
+    @staticmethod
+    def stats_ok(weight: torch.Tensor) -> bool:
+        return weight.shape[0] >= 64 and weight.shape[0] % 8 == 0          # the bf16 TMA-store epilogue form
 
     def dgrad(self, dy: torch.Tensor) -> torch.Tensor:
         x, w = self.x, self.w
@@ -100,28 +106,41 @@ class ConvOps:
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, stride, pad):
+    def forward(ctx, x, weight, stride, pad, want_stats=False):
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
         w = weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.pad = stride, pad
-        return ConvOps(x, w, stride, pad).fprop()
+        stats = native.new_stats(w.shape[0], x.device) if want_stats and ConvOps.stats_ok(w) else None
+        y = ConvOps(x, w, stride, pad).fprop(stats)
+        if not want_stats:
+            return y
+        if stats is not None:
+            ctx.mark_non_differentiable(stats)
+        return y, stats
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         x, w = ctx.saved_tensors
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         ops = ConvOps(x, w, ctx.stride, ctx.pad)
         dx = ops.dgrad(dy) if ctx.needs_input_grad[0] else None
         dw = ops.wgrad(dy) if ctx.needs_input_grad[1] else None
-        return dx, dw, None, None
+        return dx, dw, None, None, None
 
 
-def conv2d(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding: int = 0) -> torch.Tensor:
-    """x [N,C,H,W] channels_last bf16, weight [K,C,R,S] -> [N,K,P,Q] channels_last, all three passes on the tcgen05 kernels."""
-    return _ConvFn.apply(x, weight, int(stride), int(padding))
+_FUSE_STATS = os.environ.get("DLCFN_CONV_BN_STATS", "1") != "0"
+
+
+def conv2d(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding: int = 0, stats: bool = False):
+    """x [N,C,H,W] channels_last bf16, weight [K,C,R,S] -> [N,K,P,Q] channels_last, all three passes on the tcgen05 kernels.
+    stats=True -> (y, partial statistics of y or None): hand the pair to the BatchNormReLU2d that follows."""
+    if stats and _FUSE_STATS:
+        return _ConvFn.apply(x, weight, int(stride), int(padding), True)
+    y = _ConvFn.apply(x, weight, int(stride), int(padding), False)
+    return (y, None) if stats else y
 
 
 def _eligible(x: torch.Tensor, weight: torch.Tensor, stride: int = 1) -> bool:
@@ -146,11 +165,13 @@ class Conv1x1(nn.Conv2d):
             raise ValueError("Conv1x1 has no bias (every 1x1 convolution of the reference symbols is followed by BatchNorm)")
         super().__init__(in_channels, out_channels, 1, stride, 0, bias=False)
 
-    def forward(self, x):
+    def forward(self, x, stats: bool = False):
+        """stats=True returns (y, statistics-or-None) for the BatchNorm that follows (fused into the epilogue)."""
         use = _BACKEND == "tcgen05" or (_BACKEND == "auto" and self.stride[0] > 1)
         if use and _eligible(x, self.weight, self.stride[0]):
-            return conv2d(x, self.weight, self.stride[0], 0)
-        return super().forward(x)
+            return conv2d(x, self.weight, self.stride[0], 0, stats=stats)
+        y = super().forward(x)
+        return (y, None) if stats else y
 
     def extra_repr(self):
         return super().extra_repr() + f", backend={_BACKEND}"
@@ -189,10 +210,11 @@ class ConvKxK(nn.Conv2d):
             raise ValueError("ConvKxK has no bias (the convolutions of the reference symbols are followed by BatchNorm)")
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, bias=False)
 
-    def forward(self, x):
+    def forward(self, x, stats: bool = False):
         if _KXK_BACKEND == "tcgen05" and _kxk_eligible(x, self.weight, self.stride, self.padding, self.dilation, self.groups):
-            return conv_kxk(x, self.weight, self.stride[0], self.padding[0])
-        return super().forward(x)
+            return conv2d(x, self.weight, self.stride[0], self.padding[0], stats=stats)
+        y = super().forward(x)
+        return (y, None) if stats else y
 
     def extra_repr(self):
         return super().extra_repr() + f", backend={_KXK_BACKEND}"

@@ -91,18 +91,28 @@ def _declare(L) -> None:
     L.dlcfn_symm_heap_ptr.argtypes = [vp, i]
     L.dlcfn_symm_heap_ptr.restype = vp
     L.dlcfn_symm_check_error.argtypes = [vp, vp, ctypes.POINTER(i)]
+    L.dlcfn_symm_poll_error_async.argtypes = [vp, vp, vp]
+    L.dlcfn_symm_poll_error_async.restype = c_int
     L.dlcfn_symm_destroy.argtypes = [vp]
     L.dlcfn_barrier.argtypes = [vp, i, vp]
     L.dlcfn_allreduce.argtypes = [vp, sz, sz, i, f, i, i, vp]
     L.dlcfn_broadcast.argtypes = [vp, sz, sz, i, i, i, vp]
     L.dlcfn_ps_sync_step.argtypes = [vp, sz, sz, sz, sz, sz, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, vp]
     L.dlcfn_ps_async_worker.argtypes = [vp, u32, i, i, vp]
-    L.dlcfn_ps_set_next_pull_mask.argtypes = [u32]
-    L.dlcfn_ps_set_next_pull_mask.restype = None
+    L.dlcfn_ps_sync_step_ex.argtypes = [vp, sz, sz, sz, sz, sz, u32, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, i, vp]
+    L.dlcfn_ps_sync_step_ex.restype = c_int
     L.dlcfn_ps_async_server.argtypes = [vp, sz, sz, sz, sz, u32, vp, vp, vp, i, i, f, f, f, f, f, f, f, f, i, i, vp]
     L.dlcfn_gemm_bf16.argtypes = [vp, ll, i, vp, i, i, ll, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp]
     L.dlcfn_conv_bf16.argtypes = [i, vp, vp, vp, i] + [i] * 15 + [vp]
     L.dlcfn_conv_bf16.restype = c_int
+    L.dlcfn_conv_bf16_ex.argtypes = [i, vp, vp, vp, i] + [i] * 15 + [ll, ll, ll, vp, vp]
+    L.dlcfn_conv_bf16_ex.restype = c_int
+    L.dlcfn_gemm_bf16_ex.argtypes = [vp, ll, i, vp, i, i, ll, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp, vp]
+    L.dlcfn_gemm_bf16_ex.restype = c_int
+    L.dlcfn_batch_sum_bf16.argtypes = [vp, vp, i, ll, vp]
+    L.dlcfn_batch_sum_bf16.restype = c_int
+    L.dlcfn_gemm_stats_rows.argtypes = []
+    L.dlcfn_gemm_stats_rows.restype = c_int
     for fn in ("dlcfn_elementwise_sum", "dlcfn_cast_scale", "dlcfn_fused_optimizer", "dlcfn_normalize_u8_nhwc",
                "dlcfn_quantize_2bit", "dlcfn_dequantize_2bit", "dlcfn_unique_rows", "dlcfn_symm_create",
                "dlcfn_symm_get_handle", "dlcfn_symm_open_peer", "dlcfn_symm_set_peer_ptr", "dlcfn_symm_finalize",
@@ -167,6 +177,18 @@ def fused_optimizer(kind: str, grad: torch.Tensor, master: torch.Tensor, s1: tor
     _count()
 
 
+def batch_sum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 sum over dim 0 of a bf16 tensor whose dims 1.. are dense in memory (any memory format): one streaming pass."""
+    assert x.is_cuda and x.dtype == torch.bfloat16
+    N = x.shape[0]
+    inner = x[0].numel()
+    assert x.stride(0) == inner and inner % 8 == 0
+    out = torch.empty_strided(x.shape[1:], x.stride()[1:], dtype=torch.float32, device=x.device)
+    check(lib().dlcfn_batch_sum_bf16(x.data_ptr(), out.data_ptr(), N, inner, stream_ptr()), "batch_sum_bf16")
+    _count()
+    return out
+
+
 def normalize_u8_nhwc(src: torch.Tensor, dst: torch.Tensor, mean, std) -> torch.Tensor:
     assert src.dtype == torch.uint8 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
     m = (c_float * 3)(*mean)
@@ -213,7 +235,7 @@ def gemm_bf16(a: torch.Tensor, b, *, a_mn: bool = False, b_mn: bool = False, out
               out_dtype: torch.dtype = torch.bfloat16, bias: torch.Tensor | None = None, accumulate: bool = False,
               relu: bool = False, m: int | None = None, n: int | None = None, k: int | None = None,
               shard_ptrs: list[int] | None = None, rows_per_shard: int = 0, ldb: int | None = None,
-              block_n: int = 0) -> torch.Tensor:
+              block_n: int = 0, stats: torch.Tensor | None = None) -> torch.Tensor:
     """D[M,N] = A[M,K] @ B[N,K]^T (+bias) on the tcgen05 tensor cores.
 
     a_mn / b_mn select the MN-major storage ([K, rows]) of an operand.  With `shard_ptrs`, B lives
@@ -246,10 +268,10 @@ def gemm_bf16(a: torch.Tensor, b, *, a_mn: bool = False, b_mn: bool = False, out
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= N
     arr = (c_void_p * len(ptrs))(*ptrs)
-    rc = lib().dlcfn_gemm_bf16(a.data_ptr(), a.stride(0), int(a_mn), ctypes.cast(arr, c_void_p), len(ptrs),
-                               rows_per_shard, ldb_, int(b_mn), out.data_ptr(), out.stride(0),
-                               dtype_code(out.dtype), _ptr(bias), M, N, K, int(accumulate), int(relu), block_n, 0,
-                               stream_ptr())
+    rc = lib().dlcfn_gemm_bf16_ex(a.data_ptr(), a.stride(0), int(a_mn), ctypes.cast(arr, c_void_p), len(ptrs),
+                                  rows_per_shard, ldb_, int(b_mn), out.data_ptr(), out.stride(0),
+                                  dtype_code(out.dtype), _ptr(bias), M, N, K, int(accumulate), int(relu), block_n, 0,
+                                  _ptr(stats), stream_ptr())
     if rc != 0:
         raise RuntimeError(f"dlcfn gemm_bf16 failed with CUDA error {rc}: M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn} "
                            f"lda={a.stride(0)} ldb={ldb_} ldd={out.stride(0)} a%16={a.data_ptr() % 16} "
@@ -263,15 +285,32 @@ def _nhwc_ok(t: torch.Tensor) -> bool:
     return t.dim() == 4 and t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last)
 
 
-def conv_fprop(x: torch.Tensor, weight: torch.Tensor, stride: int, pad: int, block_n: int = 0) -> torch.Tensor:
+_stats_rows = 0
+
+
+def stats_rows() -> int:
+    """Rows of the partial-statistics buffer the GEMM / convolution epilogues write (4 per SM)."""
+    global _stats_rows
+    if not _stats_rows:
+        _stats_rows = int(lib().dlcfn_gemm_stats_rows())
+    return _stats_rows
+
+
+def new_stats(channels: int, device) -> torch.Tensor:
+    """Uninitialised [rows, 2, C] fp32 buffer for the fused BatchNorm statistics (the launch zero-fills it)."""
+    return torch.empty((stats_rows(), 2, channels), dtype=torch.float32, device=device)
+
+
+def conv_fprop(x: torch.Tensor, weight: torch.Tensor, stride: int, pad: int, block_n: int = 0,
+               stats: torch.Tensor | None = None) -> torch.Tensor:
     """x [N,C,H,W] channels_last, weight [K,C,R,S] channels_last (memory [K][R][S][C]) -> y [N,K,P,Q] channels_last."""
     assert _nhwc_ok(x) and _nhwc_ok(weight)
     N, C, H, W = x.shape
     K, _, R, S = weight.shape
     P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
     y = torch.empty((N, K, P, Q), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-    rc = lib().dlcfn_conv_bf16(0, x.data_ptr(), weight.data_ptr(), y.data_ptr(), 1, N, H, W, C, K, C, R, S, pad, stride, P, Q,
-                               0, block_n, 0, stream_ptr())
+    rc = lib().dlcfn_conv_bf16_ex(0, x.data_ptr(), weight.data_ptr(), y.data_ptr(), 1, N, H, W, C, K, C, R, S, pad, stride, P, Q,
+                                  0, block_n, 0, 0, 0, 0, _ptr(stats), stream_ptr())
     if rc != 0:
         raise RuntimeError(f"dlcfn conv fprop failed with CUDA error {rc}: x={tuple(x.shape)} w={tuple(weight.shape)} "
                            f"stride={stride} pad={pad}")
@@ -310,5 +349,46 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, kernel: tuple[int, int], strid
     if rc != 0:
         raise RuntimeError(f"dlcfn conv wgrad failed with CUDA error {rc}: x={tuple(x.shape)} dy={tuple(dy.shape)} "
                            f"kernel={kernel} stride={stride} pad={pad}")
+    _count(2)
+    return dw
+
+
+# ------------------------------------------------------------------ ResNet stem: 4x4 / stride 1 over the 16-channel s2d image
+def _stem_view(s2d: torch.Tensor):
+    """The space-to-depth image [N,16,Hs,Ws] (channels_last) seen as [N, Hs, Ws-3, 64] with a W stride of 16 elements:
+    one 64-channel "pixel" = 4 adjacent columns x 16 channels = one 128-byte TMA row, so the 4x4 filter becomes 4 (rows) x 1
+    taps of the implicit GEMM (dlcfn_conv_bf16_ex, overlapping view)."""
+    assert _nhwc_ok(s2d) and s2d.shape[1] == 16
+    N, _, Hs, Ws = s2d.shape
+    return N, Hs, Ws - 3, 16, Ws * 16, Hs * Ws * 16
+
+
+def stem_conv_fprop(s2d: torch.Tensor, w4: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:
+    """s2d [N,16,Hs,Ws], w4 [K,16,4,4] (both channels_last; w4 memory [K][r][s][c] = [K][4][64]) -> y [N,K,Hs-3,Ws-3]."""
+    assert _nhwc_ok(w4) and tuple(w4.shape[1:]) == (16, 4, 4)
+    N, H, Wv, xs_w, xs_h, xs_n = _stem_view(s2d)
+    K = w4.shape[0]
+    P, Q = H - 3, Wv
+    y = torch.empty((N, K, P, Q), dtype=torch.bfloat16, device=s2d.device, memory_format=torch.channels_last)
+    rc = lib().dlcfn_conv_bf16_ex(0, s2d.data_ptr(), w4.data_ptr(), y.data_ptr(), 1, N, H, Wv, 64, K, 64, 4, 1, 0, 1, P, Q,
+                                  0, 0, 0, xs_w, xs_h, xs_n, _ptr(stats), stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"dlcfn stem conv fprop failed with CUDA error {rc}: s2d={tuple(s2d.shape)} w4={tuple(w4.shape)}")
+    _count()
+    return y
+
+
+def stem_conv_wgrad(s2d: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """dw4 [K,16,4,4] channels_last = dy^T * im2col(s2d) through the same overlapping view (split-K, deterministic)."""
+    assert _nhwc_ok(dy)
+    N, H, Wv, xs_w, xs_h, xs_n = _stem_view(s2d)
+    K = dy.shape[1]
+    P, Q = H - 3, Wv
+    assert tuple(dy.shape) == (N, K, P, Q)
+    dw = torch.empty((K, 16, 4, 4), dtype=torch.bfloat16, device=s2d.device, memory_format=torch.channels_last)
+    rc = lib().dlcfn_conv_bf16_ex(2, s2d.data_ptr(), dy.data_ptr(), dw.data_ptr(), 1, N, H, Wv, 64, K, 64, 4, 1, 0, 1, P, Q,
+                                  0, 0, 0, xs_w, xs_h, xs_n, None, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"dlcfn stem conv wgrad failed with CUDA error {rc}: s2d={tuple(s2d.shape)} dy={tuple(dy.shape)}")
     _count(2)
     return dw

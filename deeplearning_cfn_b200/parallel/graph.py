@@ -80,14 +80,14 @@ class GraphedStep:
     def _signature_inputs(x, y):
         return tuple((tuple(t.shape), t.dtype, t.stride()) for t in _flatten((x, y), []))
 
-    def _capture(self) -> None:
+    def _capture(self, warmup: int | None = None) -> None:
         t = self.trainer
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):           # warm-up off the capture stream: cuDNN autotune, lazy context binds in the
-            for _ in range(self.warmup):        # autograd threads, tensor-map caches, first-use cudaFuncSetAttribute
-                t.step(self.sx, self.sy)
+            for _ in range(self.warmup if warmup is None else warmup):   # autograd threads, tensor-map caches, first-use
+                t.step(self.sx, self.sy)                                 # cudaFuncSetAttribute
         cur.wait_stream(side)
         torch.cuda.synchronize(t.device)
         if t.world > 1:
@@ -114,7 +114,7 @@ class GraphedStep:
             return t.step(x, y)                 # e.g. the last, smaller batch of an epoch
         if self._hp_signature() != self._sig_hp:
             self.graph = None                   # learning-rate schedule moved: record again with the new arguments
-            self._capture()
+            self._capture(warmup=0)             # (everything is warm: a re-capture must not train extra steps)
         if t.is_worker:
             for dst, src in zip(_flatten((self.sx, self.sy), []), _flatten((x, y), [])):
                 if dst.data_ptr() != src.data_ptr():

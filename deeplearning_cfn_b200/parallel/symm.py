@@ -130,6 +130,8 @@ class SymmetricHeap:
 
     def view(self, off: int, numel: int, dtype: torch.dtype) -> torch.Tensor:
         nb = numel * torch.empty((), dtype=dtype).element_size()
+        if off < 0 or numel < 0 or off + nb > self.heap_bytes:
+            raise IndexError(f"symmetric heap view [{off}, {off + nb}) outside the heap of {self.heap_bytes} bytes")
         return self._bytes[off: off + nb].view(dtype)
 
     def alloc_tensor(self, numel: int, dtype: torch.dtype) -> tuple[int, torch.Tensor]:
@@ -177,13 +179,12 @@ class SymmetricHeap:
         through multimem.ld_reduce and the pull through multimem.st (ranks that are not workers must keep a zero
         gradient buffer); nblocks 0 = size-based grid."""
         a = self.allreduce_algo if algo is None else algo
-        nblocks = int(nblocks) + (10000 if a == 1 and self.has_multicast else 0)
-        if pull_mask is not None:      # only these ranks (plus the server itself) receive the new weights
-            native.lib().dlcfn_ps_set_next_pull_mask(int(pull_mask))
-        native.check(native.lib().dlcfn_ps_sync_step(
-            self._ctx, grad_off, weight_off, total, shard_lo, shard_hi, worker_mask, native._ptr(master),
+        if a == 1 and not self.has_multicast:
+            a = 0
+        native.check(native.lib().dlcfn_ps_sync_step_ex(
+            self._ctx, grad_off, weight_off, total, shard_lo, shard_hi, worker_mask, int(pull_mask or 0), native._ptr(master),
             native._ptr(s1), native._ptr(s2), native.dtype_code(dtype), native.OPT_KINDS[kind], lr, wd, momentum,
-            beta1, beta2, eps, rescale, clip, self.CH_PS, nblocks, native.stream_ptr(stream)), "ps_sync_step")
+            beta1, beta2, eps, rescale, clip, self.CH_PS, int(nblocks), int(a), native.stream_ptr(stream)), "ps_sync_step")
         native._count()
 
     def ps_async_worker(self, server_mask: int, nblocks: int = 16, stream: torch.cuda.Stream | None = None) -> None:
@@ -209,6 +210,23 @@ class SymmetricHeap:
         if e.value:
             raise RuntimeError("a peer did not reach a device-side flag barrier within the timeout "
                                "(dead or stalled rank) - reference analogue: get_num_dead_node > 0")
+
+    def poll_error(self, stream: torch.cuda.Stream | None = None) -> None:
+        """Non-blocking dead-peer check: raises if the error word copied by the PREVIOUS call was set, then queues the next
+        copy (pinned host word + event) behind the work already on `stream`.  The host never waits for the GPU here."""
+        st = getattr(self, "_poll", None)
+        if st is None:
+            st = self._poll = {"host": torch.zeros(1, dtype=torch.int32).pin_memory(), "event": torch.cuda.Event(), "armed": False}
+        if st["armed"]:
+            st["event"].synchronize()            # recorded a polling interval ago: long complete
+            if int(st["host"][0]) != 0:
+                st["armed"] = False
+                self.check_error(stream)         # clears the device word, raises
+                raise RuntimeError("a peer did not reach a device-side flag barrier within the timeout (dead or stalled rank)")
+        native.check(native.lib().dlcfn_symm_poll_error_async(self._ctx, st["host"].data_ptr(), native.stream_ptr(stream)),
+                     "symm_poll_error_async")
+        st["event"].record(stream if stream is not None else torch.cuda.current_stream())
+        st["armed"] = True
 
     def close(self) -> None:
         if getattr(self, "_ctx", None):

@@ -73,6 +73,7 @@ class DataParallelTrainer:
         self.comm_blocks = comm_blocks
         self.loss_fn = loss_fn or softmax_cross_entropy     # fused loss kernels on CUDA, torch on CPU
         self.step_count = 0
+        self.check_every = int(os.environ.get("DLCFN_CHECK_EVERY", "25"))     # steps between polls of the peers' error word
 
         self.node_size, self.node_group, self.rail_group = self.world, None, None
         if mode == "hier":
@@ -353,6 +354,11 @@ class DataParallelTrainer:
                 st = self.state[gi]
                 self._apply_opt(g.grad, st, g.weight if g.dtype != torch.float32 else None)
         self.step_count += 1
+        # dead / stalled peer: the device-side barriers set an error word after their spin timeout instead of hanging; poll it
+        # without draining the queue (SymmetricHeap.poll_error) so a broken job stops within `check_every` steps
+        if self.heap is not None and self.check_every > 0 and self.step_count % self.check_every == 0 \
+                and not torch.cuda.is_current_stream_capturing():
+            self.heap.poll_error()
 
     def step(self, x=None, y=None):
         """One full training step.  Dedicated parameter-server ranks pass no data: they only serve."""

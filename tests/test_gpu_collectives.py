@@ -43,3 +43,8 @@ def test_kvstore_dist_device_world2():
 def test_ps_resident_linear_pull_fused_gemm_world2():
     r = _run(2, "sharded_linear_worker.py", 29615)
     assert r.returncode == 0 and "SHARDED_LINEAR_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_bandwidth_tool_per_key_error_is_zero_world2():
+    r = _run(2, "bandwidth_worker.py", 29616)
+    assert r.returncode == 0 and "BANDWIDTH_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -33,11 +33,11 @@ def test_experimental_wrappers_conv_roi_layernorm():
             m1 = conv.ConvKxK(64, 64, 3, 1, 1).to(BF).to(memory_format=CL)
             n0 = len(log)
             m1(xx).sum().backward()
-            assert log[n0:].count("dlcfn_conv_bf16") == 3           # fprop + dgrad + wgrad
+            assert log[n0:].count("dlcfn_conv_bf16") + log[n0:].count("dlcfn_conv_bf16_ex") == 3   # fprop + dgrad + wgrad
             odd = conv.ConvKxK(24, 64, 3, 1, 1).to(BF).to(memory_format=CL)   # Cin % 64 != 0: stays on aten
             n0 = len(log)
             odd(_cl(1, 24, 8, 8))
-            assert "dlcfn_conv_bf16" not in log[n0:]
+            assert "dlcfn_conv_bf16" not in log[n0:] and "dlcfn_conv_bf16_ex" not in log[n0:]
         finally:
             conv.set_convkxk_backend("tcgen05")
 
@@ -62,7 +62,7 @@ def test_experimental_wrappers_conv_roi_layernorm():
         z.sum().backward()
         assert z.shape == h.shape and h.grad.shape == h.shape and g.grad.shape == g.shape
     launched = set(log)
-    assert {"dlcfn_conv_bf16", "dlcfn_roi_align_fwd", "dlcfn_roi_align_bwd", "dlcfn_nms", "dlcfn_dropout_add_ln_fwd",
+    assert {"dlcfn_conv_bf16", "dlcfn_conv_bf16_ex", "dlcfn_roi_align_fwd", "dlcfn_roi_align_bwd", "dlcfn_nms", "dlcfn_dropout_add_ln_fwd",
             "dlcfn_dropout_add_ln_bwd"} <= launched, launched
 
 
@@ -89,14 +89,17 @@ def test_resnet50_training_step_walks_every_cuda_branch(backend):
         conv.set_conv1x1_backend("tcgen05")
         conv.set_convkxk_backend("tcgen05")
     per_step = {k: log.count(k) // 2 for k in set(log)}
-    assert per_step.get("dlcfn_gemm_bf16", 0) >= 3                       # classifier fwd / dgrad / wgrad at least
+    gemms = per_step.get("dlcfn_gemm_bf16", 0) + per_step.get("dlcfn_gemm_bf16_ex", 0)
+    convs = per_step.get("dlcfn_conv_bf16", 0) + per_step.get("dlcfn_conv_bf16_ex", 0)
+    assert gemms >= 3                                                    # classifier fwd / dgrad / wgrad at least
     assert any(k.startswith("dlcfn_bn") for k in per_step) and any("softmax_ce" in k for k in per_step)
     assert any("maxpool" in k for k in per_step) and per_step.get("dlcfn_fused_optimizer", 0) >= 1
     if backend == "tcgen05":
-        assert per_step.get("dlcfn_conv_bf16", 0) >= 16 * 3 + 3 * 3       # 16 3x3 layers + 3 strided 1x1 shortcuts: fprop, dgrad, wgrad
-        assert per_step["dlcfn_gemm_bf16"] >= 3 * 30                    # the 1x1 layers as GEMMs
+        assert convs >= 16 * 3 + 3 * 3 + 2                              # 16 3x3 layers + 3 strided 1x1 shortcuts (fprop, dgrad, wgrad) + stem
+        assert gemms >= 3 * 30                                          # the 1x1 layers as GEMMs
+        assert per_step.get("dlcfn_bn_forward_pre", 0) >= 16 * 2 + 1    # bn2 / bn3 of every unit + bn0 take the epilogue statistics
     else:
-        assert "dlcfn_conv_bf16" not in per_step
+        assert convs == 2                                               # the fused stem (fprop + wgrad) is independent of the backend switch
 
 
 def test_bert_step_and_zoo_models_walk_their_cuda_branches():
@@ -118,7 +121,7 @@ def test_bert_step_and_zoo_models_walk_their_cuda_branches():
         finally:
             ln.enabled = old
         n_bert = len(log)
-        assert "dlcfn_dropout_add_ln_fwd" in log and "dlcfn_gemm_bf16" in log and any("softmax_ce" in k for k in log)
+        assert "dlcfn_dropout_add_ln_fwd" in log and "dlcfn_gemm_bf16_ex" in log and any("softmax_ce" in k for k in log)
         for name in ("mobilenet0.5", "mobilenetv2_0.5", "densenet121", "inception-bn", "cifar10_cnn", "alexnet"):
             size = {"cifar10_cnn": 32, "alexnet": 160}.get(name, 64)
             m = to_b200_layout(get_model(name, 8, size)).train()
@@ -146,7 +149,7 @@ def test_every_model_family_runs_its_cuda_branches(name, size):
         out.float().logsumexp(1).sum().backward()
         missing = [n for n, p in m.named_parameters() if p.requires_grad and p.grad is None]
         assert not missing, missing[:3]
-    assert "dlcfn_gemm_bf16" in log or name.startswith("squeezenet")     # every family but SqueezeNet (conv classifier) ends in the tcgen05 Linear
+    assert "dlcfn_gemm_bf16_ex" in log or name.startswith("squeezenet")     # every family but SqueezeNet (conv classifier) ends in the tcgen05 Linear
 
 
 def test_elementwise_compression_and_sparse_wrappers():

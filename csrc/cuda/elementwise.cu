@@ -258,9 +258,76 @@ __global__ void __launch_bounds__(256) kbatch_sum_bf16(const uint4* __restrict__
     o[1] = make_float4(a[4], a[5], a[6], a[7]);
   }
 }
+
+// Column sums of a bf16 [M, N] matrix (bias gradient db = sum_rows dY of the tcgen05 Linear): block = 32 column vectors
+// (256 columns) x 8 row lanes, grid = (column strips, row slices); per-slice partials [slices][N] then one fixed-order sum -
+// deterministic.  torch's reduce_kernel took 2.07 ms per BERT-large step for the same 3.6 GB (profiles/r2/profile_bert.txt).
+__global__ void __launch_bounds__(256) kcolsum_partial(const uint4* __restrict__ x, float* __restrict__ part, long long M, int N8,
+                                                        long long ld8) {
+  __shared__ float sh[8][32][9];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col8 = blockIdx.x * 32 + cx;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (col8 < N8) {
+    long long r = (long long)blockIdx.y * 8 + ty;
+    const long long step = (long long)gridDim.y * 8;
+    for (; r + 3 * step < M; r += 4 * step) {
+      const uint4 v0 = __ldg(x + r * ld8 + col8), v1 = __ldg(x + (r + step) * ld8 + col8);
+      const uint4 v2 = __ldg(x + (r + 2 * step) * ld8 + col8), v3 = __ldg(x + (r + 3 * step) * ld8 + col8);
+      const uint4 vs[4] = {v0, v1, v2, v3};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[0] += bf16_lo(vs[j].x); a[1] += bf16_hi(vs[j].x); a[2] += bf16_lo(vs[j].y); a[3] += bf16_hi(vs[j].y);
+        a[4] += bf16_lo(vs[j].z); a[5] += bf16_hi(vs[j].z); a[6] += bf16_lo(vs[j].w); a[7] += bf16_hi(vs[j].w);
+      }
+    }
+    for (; r < M; r += step) {
+      const uint4 v = __ldg(x + r * ld8 + col8);
+      a[0] += bf16_lo(v.x); a[1] += bf16_hi(v.x); a[2] += bf16_lo(v.y); a[3] += bf16_hi(v.y);
+      a[4] += bf16_lo(v.z); a[5] += bf16_hi(v.z); a[6] += bf16_lo(v.w); a[7] += bf16_hi(v.w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[ty][cx][k] = a[k];
+  __syncthreads();
+  if (ty == 0 && col8 < N8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += sh[y][cx][k];
+      part[(size_t)blockIdx.y * N8 * 8 + (size_t)col8 * 8 + k] = t;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) kcolsum_final(const float* __restrict__ part, float* __restrict__ out, int N, int slices) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < slices; ++s) t += part[(size_t)s * N + c];
+  out[c] = t;
+}
 }  // namespace dlcfn
 
 using namespace dlcfn;
+
+// out[N] (fp32) = column sums of bf16 x[M, N] (row stride ld elements; N, ld multiples of 8).  workspace: slices * N floats
+// with slices = dlcfn_colsum_slices(M).
+DLCFN_API int dlcfn_colsum_slices(long long M) {
+  long long s = (M + 63) / 64;
+  return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
+}
+DLCFN_API int dlcfn_colsum_bf16(const void* x, float* out, long long M, int N, long long ld, float* workspace, cudaStream_t stream) {
+  (void)cudaGetLastError();
+  if (M <= 0 || N <= 0 || (N & 7) || (ld & 7) || (((uintptr_t)x) & 15)) return (int)cudaErrorInvalidValue;
+  const int slices = dlcfn_colsum_slices(M);
+  dim3 grid((N / 8 + 31) / 32, slices);
+  kcolsum_partial<<<grid, 256, 0, stream>>>((const uint4*)x, workspace, M, N / 8, ld / 8);
+  kcolsum_final<<<(N + 255) / 256, 256, 0, stream>>>(workspace, out, N, slices);
+  return (int)cudaGetLastError();
+}
 
 DLCFN_API int dlcfn_batch_sum_bf16(const void* x, float* out, int N, long long inner, cudaStream_t stream) {
   (void)cudaGetLastError();

@@ -42,6 +42,29 @@ constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kEpiThreads = 256;
 constexpr int kMaxShards = DLCFN_MAX_RANKS;
 
+// Division by a launch-time constant as multiply-high + shift (0 <= n < 2^31): the single-thread TMA producer and MMA issuer
+// sit on the critical path of every k-block, and a hardware-less 32-bit division costs them ~150 dependent cycles each
+// (six of them per k-block held the im2col kernels at ~650 cycles per k-block, profiles/r2/conv_ncu_before.md).
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d < 1 ? 1u : (uint32_t)d;
+  uint32_t l = 0;
+  while ((1ull << l) < f.d) ++l;
+  f.shr = 31 + l;
+  f.mul = (uint32_t)(((1ull << f.shr) / f.d) + 1ull);       // <= 2^32 - ... fits: d >= 2^(l-1) + 1 for l >= 1, and 2^31 + 1 for d = 1
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return (int)(((unsigned long long)(uint32_t)n * f.mul) >> f.shr);
+}
+__device__ __forceinline__ void fdivmod(int n, const FastDiv& f, int& q, int& r) {
+  q = fdiv(n, f);
+  r = n - q * (int)f.d;
+}
+
 struct __align__(64) GemmParams {
   CUtensorMap tmA;
   CUtensorMap tmB[kMaxShards];
@@ -78,9 +101,13 @@ struct __align__(64) GemmParams {
   int out_remap, out_H, out_W, out_step, out_h0, out_w0;
   // pipeline shape chosen by the host: ring depth, weights-stationary mode (B panel of bres_bytes resident in shared memory)
   int stages, b_resident, bres_bytes;
+  int raster_g;         // pair kernel: M-pair rows per raster group (tiles walk N inside a group of raster_g rows: the group's
+                        // A panel stays L2-resident while B streams once per group instead of once per wave)
   int stg_bufs;         // staging tiles per epilogue warp: 2 = a warp fills one tile while TMA still reads the other
   // fused BatchNorm statistics of the stored bf16 outputs: partial rows [4 * grid][2][N] (sum, sum of squares), or null
   float* stats;
+  // launch-time divisors (filled by fill_divisors): m tiles, tiles, im2col row length / rows per image / channel blocks
+  FastDiv fd_num_m, fd_tiles, fd_Q, fd_P, fd_cblocks;
 };
 
 // ------------------------------------------------------------------ PTX -----
@@ -313,20 +340,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
         if constexpr (CONV && B_MN && !A_MN) {
           // dgrad: the 64 contraction rows are output channels c0.. of list entry rs; the matching weights are the columns
           // of filter tap cv_tap_wi[rs] in W viewed as [Cout][R*S*Cin] (MN-major B: box {64 cin, 64 cout})
-          const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
+          int rs, cb;
+          fdivmod(kb, p.fd_cblocks, rs, cb);
+          const int c0 = cb * 64;
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_2d(sb + j * 8192, &p.tmB[0], bar, (int)p.cv_tap_wi[rs] * p.cv_cin + n_idx + 64 * j, c0);
         } else if constexpr (CONV && B_MN && A_MN) {
           // wgrad: the 64 contraction rows are output pixels k_idx..; output column panel P = (tap, 64-channel slice)
-          const int q0 = k_idx % p.cv_Q, t0 = k_idx / p.cv_Q;
-          const int p0 = t0 % p.cv_P, n0 = t0 / p.cv_P;
+          int q0, t0, p0, n0;
+          fdivmod(k_idx, p.fd_Q, t0, q0);
+          fdivmod(t0, p.fd_P, n0, p0);
           const int last_panel = p.cv_ntaps * p.cv_cblocks - 1;
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j) {
             int panel = n_idx / 64 + j;
             if (panel > last_panel) panel = last_panel;    // N tail: columns >= N are never stored
-            const int rs = panel / p.cv_cblocks, c0 = (panel - rs * p.cv_cblocks) * 64;
+            int rs, cb;
+            fdivmod(panel, p.fd_cblocks, rs, cb);
+            const int c0 = cb * 64;
             tma_load_im2col_4d(sb + j * 8192, &p.tmB[0], bar, c0, q0 * p.cv_stride + p.cv_lower_w,
                                p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)p.cv_tap_ow[rs],
                                (uint16_t)p.cv_tap_oh[rs]);   // box {64 c, 64 pixels}
@@ -351,10 +383,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       int acc = 0, prev_acc = 0;            // mirror of the MMA issuer's accumulator-stage sequence
       uint32_t acc_phase = 0, prev_acc_phase = 0;
       for (int item = item0; item < num_items; item += item_step) {
-        const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
-        const int m_idx = MC ? ((item % num_pm) * 2 + cta_rank) * kBlockM : (tile % num_m) * kBlockM;
-        const int n_idx = MC ? (item / num_pm) * BLOCK_N : (tile / num_m) * BLOCK_N;
+        int tile = 0, split = 0, mt, nt;
+        if constexpr (MC) { nt = item / num_pm; mt = (item - nt * num_pm) * 2 + cta_rank; }
+        else { fdivmod(item, p.fd_tiles, split, tile); fdivmod(tile, p.fd_num_m, nt, mt); }
+        const int m_idx = mt * kBlockM, n_idx = nt * BLOCK_N;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        // im2col position of the tile's first pixel (fprop / dgrad): once per tile, not per k-block
+        int cv_q0 = 0, cv_p0 = 0, cv_n0 = 0, cv_rs = 0, cv_cb = 0;
+        if constexpr (CONV && !A_MN) {
+          int t0;
+          fdivmod(m_idx, p.fd_Q, t0, cv_q0);
+          fdivmod(t0, p.fd_P, cv_n0, cv_p0);
+          fdivmod(kb0, p.fd_cblocks, cv_rs, cv_cb);
+        }
         if (bres) {
           if (n_idx != cur_n) {
             // every MMA that reads the old panel has completed once the previous item's accumulator is committed
@@ -374,12 +415,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
           mbar_expect_tx(full_bar(stage), stage_bytes);
           if constexpr (CONV && !A_MN) {
             // fprop / dgrad: k-block = (filter tap rs, 64-channel slice); 128 consecutive output pixels from m_idx
-            const int rs = kb / p.cv_cblocks, c0 = (kb - rs * p.cv_cblocks) * 64;
-            const int q0 = m_idx % p.cv_Q, t0 = m_idx / p.cv_Q;
-            const int p0 = t0 % p.cv_P, n0 = t0 / p.cv_P;
-            tma_load_im2col_4d(sa, &p.tmA, full_bar(stage), c0, q0 * p.cv_stride + p.cv_lower_w,
-                               p0 * p.cv_stride + p.cv_lower_h, n0, (uint16_t)p.cv_tap_ow[rs],
-                               (uint16_t)p.cv_tap_oh[rs]);   // box {64 c, 128 pixels}
+            tma_load_im2col_4d(sa, &p.tmA, full_bar(stage), cv_cb * 64, cv_q0 * p.cv_stride + p.cv_lower_w,
+                               cv_p0 * p.cv_stride + p.cv_lower_h, cv_n0, (uint16_t)p.cv_tap_ow[cv_rs],
+                               (uint16_t)p.cv_tap_oh[cv_rs]);   // box {64 c, 128 pixels}
+            if (++cv_cb == p.cv_cblocks) { cv_cb = 0; ++cv_rs; }
           } else if constexpr (!A_MN) {
             tma_load_2d(sa, &p.tmA, full_bar(stage), k_idx, m_idx);  // box {64 k, 128 m}
           } else {
@@ -428,10 +467,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
       int cur_n = -1;
       uint32_t bphase = 0;
       for (int item = item0; item < num_items; item += item_step) {
-        const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
+        int tile = 0, split = 0;
+        if constexpr (!MC) fdivmod(item, p.fd_tiles, split, tile);
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         if (bres) {
-          const int n_idx = (tile / num_m) * BLOCK_N;
+          const int n_idx = fdiv(tile, p.fd_num_m) * BLOCK_N;
           if (n_idx != cur_n) {            // the producer has (re)loaded the weight panel
             mbar_wait(bfull_bar, bphase);
             bphase ^= 1u;
@@ -496,17 +536,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     const bool stg2 = p.stg_bufs == 2;
     uint32_t stg_sel = 0;               // which of this warp's staging tiles the next box goes through
     for (int item = item0; item < num_items; item += item_step) {
-      const int tile = MC ? 0 : item % num_tiles, split = MC ? 0 : item / num_tiles;
-      const int m_idx = MC ? ((item % num_pm) * 2 + cta_rank) * kBlockM : (tile % num_m) * kBlockM;
-      const int n_idx = MC ? (item / num_pm) * BLOCK_N : (tile / num_m) * BLOCK_N;
+      int tile = 0, split = 0, mt, nt;
+      if constexpr (MC) { nt = item / num_pm; mt = (item - nt * num_pm) * 2 + cta_rank; }
+      else { fdivmod(item, p.fd_tiles, split, tile); fdivmod(tile, p.fd_num_m, nt, mt); }
+      const int m_idx = mt * kBlockM, n_idx = nt * BLOCK_N;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m_idx + q * 32 + lane;
       const bool row_ok = row < p.M;
       long long row_pix = row;         // output pixel (row of the [pixels, N] output matrix) this GEMM row is stored to
       if (CONV && p.out_remap) {
-        const int jj = row % p.cv_Q, tt = row / p.cv_Q;
-        const int ii = tt % p.cv_P, nn = tt / p.cv_P;
+        int jj, tt, ii, nn;
+        fdivmod(row, p.fd_Q, tt, jj);
+        fdivmod(tt, p.fd_P, nn, ii);
         row_pix = ((long long)nn * p.out_H + (long long)ii * p.out_step + p.out_h0) * p.out_W + (long long)jj * p.out_step + p.out_w0;
       }
       // all of this warp's accumulator columns in flight at once, one wait
@@ -710,13 +752,16 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3)
                : "memory");
 }
-// arrive on the barrier at the same shared-memory offset of cluster CTA `rank`
+// arrive on the barrier at the same shared-memory offset of cluster CTA `rank`.  RELAXED: the arrival only says "this warp's
+// tcgen05.ld of the accumulator stage has completed" (tcgen05.wait::ld + fence::before_thread_sync precede it) - no memory
+// is published.  The default .release.cluster form compiles to MEMBAR.ALL.CTA + ERRBAR in front of the arrive, which held 37 %
+// of the pair kernel's stall samples on short-K layers (profiles/r2/pair_ncu_1x1_64_256.md).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(bar), "r"(rank)
       : "memory");
 }
@@ -745,6 +790,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
   const int num_items = num_pm * num_n;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
   const int item0 = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
+  // grouped raster: items walk the N tiles of a group of raster_g M-pair rows before moving to the next group
+  const int rg = p.raster_g > 0 ? p.raster_g : num_pm;
+  auto pair_raster = [&](int item, int& pm, int& nt) {
+    const int per_group = rg * num_n;
+    const int g = item / per_group, within = item - g * per_group;
+    const int rows = min(rg, num_pm - g * rg);
+    nt = within / rows;
+    pm = g * rg + (within - nt * rows);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -778,8 +832,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int item = item0; item < num_items; item += item_step) {
-        const int m_idx = ((item % num_pm) * 2 + cta_rank) * kBlockM;
-        const int n_idx = (item / num_pm) * k2BlockN + cta_rank * k2HalfN;     // this CTA's half of the B tile
+        int pm, nt;
+        pair_raster(item, pm, nt);
+        const int m_idx = (pm * 2 + cta_rank) * kBlockM;
+        const int n_idx = nt * k2BlockN + cta_rank * k2HalfN;     // this CTA's half of the B tile
         for (int kb = 0; kb < num_kb; ++kb) {
           const int k_idx = kb * kBlockK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -843,8 +899,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
     uint32_t acc_phase = 0;
     uint32_t stg_sel = 0;           // two staging tiles per warp: fill one while TMA still reads the other
     for (int item = item0; item < num_items; item += item_step) {
-      const int m_idx = ((item % num_pm) * 2 + cta_rank) * kBlockM;
-      const int n_idx = (item / num_pm) * k2BlockN;
+      int pm, nt;
+      pair_raster(item, pm, nt);
+      const int m_idx = (pm * 2 + cta_rank) * kBlockM;
+      const int n_idx = nt * k2BlockN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       uint32_t r[kChunks][32];
@@ -1054,6 +1112,11 @@ static int launch(GemmParams& p, int num_sms, cudaStream_t stream) {
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = num_m * num_n;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  p.fd_num_m = make_fastdiv(num_m);
+  p.fd_tiles = make_fastdiv(tiles);
+  p.fd_Q = make_fastdiv(p.cv_Q);
+  p.fd_P = make_fastdiv(p.cv_P);
+  p.fd_cblocks = make_fastdiv(p.cv_cblocks);
   // split-K when the tiles alone cannot fill the machine and the reduction is long enough to cut
   p.splits = 1;
   p.kb_per_split = num_kb;
@@ -1278,6 +1341,17 @@ static int launch_pair(GemmParams& p, int num_sms, cudaStream_t stream) {
   p.ws = nullptr;
   const int num_m = (p.M + kBlockM - 1) / kBlockM, num_n = (p.N + k2BlockN - 1) / k2BlockN;
   const int pair_tiles = ((num_m + 1) / 2) * num_n;
+  // raster group: as many M-pair rows as keep the group's A panel (rows x K bf16) within ~1/4 of the 126 MB L2, at least 2
+  // rows, and only when there are several N tiles to walk (otherwise M-fastest order is already optimal)
+  {
+    static const int rg_env = [] { const char* e = getenv("DLCFN_GEMM_RASTER"); return e ? atoi(e) : -1; }();
+    const long long row_bytes = 256ll * p.K * 2;
+    int rg = (int)((32ll << 20) / (row_bytes > 0 ? row_bytes : 1));
+    if (rg < 2) rg = 2;
+    if (rg > 16) rg = 16;
+    p.raster_g = (num_n >= 2) ? rg : 0;
+    if (rg_env >= 0) p.raster_g = rg_env;
+  }
   int pairs = num_sms / 2;
   if (pairs > pair_tiles) pairs = pair_tiles;
   if (pairs < 1) pairs = 1;

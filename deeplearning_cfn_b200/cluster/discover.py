@@ -23,7 +23,8 @@ class Topology:
     # link[i][j]: relative link weight between GPU i and j (0 = no P2P, 1 = PCIe-class, >=2 NVLink-class)
     link: list = field(default_factory=list)
     source: str = "none"
-    multicast: bool | None = None
+    multicast: bool | None = None          # NVLS multicast objects supported on every device (native probe)
+    native_atomics: bool | None = None     # native atomics over every peer link
 
     def uniform(self) -> bool:
         """All off-diagonal links equal and non-zero (an NVSwitch domain)."""
@@ -54,6 +55,34 @@ class Topology:
 def from_matrix(link: list, names: list | None = None, source: str = "synthetic") -> Topology:
     n = len(link)
     return Topology(n, names or [f"gpu{i}" for i in range(n)], [list(map(int, r)) for r in link], source)
+
+
+def _probe_native() -> Topology | None:
+    """The library's own probe (csrc/cuda/symm_vmm.cu:dlcfn_probe_fabric): cudaDeviceGetP2PAttribute access / performance
+    rank / native atomics per pair (what gpu_topology.h:133-196 reads) plus CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED per
+    device.  Link weight = 0 without peer access, otherwise 2 + (worst rank - this pair's rank): best links weigh most."""
+    try:
+        import ctypes
+
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        from ..ops import native
+        L = native.lib()
+        n = torch.cuda.device_count()
+        arr = ctypes.c_int * (n * n)
+        access, perf, atom, mc = arr(), arr(), arr(), (ctypes.c_int * n)()
+        got = L.dlcfn_probe_fabric(n, access, perf, atom, mc)
+        if got != n:
+            return None
+        worst = max([perf[i * n + j] for i in range(n) for j in range(n) if i != j and access[i * n + j]] or [0])
+        link = [[0 if i == j or not access[i * n + j] else 2 + (worst - perf[i * n + j]) for j in range(n)] for i in range(n)]
+        topo = Topology(n, [torch.cuda.get_device_name(i) for i in range(n)], link, "dlcfn_probe_fabric")
+        topo.multicast = bool(n) and all(mc[i] for i in range(n))
+        topo.native_atomics = all(atom[i * n + j] for i in range(n) for j in range(n) if i != j) if n > 1 else None
+        return topo
+    except Exception:
+        return None
 
 
 def _probe_torch() -> Topology | None:
@@ -106,5 +135,11 @@ def probe_topology() -> Topology:
         n = int(fake)
         link = [[0 if i == j else 18 for j in range(n)] for i in range(n)]
         return Topology(n, [f"fake-b200-{i}" for i in range(n)], link, "DLCFN_FAKE_GPUS")
-    t = _probe_torch()
+    t = _probe_native()
+    if t is None:
+        t = _probe_torch()
+    elif t.uniform():
+        _refine_with_nvidia_smi(t)      # NV<k> link counts for the report; the uniformity verdict is the native probe's
+        if t.source != "dlcfn_probe_fabric":
+            t.source = "dlcfn_probe_fabric+nvidia-smi"
     return t if t is not None else Topology()

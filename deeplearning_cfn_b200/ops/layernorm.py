@@ -30,7 +30,7 @@ _counter = [0]          # Philox offset: advanced by the number of 8-element gro
 
 
 def enabled() -> bool:
-    return os.environ.get("DLCFN_FUSED_LN", "0") == "1"
+    return os.environ.get("DLCFN_FUSED_LN", "1") != "0"      # default since round 2 (validated on B200: tests/test_gpu_layernorm.py)
 
 
 def _declare():

@@ -91,6 +91,23 @@ def _declare(L) -> None:
     L.dlcfn_symm_heap_ptr.argtypes = [vp, i]
     L.dlcfn_symm_heap_ptr.restype = vp
     L.dlcfn_symm_check_error.argtypes = [vp, vp, ctypes.POINTER(i)]
+    ull = ctypes.c_ulonglong
+    P = ctypes.POINTER
+    L.dlcfn_vmm_supported.argtypes = [i]
+    L.dlcfn_vmm_supported.restype = c_int
+    L.dlcfn_vmm_granularity.argtypes = [i, i, i]
+    L.dlcfn_vmm_granularity.restype = sz
+    L.dlcfn_vmm_alloc.argtypes = [sz, i, sz, P(vp), P(ull), P(c_int)]
+    L.dlcfn_vmm_import.argtypes = [i, sz, i, sz, P(vp), P(ull)]
+    L.dlcfn_vmm_mc_create.argtypes = [sz, i, P(ull), P(c_int)]
+    L.dlcfn_vmm_mc_import.argtypes = [i, P(ull)]
+    L.dlcfn_vmm_mc_add_device.argtypes = [ull, i]
+    L.dlcfn_vmm_mc_bind_map.argtypes = [ull, ull, sz, i, sz, P(vp)]
+    L.dlcfn_vmm_unmap_release.argtypes = [vp, ull, sz]
+    L.dlcfn_probe_fabric.argtypes = [i, P(c_int), P(c_int), P(c_int), P(c_int)]
+    for fn in ("dlcfn_vmm_alloc", "dlcfn_vmm_import", "dlcfn_vmm_mc_create", "dlcfn_vmm_mc_import", "dlcfn_vmm_mc_add_device",
+               "dlcfn_vmm_mc_bind_map", "dlcfn_vmm_unmap_release", "dlcfn_probe_fabric"):
+        getattr(L, fn).restype = c_int
     L.dlcfn_symm_poll_error_async.argtypes = [vp, vp, vp]
     L.dlcfn_symm_poll_error_async.restype = c_int
     L.dlcfn_symm_destroy.argtypes = [vp]
@@ -109,6 +126,10 @@ def _declare(L) -> None:
     L.dlcfn_conv_bf16_ex.restype = c_int
     L.dlcfn_gemm_bf16_ex.argtypes = [vp, ll, i, vp, i, i, ll, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp, vp]
     L.dlcfn_gemm_bf16_ex.restype = c_int
+    L.dlcfn_colsum_slices.argtypes = [ll]
+    L.dlcfn_colsum_slices.restype = c_int
+    L.dlcfn_colsum_bf16.argtypes = [vp, vp, ll, i, ll, vp, vp]
+    L.dlcfn_colsum_bf16.restype = c_int
     L.dlcfn_batch_sum_bf16.argtypes = [vp, vp, i, ll, vp]
     L.dlcfn_batch_sum_bf16.restype = c_int
     L.dlcfn_gemm_stats_rows.argtypes = []
@@ -175,6 +196,18 @@ def fused_optimizer(kind: str, grad: torch.Tensor, master: torch.Tensor, s1: tor
                                       dtype_code(wout.dtype) if wout is not None else 0, n, lr, wd, momentum,
                                       beta1, beta2, eps, rescale, clip, stream_ptr()), "fused_optimizer")
     _count()
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a bf16 [M, N] matrix (bias gradients), deterministic two-stage reduction at streaming speed."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    M, N = x.shape
+    L = lib()
+    ws = torch.empty(L.dlcfn_colsum_slices(M) * N, dtype=torch.float32, device=x.device)
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    check(L.dlcfn_colsum_bf16(x.data_ptr(), out.data_ptr(), M, N, x.stride(0), ws.data_ptr(), stream_ptr()), "colsum_bf16")
+    _count(2)
+    return out
 
 
 def batch_sum(x: torch.Tensor) -> torch.Tensor:

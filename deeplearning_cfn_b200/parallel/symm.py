@@ -2,10 +2,17 @@
 
 The B200 replacement for three reference mechanisms at once: the EFS shared mount used to stage
 data/initial weights (deeplearning.template:453-474), the pinned-host `comm_buf_` of KVStoreDist
-(kvstore_dist.h:335-342) and the ZeroMQ data plane of ps-lite (zmq_van.h).  Every rank owns one
-cudaMalloc'ed arena; CUDA-IPC handles are exchanged once through the torch.distributed store and
-each rank maps all peers, after which the fused kernels in csrc/cuda/collectives.cu address any
-peer's HBM with plain loads/stores over NVLink 5 / NVSwitch.
+(kvstore_dist.h:335-342) and the ZeroMQ data plane of ps-lite (zmq_van.h).  Every rank owns one arena that all
+peers map, after which the fused kernels in csrc/cuda/collectives.cu address any peer's HBM with plain
+loads/stores over NVLink 5 / NVSwitch.
+
+Backends (DLCFN_SYMM_BACKEND = auto | vmm | torch | ipc; auto tries them in this order):
+  vmm    the library's own plumbing (csrc/cuda/symm_vmm.cu): cuMemCreate arenas exported as file descriptors, passed
+         between the ranks of the node over abstract AF_UNIX sockets (SCM_RIGHTS) and mapped with cuMemMap; NVLS multicast
+         object created by rank 0 (cuMulticastCreate / AddDevice / BindMem) - no private torch API involved
+  torch  torch.distributed._symmetric_memory (same mechanism, borrowed)
+  ipc    one cudaMalloc arena per rank + CUDA-IPC handles through the torch.distributed store (no multicast)
+`stage_put` / `stage_get` are the shared-staging API on top (initial weights, shared data: the EFS analogue).
 """
 from __future__ import annotations
 
@@ -30,6 +37,44 @@ class _RawCuda:
 def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
     """uint8 view of raw device memory (no ownership)."""
     return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
+
+
+def exchange_fds(fd: int, rank: int, world: int, group, tag: str) -> list[int]:
+    """Every rank contributes one file descriptor; returns the list of all ranks' descriptors as valid in THIS process.
+    Descriptors cross process boundaries as SCM_RIGHTS ancillary data over abstract AF_UNIX sockets (names agreed through
+    torch.distributed); -1 entries (a rank with nothing to share) stay -1."""
+    import socket
+    import uuid
+    me = f"\0dlcfn-{tag}-{os.getpid()}-{uuid.uuid4().hex[:8]}"
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(me)
+    srv.listen(world + 1)
+    names: list = [None] * world
+    dist.all_gather_object(names, (me, fd >= 0), group=group)
+    out = [-1] * world
+    out[rank] = fd
+    try:
+        if fd >= 0:
+            for p, (name, _) in enumerate(names):
+                if p == rank:
+                    continue
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.connect(name)                     # queued in the listener's backlog until it accepts
+                socket.send_fds(c, [rank.to_bytes(4, "little")], [fd])
+                c.close()
+        expect = sum(1 for p, (_, has) in enumerate(names) if has and p != rank)
+        srv.settimeout(120)
+        for _ in range(expect):
+            conn, _ = srv.accept()
+            msg, fds, _, _ = socket.recv_fds(conn, 4, 1)
+            conn.close()
+            if len(fds) != 1 or len(msg) != 4:
+                raise RuntimeError("file-descriptor exchange: malformed message")
+            out[int.from_bytes(msg, "little")] = fds[0]
+    finally:
+        srv.close()
+    dist.barrier(group=group)
+    return out
 
 
 class SymmetricHeap:
@@ -61,8 +106,18 @@ class SymmetricHeap:
         self.backend = "ipc"
         self._symm_tensor = None
         want = os.environ.get("DLCFN_SYMM_BACKEND", "auto")
+        self._vmm = None
         with torch.cuda.device(self.device):
-            if self.world > 1 and want in ("auto", "torch"):
+            if self.world > 1 and want in ("auto", "vmm"):
+                try:
+                    ctx = self._create_vmm_backend(L)
+                    self.backend = "vmm"
+                except Exception as e:          # no exportable VMM handles here (or fd passing refused): next backend
+                    if want == "vmm":
+                        raise
+                    self._why_not_vmm = repr(e)
+                    ctx = c_void_p()
+            if self.backend == "ipc" and self.world > 1 and want in ("auto", "torch"):
                 try:
                     ctx = self._create_torch_backend(L)
                     self.backend = "torch-symm"
@@ -93,6 +148,86 @@ class SymmetricHeap:
         self._top = 0
         if self.world > 1:
             dist.barrier(group=group)
+
+    # ------------------------------------------------------------------ own VMM / multicast plumbing
+    def _exchange_fds(self, fd: int, tag: str) -> list[int]:
+        return exchange_fds(fd, self.rank, self.world, self.group, tag)
+
+    def _create_vmm_backend(self, L):
+        from ctypes import c_ulonglong
+        dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        sup = int(L.dlcfn_vmm_supported(dev))
+        flags = [None] * self.world
+        dist.all_gather_object(flags, sup, group=self.group)
+        if not all(f & 1 for f in flags):
+            raise RuntimeError(f"exportable VMM allocations are not supported on every rank (flags {flags})")
+        want_mc = all(f & 2 for f in flags) and os.environ.get("DLCFN_SYMM_MULTICAST", "1") != "0"
+        gran = int(L.dlcfn_vmm_granularity(dev, self.world, int(want_mc)))
+        if gran <= 0:
+            raise RuntimeError("cuMemGetAllocationGranularity failed")
+        total = ((1 << 20) + (self.heap_bytes + 255) // 256 * 256 + gran - 1) // gran * gran
+        ptr, hdl, fd = c_void_p(), c_ulonglong(), c_int(-1)
+        native.check(L.dlcfn_vmm_alloc(total, dev, gran, ctypes.byref(ptr), ctypes.byref(hdl), ctypes.byref(fd)), "vmm_alloc")
+        st = {"total": total, "gran": gran, "local": (ptr.value, hdl.value), "peers": {}, "mc": None, "fds": [fd.value]}
+        self._vmm = st
+        fds = self._exchange_fds(fd.value, "arena")
+        ctx = c_void_p()
+        native.check(L.dlcfn_symm_create_external(ptr.value, total, self.rank, self.world, ctypes.byref(ctx)), "symm_create_external")
+        for p, pfd in enumerate(fds):
+            if p == self.rank:
+                continue
+            pp, ph = c_void_p(), c_ulonglong()
+            native.check(L.dlcfn_vmm_import(pfd, total, dev, gran, ctypes.byref(pp), ctypes.byref(ph)), "vmm_import")
+            os.close(pfd)
+            st["peers"][p] = (pp.value, ph.value)
+            native.check(L.dlcfn_symm_set_peer_ptr(ctx, p, pp.value), "symm_set_peer_ptr")
+        if want_mc:
+            mc, mfd = c_ulonglong(), c_int(-1)
+            if self.rank == 0:
+                native.check(L.dlcfn_vmm_mc_create(total, self.world, ctypes.byref(mc), ctypes.byref(mfd)), "vmm_mc_create")
+            mfds = self._exchange_fds(mfd.value if self.rank == 0 else -1, "mc")
+            if self.rank != 0:
+                native.check(L.dlcfn_vmm_mc_import(mfds[0], ctypes.byref(mc)), "vmm_mc_import")
+                os.close(mfds[0])
+            else:
+                os.close(mfd.value)
+            native.check(L.dlcfn_vmm_mc_add_device(mc.value, dev), "vmm_mc_add_device")
+            dist.barrier(group=self.group)              # every device has joined before anyone binds memory
+            mptr = c_void_p()
+            native.check(L.dlcfn_vmm_mc_bind_map(mc.value, hdl.value, total, dev, gran, ctypes.byref(mptr)), "vmm_mc_bind_map")
+            st["mc"] = (mptr.value, mc.value)
+            native.check(L.dlcfn_symm_set_multicast(ctx, mptr.value), "symm_set_multicast")
+        os.close(fd.value)
+        st["fds"] = []
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        return ctx
+
+    # ------------------------------------------------------------------ shared staging (the EFS analogue)
+    def stage_put(self, name: str, tensor: torch.Tensor) -> tuple[int, int]:
+        """Publish `tensor` (this rank's copy) under `name` in the heap: allocates the same region on every rank (all ranks
+        must call with the same name / size, like every allocation) and copies the local data in.  Peers read it with
+        `stage_get(name, src_rank)` straight out of this rank's HBM - initial weights from rank 0, shared data shards ...
+        (reference: files on the EFS mount every instance shares, deeplearning.template:453-474)."""
+        reg = self.__dict__.setdefault("_staged", {})
+        nb = tensor.numel() * tensor.element_size()
+        if name not in reg:
+            reg[name] = (self.alloc(nb), nb, tensor.dtype, tuple(tensor.shape))
+        off, cap, _, _ = reg[name]
+        if nb != cap:
+            raise ValueError(f"staged object {name!r} was registered with {cap} bytes, got {nb}")
+        self._bytes[off: off + nb].copy_(tensor.detach().contiguous().reshape(-1).view(torch.uint8))
+        return off, nb
+
+    def stage_get(self, name: str, src_rank: int, stream: torch.cuda.Stream | None = None) -> torch.Tensor:
+        """A copy of what `src_rank` staged under `name`, read over NVLink from its arena (callers order it after the
+        producer's stage_put with a barrier, e.g. `heap.barrier()`)."""
+        off, nb, dtype, shape = self._staged[name]
+        src = tensor_from_ptr(self.peer_heap_ptr(src_rank) + off, nb, self.device)
+        out = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+            out.copy_(src, non_blocking=True)
+        return out.view(dtype).view(shape)
 
     def _create_torch_backend(self, L):
         """Arena from torch symmetric memory: same layout, every peer already mapped, plus (when the fabric
@@ -233,5 +368,14 @@ class SymmetricHeap:
             torch.cuda.synchronize(self.device)
             self._bytes = None
             native.lib().dlcfn_symm_destroy(self._ctx)
+            st = getattr(self, "_vmm", None)
+            if st:                               # unmap the multicast view, the peers and the local arena; drop the handles
+                L = native.lib()
+                if st["mc"]:
+                    L.dlcfn_vmm_unmap_release(st["mc"][0], st["mc"][1], st["total"])
+                for pp, ph in st["peers"].values():
+                    L.dlcfn_vmm_unmap_release(pp, ph, st["total"])
+                L.dlcfn_vmm_unmap_release(st["local"][0], st["local"][1], st["total"])
+                self._vmm = None
             self._ctx = None
             self._symm_tensor = None

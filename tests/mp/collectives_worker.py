@@ -153,6 +153,32 @@ def main():
             if not (w.min().item() >= rank - 1e-3 and w.max().item() <= hi_b + 1e-3):
                 fail(f"ps_async worker weights out of range: {w.min().item()} {w.max().item()} [{lo_b},{hi_b}]")
 
+    # ---- both all-reduce algorithms explicitly (peer ld/st two-shot, NVLS multimem) on the same data ----
+    n = 3_000_001
+    off, t = heap.alloc_tensor(n + 16, torch.bfloat16)
+    src = (torch.arange(n, device=dev) % 17 + rank).to(torch.bfloat16)
+    want = sum((torch.arange(n, device=dev) % 17 + r).float() for r in range(world)).bfloat16()
+    for algo in ([0, 1] if heap.has_multicast else [0]):
+        t[:n].copy_(src)
+        torch.cuda.synchronize()
+        dist.barrier()
+        heap.allreduce_(off, n, torch.bfloat16, scale=1.0, algo=algo)
+        torch.cuda.synchronize()
+        if not torch.allclose(t[:n].float(), want.float(), rtol=2 ** -7, atol=1e-6):
+            fail(f"allreduce algo {algo}: max diff {(t[:n].float() - want.float()).abs().max().item()}")
+    # ---- shared staging: rank 0 publishes "initial weights", everyone reads them out of rank 0's HBM ----
+    w0 = torch.arange(10_000, device=dev, dtype=torch.float32) * (1.0 if rank == 0 else -1.0)
+    heap.stage_put("init/weights", w0)
+    torch.cuda.synchronize()
+    heap.barrier()
+    got = heap.stage_get("init/weights", 0)
+    torch.cuda.synchronize()
+    if not torch.equal(got, torch.arange(10_000, device=dev, dtype=torch.float32)):
+        fail("stage_get did not return rank 0's staged tensor")
+    backend_want = os.environ.get("DLCFN_EXPECT_SYMM_BACKEND")
+    if backend_want and heap.backend != backend_want:
+        fail(f"symmetric heap backend is {heap.backend}, expected {backend_want} ({getattr(heap, '_why_not_vmm', '')})")
+
     heap.check_error()
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)

@@ -21,6 +21,14 @@ def test_gloo_world2_data_parallel_matches_single_process(naive):
     assert r.returncode == 0 and "GLOO_TRAINER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_vmm_backend_file_descriptor_exchange_world3():
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "3", sys.executable,
+           os.path.join(ROOT, "tests/mp/fd_exchange_worker.py")]
+    from conftest import run_job
+    r = run_job(cmd, env=dict(os.environ, PYTHONPATH=ROOT), timeout=120)
+    assert r.returncode == 0 and r.stdout.count("FD_EXCHANGE_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_hierarchical_multinode_mode_matches_flat_allreduce():
     """2 virtual nodes x 2 ranks on gloo: node-local sum -> per-rail all-reduce of the slices -> node-local broadcast."""
     cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "4", sys.executable,

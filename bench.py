@@ -31,8 +31,10 @@ def parse():
                     help="ours | reference (the unmodified reference: unavailable offline) | nccl (ours with NCCL collectives) | "
                          "torch-stock (stock nn.Module ResNet-50 + torch.optim.SGD + DDP, baseline/torch_stock.py: no repo code)")
     ap.add_argument("--stock", type=int, default=int(os.environ.get("DLCFN_BENCH_STOCK", "1")),
-                    help="after the own measurement, run the stock-PyTorch arm (baseline/torch_stock.py) in a child process per rank "
-                         "and add `vs_stock` to the JSON line (ResNet only; 0 = skip)")
+                    help="after the own measurement, run the stock-PyTorch arm (baseline/torch_stock.py) in a child process and add "
+                         "`vs_stock` to the JSON line (ResNet only).  0 = never, 1 = single-GPU runs only (default), 2 = also under "
+                         "torchrun (one child per rank with its own process group); multi-GPU stock numbers are otherwise taken with "
+                         "`--impl torch-stock` (profiles/r2/)")
     ap.add_argument("--mode", default=None, help="allreduce (default) | ps_sync | ps_dedicated | nccl | nccl_ps | hier (multi-node: fused node-local + NCCL rails)")
     ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert-large", "bert-base"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 256 images / 16 sequences)")
@@ -47,8 +49,9 @@ def parse():
     ap.add_argument("--device-batches", type=int, default=4,
                     help="distinct device-resident input batches rotated by the device-timed loop (the same synthetic images the "
                          "end-to-end loop streams from the host); 1 = train on one fixed batch")
-    ap.add_argument("--cuda-graph", action="store_true",
-                    help="experimental: replay the device-timed step as one CUDA graph (parallel/graph.py); off by default")
+    ap.add_argument("--cuda-graph", action=argparse.BooleanOptionalAction, default=os.environ.get("DLCFN_BENCH_GRAPH", "1") != "0",
+                    help="replay the training step (forward, backward, fused collectives, optimizer: every kernel of the eager step) as "
+                         "one CUDA graph captured through the public API `trainer.capture` (parallel/graph.py); --no-cuda-graph = eager")
     ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn", "auto"],
                     help="backend of the 1x1 convolutions (default: ops.conv default / DLCFN_CONV1X1)")
     return ap.parse_args()
@@ -109,9 +112,10 @@ def run_stock_child(args, rank):
     env = dict(os.environ)
     if "MASTER_PORT" in env:
         env["MASTER_PORT"] = str(int(env["MASTER_PORT"]) + 17)
-    env.pop("TORCHELASTIC_RUN_ID", None)
+    for k in [k for k in env if k.startswith("TORCHELASTIC_")]:
+        env.pop(k)        # the child group makes its own TCPStore on MASTER_PORT + 17 (the agent's store lives on MASTER_PORT)
     try:
-        r = subprocess.run(stock_argv(args), env=env, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(stock_argv(args), env=env, capture_output=True, text=True, timeout=300)
     except (subprocess.TimeoutExpired, OSError) as e:      # the headline must not depend on the comparison arm
         print(f"[bench] stock arm failed: {e}", file=sys.stderr, flush=True)
         return None
@@ -263,10 +267,13 @@ def main():
         sampler.__enter__()
     t_start.record()
     step_loss = None
+    marks = [Event(enable_timing=True) for _ in range(args.steps)]        # one event per step: min / median step time
     for i in range(args.steps):
         step_loss = run_step(*dev_batches[(args.warmup + i) % nb]) if is_worker else run_step()
+        marks[i].record()
     t_end.record()
     sync_all()
+    step_ms = sorted(a.elapsed_time(b) for a, b in zip([t_start] + marks[:-1], marks))
     if sampler:
         sampler.__exit__(None, None, None)
     ms = t_start.elapsed_time(t_end)
@@ -291,9 +298,9 @@ def main():
         for _ in range(3):
             if is_worker:
                 xb, yb = pre.next()
-                trainer.step(xb, yb)
+                run_step(xb, yb)
             else:
-                trainer.step()
+                run_step()
         sync_all()
         e_start, e_end = Event(enable_timing=True), Event(enable_timing=True)
         last, losses_read = 0.0, 0
@@ -304,7 +311,7 @@ def main():
         for i in range(args.steps):
             if is_worker:
                 xb, yb = pre.next()                      # H2D of this step's inputs (pinned -> device) + normalise
-                loss = trainer.step(xb, yb)
+                loss = run_step(xb, yb)
                 k = i & 1
                 host_loss[k].copy_(loss.detach().float().reshape(1), non_blocking=True)   # D2H of this step's loss
                 loss_ev[k].record()
@@ -313,7 +320,7 @@ def main():
                     last = float(host_loss[k ^ 1][0])
                     losses_read += 1
             else:
-                trainer.step()
+                run_step()
         if is_worker:                                    # ... and the last step's, still inside the timed region
             k = (args.steps - 1) & 1
             loss_ev[k].synchronize()
@@ -351,7 +358,7 @@ def main():
     else:
         e_ms = float(t[1])
     stock = None
-    if args.stock and not dry and not is_bert and args.impl == "ours" and servers is None:
+    if args.stock and (world == 1 or args.stock >= 2) and not dry and not is_bert and args.impl == "ours" and servers is None:
         n_dev_batches = len(dev_batches)
         dev_batches = [None] * n_dev_batches            # release the device-resident inputs before the child allocates its own
         torch.cuda.empty_cache()
@@ -383,7 +390,8 @@ def main():
         else:
           rec = {"metric": "resnet50_train_images_per_sec", "value": round(value, 2), "unit": "images/sec",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+               "ms_per_step": round(ms / args.steps, 3), "ms_per_step_min": round(step_ms[0], 3),
+               "ms_per_step_median": round(step_ms[len(step_ms) // 2], 3), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": round(value / (BASELINE_IMG_S_PER_GPU * world), 3), "dtype": "fp32 (dry run)" if dry else "bf16",
                "data": "synthetic (random uint8 images normalised on the device, random labels, random-init weights)",
                "impl": "ours" if args.impl == "ours" else "nccl-baseline",

@@ -19,6 +19,7 @@
 // All of them are latency/NVLink-bound streaming kernels: 16-byte accesses, >= W independent loads in
 // flight per thread, a small grid (default 32 CTAs x 512 threads ~ 4 MB in flight) so that the rest of
 // the 148 SMs keep running backward while a bucket is on the wire.
+#include <cstdlib>
 #include "symm.cuh"
 #include "optimizer.cuh"
 
@@ -182,6 +183,52 @@ __global__ void __launch_bounds__(512) kallreduce_mc(SymmDev s, size_t off, size
   epoch_store(s, channel, e + 2);
 }
 
+// ONE-SHOT variant for latency-bound sizes (<= kOneShotMax bytes): ONE flag barrier instead of two.
+//   1. every rank PUSHES its input into the staging slot [parity][rank] of every peer's header (W stores per vector)
+//   2. flag barrier (release after the pushes, acquire before the reads)
+//   3. every rank sums the W staged copies out of its OWN memory in rank order (bit-identical on all ranks), scales, stores.
+// No exit barrier: the staging slots alternate with the epoch's parity, and a rank can only reach the pushes of call k+2 after
+// passing the barrier of call k+1, which every peer enters only after finishing its reads of call k (program order + release).
+// In place is safe - the input is read by its owner only.  Reference analogue: the small-key path of CommDevice::Reduce
+// (comm.h:598-616) where every key is one copy + one ElementwiseSum.
+template <typename T, int W>
+__global__ void __launch_bounds__(512) kallreduce_oneshot(SymmDev s, size_t off, size_t dst_off, size_t nvec, float scale,
+                                                          int channel) {
+  constexpr int N = Vec16<T>::N;
+  const uint32_t e = epoch_load(s, channel);
+  const size_t parity = e & 1u;
+  const uint4* in = reinterpret_cast<const uint4*>(s.base[s.rank] + off);
+  const size_t slot = (parity * DLCFN_MAX_RANKS + (size_t)s.rank) * kOneShotMax;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const uint4 x = in[v];
+#pragma unroll
+    for (int p = 0; p < W; ++p)      // base[p] - kHeapOff = start of peer p's allocation (header)
+      st_stream_v4(reinterpret_cast<uint4*>(s.base[p] - kHeapOff + kStageOff + slot) + v, x);
+  }
+  block_barrier(s, channel, e + 1);
+  uint4* out = reinterpret_cast<uint4*>(s.base[s.rank] + dst_off);
+  const char* mine = s.base[s.rank] - kHeapOff + kStageOff + parity * DLCFN_MAX_RANKS * kOneShotMax;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    uint4 x[W];
+#pragma unroll
+    for (int p = 0; p < W; ++p) x[p] = ld_relaxed_sys_v4(reinterpret_cast<const uint4*>(mine + (size_t)p * kOneShotMax) + v);
+    float acc[N], t[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int p = 0; p < W; ++p) {
+      Vec16<T>::unpack(x[p], t);
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[k] += t[k];
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] *= scale;
+    out[v] = Vec16<T>::pack(acc);
+  }
+  epoch_store(s, channel, e + 1);
+}
+
 // ------------------------------------------------------------ broadcast -----
 __global__ void __launch_bounds__(512) kbroadcast(SymmDev s, size_t off, size_t nvec, int root, int channel) {
   const uint32_t e = epoch_load(s, channel);
@@ -325,7 +372,7 @@ __global__ void kps_async_worker(SymmDev s, uint32_t server_mask, int channel) {
   __syncthreads();
   if ((int)threadIdx.x < s.world && ((server_mask >> threadIdx.x) & 1u)) {
     st_release_sys(sig_slot(s, threadIdx.x, channel, blockIdx.x, s.rank), k);
-    if (!spin_wait_ge(sig_slot(s, s.rank, channel + 1, blockIdx.x, threadIdx.x), k, kSpinTimeoutNs))
+    if (!spin_wait_ge(sig_slot(s, s.rank, channel + 1, blockIdx.x, threadIdx.x), k, s.timeout_ns ? s.timeout_ns : kSpinTimeoutNs))
       atomicExch(s.err, 1);
   }
   __syncthreads();
@@ -355,7 +402,7 @@ __global__ void __launch_bounds__(512) kps_async_server(SymmDev s, PSArgs a) {
           if (!((a.worker_mask >> r) & 1u) || ((sh_done >> r) & 1u)) continue;
           if ((int32_t)(ld_acquire_sys(sig_slot(s, s.rank, a.channel, blockIdx.x, r)) - k) >= 0) found = r;
         }
-        if (found < 0 && clock_now() - t0 > kSpinTimeoutNs) {
+        if (found < 0 && clock_now() - t0 > (s.timeout_ns ? s.timeout_ns : kSpinTimeoutNs)) {
           atomicExch(s.err, 1);
           found = -2;
         }
@@ -424,6 +471,16 @@ DLCFN_API int dlcfn_symm_set_multicast(void* ctx, void* mc_alloc) {
   return 0;
 }
 
+// Protocol test hooks (tests/mp/protocol_worker.py): spin timeout in ms (0 = default 4 s), schedule-fuzzing delay bound in
+// ns (0 = off), peer that this rank stops signalling (-1 = none; reference fault injection: PS_DROP_MSG, PS/src/van.cc:297-299).
+DLCFN_API int dlcfn_symm_set_debug(void* ctx, int timeout_ms, unsigned stress_ns, int drop_peer) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  c->dev.timeout_ns = (long long)timeout_ms * 1000000ll;
+  c->dev.stress_ns = stress_ns;
+  c->dev.drop_peer = drop_peer;
+  return 0;
+}
+
 DLCFN_API int dlcfn_symm_has_multicast(void* ctx) { return ((SymmCtx*)ctx)->dev.mc != nullptr ? 1 : 0; }
 
 DLCFN_API int dlcfn_symm_get_handle(void* ctx, void* out64) {
@@ -475,6 +532,15 @@ DLCFN_API int dlcfn_symm_finalize(void* ctx) {
   c->dev.mc = c->mc_alloc ? c->mc_alloc + kHeapOff : nullptr;
   c->dev.rank = c->rank;
   c->dev.world = c->world;
+  c->dev.timeout_ns = 0;
+  c->dev.stress_ns = 0;
+  c->dev.drop_peer = -1;
+  {   // environment form of the hooks, for whole-job stress runs: DLCFN_SYMM_STRESS_NS, DLCFN_SPIN_TIMEOUT_MS
+    const char* e = getenv("DLCFN_SYMM_STRESS_NS");
+    if (e) c->dev.stress_ns = (uint32_t)atoi(e);
+    e = getenv("DLCFN_SPIN_TIMEOUT_MS");
+    if (e && atoi(e) > 0) c->dev.timeout_ns = (long long)atoi(e) * 1000000ll;
+  }
   c->finalized = true;
   return 0;
 }
@@ -556,6 +622,17 @@ static int launch_allreduce(SymmCtx* c, size_t off, size_t dst_off, size_t nvec,
     kallreduce_mc<T><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel);
     return (int)cudaGetLastError();
   }
+  if (algo == 2) {
+    if (nvec * 16 > kOneShotMax) return (int)cudaErrorInvalidValue;
+    const int g1 = (int)((nvec + 511) / 512);          // <= 4 CTAs: every CTA owns its vectors and its own flag slots
+    switch (c->world) {
+#define DLCFN_ONESHOT(Wn) case Wn: kallreduce_oneshot<T, Wn><<<g1, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
+      DLCFN_ONESHOT(1) DLCFN_ONESHOT(2) DLCFN_ONESHOT(3) DLCFN_ONESHOT(4) DLCFN_ONESHOT(5) DLCFN_ONESHOT(6) DLCFN_ONESHOT(7) DLCFN_ONESHOT(8)
+#undef DLCFN_ONESHOT
+      default: return (int)cudaErrorInvalidValue;
+    }
+    return (int)cudaGetLastError();
+  }
   switch (c->world) {
     case 1: kallreduce<T, 1><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
     case 2: kallreduce<T, 2><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
@@ -571,7 +648,8 @@ static int launch_allreduce(SymmCtx* c, size_t off, size_t dst_off, size_t nvec,
 }
 
 // Fused scale + all-reduce of heap[src_off, +count*sizeof(T)) into heap[dst_off, ...) on every rank
-// (dst_off == src_off: in place).  algo 0: peer ld/st two-shot;  algo 1: NVLS multimem (needs a multicast mapping).
+// (dst_off == src_off: in place).  algo 0: peer ld/st two-shot;  algo 1: NVLS multimem (needs a multicast mapping);
+// algo 2: one-shot through the header staging slots, <= 32 KiB (one flag barrier).
 DLCFN_API int dlcfn_allreduce_ex(void* ctx, size_t src_off, size_t dst_off, size_t count, int dtype, float scale,
                                  int channel, int nblocks, int algo, cudaStream_t stream) {
   (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries

@@ -2,7 +2,7 @@
 // host comm_buf_ of KVStoreDist (kvstore_dist.h:335-342) and ps-lite's ZeroMQ data plane (C6).
 //
 // Every rank owns one device allocation laid out as
-//     [ signal pad 64 KiB | epoch counters 8 KiB | error word ... | 1 MiB: data heap ... ]
+//     [ signal pad 64 KiB | epoch counters 8 KiB | error word | 128 KiB: one-shot staging 512 KiB ... | 1 MiB: data heap ... ]
 // and maps every peer's allocation (CUDA IPC across processes, or direct peer access inside one
 // process).  Kernels receive the whole table by value (SymmDev) and address any peer's heap or
 // signal pad with plain ld/st over NVLink 5 / NVSwitch.
@@ -17,7 +17,11 @@ constexpr size_t kSigBytes = (size_t)kSigChannels * kSigMaxBlocks * DLCFN_MAX_RA
 constexpr size_t kEpochOff = kSigBytes;
 constexpr size_t kEpochBytes = (size_t)kSigChannels * kSigMaxBlocks * sizeof(uint32_t);                  // 8 KiB
 constexpr size_t kErrOff = kEpochOff + kEpochBytes;
+// one-shot all-reduce staging: [2 parities][DLCFN_MAX_RANKS sources][kOneShotMax bytes] inside the header, below the heap
+constexpr size_t kStageOff = 128u << 10;
+constexpr size_t kOneShotMax = 32u << 10;
 constexpr size_t kHeapOff = 1u << 20;
+static_assert(kStageOff >= kErrOff + 64 && kStageOff + 2 * DLCFN_MAX_RANKS * kOneShotMax <= kHeapOff, "header layout");
 constexpr long long kSpinTimeoutNs = 4000000000ll;  // 4 s: a dead peer becomes an error, not a hung GPU
 
 struct SymmDev {
@@ -27,6 +31,10 @@ struct SymmDev {
   int* err;                        // local error word
   char* mc;                        // NVLS multicast mapping of the data heaps (nullptr when unavailable)
   int rank, world;
+  // protocol test hooks (dlcfn_symm_set_debug; all zero / -1 in production):
+  long long timeout_ns;            // spin timeout of the flag waits (0 = kSpinTimeoutNs)
+  uint32_t stress_ns;              // > 0: every CTA sleeps a pseudo-random 0..stress_ns before it signals (schedule fuzzing)
+  int drop_peer;                   // >= 0: this rank never signals that peer (fault injection: the peer must time out)
 };
 
 __device__ __forceinline__ uint32_t* sig_slot(const SymmDev& s, int owner, int channel, int block, int src) {
@@ -38,8 +46,14 @@ __device__ __forceinline__ uint32_t* sig_slot(const SymmDev& s, int owner, int c
 __device__ __forceinline__ void block_barrier(const SymmDev& s, int channel, uint32_t val) {
   __syncthreads();
   if ((int)threadIdx.x < s.world) {
-    st_release_sys(sig_slot(s, threadIdx.x, channel, blockIdx.x, s.rank), val);
-    if (!spin_wait_ge(sig_slot(s, s.rank, channel, blockIdx.x, threadIdx.x), val, kSpinTimeoutNs))
+    if (s.stress_ns) {             // schedule fuzzing: a different delay per (rank, CTA, peer, round)
+      uint32_t h = (uint32_t)s.rank * 0x9E3779B9u ^ (blockIdx.x * 0x85EBCA6Bu) ^ (threadIdx.x * 0xC2B2AE35u) ^ (val * 0x27D4EB2Fu);
+      h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+      __nanosleep(h % s.stress_ns);
+    }
+    if ((int)threadIdx.x != s.drop_peer)
+      st_release_sys(sig_slot(s, threadIdx.x, channel, blockIdx.x, s.rank), val);
+    if (!spin_wait_ge(sig_slot(s, s.rank, channel, blockIdx.x, threadIdx.x), val, s.timeout_ns ? s.timeout_ns : kSpinTimeoutNs))
       atomicExch(s.err, 1);
   }
   __syncthreads();

@@ -108,6 +108,8 @@ def _declare(L) -> None:
     for fn in ("dlcfn_vmm_alloc", "dlcfn_vmm_import", "dlcfn_vmm_mc_create", "dlcfn_vmm_mc_import", "dlcfn_vmm_mc_add_device",
                "dlcfn_vmm_mc_bind_map", "dlcfn_vmm_unmap_release", "dlcfn_probe_fabric"):
         getattr(L, fn).restype = c_int
+    L.dlcfn_symm_set_debug.argtypes = [vp, i, u32, i]
+    L.dlcfn_symm_set_debug.restype = c_int
     L.dlcfn_symm_poll_error_async.argtypes = [vp, vp, vp]
     L.dlcfn_symm_poll_error_async.restype = c_int
     L.dlcfn_symm_destroy.argtypes = [vp]

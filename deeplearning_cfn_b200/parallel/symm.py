@@ -87,6 +87,7 @@ class SymmetricHeap:
     CH_BCAST = 2
     CH_BARRIER = 3
     CH_ASYNC = 4  # uses 4 and 5
+    ONESHOT_MAX = 32 << 10   # bytes: csrc/cuda/symm.cuh:kOneShotMax
 
     def __init__(self, heap_bytes: int, group: dist.ProcessGroup | None = None, device: torch.device | None = None):
         if not torch.cuda.is_available():
@@ -287,11 +288,15 @@ class SymmetricHeap:
                    stream: torch.cuda.Stream | None = None, channel: int | None = None, dst_off: int | None = None,
                    algo: int | None = None) -> None:
         """Fused bucket scale + all-reduce (reference C11: Horovod fusion buffer + ncclAllReduce).  In place unless
-        dst_off is given.  algo 0 = peer ld/st two-shot, 1 = NVLS multimem (default when a multicast mapping exists)."""
+        dst_off is given.  algo 0 = peer ld/st two-shot, 1 = NVLS multimem (default when a multicast mapping exists), 2 = one-shot
+        (<= 32 KiB, one barrier; default at that size)."""
         ch = self.CH_ALLREDUCE if channel is None else channel
         a = self.allreduce_algo if algo is None else algo
-        if algo is None and a == 1 and count * (2 if dtype == torch.bfloat16 else 4) < (2 << 20):
+        nbytes = count * (2 if dtype == torch.bfloat16 else 4)
+        if algo is None and a == 1 and nbytes < (2 << 20):
             a = 0      # below ~2 MiB the switch round trip costs more than it saves (profiles/scale8/README.md)
+        if algo is None and nbytes <= self.ONESHOT_MAX and self.world > 1 and os.environ.get("DLCFN_ALLREDUCE_ONESHOT", "1") != "0":
+            a = 2      # latency-bound: push + ONE flag barrier + local reduce (collectives.cu:kallreduce_oneshot)
         native.check(native.lib().dlcfn_allreduce_ex(self._ctx, off, off if dst_off is None else dst_off, count,
                                                      native.dtype_code(dtype), float(scale), ch, nblocks, a,
                                                      native.stream_ptr(stream)), "allreduce")
@@ -345,6 +350,11 @@ class SymmetricHeap:
         if e.value:
             raise RuntimeError("a peer did not reach a device-side flag barrier within the timeout "
                                "(dead or stalled rank) - reference analogue: get_num_dead_node > 0")
+
+    def set_debug(self, timeout_ms: int = 0, stress_ns: int = 0, drop_peer: int = -1) -> None:
+        """Protocol test hooks: flag-wait timeout, per-CTA random delay before every signal (schedule fuzzing), and fault
+        injection - stop signalling `drop_peer`, which must then surface a timeout through check_error / poll_error."""
+        native.check(native.lib().dlcfn_symm_set_debug(self._ctx, int(timeout_ms), int(stress_ns), int(drop_peer)), "symm_set_debug")
 
     def poll_error(self, stream: torch.cuda.Stream | None = None) -> None:
         """Non-blocking dead-peer check: raises if the error word copied by the PREVIOUS call was set, then queues the next

@@ -166,6 +166,22 @@ def main():
         torch.cuda.synchronize()
         if not torch.allclose(t[:n].float(), want.float(), rtol=2 ** -7, atol=1e-6):
             fail(f"allreduce algo {algo}: max diff {(t[:n].float() - want.float()).abs().max().item()}")
+    # ---- one-shot (single barrier) against two-shot on latency-bound sizes, many back-to-back calls (staging parity reuse) ----
+    for dtype, n in ((torch.bfloat16, 1), (torch.bfloat16, 4096), (torch.float32, 8192), (torch.bfloat16, 16384)):
+        off, t = heap.alloc_tensor(n + 16, dtype)
+        for it in range(6):
+            vals = ((torch.arange(n, device=dev) * 7 + rank * 3 + it) % 23).to(dtype)
+            res = {}
+            for algo in (0, 2):
+                t[:n].copy_(vals)
+                torch.cuda.synchronize()
+                dist.barrier()
+                heap.allreduce_(off, n, dtype, scale=0.25, algo=algo)
+                heap.allreduce_(off, n, dtype, scale=1.0, algo=algo)      # back to back, in place: sum of equal values = W * x
+                torch.cuda.synchronize()
+                res[algo] = t[:n].clone()
+            if not torch.equal(res[0], res[2]):
+                fail(f"one-shot all-reduce differs from two-shot: {dtype} n={n} it={it} max diff {(res[0].float() - res[2].float()).abs().max().item()}")
     # ---- shared staging: rank 0 publishes "initial weights", everyone reads them out of rank 0's HBM ----
     w0 = torch.arange(10_000, device=dev, dtype=torch.float32) * (1.0 if rank == 0 else -1.0)
     heap.stage_put("init/weights", w0)

@@ -1,0 +1,82 @@
+"""Device-side flag protocol under stress (run with torchrun, >= 2 ranks):
+  1. schedule fuzzing - every CTA sleeps a pseudo-random time before each signal; all-reduce (two-shot, one-shot, NVLS), the
+     fused parameter-server step and broadcast must still produce exact closed-form results over many rounds;
+  2. fault injection - one rank stops signalling a peer (the device-side analogue of PS_DROP_MSG, PS/src/van.cc:297-299): the
+     peer's wait must time out into the error word and surface through check_error / poll_error instead of hanging."""
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from deeplearning_cfn_b200.parallel.symm import SymmetricHeap  # noqa: E402
+
+rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lrank)
+dev = torch.device("cuda", lrank)
+dist.init_process_group("nccl", device_id=dev)
+heap = SymmetricHeap(256 << 20)
+ok = True
+
+
+def fail(msg):
+    global ok
+    ok = False
+    print(f"[rank {rank}] FAIL {msg}", flush=True)
+
+
+# ---- 1. schedule fuzzing
+heap.set_debug(stress_ns=20000)
+torch.manual_seed(0)
+sizes = [1, 777, 4096, 100_003, 2_000_000]
+bufs = [heap.alloc_tensor(n + 16, torch.float32) for n in sizes]
+wbufs = [heap.alloc_tensor(n + 16, torch.float32) for n in sizes]
+for rnd in range(40):
+    for (off, t), (woff, w), n in zip(bufs, wbufs, sizes):
+        t[:n] = float(rank + 1 + rnd % 5)
+        want = float(sum(r + 1 + rnd % 5 for r in range(world)))
+        algos = [0] + ([2] if n * 4 <= heap.ONESHOT_MAX else []) + ([1] if heap.has_multicast and n >= 4096 else [])
+        algo = algos[rnd % len(algos)]
+        heap.allreduce_(off, n, torch.float32, scale=1.0, algo=algo)
+        if rnd % 8 == 7:
+            torch.cuda.synchronize()
+            if not torch.all(t[:n] == want):
+                fail(f"fuzzed all-reduce algo {algo} n={n} round {rnd}: {t[:3].tolist()} want {want}")
+    if rnd % 4 == 3:
+        off, t = bufs[3]
+        if rank == rnd % world:
+            t[:sizes[3]] = float(100 + rnd)
+        heap.broadcast_(off, sizes[3] * 4, rnd % world)
+        torch.cuda.synchronize()
+        if not torch.all(t[:sizes[3]] == float(100 + rnd)):
+            fail(f"fuzzed broadcast round {rnd}")
+heap.check_error()
+torch.cuda.synchronize()
+dist.barrier()
+heap.set_debug()
+
+# ---- 2. fault injection: rank 0 stops signalling rank 1; rank 1 must see a timeout, nobody may hang
+heap.set_debug(timeout_ms=300, drop_peer=1 if rank == 0 else -1)
+t0 = time.time()
+heap.barrier()
+torch.cuda.synchronize()
+raised = False
+try:
+    heap.check_error()
+except RuntimeError:
+    raised = True
+if rank == 1 and not raised:
+    fail("a dropped flag store did not surface through check_error")
+if rank != 1 and rank != 0 and raised:
+    pass        # bystanders may or may not time out depending on their own wait set; only rank 1 is required to
+if time.time() - t0 > 30:
+    fail("fault injection took longer than the timeout allows (hang?)")
+flag = torch.tensor([0 if ok else 1], device=dev)
+dist.all_reduce(flag)
+if rank == 0:
+    print("PROTOCOL_OK" if flag.item() == 0 else "PROTOCOL_FAILED", flush=True)
+dist.barrier()
+dist.destroy_process_group()
+os._exit(0 if flag.item() == 0 else 1)      # the heap's flag epochs are out of step after the injected fault: skip close()

@@ -48,3 +48,8 @@ def test_ps_resident_linear_pull_fused_gemm_world2():
 def test_bandwidth_tool_per_key_error_is_zero_world2():
     r = _run(2, "bandwidth_worker.py", 29616)
     assert r.returncode == 0 and "BANDWIDTH_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_flag_protocol_under_schedule_fuzzing_and_fault_injection_world2():
+    r = _run(2, "protocol_worker.py", 29617)
+    assert r.returncode == 0 and "PROTOCOL_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -27,7 +27,7 @@
 // (tile, slice) pair is one work item of the persistent grid and writes an fp32 partial tile to a
 // stream-ordered workspace; ksplitk_reduce sums the slices in a fixed order (deterministic) and applies
 // bias / accumulate / relu / the output conversion.
-#include "common.cuh"
+#include "symm.cuh"
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -106,6 +106,21 @@ struct __align__(64) GemmParams {
   int stg_bufs;         // staging tiles per epilogue warp: 2 = a warp fills one tile while TMA still reads the other
   // fused BatchNorm statistics of the stored bf16 outputs: partial rows [4 * grid][2][N] (sum, sum of squares), or null
   float* stats;
+  // STAGED PULL (all-gather fused into the GEMM over NVLS, sg_on != 0): B is row-sharded over the ranks of the symmetric heap;
+  // at kernel entry every rank PUSHES its shard into the stage buffer of ALL ranks with multimem.st (the switch replicates),
+  // sub-chunk by sub-chunk, and bumps that chunk's arrival counter on all ranks with one multimem.red.release; the TMA
+  // producer loads B from the LOCAL stage buffer as soon as the 64-row chunks under its tile have arrived - tiles of early
+  // chunks start while later chunks are still on the wire.  (Reference C2: ncclBcast / PullImpl + Broadcast before the first
+  // consumer, kvstore_nccl.h:380-396, kvstore_dist.h:217-269.)
+  SymmDev sg;               // peer tables, multicast base, flag pads (by value, like the collectives)
+  int sg_on;
+  int sg_channel;           // flag channel of the entry barrier (all ranks have left the previous user of the stage buffer)
+  const void* sg_shard;     // this rank's shard [sg_rows_per_shard][sg_cols] bf16, row stride sg_ld
+  size_t sg_stage_off;      // stage buffer (full stored matrix) and arrival counters, byte offsets in the heap
+  size_t sg_flags_off;
+  int sg_rows_per_shard, sg_cols;
+  long long sg_ld;
+  uint32_t sg_want;         // arrival count that marks a chunk complete for THIS launch (launch sequence x sub-chunks)
   // launch-time divisors (filled by fill_divisors): m tiles, tiles, im2col row length / rows per image / channel blocks
   FastDiv fd_num_m, fd_tiles, fd_Q, fd_P, fd_cblocks;
 };
@@ -227,6 +242,82 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// ---------------------------------------------------------------- staged pull (all-gather fused into the GEMM) ----
+// Phase 0, run by the epilogue warps (idle until the first accumulator is ready): push this rank's shard of B into the stage
+// buffer of EVERY rank through the NVLS multicast mapping, (64-row chunk) x (256-column slice) work items spread over the
+// CTAs, and bump the chunk's arrival counter on all ranks.  An optional entry barrier (sg_channel >= 0) orders the launch
+// after every rank's previous user of the stage buffer; the default host path alternates two stage buffers instead: a rank
+// can only reach launch i+2 after receiving every rank's chunks of launch i+1, which they push after finishing launch i.
+template <int kPushThreads>
+__device__ __forceinline__ void staged_push(const GemmParams& p, int pt) {
+  const SymmDev& sg = p.sg;
+  if (p.sg_channel >= 0) {
+    asm volatile("bar.sync 1, %0;" ::"n"(kPushThreads) : "memory");
+    if (pt < sg.world) {
+      const uint32_t e = sg.epoch[p.sg_channel * kSigMaxBlocks + blockIdx.x];
+      st_release_sys(sig_slot(sg, pt, p.sg_channel, blockIdx.x, sg.rank), e + 1);
+      if (!spin_wait_ge(sig_slot(sg, sg.rank, p.sg_channel, blockIdx.x, pt), e + 1, sg.timeout_ns ? sg.timeout_ns : kSpinTimeoutNs))
+        atomicExch(sg.err, 1);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kPushThreads) : "memory");
+    if (pt == 0) sg.epoch[p.sg_channel * kSigMaxBlocks + blockIdx.x] += 1;
+  }
+  const int chunks = p.sg_rows_per_shard / 64;
+  const int subs = (p.sg_cols + 255) / 256;
+  const int cvec = p.sg_cols / 8;                 // 16-byte vectors per row
+  char* mc_stage = sg.mc + p.sg_stage_off;
+  uint32_t* mc_flags = reinterpret_cast<uint32_t*>(sg.mc + p.sg_flags_off);
+  for (int w = blockIdx.x; w < chunks * subs; w += gridDim.x) {
+    const int chunk = w / subs, sub = w - chunk * subs;
+    const int v0 = sub * 32, v1 = min(v0 + 32, cvec);     // vectors [v0, v1) of each row
+    const int nv = v1 - v0;
+    uint4 val[8];
+    int cnt = 0;
+    for (int i = pt; i < 64 * nv; i += kPushThreads) {      // <= 8 (4-warp epilogue: 16) vectors per thread, loads first
+      const int r = i / nv, cv = v0 + (i - r * nv);
+      if (cnt < 8)
+        val[cnt] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.sg_shard) +
+                                                       (size_t)(chunk * 64 + r) * p.sg_ld) + cv);
+      ++cnt;
+    }
+    cnt = 0;
+    for (int i = pt; i < 64 * nv; i += kPushThreads) {
+      const int r = i / nv, cv = v0 + (i - r * nv);
+      const size_t grow = (size_t)sg.rank * p.sg_rows_per_shard + chunk * 64 + r;   // row of the full stored matrix
+      const uint4 x = cnt < 8 ? val[cnt] : __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.sg_shard) +
+                                                                               (size_t)(chunk * 64 + r) * p.sg_ld) + cv);
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_stage + (grow * p.sg_cols + (size_t)cv * 8) * 2),
+                   "f"(__uint_as_float(x.x)), "f"(__uint_as_float(x.y)), "f"(__uint_as_float(x.z)), "f"(__uint_as_float(x.w))
+                   : "memory");
+      ++cnt;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kPushThreads) : "memory");     // every thread's stores precede the arrival
+    if (pt == 0) {
+      const size_t gchunk = (size_t)sg.rank * chunks + chunk;
+      asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_flags + gchunk), "r"(1u) : "memory");
+    }
+  }
+}
+
+// Producer side: wait until the 64-row chunks covering stored rows [row0, row0 + nrows) of B have arrived in the local stage
+// buffer; confirmed chunks are remembered in a caller-owned bitmap (512 chunks = 32768 stored rows) so that every chunk is
+// polled once per CTA, and the proxy fence is only paid when something new was confirmed.
+__device__ __forceinline__ void staged_wait_rows(const GemmParams& p, unsigned long long* seen, int row0, int nrows) {
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(p.sg.base[p.sg.rank] + p.sg_flags_off);
+  const int total = p.sg_rows_per_shard / 64 * p.sg.world;
+  int c1 = (row0 + nrows + 63) / 64;
+  if (c1 > total) c1 = total;
+  bool fresh = false;
+  for (int c = row0 / 64; c < c1; ++c) {
+    const bool tracked = c < 512;
+    if (tracked && ((seen[c >> 6] >> (c & 63)) & 1ull)) continue;
+    if (!spin_wait_ge(flags + c, p.sg_want, p.sg.timeout_ns ? p.sg.timeout_ns : kSpinTimeoutNs)) atomicExch(p.sg.err, 1);
+    if (tracked) seen[c >> 6] |= 1ull << (c & 63);
+    fresh = true;
+  }
+  if (fresh) asm volatile("fence.proxy.async;" ::: "memory");      // the generic-proxy acquire orders the TMA (async proxy) reads
+}
+
 // ---------------------------------------------------------------- kernel ----
 constexpr int kMaxStages = 12;
 constexpr int kStagingBytes = 8 * 4096;             // one 32-row x 128-byte store tile per epilogue warp
@@ -334,6 +425,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      unsigned long long sg_seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      auto sg_wait_rows = [&](int row0, int nrows) { staged_wait_rows(p, sg_seen, row0, nrows); };
       // one k-block of the B operand for output columns n_idx.. -> shared memory at sb (not used by the MC variant)
       auto load_b = [&](uint32_t sb, int kb, int n_idx, uint32_t bar) {
         const int k_idx = kb * kBlockK;
@@ -365,11 +458,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
           }
         } else if constexpr (!B_MN) {
           // rows of B (= output columns n) may live on a peer: pick the owner's tensor map
+          if (p.sg_on) sg_wait_rows(n_idx, BLOCK_N);           // staged pull: the chunks under this tile have arrived
           const int shard = (p.n_shards > 1) ? n_idx / p.rows_per_shard : 0;
           const int n_loc = n_idx - shard * p.rows_per_shard;
           tma_load_2d(sb, &p.tmB[shard], bar, k_idx, n_loc);  // box {64 k, BLOCK_N n}
         } else {
           // MN-major B is stored [K, N]: the CONTRACTION rows may live on a peer
+          if (p.sg_on) sg_wait_rows(k_idx, kBlockK);
           const int shard = (p.n_shards > 1) ? k_idx / p.rows_per_shard : 0;
           const int k_loc = k_idx - shard * p.rows_per_shard;
 #pragma unroll
@@ -505,6 +600,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm(const __grid_constant__
     }
   } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
+    if (!MC && !CONV && p.sg_on) staged_push<kEpiWarps * 32>(p, (int)threadIdx.x - 64);
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which part of the tile's columns this warp owns (8 warps: halves; 4 warps: all)
     constexpr int kChunks = BLOCK_N / (32 * (kEpiWarps / 4));   // 32-column chunks per warp
@@ -831,6 +927,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      unsigned long long sg_seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int item = item0; item < num_items; item += item_step) {
         int pm, nt;
         pair_raster(item, pm, nt);
@@ -850,8 +947,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
             for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &p.tmA, lbar, m_idx + 64 * j, k_idx);
           }
           if constexpr (!B_MN) {
+            if (p.sg_on) staged_wait_rows(p, sg_seen, n_idx, k2HalfN);         // staged pull: this half tile's rows have arrived
             tma_load_2d_pair(sb, &p.tmB[0], lbar, k_idx, n_idx);               // box {64 k, 128 n}
           } else {
+            if (p.sg_on) staged_wait_rows(p, sg_seen, k_idx, kBlockK);
 #pragma unroll
             for (int j = 0; j < k2HalfN / 64; ++j) tma_load_2d_pair(sb + j * 8192, &p.tmB[0], lbar, n_idx + 64 * j, k_idx);
           }
@@ -892,6 +991,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) kgemm_pair(const __grid_const
     }
   } else {
     // ===================== epilogue (warps 2..9 of both CTAs): bf16 through swizzled staging + TMA store ==========
+    if (p.sg_on) staged_push<256>(p, (int)threadIdx.x - 64);     // staged pull, phase 0: push this rank's shard (see staged_push)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int kChunks = k2BlockN / 64;
@@ -1404,10 +1504,51 @@ DLCFN_API int dlcfn_gemm_bf16(const void* A, long long lda, int a_mn, const void
                             accumulate, relu, block_n, num_sms, nullptr, stream);
 }
 
+struct StagedPull {
+  SymmCtx* ctx;
+  size_t shard_off, stage_off, flags_off;
+  int rows_per_shard, cols, channel;
+  uint32_t seq;
+};
+static int gemm_impl(const void* A, long long lda, int a_mn, const void* const* b_shards, int n_shards, int rows_per_shard,
+                     long long ldb, int b_mn, void* D, long long ldd, int d_dtype, const float* bias, int M, int N, int K,
+                     int accumulate, int relu, int block_n, int num_sms, float* stats, const StagedPull* sp, cudaStream_t stream);
+
 DLCFN_API int dlcfn_gemm_bf16_ex(const void* A, long long lda, int a_mn, const void* const* b_shards, int n_shards,
                                  int rows_per_shard, long long ldb, int b_mn, void* D, long long ldd, int d_dtype,
                                  const float* bias, int M, int N, int K, int accumulate, int relu, int block_n,
                                  int num_sms, float* stats, cudaStream_t stream) {
+  return gemm_impl(A, lda, a_mn, b_shards, n_shards, rows_per_shard, ldb, b_mn, D, ldd, d_dtype, bias, M, N, K, accumulate, relu,
+                   block_n, num_sms, stats, nullptr, stream);
+}
+
+// All-gather fused into the GEMM (see GemmParams::sg): B's stored matrix [world * rows_per_shard][cols] is row-sharded over
+// the ranks of the symmetric heap `ctx` (this rank's shard at heap offset shard_off); stage_off / flags_off are heap offsets
+// of a [world * rows_per_shard][cols] bf16 stage buffer and of world * rows_per_shard / 64 arrival counters (zero at
+// allocation, never reset); `seq` = 1, 2, 3, ... counts the launches that used THESE counters (same on every rank).  Every
+// rank of the heap must launch the same call.  b_mn = 0: B = stored matrix is [N][K] (forward); b_mn = 1: [K][N] (dgrad).
+DLCFN_API int dlcfn_gemm_bf16_staged(void* ctx, const void* A, long long lda, int a_mn, size_t shard_off, size_t stage_off,
+                                     size_t flags_off, unsigned seq, int rows_per_shard, int cols, int b_mn, void* D,
+                                     long long ldd, int d_dtype, const float* bias, int M, int N, int K, int accumulate,
+                                     int relu, int block_n, int channel, cudaStream_t stream) {
+  SymmCtx* c = (SymmCtx*)ctx;
+  if (c == nullptr || !c->finalized || c->dev.mc == nullptr) return (int)cudaErrorNotSupported;
+  if (rows_per_shard <= 0 || (rows_per_shard % 64) || cols <= 0 || (cols % 8) || (shard_off & 15) || (stage_off & 15) ||
+      (flags_off & 3) || channel >= kSigChannels)       // channel < 0: no entry barrier (the caller alternates two stage buffers)
+    return (int)cudaErrorInvalidValue;
+  const int rows_total = rows_per_shard * c->world;
+  if (!b_mn && (N > rows_total || K != cols)) return (int)cudaErrorInvalidValue;
+  if (b_mn && (K > rows_total || N > cols)) return (int)cudaErrorInvalidValue;
+  StagedPull sp{c, shard_off, stage_off, flags_off, rows_per_shard, cols, channel, seq};
+  const void* stage_local = c->dev.base[c->rank] + stage_off;
+  const void* shards[1] = {stage_local};
+  return gemm_impl(A, lda, a_mn, shards, 1, 0, cols, b_mn, D, ldd, d_dtype, bias, M, N, K, accumulate, relu, block_n, 0, nullptr,
+                   &sp, stream);
+}
+
+static int gemm_impl(const void* A, long long lda, int a_mn, const void* const* b_shards, int n_shards, int rows_per_shard,
+                     long long ldb, int b_mn, void* D, long long ldd, int d_dtype, const float* bias, int M, int N, int K,
+                     int accumulate, int relu, int block_n, int num_sms, float* stats, const StagedPull* sp, cudaStream_t stream) {
   // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread.  Autograd
   // worker threads for device 0 have none until the first runtime call (torch skips cudaSetDevice
   // when the ordinal already matches), so bind the primary context once per thread.
@@ -1452,10 +1593,22 @@ DLCFN_API int dlcfn_gemm_bf16_ex(const void* A, long long lda, int a_mn, const v
   p.stats = stats;
   static const bool splitk_env = [] { const char* e = getenv("DLCFN_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
   p.split_k_ok = (splitk_env && stats == nullptr) ? 1 : 0;
+  if (sp != nullptr) {
+    p.sg = sp->ctx->dev;
+    p.sg_on = 1;
+    p.sg_channel = sp->channel;
+    p.sg_shard = sp->ctx->dev.base[sp->ctx->rank] + sp->shard_off;
+    p.sg_stage_off = sp->stage_off;
+    p.sg_flags_off = sp->flags_off;
+    p.sg_rows_per_shard = sp->rows_per_shard;
+    p.sg_cols = sp->cols;
+    p.sg_ld = sp->cols;
+    p.sg_want = sp->seq * (uint32_t)((sp->cols + 255) / 256);
+  }
   // EXPERIMENTAL multicast-pair kernel: opt-in, wide tiles, local B, enough tile pairs to fill the machine, and a
   // reduction too short for split-K to matter (it is not combined with split-K)
   static const bool mc_env = [] { const char* e = getenv("DLCFN_GEMM_MULTICAST"); return e && e[0] == '1'; }();
-  const bool use_mc = mc_env && stats == nullptr && block_n == 256 && n_shards == 1 &&
+  const bool use_mc = mc_env && sp == nullptr && stats == nullptr && block_n == 256 && n_shards == 1 &&
                       (long long)(((M + kBlockM - 1) / kBlockM + 1) / 2) * ((N + 255) / 256) >= num_sms / 2;
   // CTA-pair kernel (cta_group::2, validated on B200 in round 2: 983 vs 629 TFLOP/s single-CTA at 16384x1024x1024): default
   // for bf16 TMA-store outputs of GEMMs with enough 256 x 256 pair tiles; DLCFN_GEMM_2CTA=0 disables

@@ -134,6 +134,8 @@ def _declare(L) -> None:
     L.dlcfn_colsum_bf16.restype = c_int
     L.dlcfn_batch_sum_bf16.argtypes = [vp, vp, i, ll, vp]
     L.dlcfn_batch_sum_bf16.restype = c_int
+    L.dlcfn_gemm_bf16_staged.argtypes = [vp, vp, ll, i, sz, sz, sz, u32, i, i, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp]
+    L.dlcfn_gemm_bf16_staged.restype = c_int
     L.dlcfn_gemm_stats_rows.argtypes = []
     L.dlcfn_gemm_stats_rows.restype = c_int
     for fn in ("dlcfn_elementwise_sum", "dlcfn_cast_scale", "dlcfn_fused_optimizer", "dlcfn_normalize_u8_nhwc",
@@ -311,6 +313,26 @@ def gemm_bf16(a: torch.Tensor, b, *, a_mn: bool = False, b_mn: bool = False, out
         raise RuntimeError(f"dlcfn gemm_bf16 failed with CUDA error {rc}: M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn} "
                            f"lda={a.stride(0)} ldb={ldb_} ldd={out.stride(0)} a%16={a.data_ptr() % 16} "
                            f"b%16={ptrs[0] % 16} d%16={out.data_ptr() % 16} shards={len(ptrs)} block_n={block_n}")
+    _count()
+    return out
+
+
+def gemm_bf16_staged(heap_ctx, a: torch.Tensor, *, shard_off: int, stage_off: int, flags_off: int, seq: int, rows_per_shard: int,
+                     cols: int, b_mn: bool, n: int, k: int, out: torch.Tensor | None = None, bias: torch.Tensor | None = None,
+                     a_mn: bool = False, block_n: int = 0, channel: int = 6) -> torch.Tensor:
+    """D = A * B^T with B row-sharded over the ranks of a symmetric heap: the all-gather happens INSIDE the GEMM (every rank
+    multicasts its shard into all stage buffers through the NVSwitch, the TMA producer consumes chunks as their arrival counters
+    tick - csrc/cuda/gemm_tcgen05.cu, GemmParams::sg).  Collective: every rank launches the same call with the same `seq`."""
+    assert a.dtype == torch.bfloat16 and a.is_cuda and a.dim() == 2 and a.stride(1) == 1
+    M = a.shape[1] if a_mn else a.shape[0]
+    if out is None:
+        out = torch.empty(M, n, dtype=torch.bfloat16, device=a.device)
+    rc = lib().dlcfn_gemm_bf16_staged(heap_ctx, a.data_ptr(), a.stride(0), int(a_mn), shard_off, stage_off, flags_off, int(seq),
+                                      rows_per_shard, cols, int(b_mn), out.data_ptr(), out.stride(0), dtype_code(out.dtype),
+                                      _ptr(bias), M, n, k, 0, 0, block_n, channel, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"dlcfn gemm_bf16_staged failed with CUDA error {rc}: M={M} N={n} K={k} b_mn={b_mn} "
+                           f"rows_per_shard={rows_per_shard} cols={cols} seq={seq}")
     _count()
     return out
 

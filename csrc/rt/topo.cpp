@@ -98,9 +98,74 @@ static void BuildTree(Mat& w, const std::vector<int>& nodes, int root, double pe
   BuildTree(w, b, child, penalty, parent);
 }
 
+// Backtracking planner (reference gpu_topology.h:789-957, MXNET_KVSTORE_TREE_BACKTRACK=1): the doubling tree - at every
+// level each node already in the tree adopts one new child - searched exhaustively, depth first, for the assignment with the
+// largest total link weight that uses only existing links (weight > 0).  KL bisection is a heuristic and can pair GPUs that
+// have no direct link on sparse fabrics; this search never does, and for n <= 8 it is instantaneous.
+struct Backtrack {
+  const Mat& w;
+  int n;
+  std::vector<int> best_parent, parent;
+  double best = -1;
+  explicit Backtrack(const Mat& m) : w(m), n((int)m.size()) {}
+
+  // members: nodes in the tree in adoption order.  Within a level the members [0, level_end) adopt in order; a member with
+  // no free linked neighbour adopts nobody; a level in which nobody adopted while GPUs are still outside is a dead end.
+  void Adopt(std::vector<int>& members, std::vector<char>& used, double total, int idx, int level_end, bool adopted) {
+    if ((int)members.size() == n) {
+      if (total > best) { best = total; best_parent = parent; }
+      return;
+    }
+    if (idx == level_end) {
+      if (adopted) Adopt(members, used, total, 0, (int)members.size(), false);
+      return;
+    }
+    const int p = members[idx];
+    bool any = false;
+    for (int c = 0; c < n; ++c) {
+      if (used[c] || w[p][c] <= 0) continue;
+      any = true;
+      used[c] = 1; parent[c] = p; members.push_back(c);
+      Adopt(members, used, total + w[p][c], idx + 1, level_end, true);
+      members.pop_back(); parent[c] = -2; used[c] = 0;
+    }
+    if (!any) Adopt(members, used, total, idx + 1, level_end, adopted);
+  }
+  bool Run(int root, std::vector<int>* out) {
+    parent.assign(n, -2);
+    parent[root] = -1;
+    best = -1;
+    std::vector<int> members{root};
+    std::vector<char> used(n, 0);
+    used[root] = 1;
+    Adopt(members, used, 0.0, 0, 1, false);
+    if (best < 0) return false;
+    *out = best_parent;
+    return true;
+  }
+};
+
 }  // namespace dlcfn
 
 using namespace dlcfn;
+
+// One doubling tree per root by exhaustive backtracking over existing links (see Backtrack); the weight of every used link
+// is multiplied by `penalty` before the next root is planned.  Returns 0, or -2 if some root has no spanning tree.
+RT_API int dlcfn_topo_plan_trees_backtrack(const double* link, int n, double penalty, int* parents) {
+  if (n <= 0 || n > 16) return -1;
+  Mat w(n, std::vector<double>(n));
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) w[i][j] = link[i * n + j];
+  for (int r = 0; r < n; ++r) {
+    Backtrack bt(w);
+    std::vector<int> parent;
+    if (!bt.Run(r, &parent)) return -2;
+    for (int i = 0; i < n; ++i) {
+      parents[r * n + i] = parent[i];
+      if (parent[i] >= 0) { w[i][parent[i]] *= penalty; w[parent[i]][i] *= penalty; }
+    }
+  }
+  return 0;
+}
 
 // link: n*n row-major weights (0 = no direct link).  Returns 1 if all off-diagonal weights are equal and > 0.
 RT_API int dlcfn_topo_is_uniform(const double* link, int n) {

@@ -50,15 +50,41 @@ class ModelParallelSequential(nn.Module):
         return x
 
 
+_SYNC_HEAP = {"heap": None, "off": 0, "buf": None}
+
+
+def set_sync_bn_heap(heap) -> None:
+    """Route the SyncBatchNorm statistics exchange (reference C12: 2C+1 floats per layer, forward and backward) through the
+    fused one-shot all-reduce kernel on the symmetric peer-HBM heap (csrc/cuda/collectives.cu:kallreduce_oneshot - push into
+    every peer's staging slot, ONE flag barrier, local reduce) instead of an NCCL call.  `heap` = a parallel.symm.SymmetricHeap
+    shared by all ranks of the process group (pass None to go back to torch.distributed)."""
+    if heap is None:
+        _SYNC_HEAP.update(heap=None, off=0, buf=None)
+        return
+    off, buf = heap.alloc_tensor(heap.ONESHOT_MAX // 4, torch.float32)
+    _SYNC_HEAP.update(heap=heap, off=off, buf=buf)
+
+
+def _exchange_sum(vec: torch.Tensor, group) -> torch.Tensor:
+    """Sum of a small fp32 vector over the ranks."""
+    h = _SYNC_HEAP["heap"]
+    if h is not None and vec.is_cuda and vec.numel() <= _SYNC_HEAP["buf"].numel() and group is None:
+        buf = _SYNC_HEAP["buf"][: vec.numel()]
+        buf.copy_(vec)
+        h.allreduce_(_SYNC_HEAP["off"], vec.numel(), torch.float32, 1.0)
+        return buf.clone()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec, group=group)
+    return vec
+
+
 class _SyncBNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps, group):
         dims = [0] + list(range(2, x.dim()))
         xf = x.float()
         n = torch.tensor([xf.numel() / xf.shape[1]], device=x.device)
-        stats = torch.cat([xf.sum(dims), (xf * xf).sum(dims), n])
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(stats, group=group)
+        stats = _exchange_sum(torch.cat([xf.sum(dims), (xf * xf).sum(dims), n]), group)
         C = x.shape[1]
         cnt = stats[-1]
         mean = stats[:C] / cnt
@@ -80,8 +106,7 @@ class _SyncBNFn(torch.autograd.Function):
         dyf = dy.float()
         sums = torch.cat([dyf.sum(dims), (dyf * xhat).sum(dims)])
         local = sums.clone()
-        if dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
-            dist.all_reduce(sums, group=ctx.group)
+        sums = _exchange_sum(sums, ctx.group)
         mean_dy, mean_dyx = sums[:C] / ctx.cnt, sums[C:] / ctx.cnt
         dx = (weight.float() * invstd).view(shape) * (dyf - mean_dy.view(shape) - xhat * mean_dyx.view(shape))
         return dx.to(dy.dtype), local[C:].to(weight.dtype), local[:C].to(weight.dtype), None, None

@@ -88,6 +88,8 @@ def _declare(L) -> None:
     L.dlcfn_topo_is_uniform.restype = c_int
     L.dlcfn_topo_plan_trees.argtypes = [POINTER(c_double), c_int, c_double, POINTER(c_int)]
     L.dlcfn_topo_plan_trees.restype = c_int
+    L.dlcfn_topo_plan_trees_backtrack.argtypes = [POINTER(c_double), c_int, c_double, POINTER(c_int)]
+    L.dlcfn_topo_plan_trees_backtrack.restype = c_int
     L.dlcfn_topo_plan_ring.argtypes = [POINTER(c_double), c_int, c_int, POINTER(c_int)]
     L.dlcfn_topo_plan_ring.restype = c_int
 
@@ -137,7 +139,13 @@ def plan_trees(link, penalty: float | None = None) -> list[list[int]]:
         penalty = float(os.environ.get("MXNET_KVSTORE_TREE_LINK_USAGE_PENALTY", "0.7"))
     n, arr = _mat(link)
     out = (c_int * (n * n))()
-    if lib().dlcfn_topo_plan_trees(arr, n, penalty, out) != 0:
+    if os.environ.get("MXNET_KVSTORE_TREE_BACKTRACK", "0") == "1":     # gpu_topology.h:789-957: exhaustive search, existing links only
+        rc = lib().dlcfn_topo_plan_trees_backtrack(arr, n, penalty, out)
+        if rc == -2:
+            raise ValueError("the link matrix has no spanning tree over direct links for some root")
+        if rc != 0:
+            raise ValueError("bad link matrix")
+    elif lib().dlcfn_topo_plan_trees(arr, n, penalty, out) != 0:
         raise ValueError("bad link matrix")
     trees = [[out[r * n + i] for i in range(n)] for r in range(n)]
     if os.environ.get("MXNET_KVSTORE_LOGTREE", "0") == "1":      # gpu_topology.h:46

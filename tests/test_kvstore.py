@@ -177,6 +177,26 @@ def test_dist_trainer_rescale_grad_and_lr_reach_the_servers():
     assert r.returncode == 0 and r.stdout.count("TRAINER_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_c_level_store_api_local_and_dist(tmp_path):
+    """A C program on the handle-based store API of libdlcfn_rt.so (MXKVStore* counterpart): local store with an updater, then
+    the same binary as scheduler / server / 2 workers of a dist_sync job under the local launcher."""
+    import shutil
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.join(ROOT, "deeplearning_cfn_b200", "_lib")
+    exe = str(tmp_path / "kvcapi")
+    subprocess.run([cc, "-O1", "-o", exe, os.path.join(ROOT, "tests/c/kvstore_capi_test.c"), "-L", libdir, "-ldlcfn_rt",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe, "local"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "CAPI_OK" in r.stdout, r.stdout + r.stderr
+    e = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "1", "--launcher", "local", exe, "dist_sync"]
+    from conftest import run_job
+    r = run_job(cmd, env=e, timeout=120)
+    assert r.returncode == 0 and r.stdout.count("CAPI_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_dist_async():
     r = _launch(3, 2, [os.path.join(ROOT, "tests/mp/dist_kvstore_worker.py"), "dist_async"])
     assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
@@ -307,6 +327,29 @@ def _path(parents, i, root):
         p.append(i)
         i = parents[i]
     return p
+
+
+def test_planner_backtracking_mode_uses_only_existing_links(monkeypatch):
+    """MXNET_KVSTORE_TREE_BACKTRACK=1 (gpu_topology.h:789-957): every edge of every tree is a direct link, every tree spans all
+    GPUs with the doubling depth, on the DGX-1 hybrid cube mesh and on a sparse ring-like fabric where KL may pair unlinked GPUs."""
+    monkeypatch.setenv("MXNET_KVSTORE_TREE_BACKTRACK", "1")
+    ring = [[0] * 8 for _ in range(8)]
+    for i in range(8):
+        for d in (1, 2):
+            ring[i][(i + d) % 8] = ring[(i + d) % 8][i] = 2 if d == 1 else 1
+    for link in (_dgx1(), ring):
+        n = len(link)
+        trees = rt.plan_trees(link)
+        for root, parents in enumerate(trees):
+            _check_tree(parents, root, n)
+            for i, p in enumerate(parents):
+                if p >= 0:
+                    assert link[i][p] > 0, f"tree {root}: edge {i}->{p} is not a direct link"
+            assert max(len(_path(parents, i, root)) for i in range(n)) - 1 <= 3        # log2(8) levels of doubling
+    monkeypatch.setenv("MXNET_KVSTORE_TREE_BACKTRACK", "0")
+    with pytest.raises(ValueError):
+        monkeypatch.setenv("MXNET_KVSTORE_TREE_BACKTRACK", "1")
+        rt.plan_trees([[0, 1, 0], [1, 0, 0], [0, 0, 0]])                               # GPU 2 is isolated
 
 
 def test_planner_uniform_nvswitch_and_dgx1():

@@ -251,6 +251,12 @@ def main():
     # ---------------------------------------------------------------- device-timed loop
     run_step = trainer.step
     graphed = None
+    # ranks that only serve (dedicated parameter servers) run no forward / backward: their step cannot be captured next to
+    # the workers' (measured at N = 8: cudaErrorStreamCaptureIsolation on the server rank), so that layout runs eagerly
+    if args.cuda_graph and servers is not None:
+        args.cuda_graph = False
+        if rank == 0:
+            print("[bench] dedicated servers: eager steps (no CUDA graph)", file=sys.stderr, flush=True)
     if args.cuda_graph:
         graphed = trainer.capture(x if is_worker else None, y if is_worker else None)
         run_step = graphed

@@ -229,6 +229,57 @@ __global__ void __launch_bounds__(512) kallreduce_oneshot(SymmDev s, size_t off,
   epoch_store(s, channel, e + 1);
 }
 
+// FLAG-IN-DATA variant ("LL", after NCCL's low-latency protocol) for the smallest messages (<= kLLMax bytes): NO barrier and NO
+// memory fence at all.  Every 4-byte payload word travels in one 8-byte store together with the call's epoch; the receiver
+// polls the 8-byte slot until the epoch matches - an 8-byte store is never torn, so a matching flag proves the payload.
+//   1. every rank pushes (word, epoch) pairs into slot [parity][rank] of every peer (W 8-byte stores per word)
+//   2. every rank polls its own W slots word by word, sums in rank order (bit-identical everywhere), scales, stores.
+// Slots alternate with the epoch parity; the reuse argument is the one of kallreduce_oneshot (a rank reaches call k+2 only
+// after it has received every peer's data of call k+1, which each peer sends after finishing call k), and a stale slot can
+// never be mistaken for fresh data because its flag is an older epoch.  Epochs advance by 1 per call; 0 is never used.
+template <typename T, int W>
+__global__ void __launch_bounds__(512) kallreduce_ll(SymmDev s, size_t off, size_t dst_off, size_t nwords, float scale, int channel) {
+  const uint32_t e = epoch_load(s, channel) + 1;
+  const size_t parity = e & 1u;
+  const uint32_t* in = reinterpret_cast<const uint32_t*>(s.base[s.rank] + off);
+  const size_t slot = (parity * DLCFN_MAX_RANKS + (size_t)s.rank) * 2 * kLLMax;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += stride) {
+    const unsigned long long pkt = ((unsigned long long)e << 32) | in[i];
+#pragma unroll
+    for (int p = 0; p < W; ++p)
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(s.base[p] - kHeapOff + kLLOff + slot) + i), "l"(pkt) : "memory");
+  }
+  uint32_t* out = reinterpret_cast<uint32_t*>(s.base[s.rank] + dst_off);
+  const char* mine = s.base[s.rank] - kHeapOff + kLLOff + parity * DLCFN_MAX_RANKS * 2 * kLLMax;
+  const long long tmo = s.timeout_ns ? s.timeout_ns : kSpinTimeoutNs;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += stride) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int p = 0; p < W; ++p) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(mine + (size_t)p * 2 * kLLMax) + i;
+      unsigned long long pkt;
+      long long t0 = 0;
+      int it = 0;
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pkt) : "l"(src) : "memory");
+        if ((uint32_t)(pkt >> 32) == e) break;
+        if ((++it & 1023) == 0) {
+          const long long now = clock_now();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > tmo) { atomicExch(s.err, 1); break; }
+        }
+      }
+      const uint32_t w = (uint32_t)pkt;
+      if (sizeof(T) == 4) a0 += __uint_as_float(w);
+      else { a0 += bf16_lo(w); a1 += bf16_hi(w); }
+    }
+    out[i] = sizeof(T) == 4 ? __float_as_uint(a0 * scale) : pack_bf16(a0 * scale, a1 * scale);
+  }
+  __syncthreads();
+  epoch_store(s, channel, e);
+}
+
 // ------------------------------------------------------------ broadcast -----
 __global__ void __launch_bounds__(512) kbroadcast(SymmDev s, size_t off, size_t nvec, int root, int channel) {
   const uint32_t e = epoch_load(s, channel);
@@ -622,9 +673,25 @@ static int launch_allreduce(SymmCtx* c, size_t off, size_t dst_off, size_t nvec,
     kallreduce_mc<T><<<g, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel);
     return (int)cudaGetLastError();
   }
+  if (algo == 3) {
+    if (nvec * 16 > kLLMax) return (int)cudaErrorInvalidValue;
+    const size_t nwords = nvec * 4;
+    // FIXED grid and a channel of its own: the slot parity comes from per-CTA epochs, which must advance in lockstep over all
+    // CTAs and calls (a size-dependent grid would let a later call's CTA 0 reuse the parity of an unread slot of CTA 3)
+    constexpr int g3 = (int)(kLLMax / 4 / 512);
+    channel = kSigChannels - 1;
+    switch (c->world) {
+#define DLCFN_LL(Wn) case Wn: kallreduce_ll<T, Wn><<<g3, 512, 0, st>>>(c->dev, off, dst_off, nwords, scale, channel); break;
+      DLCFN_LL(1) DLCFN_LL(2) DLCFN_LL(3) DLCFN_LL(4) DLCFN_LL(5) DLCFN_LL(6) DLCFN_LL(7) DLCFN_LL(8)
+#undef DLCFN_LL
+      default: return (int)cudaErrorInvalidValue;
+    }
+    return (int)cudaGetLastError();
+  }
   if (algo == 2) {
     if (nvec * 16 > kOneShotMax) return (int)cudaErrorInvalidValue;
-    const int g1 = (int)((nvec + 511) / 512);          // <= 4 CTAs: every CTA owns its vectors and its own flag slots
+    constexpr int g1 = (int)(kOneShotMax / 16 / 512);  // fixed grid, own channel (see algo 3): per-CTA epochs stay in lockstep
+    channel = kSigChannels - 2;
     switch (c->world) {
 #define DLCFN_ONESHOT(Wn) case Wn: kallreduce_oneshot<T, Wn><<<g1, 512, 0, st>>>(c->dev, off, dst_off, nvec, scale, channel); break;
       DLCFN_ONESHOT(1) DLCFN_ONESHOT(2) DLCFN_ONESHOT(3) DLCFN_ONESHOT(4) DLCFN_ONESHOT(5) DLCFN_ONESHOT(6) DLCFN_ONESHOT(7) DLCFN_ONESHOT(8)
@@ -649,7 +716,7 @@ static int launch_allreduce(SymmCtx* c, size_t off, size_t dst_off, size_t nvec,
 
 // Fused scale + all-reduce of heap[src_off, +count*sizeof(T)) into heap[dst_off, ...) on every rank
 // (dst_off == src_off: in place).  algo 0: peer ld/st two-shot;  algo 1: NVLS multimem (needs a multicast mapping);
-// algo 2: one-shot through the header staging slots, <= 32 KiB (one flag barrier).
+// algo 2: one-shot through the header staging slots, <= 16 KiB (one flag barrier); algo 3: flag-in-data ("LL"), <= 16 KiB, no barrier.
 DLCFN_API int dlcfn_allreduce_ex(void* ctx, size_t src_off, size_t dst_off, size_t count, int dtype, float scale,
                                  int channel, int nblocks, int algo, cudaStream_t stream) {
   (void)cudaGetLastError();  // drop stale non-sticky errors left by other libraries

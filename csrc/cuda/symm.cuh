@@ -19,9 +19,12 @@ constexpr size_t kEpochBytes = (size_t)kSigChannels * kSigMaxBlocks * sizeof(uin
 constexpr size_t kErrOff = kEpochOff + kEpochBytes;
 // one-shot all-reduce staging: [2 parities][DLCFN_MAX_RANKS sources][kOneShotMax bytes] inside the header, below the heap
 constexpr size_t kStageOff = 128u << 10;
-constexpr size_t kOneShotMax = 32u << 10;
+constexpr size_t kOneShotMax = 16u << 10;
+// flag-in-data ("LL") all-reduce slots: [2 parities][DLCFN_MAX_RANKS sources][2 * kLLMax bytes] (4 B payload + 4 B flag per word)
+constexpr size_t kLLOff = kStageOff + 2 * DLCFN_MAX_RANKS * kOneShotMax;      // 384 KiB
+constexpr size_t kLLMax = 16u << 10;
 constexpr size_t kHeapOff = 1u << 20;
-static_assert(kStageOff >= kErrOff + 64 && kStageOff + 2 * DLCFN_MAX_RANKS * kOneShotMax <= kHeapOff, "header layout");
+static_assert(kStageOff >= kErrOff + 64 && kLLOff + 2 * DLCFN_MAX_RANKS * 2 * kLLMax <= kHeapOff, "header layout");
 constexpr long long kSpinTimeoutNs = 4000000000ll;  // 4 s: a dead peer becomes an error, not a hung GPU
 
 struct SymmDev {

@@ -15,11 +15,83 @@ from ..ops.layernorm import dropout_add_layer_norm
 from ..ops.linear import Linear, linear
 
 
+# DLCFN_BERT_QKV_PLANES=1: q / k / v as three dense planes (see _QKVFn).  Written after the round's GPU budget was spent:
+# host-tested only, so the packed projection (measured: 412 sequences/s) stays the default.
+_QKV_PLANES = __import__("os").environ.get("DLCFN_BERT_QKV_PLANES", "0") == "1"
+
+
+class _QKVFn(torch.autograd.Function):
+    """The three attention projections of one input as three tcgen05 GEMMs that write q, k and v as separate DENSE [tokens, H]
+    planes of one buffer (so that the [B, h, S, d] views handed to the attention kernel are dense in B-S-h-d order and neither
+    the attention forward nor its backward has to re-lay anything out), with ONE parameter [3H, H] / [3H] behind them:
+        fwd    plane_j = x @ W_j^T + b_j                          (3 GEMMs, bias in the epilogue)
+        dgrad  dx = dq @ W_q + dk @ W_k + dv @ W_v                (3 GEMMs accumulating into one buffer, no add kernels)
+        wgrad  dW_j = dplane_j^T @ x, db_j = colsum(dplane_j)     (3 split-K GEMMs into the row blocks of one [3H, H] gradient)
+    The packed form (one GEMM -> [tokens, 3H] -> view / permute) cost 4 layout copies + 3 zero fills per layer and step in
+    autograd's select / permute backward (profiles/r2/profile_bert_before.txt: 99 copies, 78 fills per step)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from ..ops import native
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        H = weight.shape[1]
+        M = x2.shape[0]
+        out = torch.empty((3, M, H), dtype=torch.bfloat16, device=x.device)
+        bf = None if bias is None else (bias if bias.dtype == torch.float32 else bias.float())
+        for j in range(3):
+            native.gemm_bf16(x2, weight[j * H:(j + 1) * H], bias=None if bf is None else bf[j * H:(j + 1) * H], out=out[j])
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ..ops import native
+        x2, weight = ctx.saved_tensors
+        H = weight.shape[1]
+        M = x2.shape[0]
+        planes = []
+        for j in range(3):
+            d = dout[j]
+            planes.append(d if (d.stride(1) == 1 and d.stride(0) == H) else d.contiguous())
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, H), dtype=torch.bfloat16, device=x2.device)
+            for j in range(3):
+                native.gemm_bf16(planes[j], weight[j * H:(j + 1) * H], b_mn=True, out=dx, accumulate=j > 0)
+            dx = dx.view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            for j in range(3):
+                native.gemm_bf16(planes[j], x2, a_mn=True, b_mn=True, out=dw[j * H:(j + 1) * H])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.cat([native.colsum(planes[j]) for j in range(3)])
+        return dx, dw, db
+
+
+class QKVProjection(Linear):
+    """`Linear(hidden, 3 * hidden)` (same parameter names and shapes: `weight` [3H, H], `bias` [3H]) whose output is the three
+    dense planes (3, tokens, hidden)."""
+
+    def __init__(self, hidden: int):
+        super().__init__(hidden, 3 * hidden)
+
+    def forward(self, x):
+        w, b = self.weight, self.bias
+        if _QKV_PLANES and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16:
+            return _QKVFn.apply(x, w, b)
+        y = super().forward(x)                                           # host / fp32 path
+        return y.reshape(-1, 3, w.shape[1]).permute(1, 0, 2)
+
+
 class BertLayer(nn.Module):
     def __init__(self, hidden: int, heads: int, ffn: int, dropout: float):
         super().__init__()
         self.heads = heads
-        self.qkv = Linear(hidden, 3 * hidden)
+        self.qkv = QKVProjection(hidden)
         self.proj = Linear(hidden, hidden)
         self.ln1 = nn.LayerNorm(hidden, eps=1e-12)
         self.fc1 = Linear(hidden, ffn)
@@ -29,7 +101,7 @@ class BertLayer(nn.Module):
 
     def forward(self, x, mask=None):
         B, S, H = x.shape
-        qkv = self.qkv(x).view(B, S, 3, self.heads, H // self.heads).permute(2, 0, 3, 1, 4)
+        qkv = self.qkv(x).reshape(3, B, S, self.heads, H // self.heads).transpose(2, 3)     # three [B, h, S, d] views, dense as B-S-h-d
         a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=mask,
                                            dropout_p=self.drop if self.training else 0.0)
         a = a.transpose(1, 2).reshape(B, S, H)

@@ -319,7 +319,7 @@ def gemm_bf16(a: torch.Tensor, b, *, a_mn: bool = False, b_mn: bool = False, out
 
 def gemm_bf16_staged(heap_ctx, a: torch.Tensor, *, shard_off: int, stage_off: int, flags_off: int, seq: int, rows_per_shard: int,
                      cols: int, b_mn: bool, n: int, k: int, out: torch.Tensor | None = None, bias: torch.Tensor | None = None,
-                     a_mn: bool = False, block_n: int = 0, channel: int = 6) -> torch.Tensor:
+                     a_mn: bool = False, block_n: int = 0, channel: int = -1) -> torch.Tensor:
     """D = A * B^T with B row-sharded over the ranks of a symmetric heap: the all-gather happens INSIDE the GEMM (every rank
     multicasts its shard into all stage buffers through the NVSwitch, the TMA producer consumes chunks as their arrival counters
     tick - csrc/cuda/gemm_tcgen05.cu, GemmParams::sg).  Collective: every rank launches the same call with the same `seq`."""

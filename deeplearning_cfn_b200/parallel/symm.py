@@ -87,7 +87,7 @@ class SymmetricHeap:
     CH_BCAST = 2
     CH_BARRIER = 3
     CH_ASYNC = 4  # uses 4 and 5
-    ONESHOT_MAX = 32 << 10   # bytes: csrc/cuda/symm.cuh:kOneShotMax
+    ONESHOT_MAX = 16 << 10   # bytes: csrc/cuda/symm.cuh:kOneShotMax / kLLMax
 
     def __init__(self, heap_bytes: int, group: dist.ProcessGroup | None = None, device: torch.device | None = None):
         if not torch.cuda.is_available():
@@ -289,14 +289,17 @@ class SymmetricHeap:
                    algo: int | None = None) -> None:
         """Fused bucket scale + all-reduce (reference C11: Horovod fusion buffer + ncclAllReduce).  In place unless
         dst_off is given.  algo 0 = peer ld/st two-shot, 1 = NVLS multimem (default when a multicast mapping exists), 2 = one-shot
-        (<= 32 KiB, one barrier; default at that size)."""
+        (<= 16 KiB, one barrier), 3 = flag-in-data "LL" (<= 16 KiB, no barrier; default at that size)."""
         ch = self.CH_ALLREDUCE if channel is None else channel
         a = self.allreduce_algo if algo is None else algo
         nbytes = count * (2 if dtype == torch.bfloat16 else 4)
         if algo is None and a == 1 and nbytes < (2 << 20):
             a = 0      # below ~2 MiB the switch round trip costs more than it saves (profiles/scale8/README.md)
         if algo is None and nbytes <= self.ONESHOT_MAX and self.world > 1 and os.environ.get("DLCFN_ALLREDUCE_ONESHOT", "1") != "0":
-            a = 2      # latency-bound: push + ONE flag barrier + local reduce (collectives.cu:kallreduce_oneshot)
+            # latency-bound: push + ONE flag barrier + local reduce (kallreduce_oneshot, validated on 2 and 8 B200s).
+            # DLCFN_ALLREDUCE_ONESHOT=ll selects the flag-in-data form without any barrier (kallreduce_ll) - written after the
+            # round's GPU budget was spent, covered by tests/mp/collectives_worker.py under DLCFN_EXPERIMENTAL=1, not yet run
+            a = 3 if os.environ.get("DLCFN_ALLREDUCE_ONESHOT") == "ll" else 2
         native.check(native.lib().dlcfn_allreduce_ex(self._ctx, off, off if dst_off is None else dst_off, count,
                                                      native.dtype_code(dtype), float(scale), ch, nblocks, a,
                                                      native.stream_ptr(stream)), "allreduce")

@@ -88,6 +88,14 @@ def _declare(L) -> None:
     L.dlcfn_topo_is_uniform.restype = c_int
     L.dlcfn_topo_plan_trees.argtypes = [POINTER(c_double), c_int, c_double, POINTER(c_int)]
     L.dlcfn_topo_plan_trees.restype = c_int
+    # handle-based C-level store API (csrc/rt/kvstore_capi.cpp; for C / C++ programs - declared here for the ABI check and tests)
+    from ctypes import c_char_p as _ccp, c_void_p as _cvp
+    L.DLCFNKVGetLastError.argtypes = []
+    L.DLCFNKVGetLastError.restype = _ccp
+    L.DLCFNKVStoreCreate.argtypes = [_ccp, POINTER(_cvp)]
+    L.DLCFNKVStoreCreate.restype = c_int
+    L.DLCFNKVStoreFree.argtypes = [_cvp]
+    L.DLCFNKVStoreFree.restype = c_int
     L.dlcfn_topo_plan_trees_backtrack.argtypes = [POINTER(c_double), c_int, c_double, POINTER(c_int)]
     L.dlcfn_topo_plan_trees_backtrack.restype = c_int
     L.dlcfn_topo_plan_ring.argtypes = [POINTER(c_double), c_int, c_int, POINTER(c_int)]

@@ -37,7 +37,7 @@ for rnd in range(40):
     for (off, t), (woff, w), n in zip(bufs, wbufs, sizes):
         t[:n] = float(rank + 1 + rnd % 5)
         want = float(sum(r + 1 + rnd % 5 for r in range(world)))
-        algos = [0] + ([2] if n * 4 <= heap.ONESHOT_MAX else []) + ([1] if heap.has_multicast and n >= 4096 else [])
+        algos = [0] + (([2, 3] if os.environ.get("DLCFN_EXPERIMENTAL") == "1" else [2]) if n * 4 <= heap.ONESHOT_MAX else []) + ([1] if heap.has_multicast and n >= 4096 else [])
         algo = algos[rnd % len(algos)]
         heap.allreduce_(off, n, torch.float32, scale=1.0, algo=algo)
         if rnd % 8 == 7:

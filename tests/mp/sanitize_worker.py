@@ -19,8 +19,8 @@ off, t = heap.alloc_tensor(n, torch.float32)
 woff, w = heap.alloc_tensor(n, torch.float32)
 master = torch.zeros(n // world + 64, device=dev)
 for it in range(3):
-    for algo in [0, 2] + ([1] if heap.has_multicast else []):
-        m = n if algo != 2 else 2048
+    for algo in [0, 2] + ([3] if os.environ.get("DLCFN_EXPERIMENTAL") == "1" else []) + ([1] if heap.has_multicast else []):
+        m = n if algo not in (2, 3) else 2048
         t[:m] = float(rank + 1)
         heap.allreduce_(off, m, torch.float32, 1.0, algo=algo)
         torch.cuda.synchronize()

@@ -238,8 +238,18 @@ def _rendered_submit(kind: str, args, cmd: str):
             path = os.path.join(out_dir, "dlcfn-k8s.json")
             open(path, "w").write(json.dumps(kubernetes_manifests("dlcfn", nworker, nserver, envs, "dlcfn-b200:latest", cmd), indent=1))
             argv = ["kubectl", "create", "-f", path]
-        if shutil.which(argv[0]):
-            h.returncodes[kind] = subprocess.call(argv)
+        # run the scheduler CLI(s) when installed (threads, like the other submitters: the tracker serves the rendezvous while
+        # the submission is in flight); otherwise the rendered files are the product
+        cmds = [argv]
+        if kind == "slurm" and nserver > 0:       # slurm: one srun per role
+            cmds = [slurm_argv(nserver, max(1, nserver), envs, "server", cmd), argv]
+        if shutil.which(cmds[0][0]):
+            for i, a in enumerate(cmds):
+                def run(key=f"{kind}{i}", a=a):
+                    h.returncodes[key] = subprocess.call(a)
+                t = threading.Thread(target=run, daemon=True)
+                t.start()
+                h.threads.append(t)
         else:
             h.returncodes[kind] = None   # rendered only
         return h

@@ -243,3 +243,51 @@ def test_mpirun_terminates_the_job_when_a_rank_fails(tmp_path):
                 env=dict(os.environ, PYTHONPATH=ROOT), timeout=120)
     assert r.returncode == 1 and time.time() - t0 < 60
     assert "rank 1 exited first with code 3" in r.stderr
+
+
+def _write_exe(path, text):
+    with open(path, "w") as f:
+        f.write(text)
+    os.chmod(path, 0o755)
+
+
+@pytest.mark.parametrize("kind", ["sge", "slurm"])
+def test_batch_scheduler_submissions_run_a_job_through_shim_clis(kind, tmp_path):
+    """`launch --launcher sge|slurm` end to end: the rendered submission is handed to `qsub` / `srun` - shim commands on PATH
+    that do what the real schedulers do with it (an SGE array job: one bash per task id with SGE_TASK_ID set; srun: --ntasks
+    copies of the command with the --export environment) - and a real 2-worker / 1-server dist_sync job completes over them.
+    (Reference: dmlc_tracker/sge.py, slurm.py submit the same renderings to the real clusters.)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    _write_exe(bindir / "qsub", """#!/bin/bash
+# minimal Sun Grid Engine: run every task of the array job `#$ -t 1-N` of the submitted script
+script="$1"
+n=$(grep -oE '^#\\$ -t 1-[0-9]+' "$script" | grep -oE '[0-9]+$')
+pids=()
+for i in $(seq 1 "$n"); do SGE_TASK_ID=$i bash "$script" & pids+=($!); done
+rc=0; for p in "${pids[@]}"; do wait $p || rc=1; done; exit $rc
+""")
+    _write_exe(bindir / "srun", """#!/bin/bash
+# minimal srun: --ntasks=N --nodes=M --export=ALL,K=V,... command...
+n=1
+while [[ "$1" == --* ]]; do
+  case "$1" in
+    --ntasks=*) n="${1#--ntasks=}";;
+    --export=*) IFS=',' read -ra kv <<< "${1#--export=}"; for e in "${kv[@]}"; do [[ "$e" == *=* ]] && export "$e"; done;;
+  esac
+  shift
+done
+pids=()
+for i in $(seq 0 $((n-1))); do SLURM_PROCID=$i "$@" & pids+=($!); done
+rc=0; for p in "${pids[@]}"; do wait $p || rc=1; done; exit $rc
+""")
+    env = dict(os.environ, PYTHONPATH=root, PATH=f"{bindir}:{os.environ['PATH']}")
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "1", "--launcher", kind, "--render-dir", str(tmp_path),
+           sys.executable, os.path.join(root, "tests/mp/dist_kvstore_worker.py"), "dist_async"]
+    from conftest import run_job
+    r = run_job(cmd, env=env, timeout=240, cwd=str(tmp_path))
+    assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+    assert os.path.exists(tmp_path / ("dlcfn-sge.sh" if kind == "sge" else "dlcfn-slurm.json"))

@@ -201,6 +201,7 @@ class Agent:
             for idx, ip in enumerate(worker_ips, start=1):
                 hosts.write(f"{ip} deeplearning-worker{idx}\n")
                 w.write(f"deeplearning-worker{idx}\n")
+        self._chown_to_default_user(self.worker_file)
         gpu_count = self.get_gpu_count()
         with open(self.worker_file) as f:
             n = sum(1 for _ in f)
@@ -209,6 +210,21 @@ class Agent:
             f.write(f"export DEEPLEARNING_WORKERS_PATH={self.worker_file}\n")
             f.write(f"export DEEPLEARNING_WORKER_GPU_COUNT={gpu_count}\n")
             f.write(f"export EFS_MOUNT={self.env['EFS_MOUNT']}\n")
+
+    def _chown_to_default_user(self, path: str) -> None:
+        """The workers file belongs to the image's login user, who runs the jobs (dl_cfn_setup_v2.py:110-114: chown to
+        AWS_DL_DEFAULT_USER).  On a box where that user does not exist, or the agent is not privileged, the file keeps its
+        owner - the reference would abort the whole bootstrap on a missing user; a hostfile with the wrong owner is still usable."""
+        user = self.env.get("AWS_DL_DEFAULT_USER")
+        if not user:
+            return
+        try:
+            import grp
+            import pwd
+            os.chown(path, pwd.getpwnam(user).pw_uid, grp.getgrnam(user).gr_gid)
+            LOGGER.info("chown %s to %s", path, user)
+        except (KeyError, PermissionError, OSError) as e:
+            LOGGER.info("workers file keeps its owner (default user %r: %s)", user, e)
 
     def run(self) -> None:
         e = self.env

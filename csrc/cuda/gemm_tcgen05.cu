@@ -1478,6 +1478,13 @@ static int launch_pair(GemmParams& p, int num_sms, cudaStream_t stream) {
 
 using namespace dlcfn;
 
+// Host evaluation of the launch-time divisor arithmetic the producers use on the device (make_fastdiv + the expression of
+// fdiv), exported for the CPU test tier: quotient of n / d for 0 <= n < 2^31, d >= 1.
+DLCFN_API int dlcfn_fastdiv_host(int n, int d) {
+  const FastDiv f = make_fastdiv(d);
+  return (int)(((unsigned long long)(uint32_t)n * f.mul) >> f.shr);
+}
+
 // a_mn / b_mn: 0 = K-major ([rows, K] row-major), 1 = MN-major ([K, rows] row-major).
 // b_shards: array of n_shards device pointers (peer-mapped); shard s holds rows
 //   [s*rows_per_shard, (s+1)*rows_per_shard) of B's ROW dimension as stored

@@ -136,6 +136,8 @@ def _declare(L) -> None:
     L.dlcfn_batch_sum_bf16.restype = c_int
     L.dlcfn_gemm_bf16_staged.argtypes = [vp, vp, ll, i, sz, sz, sz, u32, i, i, i, vp, ll, i, vp, i, i, i, i, i, i, i, vp]
     L.dlcfn_gemm_bf16_staged.restype = c_int
+    L.dlcfn_fastdiv_host.argtypes = [i, i]
+    L.dlcfn_fastdiv_host.restype = c_int
     L.dlcfn_gemm_stats_rows.argtypes = []
     L.dlcfn_gemm_stats_rows.restype = c_int
     for fn in ("dlcfn_elementwise_sum", "dlcfn_cast_scale", "dlcfn_fused_optimizer", "dlcfn_normalize_u8_nhwc",

@@ -105,3 +105,20 @@ def test_gpu_tier_test_bodies_run_on_the_stand_in_gpu():
                  "-p", "no:cacheprovider"], cwd=ROOT, env=env, timeout=900)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+def test_launch_time_divisors_of_the_gemm_producers_are_exact():
+    """csrc/cuda/gemm_tcgen05.cu:FastDiv - the TMA producer / MMA issuer divide by launch-time constants (tiles, image rows,
+    channel blocks) with a multiply-high + shift; the host export evaluates the same arithmetic.  Exact for every 0 <= n < 2^31."""
+    import random
+    from deeplearning_cfn_b200.ops import native
+    L = native.lib()
+    rnd = random.Random(7)
+    ds = list(range(1, 600)) + [rnd.randrange(1, 1 << 24) for _ in range(300)] + [1 << k for k in range(31)] + \
+        [(1 << k) + 1 for k in range(1, 30)] + [(1 << k) - 1 for k in range(2, 31)]
+    top = (1 << 31) - 1
+    for d in ds:
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, top, top - 1, (top // d) * d, (top // d) * d - 1] + [rnd.randrange(0, 1 << 31) for _ in range(40)]
+        for n in ns:
+            if 0 <= n <= top:
+                assert L.dlcfn_fastdiv_host(n, d) == n // d, (n, d)

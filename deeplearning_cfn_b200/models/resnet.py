@@ -5,10 +5,11 @@ Parity target: MX/example/image-classification/symbols/resnet.py:29-177 (bottlen
 7x7/2 stem + BN + ReLU + 3x3/2 max-pool for ImageNet, 3x3 stem for CIFAR).  ResNet-50 has 157
 learnable tensors / 25.55 M parameters, which this module reproduces.
 
-B200 shape: channels_last activations, bf16 conv/FC weights with fp32 BatchNorm parameters.  The 1x1 convolutions
-(2/3 of the conv layers) are `ops.conv.Conv1x1`: in NHWC they are plain GEMMs and can run on the hand-written
-tcgen05 kernel (backend switch in ops/conv.py, cuDNN is the yardstick); the 3x3 / stem convolutions go through cuDNN;
-the classifier GEMM is always on the tcgen05 kernel (`ops.linear.Linear`) so that it can consume
+B200 shape: channels_last activations, bf16 conv/FC weights with fp32 BatchNorm parameters.  Every convolution runs on the
+hand-written tcgen05 kernels (ops/conv.py; cuDNN only as the selectable yardstick): the 1x1 layers (2/3 of the network) are
+plain GEMMs on the NHWC matrix, the 3x3 layers and the strided projection shortcuts implicit GEMMs through im2col-mode TMA,
+the 7x7 stem + `bn_data` one fused function over the space-to-depth image (`_FusedStemFn`); bn2 / bn3 / bn0 take their
+statistics from the epilogue of the convolution in front of them; the classifier GEMM (`ops.linear.Linear`) can consume
 parameter-server-resident weights directly.
 """
 from __future__ import annotations

@@ -289,7 +289,7 @@ class SymmetricHeap:
                    algo: int | None = None) -> None:
         """Fused bucket scale + all-reduce (reference C11: Horovod fusion buffer + ncclAllReduce).  In place unless
         dst_off is given.  algo 0 = peer ld/st two-shot, 1 = NVLS multimem (default when a multicast mapping exists), 2 = one-shot
-        (<= 16 KiB, one barrier), 3 = flag-in-data "LL" (<= 16 KiB, no barrier; default at that size)."""
+        (<= 16 KiB, one barrier; default at that size), 3 = flag-in-data "LL" (<= 16 KiB, no barrier; opt-in)."""
         ch = self.CH_ALLREDUCE if channel is None else channel
         a = self.allreduce_algo if algo is None else algo
         nbytes = count * (2 if dtype == torch.bfloat16 else 4)

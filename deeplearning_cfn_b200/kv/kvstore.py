@@ -360,17 +360,28 @@ class KVStoreNCCL(KVStoreLocal):
         if not groupable:
             return super().push(key, value, priority)
         import torch.cuda.nccl as nccl
+
+        def reduce_packed(packed):
+            out = torch.empty_like(packed[0])
+            nccl.reduce(packed, output=out, root=0)
+            return out
+
+        self._push_grouped(keys, vals, priority, reduce_packed)
+
+    def _push_grouped(self, keys, vals, priority, reduce_packed) -> None:
+        """Groups of <= GROUP keys; a group whose values agree in dtype / device list travels as ONE packed buffer per device
+        through `reduce_packed` (list of per-device buffers -> their sum on the first device) and is unpacked key by key into
+        the updater, in key order - the order a per-key push would have used."""
         for g0 in range(0, len(keys), self.GROUP):
             gk, gv = keys[g0:g0 + self.GROUP], vals[g0:g0 + self.GROUP]
             same = len({(v[0].dtype, len(v), tuple(t.device for t in v)) for v in gv}) == 1
             if not same:
                 for k, v in zip(gk, gv):
-                    super().push(k, v, priority)
+                    KVStoreLocal.push(self, k, v, priority)
                 continue
             ndev = len(gv[0])
             packed = [torch.cat([v[d].detach().reshape(-1) for v in gv]) for d in range(ndev)]
-            out = torch.empty_like(packed[0])
-            nccl.reduce(packed, output=out, root=0)
+            out = reduce_packed(packed)
             pos = 0
             for k, v in zip(gk, gv):
                 n = v[0].numel()

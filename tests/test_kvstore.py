@@ -731,3 +731,42 @@ def test_module_fit_with_dist_sync_store_under_the_launcher(tmp_path):
     import re
     found = re.findall(r"MODULE_DIST_OK (-?[0-9.]+) (-?[0-9.]+)", r.stdout)      # the two ranks share stdout: lines may interleave
     assert r.returncode == 0 and len(found) == 2 and found[0] == found[1], r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_nccl_store_grouped_push_packs_16_keys_and_matches_per_key_pushes():
+    """The packing / unpacking of the NCCL store's grouped multi-key push (kvstore_nccl.h:221-307: <= 16 keys per group) with a
+    host stand-in for the one NCCL reduce per group: same stored values as key-by-key pushes, ceil(K / 16) reductions, mixed
+    dtype groups fall back to per-key pushes."""
+    from deeplearning_cfn_b200.kv.kvstore import KVStoreNCCL, KVStoreLocal
+    torch.manual_seed(0)
+    shapes = [(3, 5), (7,), (2, 2, 2)] * 7                                   # 21 keys -> groups of 16 + 5
+    keys = list(range(len(shapes)))
+    vals = [[torch.randn(s) for _ in range(3)] for s in shapes]              # 3 "devices"
+    ref = KVStoreLocal("local")
+    got = KVStoreNCCL("nccl")
+    for st in (ref, got):
+        st.init(keys, [torch.zeros(s) for s in shapes])
+        st._set_updater(lambda k, g, w: w.add_(g * (1 + k)))
+    calls = []
+
+    def reduce_packed(packed):
+        calls.append(packed[0].numel())
+        return torch.stack(packed).sum(0)
+
+    ref.push(keys, vals)
+    got._push_grouped(keys, vals, 0, reduce_packed)
+    assert len(calls) == 2 and calls[0] == sum(torch.Size(s).numel() for s in shapes[:16])
+    for k, s in zip(keys, shapes):
+        a, b = torch.zeros(s), torch.zeros(s)
+        ref.pull(k, out=a)
+        got.pull(k, out=b)
+        assert torch.allclose(a, b, atol=1e-6), k
+    # a group with two dtypes is pushed key by key (host tensors: the plain reduce), nothing goes through the packed path
+    calls.clear()
+    mixed = [[torch.ones(4), torch.ones(4)], [torch.ones(4, dtype=torch.float64), torch.ones(4, dtype=torch.float64)]]
+    st = KVStoreNCCL("nccl")
+    st.init([0, 1], [torch.zeros(4), torch.zeros(4, dtype=torch.float64)])
+    st._push_grouped([0, 1], mixed, 0, reduce_packed)
+    out = torch.zeros(4)
+    st.pull(0, out=out)
+    assert calls == [] and torch.equal(out, torch.full((4,), 2.0))

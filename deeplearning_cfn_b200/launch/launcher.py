@@ -45,6 +45,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--env", action="append", default=[], help="name of an environment variable to forward")
     p.add_argument("--host-ip", type=str, default="auto")
     p.add_argument("--render-dir", type=str, default=None, help="where batch-scheduler submissions are written")
+    p.add_argument("--jobname", type=str, default=None, help="job name of the batch-scheduler submissions (default dlcfn)")
+    p.add_argument("--kube-image", type=str, default=None, help="container image of the kubernetes Jobs")
     p.add_argument("command", nargs=argparse.REMAINDER, help="command for launching the program")
     return p
 
@@ -71,7 +73,9 @@ def main(argv=None) -> int:
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s %(message)s")
     fun = get_submitter(kind, args, cmd)
     host_ip = "127.0.0.1" if kind == "local" else args.host_ip
-    trk, handle = tracker.submit(args.num_workers, args.num_servers, fun, host_ip=host_ip, pscmd=cmd)
+    # kubernetes: the scheduler is a Job of the cluster behind a Service (submitters.kubernetes_manifests), not a local process
+    trk, handle = tracker.submit(args.num_workers, args.num_servers, fun, host_ip=host_ip,
+                                 pscmd=None if kind == "kubernetes" else cmd)
     failed = handle.failed() if handle is not None else []
     if isinstance(trk, tracker.PSTracker):
         trk.stop()

@@ -177,6 +177,13 @@ def slurm_argv(n: int, nodes: int, envs: dict, role: str, cmd: str) -> list[str]
 
 def kubernetes_manifests(jobname: str, nworker: int, nserver: int, envs: dict, image: str, cmd: str,
                          gpus_per_worker: int = 1) -> list[dict]:
+    """Service + scheduler Job (parameter-server jobs), server Job, worker Job.  As in the reference (dmlc_tracker/kubernetes.py
+    :107-132) the scheduler lives IN the cluster behind a Service named `<jobname>-scheduler`, and that name is the
+    DMLC_PS_ROOT_URI of every pod; the pods of a Job carry the label the Service selects on."""
+    sched = f"{jobname}-scheduler"
+    if nserver:
+        envs = dict(envs, DMLC_PS_ROOT_URI=sched, DMLC_PS_ROOT_PORT=int(envs.get("DMLC_PS_ROOT_PORT") or 9091))
+
     def job(role: str, n: int) -> dict:
         env = [{"name": k, "value": str(v)} for k, v in dict(envs, DMLC_ROLE=role, DMLC_JOB_CLUSTER="kubernetes").items()]
         c = {"name": f"{jobname}-{role}", "image": image, "command": ["bash", "-c", cmd], "env": env}
@@ -184,9 +191,10 @@ def kubernetes_manifests(jobname: str, nworker: int, nserver: int, envs: dict, i
             c["resources"] = {"limits": {"nvidia.com/gpu": gpus_per_worker}}
         return {"apiVersion": "batch/v1", "kind": "Job", "metadata": {"name": f"{jobname}-{role}"},
                 "spec": {"parallelism": n, "completions": n,
-                         "template": {"spec": {"containers": [c], "restartPolicy": "Never"}}}}
-    svc = {"apiVersion": "v1", "kind": "Service", "metadata": {"name": f"{jobname}-scheduler"},
-           "spec": {"selector": {"app": f"{jobname}-scheduler"}, "ports": [{"port": int(envs.get("DMLC_PS_ROOT_PORT", 9091))}]}}
+                         "template": {"metadata": {"labels": {"app": f"{jobname}-{role}"}},
+                                      "spec": {"containers": [c], "restartPolicy": "Never"}}}}
+    svc = {"apiVersion": "v1", "kind": "Service", "metadata": {"name": sched},
+           "spec": {"selector": {"app": sched}, "ports": [{"protocol": "TCP", "port": int(envs.get("DMLC_PS_ROOT_PORT") or 9091)}]}}
     out = [svc, job("scheduler", 1)] if nserver else []
     if nserver:
         out.append(job("server", nserver))
@@ -232,11 +240,17 @@ def _rendered_submit(kind: str, args, cmd: str):
             argv = yarn_argv(nworker, nserver, envs, cmd)
             open(os.path.join(out_dir, "dlcfn-yarn.json"), "w").write(json.dumps(argv, indent=1))
         elif kind == "mesos":
-            open(os.path.join(out_dir, "dlcfn-mesos.json"), "w").write(json.dumps(mesos_tasks(nworker, nserver, envs, cmd), indent=1))
-            argv = ["mesos-execute"]
+            path = os.path.join(out_dir, "dlcfn-mesos.json")
+            open(path, "w").write(json.dumps(mesos_tasks(nworker, nserver, envs, cmd), indent=1))
+            argv = ["mesos-execute", f"--master={os.environ.get('MESOS_MASTER', '127.0.0.1:5050')}", f"--task_group={path}"]
         else:
             path = os.path.join(out_dir, "dlcfn-k8s.json")
-            open(path, "w").write(json.dumps(kubernetes_manifests("dlcfn", nworker, nserver, envs, "dlcfn-b200:latest", cmd), indent=1))
+            jobname = getattr(args, "jobname", None) or "dlcfn"
+            image = getattr(args, "kube_image", None) or os.environ.get("DLCFN_KUBE_IMAGE", "dlcfn-b200:latest")
+            if nserver and os.environ.get("DLCFN_KUBE_SCHEDULER_PORT"):      # port of the scheduler Service (default 9091)
+                envs = dict(envs, DMLC_PS_ROOT_PORT=int(os.environ["DLCFN_KUBE_SCHEDULER_PORT"]))
+            items = kubernetes_manifests(jobname, nworker, nserver, envs, image, cmd)
+            open(path, "w").write(json.dumps({"apiVersion": "v1", "kind": "List", "items": items}, indent=1))
             argv = ["kubectl", "create", "-f", path]
         # run the scheduler CLI(s) when installed (threads, like the other submitters: the tracker serves the rendezvous while
         # the submission is in flight); otherwise the rendered files are the product

@@ -155,6 +155,9 @@ def test_rendered_scheduler_submissions():
     k8s = submitters.kubernetes_manifests("j", 2, 1, envs, "img", "python t.py", gpus_per_worker=8)
     kinds = [(m["kind"], m["metadata"]["name"]) for m in k8s]
     assert kinds == [("Service", "j-scheduler"), ("Job", "j-scheduler"), ("Job", "j-server"), ("Job", "j-worker")]
+    # the scheduler is in the cluster: every pod finds it through the Service, whose selector matches the scheduler pods' label
+    assert all({"name": "DMLC_PS_ROOT_URI", "value": "j-scheduler"} in m["spec"]["template"]["spec"]["containers"][0]["env"] for m in k8s[1:])
+    assert k8s[0]["spec"]["selector"] == k8s[1]["spec"]["template"]["metadata"]["labels"]
     assert k8s[-1]["spec"]["parallelism"] == 2
     assert k8s[-1]["spec"]["template"]["spec"]["containers"][0]["resources"]["limits"]["nvidia.com/gpu"] == 8
     assert submitters.yarn_argv(2, 1, envs, "cmd")[-5:] == ["-nworker", "2", "-nserver", "1", "cmd"]
@@ -291,3 +294,83 @@ rc=0; for p in "${pids[@]}"; do wait $p || rc=1; done; exit $rc
     r = run_job(cmd, env=env, timeout=240, cwd=str(tmp_path))
     assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
     assert os.path.exists(tmp_path / ("dlcfn-sge.sh" if kind == "sge" else "dlcfn-slurm.json"))
+
+
+_KUBECTL_SHIM = """#!/usr/bin/env python3
+# minimal kubectl: `create -f list.json` starts every Job of the List - `parallelism` pods per Job, each the container's command
+# with the container's env - and resolves Service names to this host (cluster DNS); exits when all pods have exited
+import json, os, subprocess, sys
+assert sys.argv[1:3] == ["create", "-f"], sys.argv
+doc = json.load(open(sys.argv[3]))
+assert doc["kind"] == "List"
+services = {m["metadata"]["name"] for m in doc["items"] if m["kind"] == "Service"}
+procs = []
+for m in doc["items"]:
+    if m["kind"] != "Job":
+        continue
+    c = m["spec"]["template"]["spec"]["containers"][0]
+    env = dict(os.environ)
+    for e in c["env"]:
+        env[e["name"]] = "127.0.0.1" if e["value"] in services else e["value"]
+    for _ in range(m["spec"]["parallelism"]):
+        procs.append(subprocess.Popen(c["command"], env=env))
+    print("job.batch/" + m["metadata"]["name"] + " created", flush=True)
+sys.exit(1 if any(p.wait() for p in procs) else 0)
+"""
+
+_MESOS_SHIM = """#!/usr/bin/env python3
+# minimal mesos-execute: --master=... --task_group=tasks.json: one process per task with its env, exit status = any failure
+import json, os, subprocess, sys
+opts = dict(a[2:].split("=", 1) for a in sys.argv[1:] if a.startswith("--") and "=" in a)
+tasks = json.load(open(opts["task_group"]))
+procs = [subprocess.Popen(["bash", "-c", t["cmd"]], env=dict(os.environ, **t["env"])) for t in tasks]
+sys.exit(1 if any(p.wait() for p in procs) else 0)
+"""
+
+_YARN_SHIM = """#!/usr/bin/env python3
+# minimal `yarn jar dmlc-yarn.jar org.apache.hadoop.yarn.dmlc.Client ...`: what the application master does with the request -
+# -nserver server containers and -nworker worker containers, each the command with the -env pairs + DMLC_ROLE / DMLC_TASK_ID
+import os, subprocess, sys
+a = sys.argv[1:]
+assert a[:3] == ["jar", "dmlc-yarn.jar", "org.apache.hadoop.yarn.dmlc.Client"], a
+a, env, n = a[3:], dict(os.environ), {}
+valued = {"-jobname", "-queue", "-worker_cores", "-worker_memory_mb", "-server_cores", "-server_memory_mb"}
+i = 0
+while i < len(a) - 1:
+    if a[i] == "-env":
+        k, v = a[i + 1].split("=", 1)
+        env[k] = v
+    elif a[i] in ("-nworker", "-nserver"):
+        n[a[i][2:]] = int(a[i + 1])
+    else:
+        assert a[i] in valued, a[i]
+    i += 2
+procs = [subprocess.Popen(["bash", "-c", a[-1]], env=dict(env, DMLC_ROLE=role, DMLC_TASK_ID=str(t)))
+         for role in ("server", "worker") for t in range(n[role])]
+sys.exit(1 if any(p.wait() for p in procs) else 0)
+"""
+
+
+@pytest.mark.parametrize("kind", ["yarn", "mesos", "kubernetes"])
+def test_yarn_mesos_kubernetes_submissions_run_a_job_through_shim_clis(kind, tmp_path):
+    """`launch --launcher yarn|mesos|kubernetes` end to end: the submission goes to `yarn` / `mesos-execute` / `kubectl` - shim
+    commands on PATH that do with it what the real scheduler would (containers per role with the requested environment; for
+    kubernetes the scheduler itself is one of the Jobs and is found through the Service name) - and a real 2-worker /
+    1-server job completes over them.  (Reference: dmlc_tracker/yarn.py, mesos.py, kubernetes.py.)"""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    shim = {"yarn": ("yarn", _YARN_SHIM), "mesos": ("mesos-execute", _MESOS_SHIM), "kubernetes": ("kubectl", _KUBECTL_SHIM)}[kind]
+    _write_exe(bindir / shim[0], shim[1].replace("#!/usr/bin/env python3", "#!" + sys.executable))
+    import socket
+    with socket.socket() as sk:                      # the scheduler Service's port (the shim cluster shares this host's ports)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, PYTHONPATH=root, PATH=f"{bindir}:{os.environ['PATH']}", DLCFN_KUBE_SCHEDULER_PORT=str(port))
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "2", "-s", "1", "--launcher", kind, "--render-dir", str(tmp_path),
+           sys.executable, os.path.join(root, "tests/mp/dist_kvstore_worker.py"), "dist_async"]
+    from conftest import run_job
+    r = run_job(cmd, env=env, timeout=240, cwd=str(tmp_path))
+    assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+    assert os.path.exists(tmp_path / {"yarn": "dlcfn-yarn.json", "mesos": "dlcfn-mesos.json", "kubernetes": "dlcfn-k8s.json"}[kind])

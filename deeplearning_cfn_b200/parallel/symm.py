@@ -39,10 +39,25 @@ def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor
     return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
 
 
+def _agree(err, rank: int, world: int, group, what: str) -> None:
+    """Collective: every rank reports whether its part of `what` worked; if any rank failed, ALL ranks raise the same error
+    (a rank that raised alone would leave its peers waiting in the next collective)."""
+    if world <= 1:
+        if err is not None:
+            raise err
+        return
+    errs: list = [None] * world
+    dist.all_gather_object(errs, None if err is None else f"{type(err).__name__}: {err}", group=group)
+    bad = [f"rank {r}: {e}" for r, e in enumerate(errs) if e]
+    if bad:
+        raise RuntimeError(f"{what} failed ({'; '.join(bad)})") from err
+
+
 def exchange_fds(fd: int, rank: int, world: int, group, tag: str) -> list[int]:
     """Every rank contributes one file descriptor; returns the list of all ranks' descriptors as valid in THIS process.
     Descriptors cross process boundaries as SCM_RIGHTS ancillary data over abstract AF_UNIX sockets (names agreed through
-    torch.distributed); -1 entries (a rank with nothing to share) stay -1."""
+    torch.distributed); -1 entries (a rank with nothing to share) stay -1.  A failure on any rank (peer gone, descriptor
+    refused, DLCFN_FD_EXCHANGE_TIMEOUT seconds without a sender - default 120) raises on every rank."""
     import socket
     import uuid
     me = f"\0dlcfn-{tag}-{os.getpid()}-{uuid.uuid4().hex[:8]}"
@@ -53,27 +68,35 @@ def exchange_fds(fd: int, rank: int, world: int, group, tag: str) -> list[int]:
     dist.all_gather_object(names, (me, fd >= 0), group=group)
     out = [-1] * world
     out[rank] = fd
+    err = None
     try:
         if fd >= 0:
             for p, (name, _) in enumerate(names):
                 if p == rank:
                     continue
-                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-                c.connect(name)                     # queued in the listener's backlog until it accepts
-                socket.send_fds(c, [rank.to_bytes(4, "little")], [fd])
-                c.close()
+                with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:     # closed on failure too: the peer sees EOF
+                    c.connect(name)                 # queued in the listener's backlog until it accepts
+                    socket.send_fds(c, [rank.to_bytes(4, "little")], [fd])
         expect = sum(1 for p, (_, has) in enumerate(names) if has and p != rank)
-        srv.settimeout(120)
+        tmo = float(os.environ.get("DLCFN_FD_EXCHANGE_TIMEOUT", "120"))
+        srv.settimeout(tmo)
         for _ in range(expect):
             conn, _ = srv.accept()
-            msg, fds, _, _ = socket.recv_fds(conn, 4, 1)
-            conn.close()
+            with conn:
+                conn.settimeout(tmo)
+                msg, fds, _, _ = socket.recv_fds(conn, 4, 1)
             if len(fds) != 1 or len(msg) != 4:
                 raise RuntimeError("file-descriptor exchange: malformed message")
             out[int.from_bytes(msg, "little")] = fds[0]
+    except Exception as e:                           # reported to everybody below
+        err = e
     finally:
         srv.close()
-    dist.barrier(group=group)
+    if err is not None:
+        for p, f in enumerate(out):
+            if p != rank and f >= 0:
+                os.close(f)
+    _agree(err, rank, world, group, f"file-descriptor exchange '{tag}'")
     return out
 
 
@@ -114,6 +137,7 @@ class SymmetricHeap:
                     ctx = self._create_vmm_backend(L)
                     self.backend = "vmm"
                 except Exception as e:          # no exportable VMM handles here (or fd passing refused): next backend
+                    self._release_vmm()
                     if want == "vmm":
                         raise
                     self._why_not_vmm = repr(e)
@@ -155,6 +179,8 @@ class SymmetricHeap:
         return exchange_fds(fd, self.rank, self.world, self.group, tag)
 
     def _create_vmm_backend(self, L):
+        """Arena from the driver's virtual-memory API (csrc/cuda/symm_vmm.cu).  Every phase ends in an agreement: a rank whose
+        cuMem* / cuMulticast* call failed makes ALL ranks fall through to the next backend together."""
         from ctypes import c_ulonglong
         dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
         sup = int(L.dlcfn_vmm_supported(dev))
@@ -163,41 +189,71 @@ class SymmetricHeap:
         if not all(f & 1 for f in flags):
             raise RuntimeError(f"exportable VMM allocations are not supported on every rank (flags {flags})")
         want_mc = all(f & 2 for f in flags) and os.environ.get("DLCFN_SYMM_MULTICAST", "1") != "0"
-        gran = int(L.dlcfn_vmm_granularity(dev, self.world, int(want_mc)))
-        if gran <= 0:
-            raise RuntimeError("cuMemGetAllocationGranularity failed")
-        total = ((1 << 20) + (self.heap_bytes + 255) // 256 * 256 + gran - 1) // gran * gran
-        ptr, hdl, fd = c_void_p(), c_ulonglong(), c_int(-1)
-        native.check(L.dlcfn_vmm_alloc(total, dev, gran, ctypes.byref(ptr), ctypes.byref(hdl), ctypes.byref(fd)), "vmm_alloc")
-        st = {"total": total, "gran": gran, "local": (ptr.value, hdl.value), "peers": {}, "mc": None, "fds": [fd.value]}
+        agree = lambda err, what: _agree(err, self.rank, self.world, self.group, what)    # noqa: E731
+
+        def phase(what, fn):
+            err = None
+            try:
+                fn()
+            except Exception as e:
+                err = e
+            agree(err, what)
+
+        st = {"total": 0, "gran": 0, "local": None, "peers": {}, "mc": None, "fds": []}
         self._vmm = st
-        fds = self._exchange_fds(fd.value, "arena")
+        ptr, hdl, fd = c_void_p(), c_ulonglong(), c_int(-1)
         ctx = c_void_p()
-        native.check(L.dlcfn_symm_create_external(ptr.value, total, self.rank, self.world, ctypes.byref(ctx)), "symm_create_external")
-        for p, pfd in enumerate(fds):
-            if p == self.rank:
-                continue
-            pp, ph = c_void_p(), c_ulonglong()
-            native.check(L.dlcfn_vmm_import(pfd, total, dev, gran, ctypes.byref(pp), ctypes.byref(ph)), "vmm_import")
-            os.close(pfd)
-            st["peers"][p] = (pp.value, ph.value)
-            native.check(L.dlcfn_symm_set_peer_ptr(ctx, p, pp.value), "symm_set_peer_ptr")
+
+        def alloc():
+            gran = int(L.dlcfn_vmm_granularity(dev, self.world, int(want_mc)))
+            if gran <= 0:
+                raise RuntimeError("cuMemGetAllocationGranularity failed")
+            total = ((1 << 20) + (self.heap_bytes + 255) // 256 * 256 + gran - 1) // gran * gran
+            native.check(L.dlcfn_vmm_alloc(total, dev, gran, ctypes.byref(ptr), ctypes.byref(hdl), ctypes.byref(fd)), "vmm_alloc")
+            st.update(total=total, gran=gran, local=(ptr.value, hdl.value), fds=[fd.value])
+        phase("VMM arena allocation", alloc)
+        total, gran = st["total"], st["gran"]
+        fds = self._exchange_fds(fd.value, "arena")
+
+        def import_peers():
+            native.check(L.dlcfn_symm_create_external(ptr.value, total, self.rank, self.world, ctypes.byref(ctx)), "symm_create_external")
+            for p, pfd in enumerate(fds):
+                if p == self.rank:
+                    continue
+                pp, ph = c_void_p(), c_ulonglong()
+                try:
+                    native.check(L.dlcfn_vmm_import(pfd, total, dev, gran, ctypes.byref(pp), ctypes.byref(ph)), "vmm_import")
+                finally:
+                    os.close(pfd)
+                st["peers"][p] = (pp.value, ph.value)
+                native.check(L.dlcfn_symm_set_peer_ptr(ctx, p, pp.value), "symm_set_peer_ptr")
+        phase("mapping the peers' arenas", import_peers)
         if want_mc:
             mc, mfd = c_ulonglong(), c_int(-1)
-            if self.rank == 0:
-                native.check(L.dlcfn_vmm_mc_create(total, self.world, ctypes.byref(mc), ctypes.byref(mfd)), "vmm_mc_create")
+
+            def mc_create():
+                if self.rank == 0:
+                    native.check(L.dlcfn_vmm_mc_create(total, self.world, ctypes.byref(mc), ctypes.byref(mfd)), "vmm_mc_create")
+            phase("multicast object creation", mc_create)
             mfds = self._exchange_fds(mfd.value if self.rank == 0 else -1, "mc")
-            if self.rank != 0:
-                native.check(L.dlcfn_vmm_mc_import(mfds[0], ctypes.byref(mc)), "vmm_mc_import")
-                os.close(mfds[0])
-            else:
-                os.close(mfd.value)
-            native.check(L.dlcfn_vmm_mc_add_device(mc.value, dev), "vmm_mc_add_device")
-            dist.barrier(group=self.group)              # every device has joined before anyone binds memory
-            mptr = c_void_p()
-            native.check(L.dlcfn_vmm_mc_bind_map(mc.value, hdl.value, total, dev, gran, ctypes.byref(mptr)), "vmm_mc_bind_map")
-            st["mc"] = (mptr.value, mc.value)
-            native.check(L.dlcfn_symm_set_multicast(ctx, mptr.value), "symm_set_multicast")
+
+            def mc_join():
+                if self.rank != 0:
+                    try:
+                        native.check(L.dlcfn_vmm_mc_import(mfds[0], ctypes.byref(mc)), "vmm_mc_import")
+                    finally:
+                        os.close(mfds[0])
+                else:
+                    os.close(mfd.value)
+                native.check(L.dlcfn_vmm_mc_add_device(mc.value, dev), "vmm_mc_add_device")
+            phase("joining the multicast object", mc_join)      # also the rendezvous: every device has joined before anyone binds
+
+            def mc_bind():
+                mptr = c_void_p()
+                native.check(L.dlcfn_vmm_mc_bind_map(mc.value, hdl.value, total, dev, gran, ctypes.byref(mptr)), "vmm_mc_bind_map")
+                st["mc"] = (mptr.value, mc.value)
+                native.check(L.dlcfn_symm_set_multicast(ctx, mptr.value), "symm_set_multicast")
+            phase("binding the arena to the multicast object", mc_bind)
         os.close(fd.value)
         st["fds"] = []
         torch.cuda.synchronize(self.device)
@@ -376,19 +432,30 @@ class SymmetricHeap:
         st["event"].record(stream if stream is not None else torch.cuda.current_stream())
         st["armed"] = True
 
+    def _release_vmm(self) -> None:
+        """Unmap the multicast view, the peers and the local arena and drop their handles (also after a half-built backend)."""
+        st = getattr(self, "_vmm", None)
+        self._vmm = None
+        if not st:
+            return
+        L = native.lib()
+        if st["mc"]:
+            L.dlcfn_vmm_unmap_release(st["mc"][0], st["mc"][1], st["total"])
+        for pp, ph in st["peers"].values():
+            L.dlcfn_vmm_unmap_release(pp, ph, st["total"])
+        if st["local"]:
+            L.dlcfn_vmm_unmap_release(st["local"][0], st["local"][1], st["total"])
+        for f in st.get("fds", []):
+            try:
+                os.close(f)
+            except OSError:
+                pass
+
     def close(self) -> None:
         if getattr(self, "_ctx", None):
             torch.cuda.synchronize(self.device)
             self._bytes = None
             native.lib().dlcfn_symm_destroy(self._ctx)
-            st = getattr(self, "_vmm", None)
-            if st:                               # unmap the multicast view, the peers and the local arena; drop the handles
-                L = native.lib()
-                if st["mc"]:
-                    L.dlcfn_vmm_unmap_release(st["mc"][0], st["mc"][1], st["total"])
-                for pp, ph in st["peers"].values():
-                    L.dlcfn_vmm_unmap_release(pp, ph, st["total"])
-                L.dlcfn_vmm_unmap_release(st["local"][0], st["local"][1], st["total"])
-                self._vmm = None
+            self._release_vmm()
             self._ctx = None
             self._symm_tensor = None

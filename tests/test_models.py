@@ -96,3 +96,49 @@ def test_implicit_gemm_conv_producer_index_math(case):
     spec.loader.exec_module(mod)
     errs = mod.check(*case)
     assert "fprop" in errs and "wgrad" in errs and all(v < 1e-9 for v in errs.values()), errs
+
+
+def test_bert_qkv_planes_function_matches_the_packed_projection(monkeypatch):
+    """`models.bert._QKVFn` (q / k / v as three dense planes; opt-in DLCFN_BERT_QKV_PLANES=1, not yet run on a GPU) against the
+    packed projection it replaces, with the tcgen05 GEMM and the column-sum kernel replaced by host references of their
+    contracts (operand storage flags, `out=` views, `accumulate`): forward planes, dx (three accumulating GEMMs), dW (row blocks
+    of one gradient) and db agree."""
+    import torch.nn.functional as F
+    from deeplearning_cfn_b200.models import bert
+    from deeplearning_cfn_b200.ops import native
+
+    def gemm_ref(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, accumulate=False, **_):
+        A = a.float().t() if a_mn else a.float()              # [M, K]
+        Bt = b.float() if b_mn else b.float().t()             # [K, N]
+        d = A @ Bt
+        if bias is not None:
+            d = d + bias.float()[: d.shape[1]]
+        if out is None:
+            return d.to(out_dtype)
+        assert out.shape == d.shape and out.stride(1) == 1
+        out.copy_((out.float() + d) if accumulate else d)
+        return out
+
+    monkeypatch.setattr(native, "gemm_bf16", gemm_ref)
+    monkeypatch.setattr(native, "colsum", lambda t: t.float().sum(0))
+    torch.manual_seed(0)
+    B, S, H = 2, 8, 32
+    w = (torch.randn(3 * H, H) * 0.2).bfloat16().requires_grad_(True)
+    b = (torch.randn(3 * H) * 0.1).requires_grad_(True)
+    x = torch.randn(B, S, H).bfloat16().requires_grad_(True)
+    g = torch.randn(3, B * S, H).bfloat16()
+    planes = bert._QKVFn.apply(x, w, b)
+    assert planes.shape == (3, B * S, H) and planes.is_contiguous()
+    planes.backward(g)
+    got = (planes.detach().float(), x.grad.float().clone(), w.grad.float().clone(), b.grad.float().clone())
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    ref = F.linear(xr, wr, br).reshape(-1, 3, H).permute(1, 0, 2)
+    ref.backward(g.float())
+    for a, r in zip(got, (ref.detach(), xr.grad, wr.grad, br.grad)):
+        assert a.shape == r.shape
+        assert torch.allclose(a, r, rtol=3e-2, atol=3e-2 * float(r.abs().max())), (a - r).abs().max()
+    # and the module's view chain hands attention the same [3, B, h, S, d] tensor either way
+    heads = 4
+    v1 = planes.detach().reshape(3, B, S, heads, H // heads).transpose(2, 3)
+    v2 = F.linear(x.detach().float(), w.detach().float(), b.detach()).view(B, S, 3, heads, H // heads).permute(2, 0, 3, 1, 4)
+    assert torch.allclose(v1.float(), v2, rtol=3e-2, atol=3e-2)

@@ -258,8 +258,16 @@ def main():
         if rank == 0:
             print("[bench] dedicated servers: eager steps (no CUDA graph)", file=sys.stderr, flush=True)
     if args.cuda_graph:
-        graphed = trainer.capture(x if is_worker else None, y if is_worker else None)
-        run_step = graphed
+        try:
+            graphed = trainer.capture(x if is_worker else None, y if is_worker else None)
+            run_step = graphed
+        except Exception as e:     # the headline must not depend on the capture: a capture records without executing, so a rank
+            graphed = None         # that falls back to eager steps stays in step with peers that replay their graphs
+            print(f"[bench] rank {rank}: CUDA graph capture failed ({type(e).__name__}: {e}); eager steps", file=sys.stderr, flush=True)
+            try:
+                cuda_sync(device)
+            except Exception:
+                pass
         if rank == 0:
             print(f"[bench] {graphed!r}", file=sys.stderr, flush=True)
     nb = len(dev_batches)
@@ -293,7 +301,8 @@ def main():
 
     # ---------------------------------------------------------------- end-to-end loop (public API + H2D/D2H)
     e2e = None
-    if not args.no_e2e:
+
+    def run_e2e():
         src = SyntheticImageSource(args.batch, args.image_size, 1000) if is_worker else None
         pre = (_HostPrefetcher if dry else DevicePrefetcher)(src, device) if is_worker else None
         # the loss of every step is copied device->host (pinned, async) and READ one step later, when its copy event has
@@ -350,8 +359,17 @@ def main():
         if last != last or last in (float("inf"), float("-inf")):
             print(f"[bench] WARNING: end-to-end loss is {last}", file=sys.stderr, flush=True)
             last = None
-        e2e = {"ms": e_ms, "loss": last, "h2d": src.bytes_per_batch if is_worker else 0,
-               "clocks": e_sampler.summary() if e_sampler else {}}
+        return {"ms": e_ms, "loss": last, "h2d": src.bytes_per_batch if is_worker else 0,
+                "clocks": e_sampler.summary() if e_sampler else {}}
+
+    if not args.no_e2e:
+        if world == 1:
+            try:
+                e2e = run_e2e()
+            except Exception as e:      # single process: the device-timed headline above is still reported
+                print(f"[bench] end-to-end loop failed ({type(e).__name__}: {e}); no e2e key", file=sys.stderr, flush=True)
+        else:                           # several ranks: an exception must end the job (a rank that skipped the loop would leave
+            e2e = run_e2e()             # its peers waiting inside their steps)
 
     # ---------------------------------------------------------------- reduce over ranks
     t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(launches)], device=device, dtype=torch.float64)

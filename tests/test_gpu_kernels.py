@@ -252,12 +252,12 @@ def test_stem_space_to_depth_and_pad_kernels():
 def test_colsum_and_batch_sum_match_torch(M, N):
     from deeplearning_cfn_b200.ops import native
     torch.manual_seed(M + N)
-    x = torch.randn(M, N, device="cuda").bfloat16()
+    x = torch.randn(M, N, device=dev()).bfloat16()
     got = native.colsum(x)
     want = x.float().sum(0)
     # two fp32 summation orders of M bf16 values: the difference scales with sqrt(M) ulps of the running magnitude
     assert torch.allclose(got, want, rtol=1e-3, atol=2e-3 * max(1.0, M ** 0.5)), (got[:4], want[:4])
     assert torch.equal(got, native.colsum(x))                      # deterministic
     if M <= 8192:
-        b = torch.randn(M, 4, 6, 8, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+        b = torch.randn(M, 4, 6, 8, device=dev()).bfloat16().contiguous(memory_format=torch.channels_last)
         assert torch.allclose(native.batch_sum(b), b.float().sum(0), rtol=1e-3, atol=2e-3 * max(1.0, M ** 0.5))

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
+#include <unistd.h>
 
 namespace {
 
@@ -175,6 +176,7 @@ DLCFN_API int dlcfn_vmm_alloc(size_t bytes, int dev, size_t gran, void** out_ptr
   }
   int rc = map_handle(h, bytes, gran, dev, out_ptr);
   if (rc) {
+    close(fd);
     d.MemRelease(h);
     return rc;
   }

@@ -68,7 +68,7 @@ def set_sync_bn_heap(heap) -> None:
 def _exchange_sum(vec: torch.Tensor, group) -> torch.Tensor:
     """Sum of a small fp32 vector over the ranks."""
     h = _SYNC_HEAP["heap"]
-    if h is not None and vec.is_cuda and vec.numel() <= _SYNC_HEAP["buf"].numel() and group is None:
+    if h is not None and vec.device == _SYNC_HEAP["buf"].device and vec.numel() <= _SYNC_HEAP["buf"].numel() and group is None:
         buf = _SYNC_HEAP["buf"][: vec.numel()]
         buf.copy_(vec)
         h.allreduce_(_SYNC_HEAP["off"], vec.numel(), torch.float32, 1.0)

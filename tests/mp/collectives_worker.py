@@ -185,21 +185,11 @@ def main():
                 if not torch.equal(res[0], res[algo]):
                     fail(f"all-reduce algo {algo} differs from two-shot: {dtype} n={n} it={it} max diff {(res[0].float() - res[algo].float()).abs().max().item()}")
     # ---- SyncBatchNorm statistics exchange through the one-shot kernel vs torch.distributed (reference C12) ----
-    from deeplearning_cfn_b200.parallel import utils as putils
-    torch.manual_seed(50 + rank)
-    xs = torch.randn(4, 32, 6, 6, device=dev)
-    outs = {}
-    for mode in ("dist", "heap"):
-        putils.set_sync_bn_heap(heap if mode == "heap" else None)
-        bn = putils.SyncBatchNorm(32).to(dev).train()
-        xi = xs.clone().requires_grad_(True)
-        yb = bn(xi)
-        (yb * torch.arange(32, device=dev).view(1, 32, 1, 1)).sum().backward()
-        outs[mode] = (yb.detach(), xi.grad.clone(), bn.running_var.clone())
-    putils.set_sync_bn_heap(None)
-    for a, b in zip(outs["dist"], outs["heap"]):
-        if not torch.allclose(a, b, rtol=1e-5, atol=1e-5):
-            fail(f"SyncBatchNorm over the heap differs from torch.distributed: {(a - b).abs().max().item()}")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _syncbn_check import check_syncbn_over_heap
+    bad = check_syncbn_over_heap(heap, dev, rank)
+    if bad:
+        fail(bad)
     # ---- shared staging: rank 0 publishes "initial weights", everyone reads them out of rank 0's HBM ----
     w0 = torch.arange(10_000, device=dev, dtype=torch.float32) * (1.0 if rank == 0 else -1.0)
     heap.stage_put("init/weights", w0)

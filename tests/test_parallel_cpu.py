@@ -39,6 +39,14 @@ def test_vmm_backend_construction_agrees_on_failures_world3():
     assert r.returncode == 0 and r.stdout.count("VMM_FLOW_OK") == 3, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_syncbn_statistics_exchange_over_a_heap_matches_torch_distributed_world2():
+    cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "2", sys.executable,
+           os.path.join(ROOT, "tests/mp/syncbn_heap_worker.py")]
+    from conftest import run_job
+    r = run_job(cmd, env=dict(os.environ, PYTHONPATH=ROOT), timeout=180)
+    assert r.returncode == 0 and r.stdout.count("SYNCBN_HEAP_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_hierarchical_multinode_mode_matches_flat_allreduce():
     """2 virtual nodes x 2 ranks on gloo: node-local sum -> per-rail all-reduce of the slices -> node-local broadcast."""
     cmd = [sys.executable, "-m", "deeplearning_cfn_b200.launch.mpirun", "-np", "4", sys.executable,

@@ -154,7 +154,9 @@ def test_resnet_step_same_loss_on_both_conv1x1_backends():
                        native.launch_count - n0)
     finally:
         set_conv1x1_backend(old)
-    assert out["tcgen05"][3] > out["cudnn"][3] + 100, "the tcgen05 backend should add >= 3 GEMM launches per 1x1 conv"
+    # 36 stride-1 1x1 convolutions x 3 GEMMs, minus one launch for each of the 16 BatchNorms that take their statistics from a
+    # tcgen05 convolution's epilogue instead of their own pass (104 on the stand-in GPU): well above 60 either way
+    assert out["tcgen05"][3] > out["cudnn"][3] + 60, "the tcgen05 backend should add ~3 GEMM launches per 1x1 conv"
     assert abs(out["cudnn"][0] - out["tcgen05"][0]) < 0.05 * abs(out["cudnn"][0]) + 0.05, (out["cudnn"][0], out["tcgen05"][0])
     cos_fc = F.cosine_similarity(out["cudnn"][1].flatten(), out["tcgen05"][1].flatten(), dim=0).item()
     cos_stem = F.cosine_similarity(out["cudnn"][2].flatten(), out["tcgen05"][2].flatten(), dim=0).item()

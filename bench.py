@@ -54,7 +54,10 @@ def parse():
                          "one CUDA graph captured through the public API `trainer.capture` (parallel/graph.py); --no-cuda-graph = eager")
     ap.add_argument("--conv1x1", default=None, choices=["tcgen05", "cudnn", "auto"],
                     help="backend of the 1x1 convolutions (default: ops.conv default / DLCFN_CONV1X1)")
-    return ap.parse_args()
+    args, unknown = ap.parse_known_args()
+    if unknown:      # a harness flag this script does not know must not cost the measurement
+        print(f"[bench] ignoring unknown arguments: {unknown}", file=sys.stderr, flush=True)
+    return args
 
 
 def reference_arm(args):

@@ -1,7 +1,7 @@
 """`python -m deeplearning_cfn_b200 <command>` - the user-facing CLI.
 
 Control plane (counterparts of `aws cloudformation ...` as used by mask-rcnn-stack.sh:62-92):
-    create-stack / launch-cluster, list-stacks, describe-stacks, delete-stack, prepare-bucket, node-exec
+    validate-template, create-stack / launch-cluster, list-stacks, describe-stacks, delete-stack, prepare-bucket, node-exec
 Job plane:
     launch (tools/launch.py compatible), kill, generate-trainer, run-example, bandwidth, benchmark, im2rec, rec2idx, parse-log, diagnose
 """
@@ -47,6 +47,13 @@ def cmd_create_stack(a) -> int:
     print(json.dumps({"StackId": h.stack_dir, "StackStatus": h.status, "Outputs": h.outputs, "Hostfile": h.hostfile,
                       "Env": h.export_env(), "Workers": h.workers}, indent=1))
     return 0 if h.status == "CREATE_COMPLETE" else 1
+
+
+def cmd_validate_template(a) -> int:
+    from .cluster.spec import validate_template
+    template = a.template_body[7:] if a.template_body.startswith("file://") else a.template_body
+    print(json.dumps(validate_template(template), indent=1))
+    return 0
 
 
 def cmd_list_stacks(a) -> int:
@@ -99,8 +106,12 @@ def main(argv=None) -> int:
             print(f"{argv[0]}: error: {e.strerror}: {e.filename}", file=sys.stderr)
             return 1
 
-    ap = argparse.ArgumentParser(prog="dlcfn")
+    ap = argparse.ArgumentParser(prog="dlcfn", formatter_class=argparse.RawDescriptionHelpFormatter,
+                                 epilog="job-plane commands (each with its own --help): " + ", ".join(sorted(passthrough)))
     sub = ap.add_subparsers(dest="cmd", required=True)
+    p = sub.add_parser("validate-template", help="static check of a template (aws cloudformation validate-template)")
+    p.add_argument("--template-body", default="deeplearning.template")
+    p.set_defaults(fn=cmd_validate_template)
     for name in ("create-stack", "launch-cluster"):
         p = sub.add_parser(name)
         p.add_argument("--stack-name", default="dlcfn")

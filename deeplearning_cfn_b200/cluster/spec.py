@@ -123,6 +123,115 @@ def evaluate(node, params: dict, mappings: dict, pseudo: dict, attrs: dict | Non
     return node
 
 
+PSEUDO_PARAMETERS = ("AWS::Region", "AWS::StackName", "AWS::StackId", "AWS::AccountId", "AWS::NoValue", "AWS::NotificationARNs",
+                     "DLCFN::Region", "DLCFN::StackName", "DLCFN::StackId")
+_TOP_LEVEL = ("TemplateFormatVersion", "AWSTemplateFormatVersion", "Description", "Metadata", "Parameters", "Mappings", "Conditions",
+              "Resources", "Outputs")
+_INTRINSICS = ("Ref", "Fn::FindInMap", "Fn::Join", "Fn::If", "Fn::Equals", "Fn::GetAtt")
+
+
+def validate_template(template) -> dict:
+    """Static check of a template, the counterpart of `aws cloudformation validate-template` (the stack scripts of the reference
+    rely on CloudFormation rejecting a broken template before anything is created): known top-level sections, a Resources
+    section whose entries have a Type, parameter declarations with consistent defaults, and every `Ref` / `Fn::GetAtt` /
+    `Fn::FindInMap` / `DependsOn` / condition name pointing at something the template declares.  Returns the summary that call
+    prints ({"Parameters": [{ParameterKey, DefaultValue, NoEcho, Description}], "Description", "Capabilities"}); raises
+    TemplateError listing EVERY problem found."""
+    t = load_template(template) if isinstance(template, str) else template
+    errs: list[str] = []
+    if not isinstance(t, dict):
+        raise TemplateError("a template is a JSON object")
+    for k in t:
+        if k not in _TOP_LEVEL:
+            errs.append(f"unknown top-level section {k!r}")
+    params, maps, conds = t.get("Parameters", {}), t.get("Mappings", {}), t.get("Conditions", {})
+    res, outs = t.get("Resources"), t.get("Outputs", {})
+    if not isinstance(res, dict) or not res:
+        errs.append("the Resources section is required and must declare at least one resource")
+        res = {}
+    for name, d in params.items():
+        if not isinstance(d, dict) or "Type" not in d:
+            errs.append(f"parameter {name}: Type is required")
+            continue
+        if d["Type"] not in ("String", "Number", "CommaDelimitedList") and not str(d["Type"]).startswith(("AWS::", "List<", "DLCFN::")):
+            errs.append(f"parameter {name}: unknown Type {d['Type']!r}")
+        if "Default" in d:
+            try:
+                resolve_parameters({"Parameters": {name: d}}, {})
+            except TemplateError as e:
+                errs.append(f"parameter {name}: its Default violates its own constraints ({e})")
+    for name, r in res.items():
+        if not isinstance(r, dict) or not isinstance(r.get("Type"), str):
+            errs.append(f"resource {name}: Type is required")
+            continue
+        dep = r.get("DependsOn", [])
+        for d in ([dep] if isinstance(dep, str) else dep):
+            if d not in res:
+                errs.append(f"resource {name}: DependsOn names {d!r}, which is not a resource")
+        if "Condition" in r and r["Condition"] not in conds:
+            errs.append(f"resource {name}: unknown condition {r['Condition']!r}")
+
+    def walk(node, where: str) -> None:
+        if isinstance(node, list):
+            for i, x in enumerate(node):
+                walk(x, f"{where}[{i}]")
+            return
+        if not isinstance(node, dict):
+            return
+        if len(node) == 1:
+            (k, v), = node.items()
+            if k == "Ref":
+                if not (isinstance(v, str) and (v in params or v in res or v in PSEUDO_PARAMETERS)):
+                    errs.append(f"{where}: Ref to {v!r}, which is neither a parameter, a resource nor a pseudo parameter")
+                return
+            if k == "Fn::GetAtt":
+                target = v[0] if isinstance(v, list) and v else (v.split(".", 1)[0] if isinstance(v, str) else None)
+                if target not in res:
+                    errs.append(f"{where}: Fn::GetAtt on {target!r}, which is not a resource")
+                return
+            if k == "Fn::FindInMap":
+                if not (isinstance(v, list) and len(v) == 3):
+                    errs.append(f"{where}: Fn::FindInMap takes [map, key, key]")
+                else:
+                    if isinstance(v[0], str) and v[0] not in maps:
+                        errs.append(f"{where}: Fn::FindInMap on {v[0]!r}, which is not a mapping")
+                    elif isinstance(v[0], str) and isinstance(v[1], str) and v[1] not in maps[v[0]]:
+                        errs.append(f"{where}: mapping {v[0]} has no key {v[1]!r}")
+                    elif isinstance(v[0], str) and isinstance(v[1], str) and isinstance(v[2], str) and v[2] not in maps[v[0]][v[1]]:
+                        errs.append(f"{where}: mapping {v[0]}/{v[1]} has no key {v[2]!r}")
+                    walk(v, where + "/Fn::FindInMap")
+                return
+            if k == "Fn::If":
+                if isinstance(v, list) and v and isinstance(v[0], str) and v[0] not in conds:
+                    errs.append(f"{where}: Fn::If on unknown condition {v[0]!r}")
+                walk(v[1:] if isinstance(v, list) else v, where + "/Fn::If")
+                return
+            if k.startswith("Fn::") and k not in _INTRINSICS:
+                errs.append(f"{where}: {k} is not supported by this engine (supported: {', '.join(_INTRINSICS)})")
+        for k, v in node.items():
+            walk(v, f"{where}/{k}")
+
+    for name, c in conds.items():
+        walk(c, f"Conditions/{name}")
+    for name, r in res.items():
+        if isinstance(r, dict):
+            walk(r.get("Properties", {}), f"Resources/{name}/Properties")
+            walk(r.get("Metadata", {}), f"Resources/{name}/Metadata")
+    for name, o in outs.items():
+        if not isinstance(o, dict) or "Value" not in o:
+            errs.append(f"output {name}: Value is required")
+        else:
+            walk(o["Value"], f"Outputs/{name}/Value")
+    if errs:
+        raise TemplateError("template validation failed:\n  " + "\n  ".join(errs))
+    return {"Parameters": [{"ParameterKey": k, "DefaultValue": str(d["Default"]) if "Default" in d else None,
+                            "NoEcho": str(d.get("NoEcho", "false")).lower() == "true", "Description": d.get("Description", "")}
+                           for k, d in params.items()],
+            "Description": t.get("Description", ""),
+            "Capabilities": ["CAPABILITY_NAMED_IAM"] if any("Role" in str(r.get("Type", "")) or "Function" in str(r.get("Type", ""))
+                                                           for r in res.values() if isinstance(r, dict)) else []}
+
+
 @dataclass
 class ClusterSpec:
     """Resolved view of a stack request (what `launch_cluster` consumes)."""
@@ -147,6 +256,7 @@ class ClusterSpec:
         if not re.fullmatch(r"[A-Za-z][A-Za-z0-9-]{0,127}", stack_name):
             raise TemplateError("stack name must match [A-Za-z][A-Za-z0-9-]*")
         t = load_template(template) if isinstance(template, str) else template
+        validate_template(t)              # what CloudFormation does before it creates anything
         p = resolve_parameters(t, given)
         st = t.get("Mappings", {}).get("StackTimeouts", {}).get("Timeouts", {})
         known = {"WorkerCount", "InstanceType", "ImageType", "EFSMountPoint", "EFSFileSystemId"}

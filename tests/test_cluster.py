@@ -207,6 +207,45 @@ def test_template_parameter_validation():
     assert "MyVpcId" in load_template("private-mask-rcnn.template")["Parameters"]
 
 
+def test_validate_template_reports_every_dangling_reference(tmp_path):
+    """`validate-template` (aws cloudformation validate-template): the three shipped templates pass and print their parameter
+    summary; a template with dangling Ref / GetAtt / FindInMap / DependsOn / an unsupported intrinsic / a Default outside its
+    AllowedValues is rejected with ALL problems listed, by the API, by create-stack and by the CLI."""
+    import copy
+    from deeplearning_cfn_b200.cluster.spec import validate_template
+    for name in ("deeplearning.template", "mask-rcnn.template", "private-mask-rcnn.template"):
+        summary = validate_template(name)
+        keys = [p["ParameterKey"] for p in summary["Parameters"]]
+        assert "WorkerCount" in keys and summary["Description"] and summary["Capabilities"] == ["CAPABILITY_NAMED_IAM"]
+    t = copy.deepcopy(load_template("deeplearning.template"))
+    t["Resources"]["MasterQueue"]["Properties"] = {"Name": {"Ref": "NoSuchParameter"}, "Arn": {"Fn::GetAtt": ["Ghost", "Arn"]},
+                                                   "Sub": {"Fn::Sub": "${x}"}}
+    t["Resources"]["WorkerQueue"]["DependsOn"] = "AlsoMissing"
+    t["Outputs"]["MountTargetID"]["Value"] = {"Fn::FindInMap": ["NoSuchMap", "a", "b"]}
+    t["Parameters"]["InstanceType"]["Default"] = "p3.16xlarge"
+    t["Surprise"] = {}
+    with pytest.raises(TemplateError) as e:
+        validate_template(t)
+    msg = str(e.value)
+    for needle in ("NoSuchParameter", "Ghost", "Fn::Sub is not supported", "AlsoMissing", "NoSuchMap", "InstanceType: its Default",
+                   "unknown top-level section 'Surprise'"):
+        assert needle in msg, (needle, msg)
+    with pytest.raises(TemplateError):
+        ClusterSpec.from_template("s", t)                       # create-stack validates before it creates anything
+    with pytest.raises(TemplateError):
+        validate_template({"Parameters": {}})                   # no Resources
+    bad = tmp_path / "bad.template"
+    bad.write_text(json.dumps(t))
+    base = [sys.executable, "-m", "deeplearning_cfn_b200"]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run(base + ["validate-template", "--template-body", f"file://{bad}"], env=env, capture_output=True, text=True)
+    assert r.returncode == 1 and "Ghost" in r.stderr
+    r = subprocess.run(base + ["validate-template"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and json.loads(r.stdout)["Parameters"][0]["ParameterKey"]
+    r = subprocess.run(base + ["--help"], env=env, capture_output=True, text=True)
+    assert "run-example" in r.stdout and "validate-template" in r.stdout
+
+
 # ----------------------------------------------------------------------------- launch_cluster
 @pytest.mark.parametrize("backend", ["thread", "process"])
 def test_launch_cluster_end_to_end(tmp_path, backend):

@@ -1,7 +1,8 @@
 """`python -m deeplearning_cfn_b200 <command>` - the user-facing CLI.
 
 Control plane (counterparts of `aws cloudformation ...` as used by mask-rcnn-stack.sh:62-92):
-    validate-template, create-stack / launch-cluster, list-stacks, describe-stacks, delete-stack, prepare-bucket, node-exec
+    validate-template, create-stack / launch-cluster, list-stacks, describe-stacks, describe-stack-events, delete-stack,
+    prepare-bucket, node-exec
 Job plane:
     launch (tools/launch.py compatible), kill, generate-trainer, run-example, bandwidth, benchmark, im2rec, rec2idx, parse-log, diagnose
 """
@@ -73,6 +74,23 @@ def cmd_describe_stacks(a) -> int:
     return 0
 
 
+def cmd_describe_stack_events(a) -> int:
+    """Newest first, like `aws cloudformation describe-stack-events` - where a user of the reference looks when a stack rolls
+    back (which resource failed and why: a master that could not launch, an agent that timed out, a shrink)."""
+    import datetime
+    from .cluster.controlplane import ControlPlane
+    from .cluster.stack import DEFAULT_HOME, StackError
+    sdir = os.path.join(a.home or DEFAULT_HOME, "stacks", a.stack_name)
+    if not os.path.isdir(sdir):
+        raise StackError(f"no such stack: {a.stack_name}")
+    evs = ControlPlane(sdir).stack().get("events", [])
+    out = [{"Timestamp": datetime.datetime.fromtimestamp(e["ts"], datetime.timezone.utc).isoformat(timespec="milliseconds"),
+            "StackName": a.stack_name, "LogicalResourceId": e["id"], "ResourceStatus": e["status"],
+            "ResourceStatusReason": e.get("reason", "")} for e in reversed(evs)]
+    print(json.dumps({"StackEvents": out}, indent=1))
+    return 0
+
+
 def cmd_delete_stack(a) -> int:
     from .cluster.stack import delete_stack
     delete_stack(a.stack_name, a.home)
@@ -130,7 +148,8 @@ def main(argv=None) -> int:
     p.add_argument("--home", default=None)
     p.add_argument("--region", default=None)
     p.set_defaults(fn=cmd_list_stacks)
-    for name, fn in (("describe-stacks", cmd_describe_stacks), ("delete-stack", cmd_delete_stack)):
+    for name, fn in (("describe-stacks", cmd_describe_stacks), ("describe-stack-events", cmd_describe_stack_events),
+                     ("delete-stack", cmd_delete_stack)):
         p = sub.add_parser(name)
         p.add_argument("--stack-name", required=True)
         p.add_argument("--home", default=None)

@@ -333,6 +333,10 @@ def test_cli_create_list_describe_delete(tmp_path):
     assert "c1" in r.stdout
     r = subprocess.run(base + ["describe-stacks", "--stack-name", "c1", "--home", str(tmp_path)], env=env, capture_output=True, text=True)
     assert json.loads(r.stdout)["Hostfile"].endswith("opt/deeplearning/workers")
+    r = subprocess.run(base + ["describe-stack-events", "--stack-name", "c1", "--home", str(tmp_path)], env=env, capture_output=True, text=True)
+    evs = json.loads(r.stdout)["StackEvents"]
+    assert evs[0]["LogicalResourceId"] == "c1" and evs[0]["ResourceStatus"] == "CREATE_COMPLETE"        # newest first
+    assert {"SharedStore", "MasterAutoScalingGroup", "WorkerAutoScalingGroup"} <= {e["LogicalResourceId"] for e in evs}
     assert subprocess.run(base + ["delete-stack", "--stack-name", "c1", "--home", str(tmp_path)], env=env).returncode == 0
     r = subprocess.run(base + ["create-stack", "--stack-name", "c2", "--home", str(tmp_path), "--parameters", "WorkerCount=0"],
                        env=env, capture_output=True, text=True)

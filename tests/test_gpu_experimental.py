@@ -86,39 +86,7 @@ def test_gemm_pair_variants_match_fp32(M, N, K, epi, a_mn, b_mn):
     assert torch.equal(d, native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=epi, block_n=256))
 
 
-# ------------------------------------------------------------------------------------------------ CUDA-graph step
-@pytest.mark.parametrize("net", ["cifar10_cnn", "resnet18"])
-def test_graphed_step_matches_eager_training(net):
-    """trainer.capture: the replayed graph must train exactly like the eager step (same kernels, same order), follow a
-    learning-rate change by re-capturing, and run other batch shapes eagerly."""
-    from deeplearning_cfn_b200.models import get_model, to_b200_layout
-    from deeplearning_cfn_b200.parallel.trainer import DataParallelTrainer
-    size = 32
-    g = torch.Generator().manual_seed(0)
-    xs = [torch.randn(16, 3, size, size, generator=g).to(dev()).bfloat16().contiguous(memory_format=torch.channels_last) for _ in range(4)]
-    ys = [torch.randint(0, 10, (16,), generator=g).to(dev()) for _ in range(4)]
-
-    def make():
-        torch.manual_seed(5)
-        m = get_model(net if net != "resnet18" else "resnet", 10, size, **({"num_layers": 20} if net == "resnet18" else {}))
-        return DataParallelTrainer(to_b200_layout(m.to(dev())).train(), mode="local", optimizer="sgd_mom", lr=0.05)
-    eager, graphed = make(), make()
-    for _ in range(3):                               # the warm-up steps of capture() train on the example batch
-        eager.step(xs[0], ys[0])
-    step = graphed.capture(xs[0], ys[0], warmup=3)
-    assert step.graphed and step.launches_per_step > 0, repr(step)
-    for i in range(6):
-        if i == 3:
-            eager.set_learning_rate(0.01)
-            graphed.set_learning_rate(0.01)
-        le = float(eager.step(xs[i % 4], ys[i % 4]))
-        lg = float(step(xs[i % 4], ys[i % 4]))
-        assert abs(le - lg) <= 2e-2 * abs(le) + 1e-3, (i, le, lg)
-    assert step.captures == 2 and step.replays == 6 and graphed.step_count == eager.step_count
-    for pe, pg in zip(eager.model.parameters(), graphed.model.parameters()):
-        _frac_close(pg, pe, 2e-2, 2e-2 * float(pe.float().abs().max()) + 1e-4, frac=0.99)
-    small = step(xs[1][:8], ys[1][:8])               # another shape: eager
-    assert torch.isfinite(small) and step.replays == 6
+# (the CUDA-graph step test moved to tests/test_gpu_zz_graph.py: validated on B200 in round 2, the bench replays the graph by default)
 
 
 # ------------------------------------------------------------------------------------------------ ROIAlign / NMS kernels

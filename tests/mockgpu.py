@@ -94,8 +94,15 @@ def _check_batch_sum(x, out, N, inner, stream) -> int:
     return 1 if (N <= 0 or inner <= 0 or (inner & 7) or (_ptr_val(x) & 15) or (_ptr_val(out) & 15)) else 0
 
 
-_VALIDATORS = {"dlcfn_gemm_bf16_ex": _check_gemm, "dlcfn_conv_bf16_ex": _check_conv, "dlcfn_colsum_bf16": _check_colsum,
-               "dlcfn_batch_sum_bf16": _check_batch_sum}
+def _check_conv_plain(op, x, other, out, out_dtype, n, h, w, c, k, cin, r, s, pad, stride, oh, ow, accumulate, block_n, num_sms,
+                      stream) -> int:
+    """dlcfn_conv_bf16 = dlcfn_conv_bf16_ex with a dense NHWC view and no statistics."""
+    return _check_conv(op, x, other, out, out_dtype, n, h, w, c, k, cin, r, s, pad, stride, oh, ow, accumulate, block_n, num_sms,
+                       0, 0, 0, None, stream)
+
+
+_VALIDATORS = {"dlcfn_gemm_bf16_ex": _check_gemm, "dlcfn_conv_bf16_ex": _check_conv, "dlcfn_conv_bf16": _check_conv_plain,
+               "dlcfn_colsum_bf16": _check_colsum, "dlcfn_batch_sum_bf16": _check_batch_sum}
 
 
 class _Checker:

@@ -194,3 +194,27 @@ def test_kvstore_compression_on_device_gradients_uses_the_2bit_kernels():
         assert out.shape == (100,) and len(store._residuals) == 2
         assert all(r.dtype == torch.float32 and r.numel() == 100 for r in store._residuals.values())
     assert log.count("dlcfn_quantize_2bit") == 2 and log.count("dlcfn_dequantize_2bit") == 2
+
+
+_FAMILIES = [("resnet18", 64), ("resnet50", 64), ("resnet50-v1", 64), ("resnext50", 64), ("vgg16-bn", 64), ("alexnet", 224),
+             ("googlenet", 96), ("inception-bn", 96), ("inception-v3", 299), ("inception-v4", 299), ("inception-resnet-v2", 299),
+             ("mobilenet0.25", 64), ("mobilenetv2", 64), ("mobilenetv2-0.25", 64), ("squeezenet1.1", 96), ("densenet121", 64),
+             ("cifar10-cnn", 32), ("resnet20", 32)]
+
+
+@pytest.mark.parametrize("name,size", _FAMILIES, ids=[n for n, _ in _FAMILIES])
+def test_every_model_family_walks_forward_and_backward_past_the_entry_point_checks(name, size):
+    """bf16 channels_last forward + backward of every model family on the stand-in GPU, whose GEMM / convolution stand-ins
+    apply the argument checks of the C entry points (16-byte alignment, leading dimensions, 64-channel TMA rows, geometry): a
+    layer shape that the box would answer with cudaErrorInvalidValue fails here.  ResNets must actually take the tcgen05 path."""
+    from deeplearning_cfn_b200.models import get_model, to_b200_layout
+    torch.manual_seed(0)
+    with mock_gpu() as log:
+        m = to_b200_layout(get_model(name, 16, size)).train()
+        x = torch.randn(2, 3, size, size).bfloat16().contiguous(memory_format=torch.channels_last)
+        y = m(x)
+        assert y.shape == (2, 16)
+        y.float().logsumexp(1).sum().backward()
+    assert all(p.grad is not None for p in m.parameters() if p.requires_grad)
+    if name in ("resnet18", "resnet50"):             # (the CIFAR ResNets have 16- / 32-channel stages that stay on the library)
+        assert sum(log.count(f) for f in ("dlcfn_conv_bf16_ex", "dlcfn_conv_bf16", "dlcfn_gemm_bf16_ex")) >= 60, len(log)

@@ -57,7 +57,11 @@ def set_sync_bn_heap(heap) -> None:
     """Route the SyncBatchNorm statistics exchange (reference C12: 2C+1 floats per layer, forward and backward) through the
     fused one-shot all-reduce kernel on the symmetric peer-HBM heap (csrc/cuda/collectives.cu:kallreduce_oneshot - push into
     every peer's staging slot, ONE flag barrier, local reduce) instead of an NCCL call.  `heap` = a parallel.symm.SymmetricHeap
-    shared by all ranks of the process group (pass None to go back to torch.distributed)."""
+    shared by all ranks of the process group (pass None to go back to torch.distributed).
+
+    One heap serves ONE stream of small all-reduces: the one-shot kernel has a single staging area and flag channel per heap, so
+    give SyncBatchNorm a heap of its own (`SymmetricHeap(1 << 20)`) rather than the heap of a `DataParallelTrainer` whose
+    communication stream may be all-reducing a small bucket at the same time."""
     if heap is None:
         _SYNC_HEAP.update(heap=None, off=0, buf=None)
         return

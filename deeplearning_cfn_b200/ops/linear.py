@@ -18,6 +18,9 @@ import torch.nn.functional as F
 from . import native
 
 
+_COLSUM_MIN_ROWS = int(__import__("os").environ.get("DLCFN_COLSUM_MIN_ROWS", "2048"))
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -49,7 +52,10 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = native.gemm_bf16(dy2, x2, a_mn=True, b_mn=True, out_dtype=torch.bfloat16)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            ok = dy2.is_cuda and dy2.shape[1] % 8 == 0 and dy2.stride(0) % 8 == 0 and dy2.data_ptr() % 16 == 0
+            # tall gradients (BERT: 8192 tokens x 1024 .. 30522 columns) go through the streaming column-sum kernel - torch's
+            # strided reduce took 2.1 ms per BERT-large step for them; short ones (a classifier's 256 rows) are not worth a launch pair
+            ok = (dy2.is_cuda and dy2.shape[0] >= _COLSUM_MIN_ROWS and dy2.shape[1] % 8 == 0 and dy2.stride(0) % 8 == 0
+                  and dy2.data_ptr() % 16 == 0)
             db = native.colsum(dy2) if ok else dy2.sum(0, dtype=torch.float32)
         return dx, dw, db
 

@@ -1,4 +1,6 @@
-"""Fused peer-HBM collectives / parameter-server kernels at world size 2 (and more when available)."""
+"""Fused peer-HBM collectives / parameter-server kernels at world size 2 (and more when available).  The file sorts last in the
+GPU tier: these tests start multi-process jobs over several devices, and a box-level problem there (a busy peer GPU, a port) must
+not stop the single-GPU kernel tests from running under `pytest -x`."""
 import os
 import subprocess
 import sys

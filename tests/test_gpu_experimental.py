@@ -86,10 +86,10 @@ def test_gemm_pair_variants_match_fp32(M, N, K, epi, a_mn, b_mn):
     assert torch.equal(d, native.gemm_bf16(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=epi, block_n=256))
 
 
-# (the CUDA-graph step test moved to tests/test_gpu_zz_graph.py: validated on B200 in round 2, the bench replays the graph by default)
+# (the CUDA-graph step test moved to tests/test_gpu_y1_graph.py: validated on B200 in round 2, the bench replays the graph by default)
 
 
-# (the ROIAlign / NMS kernel tests moved to tests/test_gpu_zz_roi.py: they passed on B200 at the start of round 2)
+# (the ROIAlign / NMS kernel tests moved to tests/test_gpu_y2_roi.py: they passed on B200 at the start of round 2)
 
 
 # -------------------------------------------------------------------------- hierarchical (multi-node) trainer mode on GPUs

@@ -1,5 +1,5 @@
 """`trainer.capture` (parallel/graph.py): the whole training step as one CUDA graph - the bench's default since round 2 (validated
-on B200: 22.18 -> 21.11 ms per ResNet-50 step).  Runs late in the GPU tier (file name) because a capture that went wrong can leave
+on B200: 22.18 -> 21.11 ms per ResNet-50 step).  Runs after the kernel tests in the GPU tier (file name) because a capture that went wrong can leave
 the process in capture mode."""
 import pytest
 import torch

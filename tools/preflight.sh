@@ -14,7 +14,7 @@ step "flag-protocol model check (W = 2, 3)" python tools/protocol_model.py --wor
 if [ "${1:-}" != "--quick" ]; then
   step "CPU test tier" python -m pytest tests -x -q -m "not gpu" -p no:cacheprovider
 fi
-step "GPU test bodies on the stand-in GPU" env DLCFN_MOCK_GPU_DRYRUN=1 python -m pytest tests/test_gpu_conv.py tests/test_gpu_nn.py tests/test_gpu_layernorm.py tests/test_gpu_zz_graph.py tests/test_gpu_zz_roi.py tests/test_models.py -q -m gpu -p no:cacheprovider
+step "GPU test bodies on the stand-in GPU" env DLCFN_MOCK_GPU_DRYRUN=1 python -m pytest tests/test_gpu_conv.py tests/test_gpu_nn.py tests/test_gpu_layernorm.py tests/test_gpu_y1_graph.py tests/test_gpu_y2_roi.py tests/test_gpu_z1_zoo.py tests/test_gpu_z2_colsum.py -q -m gpu -p no:cacheprovider
 step "bench.py --dry-cpu" python bench.py --dry-cpu --steps 3 --warmup 3
 step "bench.py --dry-cpu, 2 ranks" python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29719 bench.py --gpus 2 --dry-cpu --steps 3 --warmup 3
 step "bench.py --impl reference" python bench.py --impl reference --gpus 1 --steps 2 --warmup 1

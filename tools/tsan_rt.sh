@@ -13,7 +13,7 @@ export LD_PRELOAD=$(gcc -print-file-name=libtsan.so)
 export OMP_NUM_THREADS=1 MKL_NUM_THREADS=1   # libgomp is not instrumented: its barriers look like races
 export TSAN_OPTIONS="halt_on_error=0:exitcode=0:report_signal_unsafe=0:log_path=$out/tsan:history_size=4:second_deadlock_stack=1"
 rm -f $out/tsan.*
-python -m pytest tests/test_kvstore.py tests/test_parallel_cpu.py -x -q -p no:cacheprovider -k "${1:-engine or storage or recordio or reducer or dist_sync}" 2>&1 | tail -5
+python -m pytest tests/test_kvstore.py tests/test_parallel_cpu.py -x -q -p no:cacheprovider -k "${1:-engine or storage or recordio or reducer or planner}" 2>&1 | tail -5
 n=$(ls $out/tsan.* 2>/dev/null | wc -l)
 echo "TSAN report files: $n"
 grep -h "SUMMARY: ThreadSanitizer" $out/tsan.* 2>/dev/null | sort | uniq -c | sort -rn | head -30
@@ -40,3 +40,5 @@ run_job dist_async 2 tests/mp/dist_kvstore_worker.py dist_async
 PS_RESEND=1 PS_RESEND_TIMEOUT=200 PS_DROP_MSG=10 PS_HEARTBEAT_INTERVAL=1 run_job resend_drop_heartbeat 2 tests/mp/dist_kvstore_worker.py dist_sync
 MXNET_KVSTORE_BIGARRAY_BOUND=40 run_job sync_replicas_python_callbacks 3 tests/mp/sync_replicas_worker.py
 run_job server_profiling 2 tests/mp/server_profile_worker.py $out/prof
+# round 2: shard boundaries on key units (2-bit words, row-sparse rows), dtype conversion, staging-buffer reuse under queued pushes
+run_job store_regressions_big_keys 2 tests/mp/dist_regress_worker.py store

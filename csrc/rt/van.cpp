@@ -43,12 +43,15 @@ struct Writer {
 };
 struct Reader {
   const char* p; const char* end; bool ok = true;
-  int32_t i32() { int32_t v = 0; if (p + 4 > end) { ok = false; return 0; } memcpy(&v, p, 4); p += 4; return v; }
-  uint64_t u64() { uint64_t v = 0; if (p + 8 > end) { ok = false; return 0; } memcpy(&v, p, 8); p += 8; return v; }
+  // lengths are compared with the bytes that are LEFT: a length field of a garbage frame may be any 64-bit value, and
+  // `p + n` with such an n is pointer overflow (found by UBSAN under tests/test_kvstore.py: garbage connections)
+  size_t left() const { return (size_t)(end - p); }
+  int32_t i32() { int32_t v = 0; if (left() < 4) { ok = false; return 0; } memcpy(&v, p, 4); p += 4; return v; }
+  uint64_t u64() { uint64_t v = 0; if (left() < 8) { ok = false; return 0; } memcpy(&v, p, 8); p += 8; return v; }
   std::string str() {
     uint64_t n = u64();
-    if (!ok || p + n > end) { ok = false; return {}; }
-    std::string s(p, n); p += n; return s;
+    if (!ok || n > (uint64_t)left()) { ok = false; return {}; }
+    std::string s(p, (size_t)n); p += n; return s;
   }
 };
 

@@ -611,4 +611,17 @@ void Node::ResendLoop() {
   }
 }
 
+// Test hook (tests/test_kvstore.py: message fuzzing under the sanitizers): decode one frame payload exactly as ReadLoop does and
+// re-encode what was understood.  Returns 0 for an undecodable payload, otherwise 1 + the number of node / data entries.
+int DebugRoundTrip(const char* payload, size_t n) {
+  Message m;
+  if (!Unpack(payload, n, &m)) return 0;
+  const std::string again = Pack(m);
+  return 1 + (int)m.nodes.size() + (int)m.data.size() + (again.empty() ? 1 : 0);
+}
+
 }  // namespace dlcfn
+
+extern "C" __attribute__((visibility("default"))) int dlcfn_rt_debug_unpack(const char* payload, size_t n) {
+  return dlcfn::DebugRoundTrip(payload, n);
+}

@@ -100,6 +100,9 @@ def _declare(L) -> None:
     L.dlcfn_topo_plan_trees_backtrack.restype = c_int
     L.dlcfn_topo_plan_ring.argtypes = [POINTER(c_double), c_int, c_int, POINTER(c_int)]
     L.dlcfn_topo_plan_ring.restype = c_int
+    from ctypes import c_char_p as _bytes_p, c_size_t as _sz
+    L.dlcfn_rt_debug_unpack.argtypes = [_bytes_p, _sz]         # test hook: decode + re-encode one frame payload (van.cpp)
+    L.dlcfn_rt_debug_unpack.restype = c_int
 
 
 # --------------------------------------------------------------------------- fabric planner

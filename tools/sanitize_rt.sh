@@ -11,6 +11,6 @@ export DLCFN_RT_LIB=$out/libdlcfn_rt.so
 export LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 export ASAN_OPTIONS=detect_leaks=0:abort_on_error=0:halt_on_error=0:log_path=$out/asan
 rm -f $out/asan.*
-python -m pytest tests/test_kvstore.py tests/test_parallel_cpu.py -x -q -k "${1:-dist or engine or planner or storage or recordio or reducer or sync_replicas or profiling or garbage}" 2>&1 | tail -5
+python -m pytest tests/test_kvstore.py tests/test_parallel_cpu.py -x -q -k "${1:-dist or engine or planner or storage or recordio or reducer or sync_replicas or profiling or garbage or fuzz}" 2>&1 | tail -5
 echo "ASAN reports: $(ls $out/asan.* 2>/dev/null | wc -l)"
 for f in $out/asan.*; do [ -f "$f" ] && head -30 "$f"; done 2>/dev/null | head -120

@@ -823,3 +823,44 @@ def test_message_decoder_survives_structured_fuzzing():
         assert rc >= 0
         rejected += rc == 0
     assert 1000 < rejected < 20000          # both outcomes occur: the fuzzer neither only breaks nor only preserves messages
+
+
+def test_planners_return_valid_trees_or_refuse_on_arbitrary_link_matrices(monkeypatch):
+    """KL and backtracking tree planners and the ring planner (csrc/rt/topo.cpp) on 600 random link matrices - sparse,
+    asymmetric, real-valued, with NaN / huge / negative entries: the answer is a well-formed set of trees (root marked, parents
+    in range) / a permutation, or ValueError; nothing else.  Clean under ASAN / UBSAN (tools/*_rt.sh -k planner)."""
+    import random
+    rng = random.Random(3)
+    ok = refused = 0
+    for it in range(600):
+        n = rng.randrange(1, 9)
+        kind = it % 4
+        link = [[0.0] * n for _ in range(n)]
+        for i in range(n):
+            for j in range(n):
+                if i == j:
+                    continue
+                if kind == 0:
+                    link[i][j] = rng.choice([0, 0, 1, 2, 18])
+                elif kind == 1:
+                    link[i][j] = link[j][i] = rng.choice([0, 1, 4])
+                elif kind == 2:
+                    link[i][j] = rng.random() * 20
+                else:
+                    link[i][j] = rng.choice([0, 1e30, -1, float("nan"), 3])
+        for bt in ("0", "1"):
+            monkeypatch.setenv("MXNET_KVSTORE_TREE_BACKTRACK", bt)
+            try:
+                trees = rt.plan_trees(link)
+            except ValueError:
+                refused += 1
+                continue
+            assert len(trees) == n and all(len(t) == n for t in trees)
+            for r, t in enumerate(trees):
+                assert t[r] == -1 and all(-1 <= p < n for p in t)
+            ok += 1
+        try:
+            assert sorted(rt.plan_ring(link, rng.randrange(n))) == list(range(n))
+        except ValueError:
+            pass
+    assert ok > 300 and refused > 30

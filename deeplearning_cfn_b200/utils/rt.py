@@ -124,7 +124,9 @@ def reduce_sum_cpu(srcs: list, out=None, nthreads: int | None = None, bigarray_b
         L.dlcfn_reduce_sum_cpu.restype = c_int
         L._reduce_declared = True
     t0 = srcs[0]
-    code = {torch.float32: 0, torch.bfloat16: 1}[t0.dtype]
+    code = {torch.float32: 0, torch.bfloat16: 1}.get(t0.dtype)
+    if code is None:
+        raise ValueError(f"reduce_sum_cpu supports float32 and bfloat16, got {t0.dtype}")
     srcs = [s.detach().contiguous() for s in srcs]
     assert all((not s.is_cuda) and s.dtype == t0.dtype and s.numel() == t0.numel() for s in srcs)
     if out is None:

@@ -871,3 +871,48 @@ def test_native_recordio_reader_and_pipeline_survive_corrupted_files(tmp_path):
         except Exception:                                # noqa: BLE001 - refusing the file is fine; crashing is not
             pass
     assert survived > 0
+
+
+def test_host_storage_pool_under_concurrent_random_alloc_and_release():
+    """Four threads allocate, touch and release blocks of awkward sizes at random from the pooled host storage
+    (csrc/rt/storage.cpp), in both size-class strategies: nothing is lost or handed out twice (first / last byte written by
+    the owner stay intact), and everything returns to the pool.  Clean under ASAN / UBSAN / TSAN (profiles/r2/sanitizers_r2.md)."""
+    import random
+    import threading
+    from deeplearning_cfn_b200.utils import storage
+    errors = []
+    try:
+        for kind, cut in (("Naive", 0), ("Round", 12)):
+            storage.set_strategy(kind, cut)
+
+            def worker(seed):
+                r = random.Random(seed)
+                live = []
+                try:
+                    for _ in range(250):
+                        if live and r.random() < 0.45:
+                            t, tag = live.pop(r.randrange(len(live)))
+                            if int(t[0]) != tag or int(t[-1]) != tag:
+                                errors.append(f"block of thread {seed} was overwritten")
+                            storage.release(t)
+                        else:
+                            n = r.choice([1, 7, 64, 4095, 4096, 4097, 65536, r.randrange(1, 200000)])
+                            t = storage.host_empty((n,), torch.uint8)
+                            tag = (seed * 37 + len(live)) % 251
+                            t[0] = tag
+                            t[-1] = tag
+                            live.append((t, tag))
+                    for t, tag in live:
+                        if int(t[0]) != tag or int(t[-1]) != tag:
+                            errors.append(f"block of thread {seed} was overwritten")
+                        storage.release(t)
+                except Exception as e:               # noqa: BLE001
+                    errors.append(repr(e))
+            ts = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            assert not errors, errors[:3]
+            assert storage.stats()["live_blocks"] == 0
+            storage.release_all()
+    finally:
+        storage.set_strategy("Naive", 0)

@@ -864,3 +864,41 @@ def test_planners_return_valid_trees_or_refuse_on_arbitrary_link_matrices(monkey
         except ValueError:
             pass
     assert ok > 300 and refused > 30
+
+
+def test_engine_random_dependency_graphs_keep_per_variable_order():
+    """Random read / write sets, priorities and thread counts through the native dependency engine (csrc/rt/engine.cpp): every
+    reader observes the last writer pushed before it, writers of a variable run in push order, wait_for_var may be called at any
+    time.  (30 such graphs were also run under ThreadSanitizer: profiles/r2/sanitizers_r2.md.)"""
+    import random
+    import threading
+    rng = random.Random(5)
+    for trial in range(10):
+        eng = rt.Engine(rng.choice([1, 2, 4, 8]))
+        nv = rng.randrange(1, 8)
+        vars_ = [eng.new_var() for _ in range(nv)]
+        state = {v: 0 for v in vars_}                  # index of the last writer that ran
+        pushed_last = {v: 0 for v in vars_}            # index of the last writer pushed so far
+        violations, lock = [], threading.Lock()
+        for op in range(1, rng.randrange(50, 300) + 1):
+            touched = rng.sample(vars_, rng.randrange(0, min(3, nv) + 1))
+            nw = rng.randrange(0, len(touched) + 1)
+            writes, reads = touched[:nw], touched[nw:]
+            want = {v: pushed_last[v] for v in touched}
+            for v in writes:
+                pushed_last[v] = op
+
+            def fn(op=op, reads=reads, writes=writes, want=want):
+                for v in reads + writes:
+                    if state[v] != want[v]:
+                        with lock:
+                            violations.append((op, v, state[v], want[v]))
+                for v in writes:
+                    state[v] = op
+            eng.push(fn, reads, writes, priority=rng.randrange(-5, 6))
+            if rng.random() < 0.02:
+                eng.wait_for_var(rng.choice(vars_))
+        eng.wait_all()
+        assert not violations, (trial, violations[:5])
+        assert state == pushed_last
+        eng.close()

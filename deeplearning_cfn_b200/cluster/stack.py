@@ -15,6 +15,8 @@ of the NVLink topology probe (cluster.discover), so rank order follows the fabri
 """
 from __future__ import annotations
 
+import contextlib
+import fcntl
 import json
 import os
 import shutil
@@ -141,8 +143,17 @@ class Stack:
         topo = probe_topology()
         gpus_total = self.capacity_gpus if self.capacity_gpus is not None else topo.num_gpus
         order = topo.rank_order()[:gpus_total] if topo.num_gpus else []
-        self._free_gpus = list(order) if order else list(range(gpus_total))
-        cp.update_stack(Topology=topo.summary())
+        candidates = list(order) if order else list(range(gpus_total))
+        # The box is the region: GPUs held by the other live stacks of this home are not free (two stacks on one box must not
+        # be handed the same devices).  What this stack can use is reserved under a home-wide lock BEFORE any instance starts;
+        # a stack that finds fewer GPUs than it asked for shrinks like any other capacity shortage.
+        want = (1 + spec.worker_count) * spec.gpus_per_instance
+        with _home_lock(self.home):
+            busy = _gpus_reserved_by_other_stacks(self.home, spec.stack_name)
+            self._free_gpus = [g for g in candidates if g not in busy][:want]
+            cp.update_stack(Topology=topo.summary(), ReservedGpus=list(self._free_gpus))
+        if busy:
+            cp.log_event(spec.stack_name, "CAPACITY", f"GPUs {sorted(busy)} are held by other stacks; {len(self._free_gpus)} of {want} reserved")
 
         # --- shared store (EFS): Retain on delete, reuse when an id is given
         store_id = spec.shared_store_id or ("fs-" + uuid.uuid4().hex[:8])
@@ -196,7 +207,9 @@ class Stack:
             raise StackError(f"bootstrap agent failed on {failed}")
 
         outputs = {k: self._eval(v["Value"]) for k, v in spec.template.get("Outputs", {}).items()}
-        cp.update_stack(StackStatus="CREATE_COMPLETE", Outputs=outputs)
+        used = sorted({g for gname in ("MasterAutoScalingGroup", "WorkerAutoScalingGroup")
+                       for inst in (cp.describe_group(gname) or {}).get("Instances", []) for g in inst.get("Gpus", [])})
+        cp.update_stack(StackStatus="CREATE_COMPLETE", Outputs=outputs, ReservedGpus=used)    # what a shrink left over is free again
         cp.log_event(spec.stack_name, "CREATE_COMPLETE")
         return self.handle()
 
@@ -213,6 +226,9 @@ class Stack:
                 # InsufficientInstanceCapacity: no instance is created, the function decides what to do
                 why = "fault injection" if inject_fail else f"need {per} GPUs, {len(self._free_gpus)} free"
                 cp.log_event(gname, "LAUNCH_ERROR", why)
+                if is_master:      # nothing can rendezvous without a master: fail now instead of waiting for the launch timeout
+                    raise StackError(f"InsufficientInstanceCapacity: the master needs {per} GPUs, {len(self._free_gpus)} are free "
+                                     f"on this box (other live stacks hold the rest: list-stacks / delete-stack)")
                 self._publish(self._fn_env, events.make_notification(
                     events.LAUNCH_ERROR, gname, "", status_code="Failed",
                     status_message=f"InsufficientInstanceCapacity: {why}"))
@@ -292,6 +308,39 @@ class Stack:
     # ------------------------------------------------------------------ describe / delete
     def handle(self) -> ClusterHandle:
         return describe_stack(self.spec.stack_name, self.home)
+
+
+_LIVE = ("CREATE_IN_PROGRESS", "CREATE_COMPLETE")
+
+
+@contextlib.contextmanager
+def _home_lock(home: str):
+    os.makedirs(home, exist_ok=True)
+    fd = os.open(os.path.join(home, ".capacity.lock"), os.O_CREAT | os.O_RDWR)
+    try:
+        fcntl.flock(fd, fcntl.LOCK_EX)
+        yield
+    finally:
+        fcntl.flock(fd, fcntl.LOCK_UN)
+        os.close(fd)
+
+
+def _gpus_reserved_by_other_stacks(home: str, me: str) -> set:
+    busy: set = set()
+    base = os.path.join(home, "stacks")
+    if not os.path.isdir(base):
+        return busy
+    for name in os.listdir(base):
+        if name == me:
+            continue
+        try:
+            with open(os.path.join(base, name, "stack.json")) as f:
+                st = json.load(f)
+        except (OSError, ValueError):
+            continue
+        if st.get("StackStatus") in _LIVE:
+            busy.update(st.get("ReservedGpus", []))
+    return busy
 
 
 def describe_stack(stack_name: str, home: str | None = None) -> ClusterHandle:

@@ -276,7 +276,8 @@ def test_elastic_shrink_and_store_retention(tmp_path):
     g = ControlPlane(h.stack_dir).describe_group("WorkerAutoScalingGroup")
     assert g["DesiredCapacity"] == 3 and "ReplaceUnhealthy" in g["SuspendedProcesses"]
     # fault injection: every worker launch fails -> the master alone is the cluster
-    h2 = launch_cluster("solo", home=str(tmp_path), backend="thread", WorkerCount=2, fail_instances=2, capacity_gpus=1)
+    # (a different box: stacks of one home share its GPUs, and "big" holds all eight - see the next test)
+    h2 = launch_cluster("solo", home=str(tmp_path / "box2"), backend="thread", WorkerCount=2, fail_instances=2, capacity_gpus=1)
     assert h2.env["DEEPLEARNING_WORKERS_COUNT"] == "1"
     # shared store survives deletion and can be re-attached (DeletionPolicy Retain)
     store = h.outputs["MountTargetID"]
@@ -285,6 +286,31 @@ def test_elastic_shrink_and_store_retention(tmp_path):
     assert describe_stack("big", str(tmp_path)).status == "DELETE_COMPLETE"
     h3 = launch_cluster("big", home=str(tmp_path), backend="thread", WorkerCount=1, EFSFileSystemId=store)
     assert open(os.path.join(h3.env["EFS_MOUNT"], "ckpt.bin")).read() == "weights"
+
+
+def test_stacks_of_one_box_do_not_share_gpus(tmp_path):
+    """Two live stacks in one home: the second only gets the GPUs the first left (and shrinks to them), a third finds none
+    and fails at once with InsufficientInstanceCapacity instead of waiting for the master timeout; deleting a stack frees
+    its GPUs."""
+    import time
+    home = str(tmp_path)
+    a = launch_cluster("a", home=home, backend="thread", WorkerCount=2, InstanceType="b200.2gpu")          # 6 of 8 GPUs
+    assert a.status == "CREATE_COMPLETE" and a.env["DEEPLEARNING_WORKERS_COUNT"] == "3"
+    b = launch_cluster("b", home=home, backend="thread", WorkerCount=2, InstanceType="b200.2gpu")          # 2 left: master only
+    assert b.status == "CREATE_COMPLETE" and b.env["DEEPLEARNING_WORKERS_COUNT"] == "1"
+
+    def gpus(name):
+        cp = ControlPlane(os.path.join(home, "stacks", name))
+        return {g for gn in cp.group_names() for i in cp.describe_group(gn)["Instances"] for g in i["Gpus"]}
+    assert len(gpus("a")) == 6 and len(gpus("b")) == 2 and not (gpus("a") & gpus("b"))
+    t0 = time.time()
+    with pytest.raises(StackError, match="InsufficientInstanceCapacity"):
+        launch_cluster("c", home=home, backend="thread", WorkerCount=1, InstanceType="b200.1gpu")
+    assert time.time() - t0 < 30
+    assert describe_stack("c", home).status == "ROLLBACK_COMPLETE"
+    delete_stack("a", home)
+    d = launch_cluster("d", home=home, backend="thread", WorkerCount=1, InstanceType="b200.2gpu")
+    assert d.status == "CREATE_COMPLETE" and d.env["DEEPLEARNING_WORKERS_COUNT"] == "2" and gpus("d") <= {0, 1, 2, 3, 4, 5, 6, 7} - gpus("b")
 
 
 def test_rollback_when_master_cannot_launch(tmp_path):
@@ -312,6 +338,7 @@ def test_mask_rcnn_stack_staging(tmp_path):
     home = os.path.join(h.master_root, "home")
     assert os.access(os.path.join(home, "run.sh"), os.X_OK) and os.path.exists(os.path.join(home, "setup.sh"))
     assert data_dir(efs, home) == os.path.join(efs, "data")
+    delete_stack("mr", str(tmp_path))          # it held all 8 GPUs of the box
     h2 = launch_cluster("mr2", "private-mask-rcnn.template", home=str(tmp_path), backend="thread", WorkerCount=1,
                         InstanceType="b200.4gpu", S3Bucket=bucket, EFSServesData="false")
     assert os.path.exists(os.path.join(h2.env["EFS_MOUNT"], "nodata.txt"))

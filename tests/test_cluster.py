@@ -51,6 +51,54 @@ def test_queue_duplicate_injection(tmp_path):
     assert sorted(m.body for m in q.receive(10, 0)) == ["x", "y", "y"]
 
 
+def _q_producer(path, pid, n):
+    from deeplearning_cfn_b200.cluster.queue import FileQueue as FQ
+    q = FQ(path)
+    for i in range(n):
+        q.send({"p": pid, "i": i})
+
+
+def _q_consumer(path, out, stop_at):
+    from deeplearning_cfn_b200.cluster.queue import FileQueue as FQ
+    q, got, idle = FQ(path), [], 0
+    while time.time() < stop_at and idle < 40:
+        msgs = q.receive(5, visibility_timeout=30.0)
+        if not msgs:
+            idle += 1
+            time.sleep(0.02)
+            continue
+        idle = 0
+        for m in msgs:
+            got.append([m.json()["p"], m.json()["i"]])
+            q.delete(m)
+    with open(out, "w") as f:
+        json.dump(got, f)
+
+
+def test_file_queue_under_concurrent_producers_and_consumers(tmp_path):
+    """The file-backed queue (the SQS stand-in of the control plane) with 3 producer and 3 consumer PROCESSES: every message
+    is delivered, none twice while its visibility timeout runs, and a deleted message is gone."""
+    import collections
+    import multiprocessing as mp
+    path = str(tmp_path / "q")
+    FileQueue(path)
+    P, N, C = 3, 60, 3
+    stop_at = time.time() + 60
+    ctx = mp.get_context("spawn")
+    outs = [str(tmp_path / f"c{c}.json") for c in range(C)]
+    procs = [ctx.Process(target=_q_producer, args=(path, p, N)) for p in range(P)]
+    procs += [ctx.Process(target=_q_consumer, args=(path, outs[c], stop_at)) for c in range(C)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    seen = collections.Counter()
+    for o in outs:
+        for p, i in json.load(open(o)):
+            seen[(p, i)] += 1
+    assert sum(seen.values()) == P * N and set(seen.values()) == {1}, (sum(seen.values()), [k for k, v in seen.items() if v != 1][:5])
+    assert len(FileQueue(path)) == 0
+
+
 # ----------------------------------------------------------------------------- scaling-event function
 def _cp_with_groups(tmp_path, desired=2, minsize=0):
     cp = ControlPlane(str(tmp_path / "stack"))

@@ -48,6 +48,9 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu, ngpu = False, 0
     for item in items:
+        # a kernel that never finishes must not sit on the GPU for the CPU tier's generous limit
+        if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(700 if "multigpu" in item.keywords else 300))
         if "gpu" in item.keywords and not has_gpu and os.environ.get("DLCFN_MOCK_GPU_DRYRUN") != "1":
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "multigpu" in item.keywords and ngpu < 2:

@@ -4,6 +4,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.timeout(600)          # with >= 2 GPUs smoke() also runs a 2-rank collectives check (own limit: 300 s)
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

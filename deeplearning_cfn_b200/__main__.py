@@ -123,6 +123,12 @@ def main(argv=None) -> int:
         except FileNotFoundError as e:          # a missing hostfile / log / list file is a usage error, not a crash
             print(f"{argv[0]}: error: {e.strerror}: {e.filename}", file=sys.stderr)
             return 1
+        except Exception as e:
+            from .launch.hostfile import HostfileError
+            if isinstance(e, HostfileError):      # so is a hostfile line that cannot be read
+                print(f"{argv[0]}: error: {e}", file=sys.stderr)
+                return 1
+            raise
 
     ap = argparse.ArgumentParser(prog="dlcfn", formatter_class=argparse.RawDescriptionHelpFormatter,
                                  epilog="job-plane commands (each with its own --help): " + ", ".join(sorted(passthrough)))

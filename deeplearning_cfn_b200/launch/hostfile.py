@@ -23,26 +23,39 @@ class Host:
         return resolve_alias(self.name, hosts_file)
 
 
+class HostfileError(ValueError):
+    """A line of a hostfile that cannot be understood (reported as `file:line: what`)."""
+
+
 def parse_hostfile(path: str) -> list[Host]:
     hosts = []
     with open(path) as f:
-        for raw in f:
+        for lineno, raw in enumerate(f, 1):
             line = raw.split("#", 1)[0].strip()
             if not line:
                 continue
             parts = line.split()
             name, port, slots = parts[0], 22, 1
-            if ":" in name:
-                name, p = name.rsplit(":", 1)
-                port = int(p)
+            if name.startswith("["):                         # [v6-address]:port
+                addr, closing, rest = name[1:].partition("]")
+                if not closing or not addr or (rest and not (rest.startswith(":") and rest[1:].isdigit())):
+                    raise HostfileError(f"{path}:{lineno}: cannot read host {name!r} (expected [address] or [address]:port)")
+                name, port = addr, int(rest[1:]) if rest else 22
+            elif name.count(":") == 1:                       # host:port (several colons = a bare IPv6 address)
+                host, p = name.split(":")
+                if not host or not p.isdigit():
+                    raise HostfileError(f"{path}:{lineno}: cannot read host {name!r} (expected host or host:port)")
+                name, port = host, int(p)
             for tok in parts[1:]:
                 if tok.startswith("slots="):
+                    if not tok[6:].isdigit() or int(tok[6:]) < 1:
+                        raise HostfileError(f"{path}:{lineno}: slots must be a positive integer, got {tok!r}")
                     slots = int(tok[6:])
                 elif tok.startswith("max_slots="):
                     pass
             hosts.append(Host(name, port, slots))
     if not hosts:
-        raise ValueError(f"hostfile {path} is empty")
+        raise HostfileError(f"hostfile {path} is empty")
     return hosts
 
 

@@ -24,6 +24,21 @@ def test_hostfile_formats(tmp_path):
     assert resolve_alias("unknown-host", str(hosts)) == "unknown-host"
     write_mpi_hostfile(str(tmp_path / "mpi"), ["a", "b"], 4)
     assert (tmp_path / "mpi").read_text() == "a slots=4\nb slots=4\n"
+    # IPv6 forms, and lines that cannot be read are reported as file:line instead of a bare int() traceback
+    p.write_text("fe80::1 slots=2\n[fe80::2]:2200\n[::1]\n")
+    assert [(h.name, h.port, h.slots) for h in parse_hostfile(str(p))] == [("fe80::1", 22, 2), ("fe80::2", 2200, 1), ("::1", 22, 1)]
+    from deeplearning_cfn_b200.launch.hostfile import HostfileError
+    for bad, needle in (("node1\nnode2:ssh\n", ":2:"), ("node1 slots=many\n", "slots"), ("node1 slots=0\n", "slots"), ("[::1\n", ":1:"),
+                        ("# only a comment\n", "empty")):
+        p.write_text(bad)
+        with pytest.raises(HostfileError, match=needle):
+            parse_hostfile(str(p))
+    import subprocess
+    import sys
+    p.write_text("node1:ssh\n")
+    r = subprocess.run([sys.executable, "-m", "deeplearning_cfn_b200", "launch", "-n", "1", "-H", str(p), "true"],
+                       capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    assert r.returncode == 1 and "launch: error:" in r.stderr and "Traceback" not in r.stderr
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 16, 31])

@@ -81,7 +81,7 @@ def cmd_describe_stack_events(a) -> int:
     from .cluster.controlplane import ControlPlane
     from .cluster.stack import DEFAULT_HOME, StackError
     sdir = os.path.join(a.home or DEFAULT_HOME, "stacks", a.stack_name)
-    if not os.path.isdir(sdir):
+    if not os.path.exists(os.path.join(sdir, "stack.json")):
         raise StackError(f"no such stack: {a.stack_name}")
     evs = ControlPlane(sdir).stack().get("events", [])
     out = [{"Timestamp": datetime.datetime.fromtimestamp(e["ts"], datetime.timezone.utc).isoformat(timespec="milliseconds"),
@@ -120,7 +120,8 @@ def main(argv=None) -> int:
         mod = importlib.import_module("." + passthrough[argv[0]], __package__)
         try:
             return int(mod.main(argv[1:]) or 0)
-        except FileNotFoundError as e:          # a missing hostfile / log / list file is a usage error, not a crash
+        except (FileNotFoundError, IsADirectoryError, NotADirectoryError, PermissionError) as e:
+            # a missing / unreadable hostfile, log or list file is a usage error, not a crash
             print(f"{argv[0]}: error: {e.strerror}: {e.filename}", file=sys.stderr)
             return 1
         except Exception as e:

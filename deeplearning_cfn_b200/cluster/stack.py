@@ -346,6 +346,8 @@ def _gpus_reserved_by_other_stacks(home: str, me: str) -> set:
 def describe_stack(stack_name: str, home: str | None = None) -> ClusterHandle:
     home = home or DEFAULT_HOME
     sdir = os.path.join(home, "stacks", stack_name)
+    if not os.path.exists(os.path.join(sdir, "stack.json")):       # (looking must not create the directory tree of a stack)
+        raise StackError(f"no such stack: {stack_name}")
     cp = ControlPlane(sdir)
     st = cp.stack()
     if not st:

@@ -87,11 +87,16 @@ def main(argv=None) -> int:
     cpu = a.gpu_count <= 0            # a box without GPUs: sweep the number of CPU ranks per worker instead
     xs = gpu_steps(max(1, a.gpu_count) * max(1, a.worker_count))
     for spec in a.networks:
-        _, net, batch, size = spec.split(":")
-        layers = 50
-        if "-" in net:
-            net, l = net.split("-")
-            layers = int(l)
+        try:
+            _, net, batch, size = spec.split(":")
+            layers = 50
+            if "-" in net:
+                net, l = net.split("-")
+                layers = int(l)
+            int(batch), int(size)
+        except ValueError:
+            raise SystemExit(f"benchmark: --networks takes mode:network[-layers]:batch_per_gpu:image_size (e.g. native:resnet-50:256:224), "
+                             f"got {spec!r}")
         rows, speedup = [], {}
         for kv in a.kv_stores:
             speeds = []

@@ -27,6 +27,8 @@ def parse(argv: list[str]):
     while i < len(argv):
         a = argv[i]
         if a in ("-np", "-n", "--np"):
+            if i + 1 >= len(argv) or not argv[i + 1].isdigit():
+                raise SystemExit(f"mpirun: {a} takes a process count, got {argv[i + 1] if i + 1 < len(argv) else 'nothing'!r}")
             np_ = int(argv[i + 1]); i += 2
         elif a in ("--hostfile", "-hostfile", "--machinefile", "-machinefile"):
             hostfile = argv[i + 1]; i += 2

@@ -389,3 +389,22 @@ def test_yarn_mesos_kubernetes_submissions_run_a_job_through_shim_clis(kind, tmp
     r = run_job(cmd, env=env, timeout=240, cwd=str(tmp_path))
     assert r.returncode == 0 and r.stdout.count("ASYNC_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
     assert os.path.exists(tmp_path / {"yarn": "dlcfn-yarn.json", "mesos": "dlcfn-mesos.json", "kubernetes": "dlcfn-k8s.json"}[kind])
+
+
+def test_cli_answers_bad_arguments_with_messages_not_tracebacks(tmp_path):
+    """Every user-facing command on arguments a user can plausibly get wrong: a message and a non-zero exit, never a Python
+    traceback (the list grew out of a sweep over all commands; the three that used to crash are first)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root, DLCFN_HOME=str(tmp_path / "home"), DLCFN_FAKE_GPUS="2")
+    cases = ["benchmark --networks bogus", "benchmark --networks native:resnet-50:32", "mpirun -np x true", "mpirun -np",
+             "launch -n 2 -s 1", "launch -n 1 -H /nonexistent true", "kill /nonexistent", "generate-trainer --workers_file_path /nonexistent",
+             "run-example nosuch", "run-example resnet50-ps --stack-name nosuch", "im2rec /nonexistent /nonexistent", "parse-log /nonexistent",
+             "rec2idx /nonexistent", "create-stack --parameters WorkerCount=abc", "create-stack --template-body /nonexistent",
+             "describe-stacks --stack-name nosuch", "describe-stack-events --stack-name nosuch", "delete-stack --stack-name nosuch",
+             "validate-template --template-body /nonexistent", "node-exec nosuch -- true"]
+    for args in cases:
+        r = subprocess.run([sys.executable, "-m", "deeplearning_cfn_b200"] + args.split(), env=env, capture_output=True, text=True,
+                           stdin=subprocess.DEVNULL, timeout=120, cwd=str(tmp_path))
+        assert r.returncode != 0 and "Traceback" not in r.stderr + r.stdout, (args, r.returncode, (r.stderr + r.stdout)[-400:])

@@ -75,7 +75,10 @@ def main(argv=None) -> int:
     if opt.use_thumbnail and opt.dataset in ("imagenet", "dummy"):
         side = 32
     name = opt.model + ("_bn" if opt.batch_norm and opt.model.startswith("vgg") and "bn" not in opt.model else "")
-    net = get_model(name, classes, side, in_ch=ch).to(device)
+    try:
+        net = get_model(name, classes, side, in_ch=ch).to(device)
+    except ValueError as e:           # unknown --model: a usage error
+        raise SystemExit(f"image_classification: {e}")
     if dtype != torch.float32 and use_gpu:
         net = to_b200_layout(net, dtype)
     if opt.resume:

@@ -93,7 +93,10 @@ def main(argv=None) -> int:
     use_gpu = torch.cuda.is_available()
     dev = torch.device("cuda", torch.cuda.current_device()) if use_gpu else torch.device("cpu")
     size = int(a.image_shape.split(",")[-1])
-    model = get_model(a.network, a.num_classes, size, num_layers=a.num_layers)
+    try:
+        model = get_model(a.network, a.num_classes, size, num_layers=a.num_layers)
+    except ValueError as e:           # unknown --network / a depth the family does not have: a usage error
+        raise SystemExit(f"train_imagenet: {e}")
     if a.initializer not in ("default", ""):
         # fit.py:200-215: 'xavier' -> Xavier(gaussian, in, 2), 'msra' -> MSRAPrelu, else the named mx.init class
         from deeplearning_cfn_b200.kv import initializer as init_mod

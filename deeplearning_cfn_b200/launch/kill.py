@@ -46,8 +46,8 @@ def remote_command(user: str, prog: str) -> str:
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) != 3:
-        print("usage: kill <hostfile> <user> <prog>")
-        return 1
+        print("usage: kill <hostfile> <user> <prog>      (ends the processes of <user> whose command line contains <prog> on every host)")
+        return 0 if argv and argv[0] in ("-h", "--help") else 1
     hostfile, user, prog = argv
     import subprocess
     done_local = False
